@@ -1,0 +1,237 @@
+/*
+ * inerf_b200.h -- C-ABI of libinerf_b200.so, the B200 (sm_100a) implementation
+ * of Instance-NeRF's instance-field render / train hot path.
+ *
+ * Drop-in boundary: every entry point replaces one function of the reference's
+ * pybind FFI (L0 in SURVEY.md section 8b).  Paths below are relative to
+ * /root/reference/instance_nerf/.
+ *
+ * Conventions
+ *   - plain C pointers to DEVICE memory, explicit sizes, no torch types;
+ *   - the caller allocates every output (the reference's Python wrappers do the
+ *     same: raymarching/raymarching.py:205-208, 260-262, 323-326);
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream,
+ *     which is what the reference launches on: raymarching.cu:154,488,586);
+ *   - every function returns 0 on success, a NEGATIVE inerf_status on a bad
+ *     argument and a POSITIVE cudaError_t if the launch failed.  Nothing throws.
+ *     (The reference's raymarching functions check nothing; gridencoder /
+ *     shencoder TORCH_CHECK and throw: gridencoder.cu:446-462.)
+ */
+#ifndef INERF_B200_H
+#define INERF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum inerf_status {
+    INERF_OK = 0,
+    INERF_ERR_NULL = -1,        /* required pointer is NULL */
+    INERF_ERR_SIZE = -2,        /* size / count out of range */
+    INERF_ERR_UNSUPPORTED = -3, /* configuration the kernels do not implement */
+    INERF_ERR_WORKSPACE = -4,   /* workspace too small */
+    INERF_ERR_ALIGN = -5        /* pointer not aligned as required */
+} inerf_status;
+
+typedef enum inerf_dtype { INERF_F32 = 0, INERF_F16 = 1 } inerf_dtype;
+
+/* Library / ABI version (major*1000 + minor). */
+int inerf_version(void);
+/* Human-readable text for a return code (static storage). */
+const char *inerf_error_string(int code);
+
+/* ------------------------------------------------------------------ utils -- */
+
+/* raymarching/src/raymarching.h:7  near_far_from_aabb (kernel raymarching.cu:91-145) */
+int inerf_near_far_from_aabb(const float *rays_o, const float *rays_d, const float *aabb, uint32_t N,
+                             float min_near, float *nears, float *fars, void *stream);
+/* raymarching.h:8  sph_from_ray (raymarching.cu:162-198) */
+int inerf_sph_from_ray(const float *rays_o, const float *rays_d, float radius, uint32_t N, float *coords,
+                       void *stream);
+/* raymarching.h:9  morton3D (raymarching.cu:214-232) */
+int inerf_morton3D(const int32_t *coords, uint32_t N, int32_t *indices, void *stream);
+/* raymarching.h:10 morton3D_invert (raymarching.cu:237-260) */
+int inerf_morton3D_invert(const int32_t *indices, uint32_t N, int32_t *coords, void *stream);
+/* raymarching.h:11 packbits (raymarching.cu:267-300); N = number of output BYTES (C*H^3/8) */
+int inerf_packbits(const float *grid, uint32_t N, float density_thresh, uint8_t *bitfield, void *stream);
+
+/* ------------------------------------------------------- training marching -- */
+
+/*
+ * raymarching.h:13 march_rays_train (raymarching.cu:311-490).
+ *
+ * The reference reserves sample ranges with atomicAdd, so its output order is
+ * racy.  This library is deterministic: count -> exclusive scan -> write.
+ * `rays` comes out sorted by ray id with offsets = exclusive prefix sum of the
+ * counts, i.e. exactly the canonical form of the reference's stream.
+ *
+ * Two-phase use (lets the host size xyzs/dirs/deltas exactly instead of
+ * zero-filling N*max_steps rows as raymarching.py:205-207 does):
+ *   inerf_march_rays_train_count  writes rays[N,3] and adds (total, N) to counter[2];
+ *   inerf_march_rays_train_write  writes the samples of every ray with offset+count <= M.
+ * inerf_march_rays_train does both with the reference's argument list.
+ */
+int inerf_march_rays_train_count(const float *rays_o, const float *rays_d, const uint8_t *grid, float bound,
+                                 float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H,
+                                 const float *nears, const float *fars, int32_t *rays, int32_t *counter,
+                                 const float *noises, void *stream);
+int inerf_march_rays_train_write(const float *rays_o, const float *rays_d, const uint8_t *grid, float bound,
+                                 float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M,
+                                 const float *nears, const float *fars, float *xyzs, float *dirs, float *deltas,
+                                 const int32_t *rays, const float *noises, void *stream);
+int inerf_march_rays_train(const float *rays_o, const float *rays_d, const uint8_t *grid, float bound, float dt_gamma,
+                           uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M, const float *nears,
+                           const float *fars, float *xyzs, float *dirs, float *deltas, int32_t *rays,
+                           int32_t *counter, const float *noises, void *stream);
+
+/* --------------------------------------------------- training compositing -- */
+
+/* raymarching.h:14 composite_rays_train_forward (raymarching.cu:500-588) */
+int inerf_composite_rays_train_forward(const float *sigmas, const float *rgbs, const float *deltas,
+                                       const int32_t *rays, uint32_t M, uint32_t N, float T_thresh,
+                                       float *weights_sum, float *depth, float *image, void *stream);
+/* raymarching.h:15 composite_rays_train_backward (raymarching.cu:601-693); grad_* pre-zeroed by the caller */
+int inerf_composite_rays_train_backward(const float *grad_weights_sum, const float *grad_image, const float *sigmas,
+                                        const float *rgbs, const float *deltas, const int32_t *rays,
+                                        const float *weights_sum, const float *image, uint32_t M, uint32_t N,
+                                        float T_thresh, float *grad_sigmas, float *grad_rgbs, void *stream);
+/* raymarching.h:17 composite_rays_with_masks_train_forward (raymarching.cu:705-810) */
+int inerf_composite_rays_with_masks_train_forward(const float *sigmas, const float *rgbs, const float *masks,
+                                                  const float *deltas, const int32_t *rays, uint32_t M, uint32_t N,
+                                                  uint32_t K, float T_thresh, float *weights_sum, float *depth,
+                                                  float *image, float *mask_out, void *stream);
+/* raymarching.h:18 composite_rays_with_masks_train_backward (raymarching.cu:828-951).
+ * grad_masks_acc (the reference's global scratch, raymarching.cu:844) is accepted
+ * for signature compatibility and may be NULL: the running sums live in registers. */
+int inerf_composite_rays_with_masks_train_backward(const float *grad_weights_sum, const float *grad_image,
+                                                   const float *grad_mask_out, const float *sigmas, const float *rgbs,
+                                                   const float *masks, const float *deltas, const int32_t *rays,
+                                                   const float *weights_sum, const float *image, const float *mask_out,
+                                                   uint32_t M, uint32_t N, uint32_t K, float T_thresh,
+                                                   float *grad_sigmas, float *grad_rgbs, float *grad_masks_acc,
+                                                   float *grad_masks, void *stream);
+
+/* -------------------------------------------------------------- inference -- */
+
+/* raymarching.h:20 march_rays (raymarching.cu:958-1073); xyzs/dirs/deltas pre-zeroed by the caller */
+int inerf_march_rays(uint32_t n_alive, uint32_t n_step, const int32_t *rays_alive, const float *rays_t,
+                     const float *rays_o, const float *rays_d, float bound, float dt_gamma, uint32_t max_steps,
+                     uint32_t C, uint32_t H, const uint8_t *grid, const float *nears, const float *fars, float *xyzs,
+                     float *dirs, float *deltas, const float *noises, void *stream);
+/* raymarching.h:21 composite_rays (raymarching.cu:1076-1172) */
+int inerf_composite_rays(uint32_t n_alive, uint32_t n_step, float T_thresh, int32_t *rays_alive, float *rays_t,
+                         const float *sigmas, const float *rgbs, const float *deltas, float *weights_sum,
+                         float *depth, float *image, void *stream);
+/* raymarching.h:22 composite_rays_with_masks (raymarching.cu:1175-1280) */
+int inerf_composite_rays_with_masks(uint32_t n_alive, uint32_t n_step, uint32_t K, float T_thresh,
+                                    int32_t *rays_alive, float *rays_t, const float *sigmas, const float *rgbs,
+                                    const float *masks, const float *deltas, float *weights_sum, float *depth,
+                                    float *image, float *mask_out, void *stream);
+/* Device-side stream compaction replacing `rays_alive[rays_alive >= 0]`
+ * (nerf/mask_renderer.py:370): stable, writes the survivors to `out` and their
+ * number to n_out[0].  `out` must not alias `rays_alive`. */
+int inerf_compact_alive(const int32_t *rays_alive, uint32_t n_alive, int32_t *out, int32_t *n_out, void *stream);
+
+/* ------------------------------------------------------------ grid encoder -- */
+
+/*
+ * gridencoder/src/gridencoder.h:12 grid_encode_forward (gridencoder.cu:87-242, 445-468).
+ *   inputs      float [B, D] in [0, 1]
+ *   embeddings  [offsets[L], C] of `dtype`
+ *   offsets     int32 [L + 1]
+ *   outputs     `dtype`; out_layout 0 = [L, B, C] (what the reference kernel
+ *               writes, grid.py:47), 1 = [B, L*C] (what grid.py:57 permutes to)
+ *   dy_dx       optional [B, L*D*C] of `dtype`, or NULL
+ *   S = log2(per_level_scale), H = base resolution, gridtype 0 = hash / 1 = tiled,
+ *   interp 0 = linear / 1 = smoothstep.  D in {2,3}, C in {1,2,4,8}.
+ */
+int inerf_grid_encode_forward(const float *inputs, const void *embeddings, const int32_t *offsets, void *outputs,
+                              uint32_t B, uint32_t D, uint32_t C, uint32_t L, float S, uint32_t H, void *dy_dx,
+                              uint32_t gridtype, int align_corners, uint32_t interp, int dtype, int out_layout,
+                              void *stream);
+/*
+ * gridencoder.h:13 grid_encode_backward (gridencoder.cu:245-337, 470-500).
+ *   grad            `dtype`, grad_layout 0 = [L, B, C] (grid.py:75), 1 = [B, L*C]
+ *   grad_embeddings `dtype`, pre-zeroed by the caller (grid.py:77), accumulated atomically
+ *   dy_dx / grad_inputs optional (NULL on the instance-field path, grid.py:156)
+ */
+int inerf_grid_encode_backward(const void *grad, const float *inputs, const void *embeddings, const int32_t *offsets,
+                               void *grad_embeddings, uint32_t B, uint32_t D, uint32_t C, uint32_t L, float S,
+                               uint32_t H, const void *dy_dx, void *grad_inputs, uint32_t gridtype,
+                               int align_corners, uint32_t interp, int dtype, int grad_layout, void *stream);
+
+/* -------------------------------------------------------------- SH encoder -- */
+
+/* shencoder/src/shencoder.h:9 sh_encode_forward (shencoder.cu:28-129, 386-417).
+ * inputs float [B, 3], outputs float [B, degree^2], degree in [1, 8]; dy_dx optional [B, 3*degree^2]
+ * (supported for degree <= 4). */
+int inerf_sh_encode_forward(const float *inputs, float *outputs, uint32_t B, uint32_t D, uint32_t degree,
+                            float *dy_dx, void *stream);
+/* shencoder.h:10 sh_encode_backward (shencoder.cu:359-382, 419-438) */
+int inerf_sh_encode_backward(const float *grad, const float *inputs, uint32_t B, uint32_t D, uint32_t degree,
+                             const float *dy_dx, float *grad_inputs, void *stream);
+
+/* --------------------------------------------------- fused instance field -- */
+
+/*
+ * One launch for NeRFNetwork.forward (nerf/network_mask.py:119-158): both hash
+ * encoders, SH degree 4, sigma-net 32->64->16, colour-net 31->64->64->3 and
+ * mask-net 47->64->64->K on tcgen05 tensor cores (fp16 operands, fp32 TMEM
+ * accumulators, one fp16 rounding per layer as under torch autocast).
+ *
+ * `weights` is the packed fp16 blob produced by inerf_field_pack_weights from
+ * the fp32 nn.Linear matrices ([out, in] row-major, network_mask.py:48,69,90).
+ */
+typedef struct inerf_field_desc {
+    const void *table_sigma;   /* fp16 [offsets[L], 2]  encoder.embeddings      */
+    const void *table_mask;    /* fp16 [offsets[L], 2]  encoder_mask.embeddings */
+    const int32_t *offsets;    /* int32 [L + 1] (shared by both encoders)      */
+    const void *weights;       /* packed fp16 blob, inerf_field_weights_bytes(K) bytes */
+    uint32_t L;                /* 16 */
+    uint32_t H;                /* base resolution 16 */
+    float S;                   /* log2(per_level_scale) */
+    float bound;               /* scene bound: x01 = (x + bound) / (2 bound) */
+    uint32_t K;                /* num_instances, 1..64 */
+    float density_scale;       /* mask_renderer.py:273 */
+} inerf_field_desc;
+
+size_t inerf_field_weights_bytes(uint32_t K);
+/* host-side packing (CPU pointers): w_* are fp32 row-major [out, in] */
+int inerf_field_pack_weights(const float *sigma0, const float *sigma1, const float *color0, const float *color1,
+                             const float *color2, const float *mask0, const float *mask1, const float *mask2,
+                             uint32_t K, void *packed_host);
+/* xyzs/dirs float [B,3]; sigmas float [B]; rgbs float [B,3]; masks float [B,K] (NULL = skip mask-net) */
+int inerf_field_forward(const inerf_field_desc *desc, const float *xyzs, const float *dirs, uint32_t B,
+                        float *sigmas, float *rgbs, float *masks, void *stream);
+
+/*
+ * Whole-frame inference render in ONE persistent launch, replacing the host
+ * loop of NeRFMaskRenderer.run_cuda (nerf/mask_renderer.py:322-381):
+ * march -> encode -> MLP -> composite per 128-ray tile, ray state in registers,
+ * no sample stream in HBM.  Outputs are the un-normalised accumulators the
+ * reference loop produces before mask_renderer.py:376-377.
+ */
+int inerf_render_fused(const inerf_field_desc *desc, const float *rays_o, const float *rays_d, const float *nears,
+                       const float *fars, const uint8_t *bitfield, uint32_t N, uint32_t C, uint32_t H,
+                       float dt_gamma, uint32_t max_steps, float T_thresh, float *weights_sum, float *depth,
+                       float *image, float *mask_out, int32_t *work_counter, void *stream);
+
+/* ------------------------------------------------------ occupancy grid EMA -- */
+
+/*
+ * nerf/mask_renderer.py:532-540 as two launches without host syncs:
+ *   grid[i] = max(grid[i]*decay, tmp[i]) where both >= 0; sum(clamp(grid,0)) -> mean_out[0] (pre-zeroed),
+ *   then packbits with thresh = min(mean, density_thresh).
+ */
+int inerf_occupancy_ema(float *density_grid, const float *tmp_grid, uint32_t n_cells, float decay,
+                        double *sum_out, void *stream);
+int inerf_occupancy_pack(const float *density_grid, uint32_t n_cells, const double *sum_in, float density_thresh,
+                         uint8_t *bitfield, float *mean_out, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* INERF_B200_H */

@@ -1,0 +1,346 @@
+// Alpha compositing of colour, depth and per-sample instance logits (sm_100a).
+//
+// Replaces raymarching/src/raymarching.cu:500-951 (training forward/backward,
+// with and without masks) and :1076-1280 (inference) of the reference.
+//
+// Mapping: ONE WARP PER RAY instead of the reference's one thread per ray.
+//   * the sample stream (sigma, deltas, rgb) is read 32 samples at a time with
+//     coalesced loads, alpha is evaluated for 32 samples in parallel;
+//   * lane k owns instance class k (+32, +64, ...): logits[s, :] is one coalesced
+//     128-byte load per sample and the K running sums live in registers, where
+//     the reference read-modify-writes mask_out / grad_masks_acc in global memory
+//     2K times per sample (raymarching.cu:766-768, 894-896);
+//   * the transmittance recurrence T *= (1 - alpha) is evaluated in the
+//     reference's order (every lane redundantly), so the early-stop decision
+//     `T < T_thresh` is warp-uniform and matches the reference sample for sample.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kMaxKPL = 4;  // classes per lane -> K <= 128
+constexpr unsigned kFull = 0xffffffffu;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+    return v;
+}
+
+// ---- training forward (K == 0: plain, raymarching.cu:500-577; K > 0: :705-799) ----
+template <int KPL>
+__global__ void __launch_bounds__(256) k_composite_train_fwd(
+    const float* __restrict__ sigmas, const float* __restrict__ rgbs, const float* __restrict__ masks,
+    const float* __restrict__ deltas, const int32_t* __restrict__ rays, uint32_t M, uint32_t N, uint32_t K,
+    float T_thresh, float* __restrict__ weights_sum, float* __restrict__ depth, float* __restrict__ image,
+    float* __restrict__ mask_out) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (n >= N) return;
+    const uint32_t index = (uint32_t)rays[n * 3], offset = (uint32_t)rays[n * 3 + 1], num_steps = (uint32_t)rays[n * 3 + 2];
+
+    float macc[KPL > 0 ? KPL : 1];
+#pragma unroll
+    for (int i = 0; i < (KPL > 0 ? KPL : 1); i++) macc[i] = 0.f;
+    float T = 1.0f, r = 0, g = 0, b = 0, ws = 0, t = 0, d = 0;
+
+    if (num_steps != 0 && offset + num_steps <= M) {
+        bool done = false;
+        for (uint32_t base = 0; base < num_steps && !done; base += 32) {
+            const uint32_t s = offset + base + lane;
+            const bool valid = base + lane < num_steps;
+            float alpha = 0.f, d1 = 0.f, cr = 0.f, cg = 0.f, cb = 0.f;
+            if (valid) {
+                const float2 dl = __ldg(reinterpret_cast<const float2*>(deltas) + s);
+                alpha = 1.0f - __expf(-__ldg(sigmas + s) * dl.x);
+                d1 = dl.y;
+                cr = __ldg(rgbs + (size_t)s * 3); cg = __ldg(rgbs + (size_t)s * 3 + 1); cb = __ldg(rgbs + (size_t)s * 3 + 2);
+            }
+            const uint32_t cnt = min(32u, num_steps - base);
+            for (uint32_t j = 0; j < cnt; j++) {
+                const float a = __shfl_sync(kFull, alpha, j);
+                const float weight = a * T;
+                r = fmaf(weight, __shfl_sync(kFull, cr, j), r);
+                g = fmaf(weight, __shfl_sync(kFull, cg, j), g);
+                b = fmaf(weight, __shfl_sync(kFull, cb, j), b);
+                if (KPL > 0) {
+                    const float* mrow = masks + (size_t)(offset + base + j) * K;
+#pragma unroll
+                    for (int i = 0; i < KPL; i++) {
+                        const uint32_t k = lane + 32u * i;
+                        if (k < K) macc[i] = fmaf(weight, __ldg(mrow + k), macc[i]);
+                    }
+                }
+                t += __shfl_sync(kFull, d1, j);
+                d = fmaf(weight, t, d);
+                ws += weight;
+                T *= 1.0f - a;
+                if (T < T_thresh) { done = true; break; }
+            }
+        }
+    }
+    if (lane == 0) {
+        weights_sum[index] = ws;
+        depth[index] = d;
+        image[(size_t)index * 3] = r; image[(size_t)index * 3 + 1] = g; image[(size_t)index * 3 + 2] = b;
+    }
+    if (KPL > 0) {
+#pragma unroll
+        for (int i = 0; i < KPL; i++) {
+            const uint32_t k = lane + 32u * i;
+            if (k < K) mask_out[(size_t)index * K + k] = macc[i];
+        }
+    }
+}
+
+// ---- training backward (K == 0: raymarching.cu:601-682; K > 0: :828-940) ----
+template <int KPL>
+__global__ void __launch_bounds__(256) k_composite_train_bwd(
+    const float* __restrict__ grad_weights_sum, const float* __restrict__ grad_image, const float* __restrict__ grad_mask_out,
+    const float* __restrict__ sigmas, const float* __restrict__ rgbs, const float* __restrict__ masks,
+    const float* __restrict__ deltas, const int32_t* __restrict__ rays, const float* __restrict__ weights_sum,
+    const float* __restrict__ image, const float* __restrict__ mask_out, uint32_t M, uint32_t N, uint32_t K, float T_thresh,
+    float* __restrict__ grad_sigmas, float* __restrict__ grad_rgbs, float* __restrict__ grad_masks) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (n >= N) return;
+    const uint32_t index = (uint32_t)rays[n * 3], offset = (uint32_t)rays[n * 3 + 1], num_steps = (uint32_t)rays[n * 3 + 2];
+    if (num_steps == 0 || offset + num_steps > M) return;
+
+    const float gr = grad_image[(size_t)index * 3], gg = grad_image[(size_t)index * 3 + 1], gb = grad_image[(size_t)index * 3 + 2];
+    const float r_final = image[(size_t)index * 3], g_final = image[(size_t)index * 3 + 1], b_final = image[(size_t)index * 3 + 2];
+    const float ws_term = grad_weights_sum[index] * (1 - weights_sum[index]);
+    float gm[KPL > 0 ? KPL : 1], mfin[KPL > 0 ? KPL : 1], macc[KPL > 0 ? KPL : 1];
+#pragma unroll
+    for (int i = 0; i < (KPL > 0 ? KPL : 1); i++) {
+        const uint32_t k = lane + 32u * i;
+        const bool ok = KPL > 0 && k < K;
+        gm[i] = ok ? grad_mask_out[(size_t)index * K + k] : 0.f;
+        mfin[i] = ok ? mask_out[(size_t)index * K + k] : 0.f;
+        macc[i] = 0.f;
+    }
+    float T = 1.0f, r = 0, g = 0, b = 0;
+
+    for (uint32_t base = 0; base < num_steps; base += 32) {
+        const uint32_t s = offset + base + lane;
+        const bool valid = base + lane < num_steps;
+        float alpha = 0.f, d0 = 0.f, cr = 0.f, cg = 0.f, cb = 0.f;
+        if (valid) {
+            d0 = __ldg(deltas + (size_t)s * 2);
+            alpha = 1.0f - __expf(-__ldg(sigmas + s) * d0);
+            cr = __ldg(rgbs + (size_t)s * 3); cg = __ldg(rgbs + (size_t)s * 3 + 1); cb = __ldg(rgbs + (size_t)s * 3 + 2);
+        }
+        float my_w = 0.f, my_gs = 0.f;  // lane j keeps the results of sample base + j
+        bool my_written = false;
+        const uint32_t cnt = min(32u, num_steps - base);
+        bool done = false;
+        for (uint32_t j = 0; j < cnt; j++) {
+            const float a = __shfl_sync(kFull, alpha, j);
+            const float weight = a * T;
+            const float rj = __shfl_sync(kFull, cr, j), gj = __shfl_sync(kFull, cg, j), bj = __shfl_sync(kFull, cb, j);
+            r = fmaf(weight, rj, r);
+            g = fmaf(weight, gj, g);
+            b = fmaf(weight, bj, b);
+            T *= 1.0f - a;
+            float part = 0.f;
+            if (KPL > 0) {
+                const size_t row = (size_t)(offset + base + j) * K;
+#pragma unroll
+                for (int i = 0; i < KPL; i++) {
+                    const uint32_t k = lane + 32u * i;
+                    if (k < K) {
+                        const float m = __ldg(masks + row + k);
+                        macc[i] = fmaf(weight, m, macc[i]);
+                        grad_masks[row + k] = gm[i] * weight;
+                        part += gm[i] * (T * m - (mfin[i] - macc[i]));
+                    }
+                }
+                part = warp_sum(part);
+            }
+            const float gs = gr * (T * rj - (r_final - r)) + gg * (T * gj - (g_final - g)) + gb * (T * bj - (b_final - b)) + ws_term + part;
+            if (lane == j) { my_w = weight; my_gs = gs; my_written = true; }
+            if (T < T_thresh) { done = true; break; }
+        }
+        if (my_written) {
+            grad_sigmas[s] = d0 * my_gs;
+            grad_rgbs[(size_t)s * 3] = gr * my_w; grad_rgbs[(size_t)s * 3 + 1] = gg * my_w; grad_rgbs[(size_t)s * 3 + 2] = gb * my_w;
+        }
+        if (done) break;
+    }
+}
+
+// ---- inference (K == 0: raymarching.cu:1076-1163; K > 0: :1175-1271) ----
+template <int KPL>
+__global__ void __launch_bounds__(256) k_composite_infer(
+    uint32_t n_alive, uint32_t n_step, uint32_t K, float T_thresh, int32_t* __restrict__ rays_alive, float* __restrict__ rays_t,
+    const float* __restrict__ sigmas, const float* __restrict__ rgbs, const float* __restrict__ masks,
+    const float* __restrict__ deltas, float* __restrict__ weights_sum, float* __restrict__ depth, float* __restrict__ image,
+    float* __restrict__ mask_out) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (n >= n_alive) return;
+    const int32_t index = rays_alive[n];
+    const size_t s0 = (size_t)n * n_step;
+
+    float t = rays_t[index], weight_sum = weights_sum[index], d = depth[index];
+    float r = image[(size_t)index * 3], g = image[(size_t)index * 3 + 1], b = image[(size_t)index * 3 + 2];
+    float macc[KPL > 0 ? KPL : 1];
+#pragma unroll
+    for (int i = 0; i < (KPL > 0 ? KPL : 1); i++) {
+        const uint32_t k = lane + 32u * i;
+        macc[i] = (KPL > 0 && k < K) ? mask_out[(size_t)index * K + k] : 0.f;
+    }
+    uint32_t step = 0;
+    bool stop = false;
+    for (uint32_t base = 0; base < n_step && !stop; base += 32) {
+        const bool valid = base + lane < n_step;
+        const size_t s = s0 + base + lane;
+        float d0 = 0.f, d1 = 0.f, alpha = 0.f, cr = 0.f, cg = 0.f, cb = 0.f;
+        if (valid) {
+            const float2 dl = __ldg(reinterpret_cast<const float2*>(deltas) + s);
+            d0 = dl.x; d1 = dl.y;
+            alpha = 1.0f - __expf(-__ldg(sigmas + s) * d0);
+            cr = __ldg(rgbs + s * 3); cg = __ldg(rgbs + s * 3 + 1); cb = __ldg(rgbs + s * 3 + 2);
+        }
+        const uint32_t cnt = min(32u, n_step - base);
+        for (uint32_t j = 0; j < cnt; j++) {
+            if (__shfl_sync(kFull, d0, j) == 0.f) { stop = true; break; }  // ray finished (:1116)
+            const float a = __shfl_sync(kFull, alpha, j);
+            const float T = 1 - weight_sum;
+            const float weight = a * T;
+            weight_sum += weight;
+            t += __shfl_sync(kFull, d1, j);
+            d = fmaf(weight, t, d);
+            r = fmaf(weight, __shfl_sync(kFull, cr, j), r);
+            g = fmaf(weight, __shfl_sync(kFull, cg, j), g);
+            b = fmaf(weight, __shfl_sync(kFull, cb, j), b);
+            if (KPL > 0) {
+                const float* mrow = masks + (s0 + base + j) * K;
+#pragma unroll
+                for (int i = 0; i < KPL; i++) {
+                    const uint32_t k = lane + 32u * i;
+                    if (k < K) macc[i] = fmaf(weight, __ldg(mrow + k), macc[i]);
+                }
+            }
+            if (T < T_thresh) { stop = true; break; }
+            step++;
+        }
+    }
+    if (lane == 0) {
+        if (step < n_step) rays_alive[n] = -1; else rays_t[index] = t;
+        weights_sum[index] = weight_sum;
+        depth[index] = d;
+        image[(size_t)index * 3] = r; image[(size_t)index * 3 + 1] = g; image[(size_t)index * 3 + 2] = b;
+    }
+    if (KPL > 0) {
+#pragma unroll
+        for (int i = 0; i < KPL; i++) {
+            const uint32_t k = lane + 32u * i;
+            if (k < K) mask_out[(size_t)index * K + k] = macc[i];
+        }
+    }
+}
+
+template <typename F>
+int dispatch_kpl(uint32_t K, F&& f) {
+    if (K == 0) return f(std::integral_constant<int, 0>{});
+    if (K <= 32) return f(std::integral_constant<int, 1>{});
+    if (K <= 64) return f(std::integral_constant<int, 2>{});
+    if (K <= 32 * kMaxKPL) return f(std::integral_constant<int, kMaxKPL>{});
+    return INERF_ERR_UNSUPPORTED;
+}
+
+int composite_train_fwd(const float* sigmas, const float* rgbs, const float* masks, const float* deltas, const int32_t* rays,
+                        uint32_t M, uint32_t N, uint32_t K, float T_thresh, float* weights_sum, float* depth, float* image,
+                        float* mask_out, void* stream) {
+    if (N == 0) return INERF_OK;
+    INERF_REQUIRE(rays); INERF_REQUIRE(weights_sum); INERF_REQUIRE(depth); INERF_REQUIRE(image);
+    if (M) { INERF_REQUIRE(sigmas); INERF_REQUIRE(rgbs); INERF_REQUIRE(deltas); }
+    if (K) { INERF_REQUIRE(mask_out); if (M) INERF_REQUIRE(masks); }
+    if ((uintptr_t)deltas & 7u) return INERF_ERR_ALIGN;
+    return dispatch_kpl(K, [&](auto kpl) {
+        k_composite_train_fwd<decltype(kpl)::value><<<div_up((unsigned long long)N * 32, 256), 256, 0, (cudaStream_t)stream>>>(
+            sigmas, rgbs, masks, deltas, rays, M, N, K, T_thresh, weights_sum, depth, image, mask_out);
+        INERF_LAUNCH_CHECK();
+        return (int)INERF_OK;
+    });
+}
+
+int composite_train_bwd(const float* grad_weights_sum, const float* grad_image, const float* grad_mask_out, const float* sigmas,
+                        const float* rgbs, const float* masks, const float* deltas, const int32_t* rays, const float* weights_sum,
+                        const float* image, const float* mask_out, uint32_t M, uint32_t N, uint32_t K, float T_thresh,
+                        float* grad_sigmas, float* grad_rgbs, float* grad_masks, void* stream) {
+    if (N == 0 || M == 0) return INERF_OK;
+    INERF_REQUIRE(grad_weights_sum); INERF_REQUIRE(grad_image); INERF_REQUIRE(sigmas); INERF_REQUIRE(rgbs); INERF_REQUIRE(deltas);
+    INERF_REQUIRE(rays); INERF_REQUIRE(weights_sum); INERF_REQUIRE(image); INERF_REQUIRE(grad_sigmas); INERF_REQUIRE(grad_rgbs);
+    if (K) { INERF_REQUIRE(grad_mask_out); INERF_REQUIRE(masks); INERF_REQUIRE(mask_out); INERF_REQUIRE(grad_masks); }
+    return dispatch_kpl(K, [&](auto kpl) {
+        k_composite_train_bwd<decltype(kpl)::value><<<div_up((unsigned long long)N * 32, 256), 256, 0, (cudaStream_t)stream>>>(
+            grad_weights_sum, grad_image, grad_mask_out, sigmas, rgbs, masks, deltas, rays, weights_sum, image, mask_out, M, N, K,
+            T_thresh, grad_sigmas, grad_rgbs, grad_masks);
+        INERF_LAUNCH_CHECK();
+        return (int)INERF_OK;
+    });
+}
+
+int composite_infer(uint32_t n_alive, uint32_t n_step, uint32_t K, float T_thresh, int32_t* rays_alive, float* rays_t,
+                    const float* sigmas, const float* rgbs, const float* masks, const float* deltas, float* weights_sum,
+                    float* depth, float* image, float* mask_out, void* stream) {
+    if (n_alive == 0 || n_step == 0) return INERF_OK;
+    INERF_REQUIRE(rays_alive); INERF_REQUIRE(rays_t); INERF_REQUIRE(sigmas); INERF_REQUIRE(rgbs); INERF_REQUIRE(deltas);
+    INERF_REQUIRE(weights_sum); INERF_REQUIRE(depth); INERF_REQUIRE(image);
+    if (K) { INERF_REQUIRE(masks); INERF_REQUIRE(mask_out); }
+    if ((uintptr_t)deltas & 7u) return INERF_ERR_ALIGN;
+    return dispatch_kpl(K, [&](auto kpl) {
+        k_composite_infer<decltype(kpl)::value><<<div_up((unsigned long long)n_alive * 32, 256), 256, 0, (cudaStream_t)stream>>>(
+            n_alive, n_step, K, T_thresh, rays_alive, rays_t, sigmas, rgbs, masks, deltas, weights_sum, depth, image, mask_out);
+        INERF_LAUNCH_CHECK();
+        return (int)INERF_OK;
+    });
+}
+
+}  // namespace
+
+extern "C" int inerf_composite_rays_train_forward(const float* sigmas, const float* rgbs, const float* deltas, const int32_t* rays,
+                                                  uint32_t M, uint32_t N, float T_thresh, float* weights_sum, float* depth,
+                                                  float* image, void* stream) {
+    return composite_train_fwd(sigmas, rgbs, nullptr, deltas, rays, M, N, 0, T_thresh, weights_sum, depth, image, nullptr, stream);
+}
+extern "C" int inerf_composite_rays_with_masks_train_forward(const float* sigmas, const float* rgbs, const float* masks,
+                                                             const float* deltas, const int32_t* rays, uint32_t M, uint32_t N,
+                                                             uint32_t K, float T_thresh, float* weights_sum, float* depth,
+                                                             float* image, float* mask_out, void* stream) {
+    if (K == 0) return INERF_ERR_SIZE;
+    return composite_train_fwd(sigmas, rgbs, masks, deltas, rays, M, N, K, T_thresh, weights_sum, depth, image, mask_out, stream);
+}
+extern "C" int inerf_composite_rays_train_backward(const float* grad_weights_sum, const float* grad_image, const float* sigmas,
+                                                   const float* rgbs, const float* deltas, const int32_t* rays,
+                                                   const float* weights_sum, const float* image, uint32_t M, uint32_t N,
+                                                   float T_thresh, float* grad_sigmas, float* grad_rgbs, void* stream) {
+    return composite_train_bwd(grad_weights_sum, grad_image, nullptr, sigmas, rgbs, nullptr, deltas, rays, weights_sum, image, nullptr,
+                               M, N, 0, T_thresh, grad_sigmas, grad_rgbs, nullptr, stream);
+}
+extern "C" int inerf_composite_rays_with_masks_train_backward(const float* grad_weights_sum, const float* grad_image,
+                                                              const float* grad_mask_out, const float* sigmas, const float* rgbs,
+                                                              const float* masks, const float* deltas, const int32_t* rays,
+                                                              const float* weights_sum, const float* image, const float* mask_out,
+                                                              uint32_t M, uint32_t N, uint32_t K, float T_thresh, float* grad_sigmas,
+                                                              float* grad_rgbs, float* grad_masks_acc, float* grad_masks, void* stream) {
+    (void)grad_masks_acc;
+    if (K == 0) return INERF_ERR_SIZE;
+    return composite_train_bwd(grad_weights_sum, grad_image, grad_mask_out, sigmas, rgbs, masks, deltas, rays, weights_sum, image,
+                               mask_out, M, N, K, T_thresh, grad_sigmas, grad_rgbs, grad_masks, stream);
+}
+extern "C" int inerf_composite_rays(uint32_t n_alive, uint32_t n_step, float T_thresh, int32_t* rays_alive, float* rays_t,
+                                    const float* sigmas, const float* rgbs, const float* deltas, float* weights_sum, float* depth,
+                                    float* image, void* stream) {
+    return composite_infer(n_alive, n_step, 0, T_thresh, rays_alive, rays_t, sigmas, rgbs, nullptr, deltas, weights_sum, depth, image,
+                           nullptr, stream);
+}
+extern "C" int inerf_composite_rays_with_masks(uint32_t n_alive, uint32_t n_step, uint32_t K, float T_thresh, int32_t* rays_alive,
+                                               float* rays_t, const float* sigmas, const float* rgbs, const float* masks,
+                                               const float* deltas, float* weights_sum, float* depth, float* image, float* mask_out,
+                                               void* stream) {
+    if (K == 0) return INERF_ERR_SIZE;
+    return composite_infer(n_alive, n_step, K, T_thresh, rays_alive, rays_t, sigmas, rgbs, masks, deltas, weights_sum, depth, image,
+                           mask_out, stream);
+}

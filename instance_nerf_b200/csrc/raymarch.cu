@@ -1,0 +1,451 @@
+// Ray generation helpers and occupancy-grid marching for sm_100a.
+//
+// Replaces raymarching/src/raymarching.cu:91-490 and :958-1073 of the reference
+// (near/far, Morton, packbits, march_rays_train, march_rays).  The arithmetic is
+// spelled with explicit round-to-nearest intrinsics (__fmaf_rn / __fmul_rn /
+// __fadd_rn / __fdiv_rn) in exactly the places where nvcc's default -fmad=true
+// contracts the reference's expressions, so the sample stream is bit-identical
+// to the reference's and independent of compiler flags.
+//
+// Unlike the reference (atomicAdd reservation, racy order) training marching is
+// deterministic: count -> exclusive scan -> write, rays in id order.
+#include "common.cuh"
+
+namespace {
+
+constexpr float kSqrt3 = 1.7320508075688772f;
+
+// ---- Morton (raymarching.cu:56-81) -----------------------------------------
+__host__ __device__ __forceinline__ uint32_t expand_bits(uint32_t v) {
+    v = (v * 0x00010001u) & 0xFF0000FFu;
+    v = (v * 0x00000101u) & 0x0F00F00Fu;
+    v = (v * 0x00000011u) & 0xC30C30C3u;
+    v = (v * 0x00000005u) & 0x49249249u;
+    return v;
+}
+__host__ __device__ __forceinline__ uint32_t morton3D_enc(uint32_t x, uint32_t y, uint32_t z) {
+    return expand_bits(x) | (expand_bits(y) << 1) | (expand_bits(z) << 2);
+}
+__host__ __device__ __forceinline__ uint32_t morton3D_dec(uint32_t x) {
+    x = x & 0x49249249u;
+    x = (x | (x >> 2)) & 0xc30c30c3u;
+    x = (x | (x >> 4)) & 0x0f00f00fu;
+    x = (x | (x >> 8)) & 0xff0000ffu;
+    x = (x | (x >> 16)) & 0x0000ffffu;
+    return x;
+}
+
+// frexpf exponent clamped to [0, C-1] (raymarching.cu:42-54).  For the clamped
+// result the biased-exponent field is enough: zero / denormals give <= 0.
+__device__ __forceinline__ int clamped_exponent(float mx, int C) {
+    const int e = (int)((__float_as_uint(mx) >> 23) & 0xffu) - 126;
+    return min(C - 1, max(0, e));
+}
+
+struct Walk {
+    float ox, oy, oz, dx, dy, dz, rdx, rdy, rdz;
+    float sx, sy, sz;  // 0.5 * sign(d)
+    float bound, dt_gamma, dt_min, dt_max, rH, H3, Hf, Hm1, far;
+    int C;
+    const uint8_t* __restrict__ grid;
+
+    __device__ __forceinline__ void init(const float* __restrict__ o, const float* __restrict__ d,
+                                         const uint8_t* __restrict__ g, float bound_, float dt_gamma_,
+                                         uint32_t max_steps, uint32_t C_, uint32_t H, float far_) {
+        ox = o[0]; oy = o[1]; oz = o[2];
+        dx = d[0]; dy = d[1]; dz = d[2];
+        rdx = __fdiv_rn(1.0f, dx); rdy = __fdiv_rn(1.0f, dy); rdz = __fdiv_rn(1.0f, dz);
+        sx = copysignf(0.5f, dx); sy = copysignf(0.5f, dy); sz = copysignf(0.5f, dz);
+        bound = bound_; dt_gamma = dt_gamma_;
+        Hf = (float)H; Hm1 = (float)(H - 1);
+        rH = __fdiv_rn(1.0f, Hf);
+        H3 = (float)(H * H * H);
+        dt_min = __fdiv_rn(2.0f * kSqrt3, (float)max_steps);                                   // :345
+        dt_max = __fdiv_rn(__fmul_rn(2.0f * kSqrt3, (float)(1 << (C_ - 1))), Hf);              // :346
+        far = far_; C = (int)C_; grid = g;
+    }
+    __device__ __forceinline__ float step_size(float t) const { return clampf(__fmul_rn(t, dt_gamma), dt_min, dt_max); }
+
+    // One DDA walk (raymarching.cu:359-400 / :427-479 / :1008-1062).
+    template <bool WRITE>
+    __device__ __forceinline__ uint32_t run(float t, uint32_t limit, float* __restrict__ xyzs, float* __restrict__ dirs,
+                                            float* __restrict__ deltas) const {
+        uint32_t step = 0;
+        float last_t = t;
+        while (t < far && step < limit) {
+            const float x = clampf(__fmaf_rn(t, dx, ox), -bound, bound);
+            const float y = clampf(__fmaf_rn(t, dy, oy), -bound, bound);
+            const float z = clampf(__fmaf_rn(t, dz, oz), -bound, bound);
+            const float dt = step_size(t);
+            // mip level: max(mip_from_pos, mip_from_dt)
+            const float mx = fmaxf(fabsf(x), fmaxf(fabsf(y), fabsf(z)));
+            const float md = __fmul_rn(__fmul_rn(dt, Hf), 0.5f);
+            const int level = max(clamped_exponent(mx, C), clamped_exponent(md, C));
+            const float mip_bound = fminf(__uint_as_float((uint32_t)(127 + level) << 23), bound);
+            const float mip_rbound = __fdiv_rn(1.0f, mip_bound);
+            // (x * mip_rbound + 1) is one float FMA in the reference; the * 0.5 * H that follows is done in
+            // double there and is exact for H a power of two, so a float multiply by 0.5 * H gives the same bits.
+            const float hH = __fmul_rn(0.5f, Hf);
+            const int nx = (int)clampf(__fmul_rn(__fmaf_rn(x, mip_rbound, 1.0f), hH), 0.0f, Hm1);
+            const int ny = (int)clampf(__fmul_rn(__fmaf_rn(y, mip_rbound, 1.0f), hH), 0.0f, Hm1);
+            const int nz = (int)clampf(__fmul_rn(__fmaf_rn(z, mip_rbound, 1.0f), hH), 0.0f, Hm1);
+            const uint32_t index = (uint32_t)__fmaf_rn((float)level, H3, (float)morton3D_enc(nx, ny, nz));
+            const bool occ = grid[index >> 3] & (1u << (index & 7u));
+            if (occ) {
+                if (WRITE) {
+                    xyzs[0] = x; xyzs[1] = y; xyzs[2] = z;
+                    dirs[0] = dx; dirs[1] = dy; dirs[2] = dz;
+                }
+                t = __fadd_rn(t, dt);
+                if (WRITE) {
+                    deltas[0] = dt;
+                    deltas[1] = __fsub_rn(t, last_t);
+                    last_t = t;
+                    xyzs += 3; dirs += 3; deltas += 2;
+                }
+                step++;
+            } else {
+                // distance to the next voxel face along each axis (:390-394)
+                const float tx = __fmul_rn(__fmaf_rn(__fmaf_rn(__fmul_rn(__fadd_rn(__fadd_rn((float)nx, 0.5f), sx), rH), 2.0f, -1.0f), mip_bound, -x), rdx);
+                const float ty = __fmul_rn(__fmaf_rn(__fmaf_rn(__fmul_rn(__fadd_rn(__fadd_rn((float)ny, 0.5f), sy), rH), 2.0f, -1.0f), mip_bound, -y), rdy);
+                const float tz = __fmul_rn(__fmaf_rn(__fmaf_rn(__fmul_rn(__fadd_rn(__fadd_rn((float)nz, 0.5f), sz), rH), 2.0f, -1.0f), mip_bound, -z), rdz);
+                const float tt = __fadd_rn(t, fmaxf(0.0f, fminf(tx, fminf(ty, tz))));
+                do { t = __fadd_rn(t, step_size(t)); } while (t < tt);
+            }
+        }
+        return step;
+    }
+};
+
+// ---- utils -------------------------------------------------------------------
+
+__global__ void k_near_far_from_aabb(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                                     const float* __restrict__ aabb, uint32_t N, float min_near,
+                                     float* __restrict__ nears, float* __restrict__ fars) {
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    const float ox = rays_o[n * 3], oy = rays_o[n * 3 + 1], oz = rays_o[n * 3 + 2];
+    const float rdx = __fdiv_rn(1.0f, rays_d[n * 3]), rdy = __fdiv_rn(1.0f, rays_d[n * 3 + 1]), rdz = __fdiv_rn(1.0f, rays_d[n * 3 + 2]);
+    const float kMax = 3.402823466e+38f;
+    float near = __fmul_rn(__fsub_rn(aabb[0], ox), rdx), far = __fmul_rn(__fsub_rn(aabb[3], ox), rdx), tmp;
+    if (near > far) { tmp = near; near = far; far = tmp; }
+    float near_y = __fmul_rn(__fsub_rn(aabb[1], oy), rdy), far_y = __fmul_rn(__fsub_rn(aabb[4], oy), rdy);
+    if (near_y > far_y) { tmp = near_y; near_y = far_y; far_y = tmp; }
+    if (near > far_y || near_y > far) { nears[n] = kMax; fars[n] = kMax; return; }
+    if (near_y > near) near = near_y;
+    if (far_y < far) far = far_y;
+    float near_z = __fmul_rn(__fsub_rn(aabb[2], oz), rdz), far_z = __fmul_rn(__fsub_rn(aabb[5], oz), rdz);
+    if (near_z > far_z) { tmp = near_z; near_z = far_z; far_z = tmp; }
+    if (near > far_z || near_z > far) { nears[n] = kMax; fars[n] = kMax; return; }
+    if (near_z > near) near = near_z;
+    if (far_z < far) far = far_z;
+    if (near < min_near) near = min_near;
+    nears[n] = near;
+    fars[n] = far;
+}
+
+// raymarching.cu:162-198
+__global__ void k_sph_from_ray(const float* __restrict__ rays_o, const float* __restrict__ rays_d, float radius,
+                               uint32_t N, float* __restrict__ coords) {
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    const float ox = rays_o[n * 3], oy = rays_o[n * 3 + 1], oz = rays_o[n * 3 + 2];
+    const float dx = rays_d[n * 3], dy = rays_d[n * 3 + 1], dz = rays_d[n * 3 + 2];
+    const float A = dx * dx + dy * dy + dz * dz;
+    const float B = ox * dx + oy * dy + oz * dz;
+    const float Cc = ox * ox + oy * oy + oz * oz - radius * radius;
+    const float t = (-B + sqrtf(B * B - A * Cc)) / A;
+    const float x = ox + t * dx, y = oy + t * dy, z = oz + t * dz;
+    const float theta = atan2f(sqrtf(x * x + z * z), y);
+    const float phi = atan2f(z, x);
+    const float kRPi = 0.3183098861837907f;
+    coords[n * 2] = 2 * theta * kRPi - 1;
+    coords[n * 2 + 1] = phi * kRPi;
+}
+
+__global__ void k_morton3D(const int32_t* __restrict__ coords, uint32_t N, int32_t* __restrict__ indices) {
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    indices[n] = (int32_t)morton3D_enc(coords[n * 3], coords[n * 3 + 1], coords[n * 3 + 2]);
+}
+__global__ void k_morton3D_invert(const int32_t* __restrict__ indices, uint32_t N, int32_t* __restrict__ coords) {
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    const int32_t ind = indices[n];
+    coords[n * 3 + 0] = (int32_t)morton3D_dec((uint32_t)(ind >> 0));
+    coords[n * 3 + 1] = (int32_t)morton3D_dec((uint32_t)(ind >> 1));
+    coords[n * 3 + 2] = (int32_t)morton3D_dec((uint32_t)(ind >> 2));
+}
+
+// One thread packs 32 cells (4 bytes out, 8 x float4 in): coalesced 128-bit
+// loads instead of the reference's 1 byte per thread (raymarching.cu:267-289).
+__global__ void k_packbits(const float* __restrict__ grid, uint32_t N, float thresh, uint8_t* __restrict__ bitfield) {
+    const uint32_t nwords = N >> 2;
+    for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < nwords; w += gridDim.x * blockDim.x) {
+        const float4* g = reinterpret_cast<const float4*>(grid) + (size_t)w * 8;
+        uint32_t bits = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const float4 v = __ldg(g + i);
+            bits |= (uint32_t)(v.x > thresh) << (i * 4 + 0);
+            bits |= (uint32_t)(v.y > thresh) << (i * 4 + 1);
+            bits |= (uint32_t)(v.z > thresh) << (i * 4 + 2);
+            bits |= (uint32_t)(v.w > thresh) << (i * 4 + 3);
+        }
+        reinterpret_cast<uint32_t*>(bitfield)[w] = bits;
+    }
+    // tail bytes (N not a multiple of 4)
+    if (blockIdx.x == 0 && threadIdx.x < (N & 3u)) {
+        const uint32_t n = (N & ~3u) + threadIdx.x;
+        uint8_t bits = 0;
+        for (int i = 0; i < 8; i++) bits |= (grid[(size_t)n * 8 + i] > thresh) ? (uint8_t)(1u << i) : 0;
+        bitfield[n] = bits;
+    }
+}
+
+// ---- training marching ---------------------------------------------------------
+
+__global__ void __launch_bounds__(128) k_march_count(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                                                     const uint8_t* __restrict__ grid, float bound, float dt_gamma,
+                                                     uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H,
+                                                     const float* __restrict__ nears, const float* __restrict__ fars,
+                                                     const float* __restrict__ noises, int32_t* __restrict__ rays) {
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    Walk w;
+    w.init(rays_o + (size_t)n * 3, rays_d + (size_t)n * 3, grid, bound, dt_gamma, max_steps, C, H, fars[n]);
+    float t0 = nears[n];
+    t0 = __fmaf_rn(w.step_size(t0), noises[n], t0);  // :351
+    rays[n * 3 + 2] = (int32_t)w.run<false>(t0, max_steps, nullptr, nullptr, nullptr);
+}
+
+// Single-CTA exclusive scan of the counts (N is at most a few million rays; the
+// scan reads 4 B and writes 8 B per ray, microseconds next to the marching).
+__global__ void __launch_bounds__(1024) k_march_scan(int32_t* __restrict__ rays, uint32_t N, int32_t* __restrict__ counter) {
+    __shared__ uint32_t warp_sums[32];
+    __shared__ uint32_t carry_s;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry_s = (uint32_t)counter[0];
+    __syncthreads();
+    for (uint32_t base = 0; base < N; base += 1024) {
+        const uint32_t n = base + threadIdx.x;
+        const uint32_t v = n < N ? (uint32_t)rays[n * 3 + 2] : 0u;
+        uint32_t incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= (uint32_t)o) incl += up;
+        }
+        if (lane == 31) warp_sums[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t ws = warp_sums[lane], wi = ws;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t up = __shfl_up_sync(0xffffffffu, wi, o);
+                if (lane >= (uint32_t)o) wi += up;
+            }
+            warp_sums[lane] = wi - ws;  // exclusive warp offsets
+        }
+        __syncthreads();
+        const uint32_t carry = carry_s;
+        const uint32_t excl = carry + warp_sums[warp] + incl - v;
+        if (n < N) { rays[n * 3] = (int32_t)n; rays[n * 3 + 1] = (int32_t)excl; }
+        __syncthreads();
+        if (threadIdx.x == 1023) carry_s = excl + v;  // last thread holds the chunk's inclusive total
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { counter[0] = (int32_t)carry_s; counter[1] += (int32_t)N; }
+}
+
+__global__ void __launch_bounds__(128) k_march_write(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                                                     const uint8_t* __restrict__ grid, float bound, float dt_gamma,
+                                                     uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M,
+                                                     const float* __restrict__ nears, const float* __restrict__ fars,
+                                                     const float* __restrict__ noises, const int32_t* __restrict__ rays,
+                                                     float* __restrict__ xyzs, float* __restrict__ dirs, float* __restrict__ deltas) {
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    const uint32_t offset = (uint32_t)rays[n * 3 + 1], num_steps = (uint32_t)rays[n * 3 + 2];
+    if (num_steps == 0 || offset + num_steps > M) return;  // :415-416
+    Walk w;
+    w.init(rays_o + (size_t)n * 3, rays_d + (size_t)n * 3, grid, bound, dt_gamma, max_steps, C, H, fars[n]);
+    float t0 = nears[n];
+    t0 = __fmaf_rn(w.step_size(t0), noises[n], t0);
+    w.run<true>(t0, num_steps, xyzs + (size_t)offset * 3, dirs + (size_t)offset * 3, deltas + (size_t)offset * 2);
+}
+
+// ---- inference marching (raymarching.cu:958-1063) -------------------------------
+
+__global__ void __launch_bounds__(128) k_march_rays(uint32_t n_alive, uint32_t n_step, const int32_t* __restrict__ rays_alive,
+                                                    const float* __restrict__ rays_t, const float* __restrict__ rays_o,
+                                                    const float* __restrict__ rays_d, float bound, float dt_gamma,
+                                                    uint32_t max_steps, uint32_t C, uint32_t H, const uint8_t* __restrict__ grid,
+                                                    const float* __restrict__ fars, float* __restrict__ xyzs,
+                                                    float* __restrict__ dirs, float* __restrict__ deltas,
+                                                    const float* __restrict__ noises) {
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= n_alive) return;
+    const int32_t index = rays_alive[n];
+    Walk w;
+    w.init(rays_o + (size_t)index * 3, rays_d + (size_t)index * 3, grid, bound, dt_gamma, max_steps, C, H, fars[index]);
+    float t = rays_t[index];
+    t = __fmaf_rn(w.step_size(t), noises[n], t);  // :1004
+    const size_t s = (size_t)n * n_step;
+    w.run<true>(t, n_step, xyzs + s * 3, dirs + s * 3, deltas + s * 2);
+}
+
+// Stable compaction of rays_alive >= 0 (replaces the boolean-index + sync at mask_renderer.py:370).
+__global__ void __launch_bounds__(1024) k_compact_alive(const int32_t* __restrict__ in, uint32_t n, int32_t* __restrict__ out,
+                                                        int32_t* __restrict__ n_out) {
+    __shared__ uint32_t warp_sums[32];
+    __shared__ uint32_t carry_s;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < n; base += 1024) {
+        const uint32_t i = base + threadIdx.x;
+        const int32_t v = i < n ? in[i] : -1;
+        const bool keep = v >= 0;
+        const uint32_t ballot = __ballot_sync(0xffffffffu, keep);
+        const uint32_t prefix = __popc(ballot & ((1u << lane) - 1u));
+        if (lane == 0) warp_sums[warp] = __popc(ballot);
+        __syncthreads();
+        if (warp == 0) {
+            const uint32_t ws = warp_sums[lane];
+            uint32_t wi = ws;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t up = __shfl_up_sync(0xffffffffu, wi, o);
+                if (lane >= (uint32_t)o) wi += up;
+            }
+            warp_sums[lane] = wi - ws;
+        }
+        __syncthreads();
+        const uint32_t carry = carry_s;
+        const uint32_t pos = carry + warp_sums[warp] + prefix;
+        if (keep) out[pos] = v;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry_s = pos + (keep ? 1u : 0u);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) n_out[0] = (int32_t)carry_s;
+}
+
+}  // namespace
+
+// ---- C ABI ---------------------------------------------------------------------
+
+extern "C" int inerf_near_far_from_aabb(const float* rays_o, const float* rays_d, const float* aabb, uint32_t N,
+                                        float min_near, float* nears, float* fars, void* stream) {
+    if (N == 0) return INERF_OK;
+    INERF_REQUIRE(rays_o); INERF_REQUIRE(rays_d); INERF_REQUIRE(aabb); INERF_REQUIRE(nears); INERF_REQUIRE(fars);
+    k_near_far_from_aabb<<<div_up(N, 256), 256, 0, (cudaStream_t)stream>>>(rays_o, rays_d, aabb, N, min_near, nears, fars);
+    INERF_LAUNCH_CHECK();
+    return INERF_OK;
+}
+
+extern "C" int inerf_sph_from_ray(const float* rays_o, const float* rays_d, float radius, uint32_t N, float* coords, void* stream) {
+    if (N == 0) return INERF_OK;
+    INERF_REQUIRE(rays_o); INERF_REQUIRE(rays_d); INERF_REQUIRE(coords);
+    k_sph_from_ray<<<div_up(N, 256), 256, 0, (cudaStream_t)stream>>>(rays_o, rays_d, radius, N, coords);
+    INERF_LAUNCH_CHECK();
+    return INERF_OK;
+}
+
+extern "C" int inerf_morton3D(const int32_t* coords, uint32_t N, int32_t* indices, void* stream) {
+    if (N == 0) return INERF_OK;
+    INERF_REQUIRE(coords); INERF_REQUIRE(indices);
+    k_morton3D<<<div_up(N, 256), 256, 0, (cudaStream_t)stream>>>(coords, N, indices);
+    INERF_LAUNCH_CHECK();
+    return INERF_OK;
+}
+
+extern "C" int inerf_morton3D_invert(const int32_t* indices, uint32_t N, int32_t* coords, void* stream) {
+    if (N == 0) return INERF_OK;
+    INERF_REQUIRE(indices); INERF_REQUIRE(coords);
+    k_morton3D_invert<<<div_up(N, 256), 256, 0, (cudaStream_t)stream>>>(indices, N, coords);
+    INERF_LAUNCH_CHECK();
+    return INERF_OK;
+}
+
+extern "C" int inerf_packbits(const float* grid, uint32_t N, float density_thresh, uint8_t* bitfield, void* stream) {
+    if (N == 0) return INERF_OK;
+    INERF_REQUIRE(grid); INERF_REQUIRE(bitfield);
+    if (((uintptr_t)grid & 15u) || ((uintptr_t)bitfield & 3u)) return INERF_ERR_ALIGN;
+    const unsigned int blocks = min(div_up(max(N >> 2, 1u), 256), (unsigned int)(kNumSMs * 8));
+    k_packbits<<<blocks, 256, 0, (cudaStream_t)stream>>>(grid, N, density_thresh, bitfield);
+    INERF_LAUNCH_CHECK();
+    return INERF_OK;
+}
+
+static int check_march_args(uint32_t C, uint32_t H, uint32_t max_steps) {
+    if (C == 0 || C > 16 || H == 0 || H > 1024 || max_steps == 0) return INERF_ERR_SIZE;
+    if (H & (H - 1)) return INERF_ERR_UNSUPPORTED;  // the float rewrite of the double sub-expression needs H = 2^k
+    return INERF_OK;
+}
+
+extern "C" int inerf_march_rays_train_count(const float* rays_o, const float* rays_d, const uint8_t* grid, float bound,
+                                            float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H,
+                                            const float* nears, const float* fars, int32_t* rays, int32_t* counter,
+                                            const float* noises, void* stream) {
+    if (int e = check_march_args(C, H, max_steps)) return e;
+    INERF_REQUIRE(counter);
+    if (N == 0) return INERF_OK;
+    INERF_REQUIRE(rays_o); INERF_REQUIRE(rays_d); INERF_REQUIRE(grid); INERF_REQUIRE(nears); INERF_REQUIRE(fars);
+    INERF_REQUIRE(rays); INERF_REQUIRE(noises);
+    k_march_count<<<div_up(N, 128), 128, 0, (cudaStream_t)stream>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H,
+                                                                  nears, fars, noises, rays);
+    INERF_LAUNCH_CHECK();
+    k_march_scan<<<1, 1024, 0, (cudaStream_t)stream>>>(rays, N, counter);
+    INERF_LAUNCH_CHECK();
+    return INERF_OK;
+}
+
+extern "C" int inerf_march_rays_train_write(const float* rays_o, const float* rays_d, const uint8_t* grid, float bound,
+                                            float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M,
+                                            const float* nears, const float* fars, float* xyzs, float* dirs, float* deltas,
+                                            const int32_t* rays, const float* noises, void* stream) {
+    if (int e = check_march_args(C, H, max_steps)) return e;
+    if (N == 0 || M == 0) return INERF_OK;
+    INERF_REQUIRE(rays_o); INERF_REQUIRE(rays_d); INERF_REQUIRE(grid); INERF_REQUIRE(nears); INERF_REQUIRE(fars);
+    INERF_REQUIRE(rays); INERF_REQUIRE(noises); INERF_REQUIRE(xyzs); INERF_REQUIRE(dirs); INERF_REQUIRE(deltas);
+    k_march_write<<<div_up(N, 128), 128, 0, (cudaStream_t)stream>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, M,
+                                                                  nears, fars, noises, rays, xyzs, dirs, deltas);
+    INERF_LAUNCH_CHECK();
+    return INERF_OK;
+}
+
+extern "C" int inerf_march_rays_train(const float* rays_o, const float* rays_d, const uint8_t* grid, float bound, float dt_gamma,
+                                      uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M, const float* nears,
+                                      const float* fars, float* xyzs, float* dirs, float* deltas, int32_t* rays,
+                                      int32_t* counter, const float* noises, void* stream) {
+    if (int e = inerf_march_rays_train_count(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, nears, fars, rays,
+                                             counter, noises, stream)) return e;
+    return inerf_march_rays_train_write(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, M, nears, fars, xyzs, dirs,
+                                        deltas, rays, noises, stream);
+}
+
+extern "C" int inerf_march_rays(uint32_t n_alive, uint32_t n_step, const int32_t* rays_alive, const float* rays_t,
+                                const float* rays_o, const float* rays_d, float bound, float dt_gamma, uint32_t max_steps,
+                                uint32_t C, uint32_t H, const uint8_t* grid, const float* nears, const float* fars, float* xyzs,
+                                float* dirs, float* deltas, const float* noises, void* stream) {
+    (void)nears;  // passed but unused by the reference kernel as well (raymarching.cu:995)
+    if (int e = check_march_args(C, H, max_steps)) return e;
+    if (n_alive == 0 || n_step == 0) return INERF_OK;
+    INERF_REQUIRE(rays_alive); INERF_REQUIRE(rays_t); INERF_REQUIRE(rays_o); INERF_REQUIRE(rays_d); INERF_REQUIRE(grid);
+    INERF_REQUIRE(fars); INERF_REQUIRE(xyzs); INERF_REQUIRE(dirs); INERF_REQUIRE(deltas); INERF_REQUIRE(noises);
+    k_march_rays<<<div_up(n_alive, 128), 128, 0, (cudaStream_t)stream>>>(n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, bound,
+                                                                       dt_gamma, max_steps, C, H, grid, fars, xyzs, dirs, deltas, noises);
+    INERF_LAUNCH_CHECK();
+    return INERF_OK;
+}
+
+extern "C" int inerf_compact_alive(const int32_t* rays_alive, uint32_t n_alive, int32_t* out, int32_t* n_out, void* stream) {
+    INERF_REQUIRE(n_out);
+    if (n_alive) { INERF_REQUIRE(rays_alive); INERF_REQUIRE(out); }
+    if (rays_alive == out && n_alive) return INERF_ERR_UNSUPPORTED;
+    k_compact_alive<<<1, 1024, 0, (cudaStream_t)stream>>>(rays_alive, n_alive, out, n_out);
+    INERF_LAUNCH_CHECK();
+    return INERF_OK;
+}

@@ -1,0 +1,210 @@
+"""NeRFNetwork with the instance-logit head (mirrors nerf/network_mask.py:10-272).
+
+Same constructor arguments, sub-module names and therefore the same state-dict
+keys as the reference (`encoder.embeddings`, `encoder.offsets`,
+`sigma_net.{0,1}.weight`, `color_net.{0,1,2}.weight`, `encoder_mask.*`,
+`mask_net.{0,1,2}.weight`), so reference checkpoints load unchanged.
+
+Two execution paths, both on libinerf_b200:
+* fused (default for no-grad CUDA calls with the standard architecture): ONE
+  kernel for hash encode x2 + SH + the three MLPs on tcgen05 tensor cores;
+* modular (autograd / non-standard widths): GridEncoder + SHEncoder kernels and
+  nn.Linear, exactly the reference's operator sequence (network_mask.py:119-158).
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .._lib import FieldDesc, call, lib, ptr, stream_ptr
+from ..activation import trunc_exp
+from ..encoding import get_encoder
+from .renderer import NeRFMaskRenderer
+
+
+class NeRFNetwork(NeRFMaskRenderer):
+    def __init__(self, encoding="hashgrid", encoding_dir="sphere_harmonics", encoding_bg="hashgrid", num_layers=2, hidden_dim=64,
+                 geo_feat_dim=15, num_layers_color=3, hidden_dim_color=64, num_layers_bg=2, hidden_dim_bg=64, num_layers_mask=3,
+                 hidden_dim_mask=64, num_instances=2, bound=1, **kwargs):
+        super().__init__(bound, num_instances=num_instances, **kwargs)
+        self.num_layers = num_layers
+        self.hidden_dim = hidden_dim
+        self.geo_feat_dim = geo_feat_dim
+        self.encoder, self.in_dim = get_encoder(encoding, desired_resolution=2048 * bound)
+        self.sigma_net = nn.ModuleList([
+            nn.Linear(self.in_dim if l == 0 else hidden_dim, 1 + geo_feat_dim if l == num_layers - 1 else hidden_dim, bias=False)
+            for l in range(num_layers)])
+
+        self.num_layers_color = num_layers_color
+        self.hidden_dim_color = hidden_dim_color
+        self.encoder_dir, self.in_dim_dir = get_encoder(encoding_dir)
+        self.color_net = nn.ModuleList([
+            nn.Linear(self.in_dim_dir + geo_feat_dim if l == 0 else hidden_dim_color, 3 if l == num_layers_color - 1 else hidden_dim_color,
+                      bias=False) for l in range(num_layers_color)])
+
+        self.num_layers_mask = num_layers_mask
+        self.hidden_dim_mask = hidden_dim_mask
+        self.encoder_mask, self.in_dim_mask = get_encoder(encoding, desired_resolution=2048 * bound)
+        self.mask_net = nn.ModuleList([
+            nn.Linear(self.in_dim_mask + geo_feat_dim if l == 0 else hidden_dim_mask,
+                      num_instances if l == num_layers_mask - 1 else hidden_dim_mask, bias=False) for l in range(num_layers_mask)])
+
+        if self.bg_radius > 0:
+            # background model (network_mask.py:95-114): outside the instance-field hot path, kept modular
+            self.num_layers_bg = num_layers_bg
+            self.hidden_dim_bg = hidden_dim_bg
+            self.encoder_bg, self.in_dim_bg = get_encoder(encoding_bg, input_dim=2, num_levels=4, log2_hashmap_size=19,
+                                                          desired_resolution=2048)
+            self.bg_net = nn.ModuleList([
+                nn.Linear(self.in_dim_bg + self.in_dim_dir if l == 0 else hidden_dim_bg, 3 if l == num_layers_bg - 1 else hidden_dim_bg,
+                          bias=False) for l in range(num_layers_bg)])
+        else:
+            self.bg_net = None
+
+        self.use_fused = True     # set False to force the modular operator sequence
+        self._packed = None       # (key, fp16 weight blob on device)
+        self._work_counter = None
+
+    # ---- fused path ------------------------------------------------------------------
+    def _standard_arch(self) -> bool:
+        e = self.encoder
+        return (self.num_layers == 2 and self.hidden_dim == 64 and self.geo_feat_dim == 15 and self.num_layers_color == 3
+                and self.hidden_dim_color == 64 and self.num_layers_mask == 3 and self.hidden_dim_mask == 64
+                and getattr(e, "num_levels", 0) == 16 and getattr(e, "level_dim", 0) == 2 and getattr(e, "gridtype", "") == "hash"
+                and not e.align_corners and e.interp_id == 0 and getattr(self.encoder_dir, "degree", 0) == 4
+                and 1 <= self.num_instances <= 64 and hasattr(lib(), "inerf_field_forward"))
+
+    def fused_available(self) -> bool:
+        return bool(self.use_fused and self._standard_arch() and self.encoder.embeddings.is_cuda)
+
+    def fused_render_available(self, render_mask: bool) -> bool:
+        return self.fused_available() and self.bg_radius <= 0 and hasattr(lib(), "inerf_render_fused")
+
+    def _packed_weights(self) -> torch.Tensor:
+        ws = [m.weight for m in (*self.sigma_net, *self.color_net, *self.mask_net)]
+        key = tuple((w.data_ptr(), w._version) for w in ws) + (str(ws[0].device),)
+        if self._packed is None or self._packed[0] != key:
+            K = self.num_instances
+            nbytes = lib().inerf_field_weights_bytes(K)
+            host = [w.detach().float().cpu().contiguous() for w in ws]
+            blob = torch.empty(nbytes, dtype=torch.uint8).pin_memory() if torch.cuda.is_available() else torch.empty(nbytes, dtype=torch.uint8)
+            call("inerf_field_pack_weights", *[h.data_ptr() for h in host], K, blob.data_ptr())
+            self._packed = (key, blob.to(ws[0].device))
+        return self._packed[1]
+
+    def _field_desc(self) -> FieldDesc:
+        e, em = self.encoder, self.encoder_mask
+        d = FieldDesc()
+        self._keepalive = (e.half_table(), em.half_table(), self._packed_weights())
+        d.table_sigma = self._keepalive[0].data_ptr()
+        d.table_mask = self._keepalive[1].data_ptr()
+        d.offsets = e.offsets.data_ptr()
+        d.weights = self._keepalive[2].data_ptr()
+        d.L = e.num_levels
+        d.H = e.base_resolution
+        d.S = float(np.log2(e.per_level_scale))
+        d.bound = float(self.bound)
+        d.K = self.num_instances
+        d.density_scale = float(self.density_scale)
+        return d
+
+    @torch.no_grad()
+    def forward_fused(self, x, d, want_masks=True):
+        x = x.float().contiguous().view(-1, 3)
+        d = d.float().contiguous().view(-1, 3)
+        B = x.shape[0]
+        dev = x.device
+        sigmas = torch.empty(B, dtype=torch.float32, device=dev)
+        rgbs = torch.empty(B, 3, dtype=torch.float32, device=dev)
+        masks = torch.empty(B, self.num_instances, dtype=torch.float32, device=dev) if want_masks else None
+        desc = self._field_desc()
+        call("inerf_field_forward", ctypes.byref(desc), ptr(x), ptr(d), B, ptr(sigmas), ptr(rgbs), ptr(masks), stream_ptr(dev))
+        return sigmas, rgbs, masks
+
+    def _render_fused(self, rays_o, rays_d, nears, fars, render_mask, dt_gamma, max_steps, T_thresh):
+        N = rays_o.shape[0]
+        dev = rays_o.device
+        K = self.num_instances
+        weights_sum = torch.empty(N, dtype=torch.float32, device=dev)
+        depth = torch.empty(N, dtype=torch.float32, device=dev)
+        image = torch.empty(N, 3, dtype=torch.float32, device=dev)
+        mask_out = torch.empty(N, K, dtype=torch.float32, device=dev) if render_mask else None
+        if self._work_counter is None or self._work_counter.device != dev:
+            self._work_counter = torch.zeros(1, dtype=torch.int32, device=dev)
+        desc = self._field_desc()
+        call("inerf_render_fused", ctypes.byref(desc), ptr(rays_o), ptr(rays_d), ptr(nears), ptr(fars), ptr(self.density_bitfield),
+             N, self.cascade, self.grid_size, float(dt_gamma), int(max_steps), float(T_thresh), ptr(weights_sum), ptr(depth),
+             ptr(image), ptr(mask_out), ptr(self._work_counter), stream_ptr(dev))
+        return weights_sum, depth, image, mask_out
+
+    # ---- reference operator sequence ----------------------------------------------------
+    def _mlp(self, net, h):
+        n = len(net)
+        for l in range(n):
+            h = net[l](h)
+            if l != n - 1:
+                h = F.relu(h, inplace=True)
+        return h
+
+    def forward(self, x, d):
+        """x [N,3] in [-bound,bound], d [N,3] unit -> (sigma [N], rgb [N,3], mask_logits [N,K])"""
+        if not torch.is_grad_enabled() and x.is_cuda and self.fused_available():
+            return self.forward_fused(x, d)
+        h = self._mlp(self.sigma_net, self.encoder(x, bound=self.bound))
+        sigma = trunc_exp(h[..., 0])
+        geo_feat = h[..., 1:]
+        h = self._mlp(self.color_net, torch.cat([self.encoder_dir(d), geo_feat], dim=-1))
+        color = torch.sigmoid(h)
+        m = torch.cat([self.encoder_mask(x, bound=self.bound), geo_feat], dim=-1)
+        mask_logits = self._mlp(self.mask_net, m)
+        return sigma, color, mask_logits
+
+    def density(self, x):
+        h = self._mlp(self.sigma_net, self.encoder(x, bound=self.bound))
+        return {"sigma": trunc_exp(h[..., 0]), "geo_feat": h[..., 1:]}
+
+    def background(self, x, d):
+        h = torch.cat([self.encoder_dir(d), self.encoder_bg(x)], dim=-1)
+        return torch.sigmoid(self._mlp(self.bg_net, h))
+
+    def color(self, x, d, mask=None, geo_feat=None, **kwargs):
+        if mask is not None:
+            rgbs = torch.zeros(mask.shape[0], 3, dtype=x.dtype, device=x.device)
+            if not mask.any():
+                return rgbs
+            x, d, geo_feat = x[mask], d[mask], geo_feat[mask]
+        h = torch.sigmoid(self._mlp(self.color_net, torch.cat([self.encoder_dir(d), geo_feat], dim=-1)))
+        if mask is not None:
+            rgbs[mask] = h.to(rgbs.dtype)
+            return rgbs
+        return h
+
+    def mask(self, x, mask=None, geo_feat=None, **kwargs):
+        if mask is not None:
+            mask_logits = torch.zeros(mask.shape[0], self.num_instances, dtype=x.dtype, device=x.device)
+            if not mask.any():
+                return mask_logits
+            x, geo_feat = x[mask], geo_feat[mask]
+        h = self._mlp(self.mask_net, torch.cat([self.encoder_mask(x, bound=self.bound), geo_feat], dim=-1))
+        if mask is not None:
+            mask_logits[mask] = h.to(mask_logits.dtype)
+            return mask_logits
+        return h
+
+    def get_params(self, lr):
+        params = [
+            {"params": self.encoder.parameters(), "lr": lr},
+            {"params": self.sigma_net.parameters(), "lr": lr},
+            {"params": self.encoder_dir.parameters(), "lr": lr},
+            {"params": self.color_net.parameters(), "lr": lr},
+            {"params": self.encoder_mask.parameters(), "lr": lr},
+            {"params": self.mask_net.parameters(), "lr": lr},
+        ]
+        if self.bg_radius > 0:
+            params.append({"params": self.encoder_bg.parameters(), "lr": lr})
+            params.append({"params": self.bg_net.parameters(), "lr": lr})
+        return params

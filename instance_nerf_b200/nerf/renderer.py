@@ -1,0 +1,443 @@
+"""NeRFRenderer / NeRFMaskRenderer for the B200 path.
+
+Keeps the reference's API (nerf/renderer.py:61-573, nerf/mask_renderer.py:62-589):
+`render / run / run_cuda / update_extra_state / mark_untrained_grid /
+reset_extra_state`, the same keyword arguments, return-dict keys, buffers
+(`aabb_train aabb_infer density_grid density_bitfield step_counter`) and Python
+state (`mean_density iter_density mean_count local_step`), so Trainer /
+MaskTrainer (nerf/utils.py:1299,1387,1421) run unmodified.
+
+What changed underneath:
+* every op goes through libinerf_b200 (hand-written sm_100a kernels);
+* inference `run_cuda` is ONE persistent kernel launch (march + hash encode +
+  tcgen05 MLP + composite per 128-ray tile) when the network supports the fused
+  path (`fused_render_available`), instead of a host loop with two device syncs
+  per iteration (mask_renderer.py:342-374).  The reference loop is kept as
+  `run_cuda_loop` (used for parity tests and non-standard configurations);
+* the occupancy EMA + packbits tail runs as two launches with no `.item()`.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .. import raymarching
+from .._lib import call, ptr, stream_ptr
+
+
+def custom_meshgrid(*args):
+    return torch.meshgrid(*args, indexing="ij")
+
+
+def sample_pdf(bins, weights, n_samples, det=False):
+    """Inverse-CDF sampling used by `run(upsample_steps>0)` (mask_renderer.py:13-47)."""
+    weights = weights + 1e-5
+    pdf = weights / torch.sum(weights, -1, keepdim=True)
+    cdf = torch.cumsum(pdf, -1)
+    cdf = torch.cat([torch.zeros_like(cdf[..., :1]), cdf], -1)
+    if det:
+        u = torch.linspace(0.0 + 0.5 / n_samples, 1.0 - 0.5 / n_samples, steps=n_samples, device=weights.device)
+        u = u.expand(list(cdf.shape[:-1]) + [n_samples])
+    else:
+        u = torch.rand(list(cdf.shape[:-1]) + [n_samples], device=weights.device)
+    u = u.contiguous()
+    inds = torch.searchsorted(cdf, u, right=True)
+    below = torch.clamp(inds - 1, min=0)
+    above = torch.clamp(inds, max=cdf.shape[-1] - 1)
+    inds_g = torch.stack([below, above], -1)
+    shape = [inds_g.shape[0], inds_g.shape[1], cdf.shape[-1]]
+    cdf_g = torch.gather(cdf.unsqueeze(1).expand(shape), 2, inds_g)
+    bins_g = torch.gather(bins.unsqueeze(1).expand(shape), 2, inds_g)
+    denom = cdf_g[..., 1] - cdf_g[..., 0]
+    denom = torch.where(denom < 1e-5, torch.ones_like(denom), denom)
+    t = (u - cdf_g[..., 0]) / denom
+    return bins_g[..., 0] + t * (bins_g[..., 1] - bins_g[..., 0])
+
+
+class NeRFRenderer(nn.Module):
+    """Base renderer (nerf/renderer.py:61-123 ctor + state) with the instance-mask
+    extensions of NeRFMaskRenderer folded in: `render_mask=False` gives the plain
+    RGB-sigma behaviour of the base class."""
+
+    def __init__(self, bound=1, cuda_ray=False, density_scale=1, min_near=0.2, density_thresh=0.01, bg_radius=-1, num_instances=2):
+        super().__init__()
+        self.bound = bound
+        self.cascade = 1 + math.ceil(math.log2(bound))
+        self.grid_size = 128
+        self.density_scale = density_scale
+        self.min_near = min_near
+        self.density_thresh = density_thresh
+        self.bg_radius = bg_radius
+        self.num_instances = num_instances
+
+        aabb_train = torch.FloatTensor([-bound, -bound, -bound, bound, bound, bound])
+        self.register_buffer("aabb_train", aabb_train)
+        self.register_buffer("aabb_infer", aabb_train.clone())
+
+        self.cuda_ray = cuda_ray
+        if cuda_ray:
+            self.register_buffer("density_grid", torch.zeros([self.cascade, self.grid_size ** 3]))
+            self.register_buffer("density_bitfield", torch.zeros(self.cascade * self.grid_size ** 3 // 8, dtype=torch.uint8))
+            self._mean_density = 0
+            self.iter_density = 0
+            self.register_buffer("step_counter", torch.zeros(16, 2, dtype=torch.int32))
+            self.mean_count = 0
+            self.local_step = 0
+
+    # mean_density is produced on the device by the fused EMA kernel; it is read back only when somebody asks.
+    @property
+    def mean_density(self):
+        if isinstance(self._mean_density, torch.Tensor):
+            self._mean_density = float(self._mean_density.item())
+        return self._mean_density
+
+    @mean_density.setter
+    def mean_density(self, v):
+        self._mean_density = v
+
+    # -- network hooks (implemented by NeRFNetwork) ---------------------------------
+    def forward(self, x, d):
+        raise NotImplementedError()
+
+    def density(self, x):
+        raise NotImplementedError()
+
+    def color(self, x, d, mask=None, **kwargs):
+        raise NotImplementedError()
+
+    def mask(self, x, mask=None, **kwargs):
+        raise NotImplementedError()
+
+    def fused_render_available(self, render_mask: bool) -> bool:
+        return False
+
+    def reset_extra_state(self):
+        if not self.cuda_ray:
+            return
+        self.density_grid.zero_()
+        self.mean_density = 0
+        self.iter_density = 0
+        self.step_counter.zero_()
+        self.mean_count = 0
+        self.local_step = 0
+
+    # -- non-cuda_ray renderer (mask_renderer.py:89-231) ------------------------------
+    def run(self, rays_o, rays_d, render_mask=False, num_steps=128, upsample_steps=128, bg_color=None, perturb=False, **kwargs):
+        prefix = rays_o.shape[:-1]
+        rays_o = rays_o.contiguous().view(-1, 3)
+        rays_d = rays_d.contiguous().view(-1, 3)
+        N = rays_o.shape[0]
+        device = rays_o.device
+        aabb = self.aabb_train if self.training else self.aabb_infer
+
+        nears, fars = raymarching.near_far_from_aabb(rays_o, rays_d, aabb, self.min_near)
+        nears = nears.unsqueeze(-1)
+        fars = fars.unsqueeze(-1)
+
+        z_vals = torch.linspace(0.0, 1.0, num_steps, device=device).unsqueeze(0).expand((N, num_steps))
+        z_vals = nears + (fars - nears) * z_vals
+        sample_dist = (fars - nears) / num_steps
+        if perturb:
+            z_vals = z_vals + (torch.rand(z_vals.shape, device=device) - 0.5) * sample_dist
+
+        xyzs = rays_o.unsqueeze(-2) + rays_d.unsqueeze(-2) * z_vals.unsqueeze(-1)
+        xyzs = torch.min(torch.max(xyzs, aabb[:3]), aabb[3:])
+
+        density_outputs = self.density(xyzs.reshape(-1, 3))
+        for k, v in density_outputs.items():
+            density_outputs[k] = v.view(N, num_steps, -1)
+
+        if upsample_steps > 0:
+            with torch.no_grad():
+                deltas = z_vals[..., 1:] - z_vals[..., :-1]
+                deltas = torch.cat([deltas, sample_dist * torch.ones_like(deltas[..., :1])], dim=-1)
+                alphas = 1 - torch.exp(-deltas * self.density_scale * density_outputs["sigma"].squeeze(-1))
+                alphas_shifted = torch.cat([torch.ones_like(alphas[..., :1]), 1 - alphas + 1e-15], dim=-1)
+                weights = alphas * torch.cumprod(alphas_shifted, dim=-1)[..., :-1]
+                z_vals_mid = z_vals[..., :-1] + 0.5 * deltas[..., :-1]
+                new_z_vals = sample_pdf(z_vals_mid, weights[:, 1:-1], upsample_steps, det=not self.training).detach()
+                new_xyzs = rays_o.unsqueeze(-2) + rays_d.unsqueeze(-2) * new_z_vals.unsqueeze(-1)
+                new_xyzs = torch.min(torch.max(new_xyzs, aabb[:3]), aabb[3:])
+            new_density_outputs = self.density(new_xyzs.reshape(-1, 3))
+            for k, v in new_density_outputs.items():
+                new_density_outputs[k] = v.view(N, upsample_steps, -1)
+            z_vals = torch.cat([z_vals, new_z_vals], dim=1)
+            z_vals, z_index = torch.sort(z_vals, dim=1)
+            xyzs = torch.cat([xyzs, new_xyzs], dim=1)
+            xyzs = torch.gather(xyzs, dim=1, index=z_index.unsqueeze(-1).expand_as(xyzs))
+            for k in density_outputs:
+                tmp_output = torch.cat([density_outputs[k], new_density_outputs[k]], dim=1)
+                density_outputs[k] = torch.gather(tmp_output, dim=1, index=z_index.unsqueeze(-1).expand_as(tmp_output))
+
+        deltas = z_vals[..., 1:] - z_vals[..., :-1]
+        deltas = torch.cat([deltas, sample_dist * torch.ones_like(deltas[..., :1])], dim=-1)
+        alphas = 1 - torch.exp(-deltas * self.density_scale * density_outputs["sigma"].squeeze(-1))
+        alphas_shifted = torch.cat([torch.ones_like(alphas[..., :1]), 1 - alphas + 1e-15], dim=-1)
+        weights = alphas * torch.cumprod(alphas_shifted, dim=-1)[..., :-1]
+
+        dirs = rays_d.view(-1, 1, 3).expand_as(xyzs)
+        for k, v in density_outputs.items():
+            density_outputs[k] = v.view(-1, v.shape[-1])
+
+        mask = weights > 1e-4
+        rgbs = self.color(xyzs.reshape(-1, 3), dirs.reshape(-1, 3), mask=mask.reshape(-1), **density_outputs)
+        rgbs = rgbs.view(N, -1, 3)
+        if render_mask:
+            instance_mask_logits = self.mask(xyzs.reshape(-1, 3), mask=mask.reshape(-1), **density_outputs)
+            instance_mask_logits = instance_mask_logits.view(N, -1, self.num_instances)
+
+        weights_sum = weights.sum(dim=-1)
+        ori_z_vals = ((z_vals - nears) / (fars - nears)).clamp(0, 1)
+        depth = torch.sum(weights * ori_z_vals, dim=-1)
+        image = torch.sum(weights.unsqueeze(-1) * rgbs, dim=-2)
+
+        if self.bg_radius > 0:
+            sph = raymarching.sph_from_ray(rays_o, rays_d, self.bg_radius)
+            bg_color = self.background(sph, rays_d.reshape(-1, 3))
+        elif bg_color is None:
+            bg_color = 1
+        image = image + (1 - weights_sum).unsqueeze(-1) * bg_color
+
+        if render_mask:
+            instance_mask_logits = torch.sum(weights.unsqueeze(-1) * instance_mask_logits, dim=-2)
+            instance_mask_logits = instance_mask_logits.view(*prefix, self.num_instances)
+        else:
+            instance_mask_logits = None
+        return {
+            "depth": depth.view(*prefix),
+            "image": image.view(*prefix, 3),
+            "instance_mask_logits": instance_mask_logits,
+            "weights_sum": weights_sum,
+        }
+
+    # -- cuda_ray renderer (mask_renderer.py:234-387) --------------------------------
+    def run_cuda(self, rays_o, rays_d, render_mask=False, dt_gamma=0, bg_color=None, perturb=False, force_all_rays=False,
+                 max_steps=1024, T_thresh=1e-4, **kwargs):
+        prefix = rays_o.shape[:-1]
+        rays_o = rays_o.contiguous().view(-1, 3)
+        rays_d = rays_d.contiguous().view(-1, 3)
+        N = rays_o.shape[0]
+
+        nears, fars = raymarching.near_far_from_aabb(rays_o, rays_d, self.aabb_train if self.training else self.aabb_infer,
+                                                     self.min_near)
+        if self.bg_radius > 0:
+            sph = raymarching.sph_from_ray(rays_o, rays_d, self.bg_radius)
+            bg_color = self.background(sph, rays_d)
+        elif bg_color is None:
+            bg_color = 1
+
+        results = {}
+        if self.training:
+            counter = self.step_counter[self.local_step % 16]
+            counter.zero_()
+            self.local_step += 1
+            xyzs, dirs, deltas, rays = raymarching.march_rays_train(
+                rays_o, rays_d, self.bound, self.density_bitfield, self.cascade, self.grid_size, nears, fars, counter,
+                self.mean_count, perturb, 128, force_all_rays, dt_gamma, max_steps, noises=kwargs.get("noises"))
+            sigmas, rgbs, masks = self._field(xyzs, dirs, render_mask)
+            sigmas = self.density_scale * sigmas
+            if not render_mask:
+                weights_sum, depth, image = raymarching.composite_rays_train(sigmas, rgbs, deltas, rays, T_thresh)
+            else:
+                weights_sum, depth, image, mask_out = raymarching.composite_rays_with_masks_train(
+                    sigmas, rgbs, masks, deltas, rays, T_thresh)
+            results["weights_sum"] = weights_sum
+        else:
+            if not perturb and self.fused_render_available(render_mask):
+                weights_sum, depth, image, mask_out = self._render_fused(rays_o, rays_d, nears, fars, render_mask, dt_gamma,
+                                                                         max_steps, T_thresh)
+            else:
+                weights_sum, depth, image, mask_out = self.run_cuda_loop(rays_o, rays_d, nears, fars, render_mask, dt_gamma,
+                                                                         perturb, max_steps, T_thresh)
+
+        image = image + (1 - weights_sum).unsqueeze(-1) * bg_color
+        depth = torch.clamp(depth - nears, min=0) / (fars - nears)
+        results["depth"] = depth.view(*prefix)
+        results["image"] = image.view(*prefix, 3)
+        results["instance_mask_logits"] = mask_out.view(*prefix, self.num_instances) if render_mask else None
+        return results
+
+    def _field(self, xyzs, dirs, render_mask):
+        out = self(xyzs, dirs)
+        if len(out) == 3:
+            return out
+        return out[0], out[1], None  # stage-1 network: (sigma, rgb)
+
+    def run_cuda_loop(self, rays_o, rays_d, nears, fars, render_mask, dt_gamma, perturb, max_steps, T_thresh):
+        """The reference's alive-ray loop (mask_renderer.py:330-374) on this library's kernels, with the
+        same n_step schedule; compaction and the alive count stay on the device except for ONE 4-byte
+        read per iteration (the reference pays two syncs: `.shape` of a boolean-indexed tensor, :345,:370)."""
+        N = rays_o.shape[0]
+        device = rays_o.device
+        K = self.num_instances
+        weights_sum = torch.zeros(N, dtype=torch.float32, device=device)
+        depth = torch.zeros(N, dtype=torch.float32, device=device)
+        image = torch.zeros(N, 3, dtype=torch.float32, device=device)
+        mask_out = torch.zeros(N, K, dtype=torch.float32, device=device) if render_mask else None
+
+        n_alive = N
+        rays_alive = torch.arange(n_alive, dtype=torch.int32, device=device)
+        rays_t = nears.clone()
+        step = 0
+        while step < max_steps and n_alive > 0:
+            n_step = max(min(N // n_alive, 8), 1)
+            xyzs, dirs, deltas = raymarching.march_rays(n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, self.bound,
+                                                        self.density_bitfield, self.cascade, self.grid_size, nears, fars, 128,
+                                                        perturb if step == 0 else False, dt_gamma, max_steps)
+            sigmas, rgbs, masks = self._field(xyzs, dirs, render_mask)
+            sigmas = self.density_scale * sigmas
+            if not render_mask:
+                raymarching.composite_rays(n_alive, n_step, rays_alive, rays_t, sigmas, rgbs, deltas, weights_sum, depth, image,
+                                           T_thresh)
+            else:
+                raymarching.composite_rays_with_masks(n_alive, n_step, K, rays_alive, rays_t, sigmas, rgbs, masks, deltas,
+                                                      weights_sum, depth, image, mask_out, T_thresh)
+            rays_alive, n_out = raymarching.compact_alive(rays_alive, n_alive)
+            n_alive = int(n_out.item())
+            step += n_step
+        return weights_sum, depth, image, mask_out
+
+    def _render_fused(self, rays_o, rays_d, nears, fars, render_mask, dt_gamma, max_steps, T_thresh):
+        raise NotImplementedError()
+
+    # -- occupancy grid lifecycle ------------------------------------------------------
+    @torch.no_grad()
+    def mark_untrained_grid(self, poses, intrinsic, S=64):
+        """mask_renderer.py:389-452: cells no training camera sees get density -1 (never occupied)."""
+        if not self.cuda_ray:
+            return
+        if isinstance(poses, np.ndarray):
+            poses = torch.from_numpy(poses)
+        B = poses.shape[0]
+        fx, fy, cx, cy = intrinsic
+        dev = self.density_bitfield.device
+        G = self.grid_size
+        X = torch.arange(G, dtype=torch.int32, device=dev).split(S)
+        count = torch.zeros_like(self.density_grid)
+        poses = poses.to(dev).float()
+        for xs in X:
+            for ys in X:
+                for zs in X:
+                    xx, yy, zz = custom_meshgrid(xs, ys, zs)
+                    coords = torch.cat([xx.reshape(-1, 1), yy.reshape(-1, 1), zz.reshape(-1, 1)], dim=-1)
+                    indices = raymarching.morton3D(coords).long()
+                    world_xyzs = (2 * coords.float() / (G - 1) - 1).unsqueeze(0)
+                    for cas in range(self.cascade):
+                        bound = min(2 ** cas, self.bound)
+                        half_grid_size = bound / G
+                        cas_world_xyzs = world_xyzs * (bound - half_grid_size)
+                        head = 0
+                        while head < B:
+                            tail = min(head + S, B)
+                            cam_xyzs = cas_world_xyzs - poses[head:tail, :3, 3].unsqueeze(1)
+                            cam_xyzs = cam_xyzs @ poses[head:tail, :3, :3]
+                            mask_z = cam_xyzs[:, :, 2] > 0
+                            mask_x = torch.abs(cam_xyzs[:, :, 0]) < cx / fx * cam_xyzs[:, :, 2] + half_grid_size * 2
+                            mask_y = torch.abs(cam_xyzs[:, :, 1]) < cy / fy * cam_xyzs[:, :, 2] + half_grid_size * 2
+                            count[cas, indices] += (mask_z & mask_x & mask_y).sum(0).reshape(-1)
+                            head += S
+        self.density_grid[count == 0] = -1
+
+    @torch.no_grad()
+    def update_extra_state(self, decay=0.95, S=128, noises=None):
+        """mask_renderer.py:454-548.  Sampling follows the reference (same RNG consumption order: one
+        `rand_like` per (block, cascade)); `noises` optionally injects those tensors for parity tests.
+        The EMA / mean / threshold / packbits tail is two kernel launches with no host sync."""
+        if not self.cuda_ray:
+            return
+        dev = self.density_bitfield.device
+        G = self.grid_size
+        tmp_grid = -torch.ones_like(self.density_grid)
+        noise_iter = iter(noises) if noises is not None else None
+
+        def jitter(like):
+            return next(noise_iter) if noise_iter is not None else torch.rand_like(like)
+
+        if self.iter_density < 16:
+            X = torch.arange(G, dtype=torch.int32, device=dev).split(S)
+            for xs in X:
+                for ys in X:
+                    for zs in X:
+                        xx, yy, zz = custom_meshgrid(xs, ys, zs)
+                        coords = torch.cat([xx.reshape(-1, 1), yy.reshape(-1, 1), zz.reshape(-1, 1)], dim=-1)
+                        indices = raymarching.morton3D(coords).long()
+                        xyzs = 2 * coords.float() / (G - 1) - 1
+                        for cas in range(self.cascade):
+                            bound = min(2 ** cas, self.bound)
+                            half_grid_size = bound / G
+                            cas_xyzs = xyzs * (bound - half_grid_size)
+                            cas_xyzs += (jitter(cas_xyzs) * 2 - 1) * half_grid_size
+                            sigmas = self.density(cas_xyzs)["sigma"].reshape(-1).detach().float()
+                            sigmas *= self.density_scale
+                            tmp_grid[cas, indices] = sigmas
+        else:
+            N = G ** 3 // 4
+            for cas in range(self.cascade):
+                coords = torch.randint(0, G, (N, 3), device=dev)
+                indices = raymarching.morton3D(coords).long()
+                occ_indices = torch.nonzero(self.density_grid[cas] > 0).squeeze(-1)
+                rand_mask = torch.randint(0, occ_indices.shape[0], [N], dtype=torch.long, device=dev)
+                occ_indices = occ_indices[rand_mask]
+                occ_coords = raymarching.morton3D_invert(occ_indices)
+                indices = torch.cat([indices, occ_indices], dim=0)
+                coords = torch.cat([coords, occ_coords], dim=0)
+                xyzs = 2 * coords.float() / (G - 1) - 1
+                bound = min(2 ** cas, self.bound)
+                half_grid_size = bound / G
+                cas_xyzs = xyzs * (bound - half_grid_size)
+                cas_xyzs += (jitter(cas_xyzs) * 2 - 1) * half_grid_size
+                sigmas = self.density(cas_xyzs)["sigma"].reshape(-1).detach().float()
+                sigmas *= self.density_scale
+                tmp_grid[cas, indices] = sigmas
+
+        self.ema_update_(tmp_grid, decay)
+        self.iter_density += 1
+
+        total_step = min(16, self.local_step)
+        if total_step > 0:
+            self.mean_count = int(self.step_counter[:total_step, 0].sum().item() / total_step)
+        self.local_step = 0
+
+    @torch.no_grad()
+    def ema_update_(self, tmp_grid, decay=0.95):
+        """density_grid = max(density_grid*decay, tmp) where both >= 0; mean; threshold; packbits
+        (mask_renderer.py:532-540) -- all on the device."""
+        grid = self.density_grid
+        n_cells = grid.numel()
+        dev = grid.device
+        total = torch.zeros(1, dtype=torch.float64, device=dev)
+        mean = torch.empty(1, dtype=torch.float32, device=dev)
+        st = stream_ptr(dev)
+        call("inerf_occupancy_ema", ptr(grid), ptr(tmp_grid.contiguous()), n_cells, float(decay), ptr(total), st)
+        call("inerf_occupancy_pack", ptr(grid), n_cells, ptr(total), float(self.density_thresh), ptr(self.density_bitfield),
+             ptr(mean), st)
+        self._mean_density = mean
+
+    # -- entry point (mask_renderer.py:551-589) ------------------------------------------
+    def render(self, rays_o, rays_d, staged=False, max_ray_batch=4096, render_mask=False, **kwargs):
+        _run = self.run_cuda if self.cuda_ray else self.run
+        B, N = rays_o.shape[:2]
+        device = rays_o.device
+        if staged and not self.cuda_ray:
+            depth = torch.empty((B, N), device=device)
+            image = torch.empty((B, N, 3), device=device)
+            mask_logits = torch.empty((B, N, self.num_instances), device=device) if render_mask else None
+            for b in range(B):
+                head = 0
+                while head < N:
+                    tail = min(head + max_ray_batch, N)
+                    r = _run(rays_o[b:b + 1, head:tail], rays_d[b:b + 1, head:tail], render_mask, **kwargs)
+                    depth[b:b + 1, head:tail] = r["depth"]
+                    image[b:b + 1, head:tail] = r["image"]
+                    if render_mask:
+                        mask_logits[b:b + 1, head:tail] = r["instance_mask_logits"]
+                    head += max_ray_batch
+            return {"depth": depth, "image": image, "instance_mask_logits": mask_logits}
+        return _run(rays_o, rays_d, render_mask, **kwargs)
+
+
+class NeRFMaskRenderer(NeRFRenderer):
+    """Name kept for drop-in compatibility with nerf/mask_renderer.py:62."""

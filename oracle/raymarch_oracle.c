@@ -1,0 +1,335 @@
+/*
+ * TEST INFRASTRUCTURE ONLY -- CPU restatement (oracle) of the reference's
+ * raymarching kernels.  Nothing in the product path may link or call this file;
+ * only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg use it,
+ * and only as the checker.
+ *
+ * Every function cites the reference lines it restates
+ * (paths relative to /root/reference/instance_nerf/raymarching/src/).
+ *
+ * Float semantics: the reference is compiled by nvcc with the default
+ * -fmad=true, so every `a * b + c` in float is contracted into one FMA.  This
+ * file is compiled with -ffp-contract=off and spells each of those
+ * contractions as an explicit fmaf(), so that gcc reproduces the device
+ * arithmetic bit for bit (validated against the reference kernels themselves
+ * on a B200: tests/test_parity_gpu.py, fixtures in tests/golden/).
+ *
+ * Ordering: the reference reserves sample ranges with atomicAdd
+ * (raymarching.cu:405-406), so its `rays` rows and sample offsets are in
+ * arrival order.  The oracle emits the CANONICAL form (SURVEY.md section 8a
+ * row 3): rows sorted by ray id, offsets = exclusive prefix sum of counts.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#define SQRT3 1.7320508075688772f /* raymarching.cu:19 */
+
+static inline float clampf(float x, float lo, float hi) { /* raymarching.cu:34-36 */
+    return fminf(hi, fmaxf(lo, x));
+}
+static inline float signf_(float x) { return copysignf(1.0f, x); } /* :30-32 */
+
+/* raymarching.cu:42-47 */
+static inline int mip_from_pos(float x, float y, float z, float max_cascade) {
+    const float mx = fmaxf(fabsf(x), fmaxf(fabsf(y), fabsf(z)));
+    int exponent;
+    frexpf(mx, &exponent);
+    return (int)fminf(max_cascade - 1, fmaxf(0.0f, (float)exponent));
+}
+/* raymarching.cu:49-54 : dt * H in float, then * 0.5 in double, stored to float */
+static inline int mip_from_dt(float dt, float H, float max_cascade) {
+    const float mx = (float)((double)(dt * H) * 0.5);
+    int exponent;
+    frexpf(mx, &exponent);
+    return (int)fminf(max_cascade - 1, fmaxf(0.0f, (float)exponent));
+}
+/* raymarching.cu:56-63 */
+static inline uint32_t expand_bits(uint32_t v) {
+    v = (v * 0x00010001u) & 0xFF0000FFu;
+    v = (v * 0x00000101u) & 0x0F00F00Fu;
+    v = (v * 0x00000011u) & 0xC30C30C3u;
+    v = (v * 0x00000005u) & 0x49249249u;
+    return v;
+}
+/* raymarching.cu:65-71 */
+static inline uint32_t morton3D_(uint32_t x, uint32_t y, uint32_t z) {
+    return expand_bits(x) | (expand_bits(y) << 1) | (expand_bits(z) << 2);
+}
+/* raymarching.cu:73-81 */
+static inline uint32_t morton3D_invert_(uint32_t x) {
+    x = x & 0x49249249;
+    x = (x | (x >> 2)) & 0xc30c30c3;
+    x = (x | (x >> 4)) & 0x0f00f00f;
+    x = (x | (x >> 8)) & 0xff0000ff;
+    x = (x | (x >> 16)) & 0x0000ffff;
+    return x;
+}
+
+/* raymarching.cu:91-145 */
+void oracle_near_far_from_aabb(const float *rays_o, const float *rays_d, const float *aabb,
+                               uint32_t N, float min_near, float *nears, float *fars) {
+    for (uint32_t n = 0; n < N; n++) {
+        const float ox = rays_o[n * 3], oy = rays_o[n * 3 + 1], oz = rays_o[n * 3 + 2];
+        const float dx = rays_d[n * 3], dy = rays_d[n * 3 + 1], dz = rays_d[n * 3 + 2];
+        const float rdx = 1 / dx, rdy = 1 / dy, rdz = 1 / dz;
+        float near = (aabb[0] - ox) * rdx, far = (aabb[3] - ox) * rdx, tmp;
+        if (near > far) { tmp = near; near = far; far = tmp; }
+        float near_y = (aabb[1] - oy) * rdy, far_y = (aabb[4] - oy) * rdy;
+        if (near_y > far_y) { tmp = near_y; near_y = far_y; far_y = tmp; }
+        if (near > far_y || near_y > far) { nears[n] = fars[n] = 3.402823466e+38f; continue; }
+        if (near_y > near) near = near_y;
+        if (far_y < far) far = far_y;
+        float near_z = (aabb[2] - oz) * rdz, far_z = (aabb[5] - oz) * rdz;
+        if (near_z > far_z) { tmp = near_z; near_z = far_z; far_z = tmp; }
+        if (near > far_z || near_z > far) { nears[n] = fars[n] = 3.402823466e+38f; continue; }
+        if (near_z > near) near = near_z;
+        if (far_z < far) far = far_z;
+        if (near < min_near) near = min_near;
+        nears[n] = near;
+        fars[n] = far;
+    }
+}
+
+/* raymarching.cu:214-226 */
+void oracle_morton3D(const int32_t *coords, uint32_t N, int32_t *indices) {
+    for (uint32_t n = 0; n < N; n++)
+        indices[n] = (int32_t)morton3D_(coords[n * 3], coords[n * 3 + 1], coords[n * 3 + 2]);
+}
+/* raymarching.cu:237-254 */
+void oracle_morton3D_invert(const int32_t *indices, uint32_t N, int32_t *coords) {
+    for (uint32_t n = 0; n < N; n++) {
+        const int32_t ind = indices[n];
+        coords[n * 3 + 0] = (int32_t)morton3D_invert_((uint32_t)(ind >> 0));
+        coords[n * 3 + 1] = (int32_t)morton3D_invert_((uint32_t)(ind >> 1));
+        coords[n * 3 + 2] = (int32_t)morton3D_invert_((uint32_t)(ind >> 2));
+    }
+}
+/* raymarching.cu:267-289 ; N = number of output bytes */
+void oracle_packbits(const float *grid, uint32_t N, float density_thresh, uint8_t *bitfield) {
+    for (uint32_t n = 0; n < N; n++) {
+        uint8_t bits = 0;
+        for (int i = 0; i < 8; i++) bits |= (grid[(size_t)n * 8 + i] > density_thresh) ? (uint8_t)(1u << i) : 0;
+        bitfield[n] = bits;
+    }
+}
+
+/* One DDA walk shared by the train passes and the inference kernel
+ * (raymarching.cu:359-400, :427-479, :1008-1062).  Emits up to `limit` samples
+ * starting from *t_io; if xyzs == NULL only counts. Returns the sample count. */
+typedef struct {
+    float ox, oy, oz, dx, dy, dz, rdx, rdy, rdz;
+    float bound, dt_gamma, dt_min, dt_max, rH, H3, Hf, Cf, far;
+    uint32_t H;
+    const uint8_t *grid;
+} walk_t;
+
+static uint32_t walk(const walk_t *w, float t, uint32_t limit, float *xyzs, float *dirs, float *deltas) {
+    uint32_t step = 0;
+    float last_t = t;
+    while (t < w->far && step < limit) {
+        const float x = clampf(fmaf(t, w->dx, w->ox), -w->bound, w->bound);
+        const float y = clampf(fmaf(t, w->dy, w->oy), -w->bound, w->bound);
+        const float z = clampf(fmaf(t, w->dz, w->oz), -w->bound, w->bound);
+        const float dt = clampf(t * w->dt_gamma, w->dt_min, w->dt_max);
+        const int level_p = mip_from_pos(x, y, z, w->Cf), level_d = mip_from_dt(dt, w->Hf, w->Cf);
+        const int level = level_p > level_d ? level_p : level_d;
+        const float mip_bound = fminf(scalbnf(1.0f, level), w->bound);
+        const float mip_rbound = 1 / mip_bound;
+        /* (x * mip_rbound + 1) is one float FMA; * 0.5 * H is done in double (exact for H = 128) */
+        const int nx = (int)clampf((float)(0.5 * (double)fmaf(x, mip_rbound, 1.0f) * (double)w->H), 0.0f, (float)(w->H - 1));
+        const int ny = (int)clampf((float)(0.5 * (double)fmaf(y, mip_rbound, 1.0f) * (double)w->H), 0.0f, (float)(w->H - 1));
+        const int nz = (int)clampf((float)(0.5 * (double)fmaf(z, mip_rbound, 1.0f) * (double)w->H), 0.0f, (float)(w->H - 1));
+        const uint32_t index = (uint32_t)fmaf((float)level, w->H3, (float)morton3D_((uint32_t)nx, (uint32_t)ny, (uint32_t)nz));
+        const int occ = w->grid[index / 8] & (1 << (index % 8));
+        if (occ) {
+            if (xyzs) {
+                xyzs[0] = x; xyzs[1] = y; xyzs[2] = z;
+                dirs[0] = w->dx; dirs[1] = w->dy; dirs[2] = w->dz;
+            }
+            t += dt;
+            if (xyzs) {
+                deltas[0] = dt;
+                deltas[1] = t - last_t;
+                last_t = t;
+                xyzs += 3; dirs += 3; deltas += 2;
+            }
+            step++;
+        } else {
+            const float tx = (fmaf(fmaf(fmaf(0.5f, signf_(w->dx), (float)nx + 0.5f) * w->rH, 2.0f, -1.0f), mip_bound, -x)) * w->rdx;
+            const float ty = (fmaf(fmaf(fmaf(0.5f, signf_(w->dy), (float)ny + 0.5f) * w->rH, 2.0f, -1.0f), mip_bound, -y)) * w->rdy;
+            const float tz = (fmaf(fmaf(fmaf(0.5f, signf_(w->dz), (float)nz + 0.5f) * w->rH, 2.0f, -1.0f), mip_bound, -z)) * w->rdz;
+            const float tt = t + fmaxf(0.0f, fminf(tx, fminf(ty, tz)));
+            do { t += clampf(t * w->dt_gamma, w->dt_min, w->dt_max); } while (t < tt);
+        }
+    }
+    return step;
+}
+
+static void walk_init(walk_t *w, const float *o, const float *d, const uint8_t *grid, float bound,
+                      float dt_gamma, uint32_t max_steps, uint32_t C, uint32_t H, float far) {
+    w->ox = o[0]; w->oy = o[1]; w->oz = o[2];
+    w->dx = d[0]; w->dy = d[1]; w->dz = d[2];
+    w->rdx = 1 / w->dx; w->rdy = 1 / w->dy; w->rdz = 1 / w->dz;
+    w->bound = bound; w->dt_gamma = dt_gamma;
+    w->rH = 1 / (float)H;
+    w->H3 = (float)(H * H * H);
+    w->Hf = (float)H; w->Cf = (float)C; w->H = H;
+    w->dt_min = 2 * SQRT3 / (float)max_steps;                 /* :345 */
+    w->dt_max = 2 * SQRT3 * (float)(1 << (C - 1)) / (float)H;   /* :346 */
+    w->far = far;
+    w->grid = grid;
+}
+
+/* raymarching.cu:311-480 in canonical order.  counter[0] = total samples,
+ * counter[1] = N (every ray reserves a row, also empty ones, :405-413). */
+void oracle_march_rays_train(const float *rays_o, const float *rays_d, const uint8_t *grid, float bound,
+                             float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M,
+                             const float *nears, const float *fars, float *xyzs, float *dirs, float *deltas,
+                             int32_t *rays, int32_t *counter, const float *noises) {
+    uint32_t offset = 0;
+    for (uint32_t n = 0; n < N; n++) {
+        walk_t w;
+        walk_init(&w, rays_o + n * 3, rays_d + n * 3, grid, bound, dt_gamma, max_steps, C, H, fars[n]);
+        float t0 = nears[n];
+        t0 = fmaf(clampf(t0 * dt_gamma, w.dt_min, w.dt_max), noises[n], t0); /* :351 */
+        const uint32_t num_steps = walk(&w, t0, max_steps, NULL, NULL, NULL);
+        rays[n * 3] = (int32_t)n;
+        rays[n * 3 + 1] = (int32_t)offset;
+        rays[n * 3 + 2] = (int32_t)num_steps;
+        if (num_steps != 0 && offset + num_steps <= M)          /* :415-416 */
+            walk(&w, t0, num_steps, xyzs + (size_t)offset * 3, dirs + (size_t)offset * 3, deltas + (size_t)offset * 2);
+        offset += num_steps;
+    }
+    counter[0] += (int32_t)offset;
+    counter[1] += (int32_t)N;
+}
+
+/* raymarching.cu:958-1063 */
+void oracle_march_rays(uint32_t n_alive, uint32_t n_step, const int32_t *rays_alive, const float *rays_t,
+                       const float *rays_o, const float *rays_d, float bound, float dt_gamma, uint32_t max_steps,
+                       uint32_t C, uint32_t H, const uint8_t *grid, const float *nears, const float *fars,
+                       float *xyzs, float *dirs, float *deltas, const float *noises) {
+    (void)nears;
+    for (uint32_t n = 0; n < n_alive; n++) {
+        const int32_t index = rays_alive[n];
+        walk_t w;
+        walk_init(&w, rays_o + (size_t)index * 3, rays_d + (size_t)index * 3, grid, bound, dt_gamma, max_steps, C, H, fars[index]);
+        float t = rays_t[index];
+        t = fmaf(clampf(t * dt_gamma, w.dt_min, w.dt_max), noises[n], t); /* :1004 */
+        walk(&w, t, n_step, xyzs + (size_t)n * n_step * 3, dirs + (size_t)n * n_step * 3, deltas + (size_t)n * n_step * 2);
+    }
+}
+
+/* __expf(x) on the device is ex2.approx(x * log2(e)); the CPU uses expf, so
+ * compositing parity is tolerance-based (1e-5 relative), not bit-exact. */
+static inline float fast_expf(float x) { return expf(x); }
+
+/* raymarching.cu:500-577 (K == 0) and :705-799 (K > 0) */
+void oracle_composite_rays_train_forward(const float *sigmas, const float *rgbs, const float *masks, const float *deltas,
+                                         const int32_t *rays, uint32_t M, uint32_t N, uint32_t K, float T_thresh,
+                                         float *weights_sum, float *depth, float *image, float *mask_out) {
+    for (uint32_t n = 0; n < N; n++) {
+        const uint32_t index = rays[n * 3], offset = rays[n * 3 + 1], num_steps = rays[n * 3 + 2];
+        float *mo = K ? mask_out + (size_t)index * K : NULL;
+        for (uint32_t k = 0; k < K; k++) mo[k] = 0;
+        if (num_steps == 0 || offset + num_steps > M) {
+            weights_sum[index] = 0; depth[index] = 0;
+            image[index * 3] = image[index * 3 + 1] = image[index * 3 + 2] = 0;
+            continue;
+        }
+        float T = 1.0f, r = 0, g = 0, b = 0, ws = 0, t = 0, d = 0;
+        for (uint32_t s = offset; s < offset + num_steps; s++) {
+            const float alpha = 1.0f - fast_expf(-sigmas[s] * deltas[s * 2]);
+            const float weight = alpha * T;
+            r = fmaf(weight, rgbs[s * 3], r);
+            g = fmaf(weight, rgbs[s * 3 + 1], g);
+            b = fmaf(weight, rgbs[s * 3 + 2], b);
+            for (uint32_t k = 0; k < K; k++) mo[k] = fmaf(weight, masks[(size_t)s * K + k], mo[k]);
+            t += deltas[s * 2 + 1];
+            d = fmaf(weight, t, d);
+            ws += weight;
+            T *= 1.0f - alpha;
+            if (T < T_thresh) break;
+        }
+        weights_sum[index] = ws; depth[index] = d;
+        image[index * 3] = r; image[index * 3 + 1] = g; image[index * 3 + 2] = b;
+    }
+}
+
+/* raymarching.cu:601-682 (K == 0) and :828-940 (K > 0).  grad_* outputs must be
+ * zero-filled by the caller (raymarching.py:283-284, 351-354). */
+void oracle_composite_rays_train_backward(const float *grad_weights_sum, const float *grad_image, const float *grad_mask_out,
+                                          const float *sigmas, const float *rgbs, const float *masks, const float *deltas,
+                                          const int32_t *rays, const float *weights_sum, const float *image, const float *mask_out,
+                                          uint32_t M, uint32_t N, uint32_t K, float T_thresh,
+                                          float *grad_sigmas, float *grad_rgbs, float *grad_masks) {
+    float acc[1024];
+    for (uint32_t n = 0; n < N; n++) {
+        const uint32_t index = rays[n * 3], offset = rays[n * 3 + 1], num_steps = rays[n * 3 + 2];
+        if (num_steps == 0 || offset + num_steps > M) continue;
+        const float *gi = grad_image + (size_t)index * 3;
+        const float *gm = K ? grad_mask_out + (size_t)index * K : NULL;
+        const float *mfin = K ? mask_out + (size_t)index * K : NULL;
+        const float r_final = image[index * 3], g_final = image[index * 3 + 1], b_final = image[index * 3 + 2];
+        const float ws_final = weights_sum[index];
+        float T = 1.0f, r = 0, g = 0, b = 0, ws = 0;
+        for (uint32_t k = 0; k < K; k++) acc[k] = 0;
+        for (uint32_t s = offset; s < offset + num_steps; s++) {
+            const float alpha = 1.0f - fast_expf(-sigmas[s] * deltas[s * 2]);
+            const float weight = alpha * T;
+            r = fmaf(weight, rgbs[s * 3], r);
+            g = fmaf(weight, rgbs[s * 3 + 1], g);
+            b = fmaf(weight, rgbs[s * 3 + 2], b);
+            ws += weight;
+            for (uint32_t k = 0; k < K; k++) acc[k] = fmaf(weight, masks[(size_t)s * K + k], acc[k]);
+            T *= 1.0f - alpha;
+            grad_rgbs[s * 3] = gi[0] * weight;
+            grad_rgbs[s * 3 + 1] = gi[1] * weight;
+            grad_rgbs[s * 3 + 2] = gi[2] * weight;
+            for (uint32_t k = 0; k < K; k++) grad_masks[(size_t)s * K + k] = gm[k] * weight;
+            float gs = deltas[s * 2] * (gi[0] * (T * rgbs[s * 3] - (r_final - r)) +
+                                        gi[1] * (T * rgbs[s * 3 + 1] - (g_final - g)) +
+                                        gi[2] * (T * rgbs[s * 3 + 2] - (b_final - b)) +
+                                        grad_weights_sum[index] * (1 - ws_final));
+            for (uint32_t k = 0; k < K; k++)
+                gs += deltas[s * 2] * (gm[k] * (T * masks[(size_t)s * K + k] - (mfin[k] - acc[k])));
+            grad_sigmas[s] = gs;
+            if (T < T_thresh) break;
+        }
+    }
+}
+
+/* raymarching.cu:1076-1163 (K == 0) and :1175-1271 (K > 0) */
+void oracle_composite_rays(uint32_t n_alive, uint32_t n_step, uint32_t K, float T_thresh, int32_t *rays_alive, float *rays_t,
+                           const float *sigmas, const float *rgbs, const float *masks, const float *deltas,
+                           float *weights_sum, float *depth, float *image, float *mask_out) {
+    for (uint32_t n = 0; n < n_alive; n++) {
+        const int32_t index = rays_alive[n];
+        const float *sg = sigmas + (size_t)n * n_step, *rg = rgbs + (size_t)n * n_step * 3;
+        const float *mk = K ? masks + (size_t)n * n_step * K : NULL, *dl = deltas + (size_t)n * n_step * 2;
+        float *mo = K ? mask_out + (size_t)index * K : NULL;
+        float t = rays_t[index], weight_sum = weights_sum[index], d = depth[index];
+        float r = image[index * 3], g = image[index * 3 + 1], b = image[index * 3 + 2];
+        uint32_t step = 0;
+        while (step < n_step) {
+            if (dl[0] == 0) break;
+            const float alpha = 1.0f - fast_expf(-sg[0] * dl[0]);
+            const float T = 1 - weight_sum;
+            const float weight = alpha * T;
+            weight_sum += weight;
+            t += dl[1];
+            d = fmaf(weight, t, d);
+            r = fmaf(weight, rg[0], r);
+            g = fmaf(weight, rg[1], g);
+            b = fmaf(weight, rg[2], b);
+            for (uint32_t k = 0; k < K; k++) mo[k] = fmaf(weight, mk[k], mo[k]);
+            if (T < T_thresh) break;
+            sg++; rg += 3; dl += 2; if (K) mk += K;
+            step++;
+        }
+        if (step < n_step) rays_alive[n] = -1; else rays_t[index] = t;
+        weights_sum[index] = weight_sum; depth[index] = d;
+        image[index * 3] = r; image[index * 3 + 1] = g; image[index * 3 + 2] = b;
+    }
+}
