@@ -1,0 +1,159 @@
+// inerf_field_forward: NeRFNetwork.forward (nerf/network_mask.py:119-158) as ONE persistent kernel.
+//
+// Per 128-sample tile: both hash encoders gathered straight into UMMA operand tiles in shared memory
+// (no [B,32] activation ever touches HBM), SH degree 4, then sigma-net, colour-net and mask-net as a chain
+// of tcgen05.mma (fp16 x fp16 -> fp32 in TMEM) with TMEM->register epilogues that apply ReLU / exp / sigmoid
+// and write the next layer's operand tile.  Weights (< 40 KB fp16) stay resident in shared memory for the
+// life of the CTA; two CTAs per SM overlap one tile's gathers with the other's MMA chain.
+#include <vector>
+
+#include "field_device.cuh"
+
+namespace {
+
+using namespace field;
+
+__global__ void __launch_bounds__(kThreads, 2) k_field_forward(inerf_field_desc desc, const float* __restrict__ xyzs,
+                                                               const float* __restrict__ dirs, uint32_t B, float* __restrict__ sigmas,
+                                                               float* __restrict__ rgbs, float* __restrict__ masks) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    LevelGeom* lg;
+    uint64_t* bar;
+    const uint32_t tmem_base = cta_setup(smem, desc, lg, bar);
+    uint32_t phase = 0;
+    const uint32_t K = desc.K, Kp = weight_layout(K).Kp;
+    const bool with_masks = masks != nullptr;
+    const float inv2b = __fdiv_rn(1.0f, __fmul_rn(2.0f, desc.bound));
+    const __half2* tab_s = reinterpret_cast<const __half2*>(desc.table_sigma);
+    const __half2* tab_m = reinterpret_cast<const __half2*>(desc.table_mask);
+    const uint32_t num_tiles = (B + kTile - 1) / kTile;
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    for (uint32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        // ---- gather phase: thread -> (sample row, half of the levels) ----
+        const uint32_t row = threadIdx.x & (kTile - 1), half = threadIdx.x >> 7;
+        const uint32_t s = tile * kTile + row;
+        float x01[3] = {0.5f, 0.5f, 0.5f};
+        bool oob = false;
+        if (s < B) {
+#pragma unroll
+            for (int d = 0; d < 3; d++) {
+                x01[d] = __fmul_rn(__fadd_rn(__ldg(xyzs + (size_t)s * 3 + d), desc.bound), inv2b);  // grid.py:149
+                oob |= (x01[d] < 0.f || x01[d] > 1.f);
+            }
+        }
+        encode8(x01, oob, half * 8, lg, tab_s, tab_m, smem, row);
+        if (half == 0) {
+            float dx = 0.f, dy = 0.f, dz = 0.f;
+            if (s < B) { dx = __ldg(dirs + (size_t)s * 3); dy = __ldg(dirs + (size_t)s * 3 + 1); dz = __ldg(dirs + (size_t)s * 3 + 2); }
+            sh16_to_smem(dx, dy, dz, smem, row);
+        }
+        umma::fence_async_smem();
+        umma::fence_before_sync();
+        __syncthreads();
+
+        const float sigma = mlp_chain(smem, tmem_base, bar, phase, K, desc.density_scale, with_masks);
+
+        // ---- output epilogue ----
+        const uint32_t orow = tile * kTile + (warp & 3u) * 32u + lane;
+        if (warp < 4) {
+            float rgb[3];
+            epilogue_rgb(tmem_base, rgb);
+            if (orow < B) {
+                sigmas[orow] = sigma;
+                rgbs[(size_t)orow * 3] = rgb[0]; rgbs[(size_t)orow * 3 + 1] = rgb[1]; rgbs[(size_t)orow * 3 + 2] = rgb[2];
+            }
+        }
+        if (with_masks) {
+            // warps 0..3 take logits [0, Kp/2), warps 4..7 take [Kp/2, Kp), 16 columns per TMEM load
+            const uint32_t chunks = Kp / 16, c_begin = (warp >> 2) ? (chunks + 1) / 2 : 0, c_end = (warp >> 2) ? chunks : (chunks + 1) / 2;
+            for (uint32_t c = c_begin; c < c_end; c++) {
+                uint32_t v[16];
+                umma::tmem_ld16(tmem_base + D_d + (((warp & 3u) * 32u) << 16) + c * 16, v);
+                umma::tmem_ld_wait();
+                if (orow < B) {
+                    float* out = masks + (size_t)orow * K + c * 16;
+#pragma unroll
+                    for (int i = 0; i < 16; i++)
+                        if (c * 16 + i < K) out[i] = __half2float(__float2half_rn(__uint_as_float(v[i])));
+                }
+            }
+        }
+        umma::fence_before_sync();
+        __syncthreads();  // TMEM / operand tiles are reused by the next tile
+    }
+    cta_teardown(tmem_base);
+}
+
+inline uint16_t f2h_bits(float f) {
+    const __half h = __float2half_rn(f);
+    uint16_t b;
+    memcpy(&b, &h, 2);
+    return b;
+}
+
+// W is [n_out, n_in] row-major fp32 -> B-operand tile [Npad x Kpad] with zero padding
+void pack_layer(uint8_t* dst, const float* W, uint32_t n_out, uint32_t n_in, uint32_t Npad, uint32_t Kpad) {
+    const uint32_t sbo = sbo_of(Kpad);
+    for (uint32_t n = 0; n < Npad; n++)
+        for (uint32_t k = 0; k < Kpad; k++) {
+            const float v = (n < n_out && k < n_in) ? W[(size_t)n * n_in + k] : 0.f;
+            const uint16_t b = f2h_bits(v);
+            memcpy(dst + umma::tile_off(n, k, kLBO, sbo), &b, 2);
+        }
+}
+
+int validate_desc(const inerf_field_desc* d) {
+    INERF_REQUIRE(d);
+    INERF_REQUIRE(d->table_sigma); INERF_REQUIRE(d->table_mask); INERF_REQUIRE(d->offsets); INERF_REQUIRE(d->weights);
+    if (d->L != 16 || d->K == 0 || d->K > 64 || d->H == 0 || !(d->bound > 0.f)) return INERF_ERR_UNSUPPORTED;
+    if (((uintptr_t)d->weights & 15u) || ((uintptr_t)d->table_sigma & 3u) || ((uintptr_t)d->table_mask & 3u)) return INERF_ERR_ALIGN;
+    return INERF_OK;
+}
+
+}  // namespace
+
+namespace field {
+int validate(const inerf_field_desc* d) { return validate_desc(d); }
+}
+
+extern "C" size_t inerf_field_weights_bytes(uint32_t K) { return (K == 0 || K > 64) ? 0 : field::weight_layout(K).total; }
+
+extern "C" int inerf_field_pack_weights(const float* sigma0, const float* sigma1, const float* color0, const float* color1,
+                                        const float* color2, const float* mask0, const float* mask1, const float* mask2, uint32_t K,
+                                        void* packed_host) {
+    if (K == 0 || K > 64) return INERF_ERR_SIZE;
+    INERF_REQUIRE(sigma0); INERF_REQUIRE(sigma1); INERF_REQUIRE(color0); INERF_REQUIRE(color1); INERF_REQUIRE(color2);
+    INERF_REQUIRE(mask0); INERF_REQUIRE(mask1); INERF_REQUIRE(mask2); INERF_REQUIRE(packed_host);
+    const field::WeightLayout wl = field::weight_layout(K);
+    uint8_t* p = static_cast<uint8_t*>(packed_host);
+    memset(p, 0, wl.total);
+    pack_layer(p + wl.s0, sigma0, 64, 32, 64, 32);
+    pack_layer(p + wl.s1, sigma1, 16, 64, 16, 64);
+    pack_layer(p + wl.c0, color0, 64, 31, 64, 32);
+    pack_layer(p + wl.c1, color1, 64, 64, 64, 64);
+    pack_layer(p + wl.c2, color2, 3, 64, 16, 64);
+    pack_layer(p + wl.m0, mask0, 64, 47, 64, 48);
+    pack_layer(p + wl.m1, mask1, 64, 64, 64, 64);
+    pack_layer(p + wl.m2, mask2, K, 64, wl.Kp, 64);
+    return INERF_OK;
+}
+
+extern "C" int inerf_field_forward(const inerf_field_desc* desc, const float* xyzs, const float* dirs, uint32_t B, float* sigmas,
+                                   float* rgbs, float* masks, void* stream) {
+    if (int e = validate_desc(desc)) return e;
+    if (B == 0) return INERF_OK;
+    INERF_REQUIRE(xyzs); INERF_REQUIRE(dirs); INERF_REQUIRE(sigmas); INERF_REQUIRE(rgbs);
+    const uint32_t smem_bytes = field::Smem::bytes(desc->K);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(k_field_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
+        if (e != cudaSuccess) return (int)e;
+        attr_set = true;
+    }
+    const uint32_t num_tiles = (B + field::kTile - 1) / field::kTile;
+    const uint32_t grid = num_tiles < 2u * kNumSMs ? num_tiles : 2u * kNumSMs;
+    k_field_forward<<<grid, field::kThreads, smem_bytes, (cudaStream_t)stream>>>(*desc, xyzs, dirs, B, sigmas, rgbs, masks);
+    INERF_LAUNCH_CHECK();
+    return INERF_OK;
+}

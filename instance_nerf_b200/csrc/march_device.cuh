@@ -1,0 +1,145 @@
+// Occupancy-grid DDA shared by the marching kernels (raymarch.cu) and the fused renderer (render_fused.cu).
+// See raymarch.cu for the float-semantics contract (explicit round-to-nearest intrinsics where nvcc
+// contracts the reference's expressions; bit-identical sample stream to raymarching.cu:311-480, 958-1063).
+#pragma once
+#include "common.cuh"
+
+namespace march {
+
+constexpr float kSqrt3 = 1.7320508075688772f;
+
+// ---- Morton (raymarching.cu:56-81) -----------------------------------------
+__host__ __device__ __forceinline__ uint32_t expand_bits(uint32_t v) {
+    v = (v * 0x00010001u) & 0xFF0000FFu;
+    v = (v * 0x00000101u) & 0x0F00F00Fu;
+    v = (v * 0x00000011u) & 0xC30C30C3u;
+    v = (v * 0x00000005u) & 0x49249249u;
+    return v;
+}
+__host__ __device__ __forceinline__ uint32_t morton3D_enc(uint32_t x, uint32_t y, uint32_t z) {
+    return expand_bits(x) | (expand_bits(y) << 1) | (expand_bits(z) << 2);
+}
+__host__ __device__ __forceinline__ uint32_t morton3D_dec(uint32_t x) {
+    x = x & 0x49249249u;
+    x = (x | (x >> 2)) & 0xc30c30c3u;
+    x = (x | (x >> 4)) & 0x0f00f00fu;
+    x = (x | (x >> 8)) & 0xff0000ffu;
+    x = (x | (x >> 16)) & 0x0000ffffu;
+    return x;
+}
+
+// frexpf exponent clamped to [0, C-1] (raymarching.cu:42-54).  For the clamped
+// result the biased-exponent field is enough: zero / denormals give <= 0.
+__device__ __forceinline__ int clamped_exponent(float mx, int C) {
+    const int e = (int)((__float_as_uint(mx) >> 23) & 0xffu) - 126;
+    return min(C - 1, max(0, e));
+}
+
+struct Walk {
+    float ox, oy, oz, dx, dy, dz, rdx, rdy, rdz;
+    float sx, sy, sz;  // 0.5 * sign(d)
+    float bound, dt_gamma, dt_min, dt_max, rH, H3, Hf, Hm1, far;
+    int C;
+    const uint8_t* __restrict__ grid;
+
+    __device__ __forceinline__ void init(const float* __restrict__ o, const float* __restrict__ d,
+                                         const uint8_t* __restrict__ g, float bound_, float dt_gamma_,
+                                         uint32_t max_steps, uint32_t C_, uint32_t H, float far_) {
+        ox = o[0]; oy = o[1]; oz = o[2];
+        dx = d[0]; dy = d[1]; dz = d[2];
+        rdx = __fdiv_rn(1.0f, dx); rdy = __fdiv_rn(1.0f, dy); rdz = __fdiv_rn(1.0f, dz);
+        sx = copysignf(0.5f, dx); sy = copysignf(0.5f, dy); sz = copysignf(0.5f, dz);
+        bound = bound_; dt_gamma = dt_gamma_;
+        Hf = (float)H; Hm1 = (float)(H - 1);
+        rH = __fdiv_rn(1.0f, Hf);
+        H3 = (float)(H * H * H);
+        dt_min = __fdiv_rn(2.0f * kSqrt3, (float)max_steps);                                   // :345
+        dt_max = __fdiv_rn(__fmul_rn(2.0f * kSqrt3, (float)(1 << (C_ - 1))), Hf);              // :346
+        far = far_; C = (int)C_; grid = g;
+    }
+    __device__ __forceinline__ float step_size(float t) const { return clampf(__fmul_rn(t, dt_gamma), dt_min, dt_max); }
+
+    // One DDA walk (raymarching.cu:359-400 / :427-479 / :1008-1062).
+    template <bool WRITE>
+    __device__ __forceinline__ uint32_t run(float t, uint32_t limit, float* __restrict__ xyzs, float* __restrict__ dirs,
+                                            float* __restrict__ deltas) const {
+        uint32_t step = 0;
+        float last_t = t;
+        while (t < far && step < limit) {
+            const float x = clampf(__fmaf_rn(t, dx, ox), -bound, bound);
+            const float y = clampf(__fmaf_rn(t, dy, oy), -bound, bound);
+            const float z = clampf(__fmaf_rn(t, dz, oz), -bound, bound);
+            const float dt = step_size(t);
+            // mip level: max(mip_from_pos, mip_from_dt)
+            const float mx = fmaxf(fabsf(x), fmaxf(fabsf(y), fabsf(z)));
+            const float md = __fmul_rn(__fmul_rn(dt, Hf), 0.5f);
+            const int level = max(clamped_exponent(mx, C), clamped_exponent(md, C));
+            const float mip_bound = fminf(__uint_as_float((uint32_t)(127 + level) << 23), bound);
+            const float mip_rbound = __fdiv_rn(1.0f, mip_bound);
+            // (x * mip_rbound + 1) is one float FMA in the reference; the * 0.5 * H that follows is done in
+            // double there and is exact for H a power of two, so a float multiply by 0.5 * H gives the same bits.
+            const float hH = __fmul_rn(0.5f, Hf);
+            const int nx = (int)clampf(__fmul_rn(__fmaf_rn(x, mip_rbound, 1.0f), hH), 0.0f, Hm1);
+            const int ny = (int)clampf(__fmul_rn(__fmaf_rn(y, mip_rbound, 1.0f), hH), 0.0f, Hm1);
+            const int nz = (int)clampf(__fmul_rn(__fmaf_rn(z, mip_rbound, 1.0f), hH), 0.0f, Hm1);
+            const uint32_t index = (uint32_t)__fmaf_rn((float)level, H3, (float)morton3D_enc(nx, ny, nz));
+            const bool occ = grid[index >> 3] & (1u << (index & 7u));
+            if (occ) {
+                if (WRITE) {
+                    xyzs[0] = x; xyzs[1] = y; xyzs[2] = z;
+                    dirs[0] = dx; dirs[1] = dy; dirs[2] = dz;
+                }
+                t = __fadd_rn(t, dt);
+                if (WRITE) {
+                    deltas[0] = dt;
+                    deltas[1] = __fsub_rn(t, last_t);
+                    last_t = t;
+                    xyzs += 3; dirs += 3; deltas += 2;
+                }
+                step++;
+            } else {
+                // distance to the next voxel face along each axis (:390-394)
+                const float tx = __fmul_rn(__fmaf_rn(__fmaf_rn(__fmul_rn(__fadd_rn(__fadd_rn((float)nx, 0.5f), sx), rH), 2.0f, -1.0f), mip_bound, -x), rdx);
+                const float ty = __fmul_rn(__fmaf_rn(__fmaf_rn(__fmul_rn(__fadd_rn(__fadd_rn((float)ny, 0.5f), sy), rH), 2.0f, -1.0f), mip_bound, -y), rdy);
+                const float tz = __fmul_rn(__fmaf_rn(__fmaf_rn(__fmul_rn(__fadd_rn(__fadd_rn((float)nz, 0.5f), sz), rH), 2.0f, -1.0f), mip_bound, -z), rdz);
+                const float tt = __fadd_rn(t, fmaxf(0.0f, fminf(tx, fminf(ty, tz))));
+                do { t = __fadd_rn(t, step_size(t)); } while (t < tt);
+            }
+        }
+        return step;
+    }
+
+    // Advance from `t` to the next occupied sample.  On success returns true with the sample position in
+    // (x, y, z), its step in dt, and t advanced past it; on exhaustion (t >= far) returns false.
+    __device__ __forceinline__ bool next_sample(float& t, float& x, float& y, float& z, float& dt) const {
+        while (t < far) {
+            x = clampf(__fmaf_rn(t, dx, ox), -bound, bound);
+            y = clampf(__fmaf_rn(t, dy, oy), -bound, bound);
+            z = clampf(__fmaf_rn(t, dz, oz), -bound, bound);
+            dt = step_size(t);
+            const float mx = fmaxf(fabsf(x), fmaxf(fabsf(y), fabsf(z)));
+            const float md = __fmul_rn(__fmul_rn(dt, Hf), 0.5f);
+            const int level = max(clamped_exponent(mx, C), clamped_exponent(md, C));
+            const float mip_bound = fminf(__uint_as_float((uint32_t)(127 + level) << 23), bound);
+            const float mip_rbound = __fdiv_rn(1.0f, mip_bound);
+            const float hH = __fmul_rn(0.5f, Hf);
+            const int nx = (int)clampf(__fmul_rn(__fmaf_rn(x, mip_rbound, 1.0f), hH), 0.0f, Hm1);
+            const int ny = (int)clampf(__fmul_rn(__fmaf_rn(y, mip_rbound, 1.0f), hH), 0.0f, Hm1);
+            const int nz = (int)clampf(__fmul_rn(__fmaf_rn(z, mip_rbound, 1.0f), hH), 0.0f, Hm1);
+            const uint32_t index = (uint32_t)__fmaf_rn((float)level, H3, (float)morton3D_enc(nx, ny, nz));
+            if (grid[index >> 3] & (1u << (index & 7u))) {
+                t = __fadd_rn(t, dt);
+                return true;
+            }
+            const float tx = __fmul_rn(__fmaf_rn(__fmaf_rn(__fmul_rn(__fadd_rn(__fadd_rn((float)nx, 0.5f), sx), rH), 2.0f, -1.0f), mip_bound, -x), rdx);
+            const float ty = __fmul_rn(__fmaf_rn(__fmaf_rn(__fmul_rn(__fadd_rn(__fadd_rn((float)ny, 0.5f), sy), rH), 2.0f, -1.0f), mip_bound, -y), rdy);
+            const float tz = __fmul_rn(__fmaf_rn(__fmaf_rn(__fmul_rn(__fadd_rn(__fadd_rn((float)nz, 0.5f), sz), rH), 2.0f, -1.0f), mip_bound, -z), rdz);
+            const float tt = __fadd_rn(t, fmaxf(0.0f, fminf(tx, fminf(ty, tz))));
+            do { t = __fadd_rn(t, step_size(t)); } while (t < tt);
+        }
+        return false;
+    }
+};
+
+
+}  // namespace march
