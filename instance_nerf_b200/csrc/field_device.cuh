@@ -241,8 +241,11 @@ __device__ __forceinline__ void epilogue_rgb(uint32_t tmem_base, float rgb[3]) {
 // (written by all threads, followed by fence_async_smem + __syncthreads by the caller).
 // After return: D_c holds the colour pre-activations, D_d the logits (if with_masks); returns sigma for warps 0..3.
 // `phase` is the running mbarrier parity, updated in place.
+// `on_sigma(sigma)` runs in every thread right after the sigma-net epilogue (sigma is valid in warps 0..3) and
+// before the next block-wide barrier, so whatever it writes to shared memory is visible after the chain.
+template <typename OnSigma>
 __device__ __forceinline__ float mlp_chain(uint8_t* smem, uint32_t tmem_base, uint64_t* bar, uint32_t& phase, uint32_t K,
-                                           float density_scale, bool with_masks) {
+                                           float density_scale, bool with_masks, OnSigma&& on_sigma) {
     const uint32_t sbase = umma::smem_u32(smem);
     const WeightLayout wl = weight_layout(K);
     const bool issuer = threadIdx.x == 0;
@@ -268,6 +271,7 @@ __device__ __forceinline__ float mlp_chain(uint8_t* smem, uint32_t tmem_base, ui
     umma::mbar_wait(bar, phase); phase ^= 1u;
     umma::fence_after_sync();
     const float sigma = epilogue_sigma(tmem_base, smem, density_scale);
+    on_sigma(sigma);
     umma::fence_async_smem(); umma::fence_before_sync();
     __syncthreads();
     // colour layer 0 + mask layer 0

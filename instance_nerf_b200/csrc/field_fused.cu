@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_field_forward(inerf_field_desc 
         umma::fence_before_sync();
         __syncthreads();
 
-        const float sigma = mlp_chain(smem, tmem_base, bar, phase, K, desc.density_scale, with_masks);
+        const float sigma = mlp_chain(smem, tmem_base, bar, phase, K, desc.density_scale, with_masks, [](float) {});
 
         // ---- output epilogue ----
         const uint32_t orow = tile * kTile + (warp & 3u) * 32u + lane;

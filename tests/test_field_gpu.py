@@ -59,3 +59,45 @@ def test_field_fused_oob_is_zero_features(cuda):
     assert torch.equal(s1, s0.float())            # sigma = exp(0) = 1 exactly
     torch.testing.assert_close(c1, c0.float(), rtol=0, atol=2e-3)
     torch.testing.assert_close(k1, k0.float(), rtol=2e-2, atol=2e-2)
+
+
+def _render_both(m, o, d, **kw):
+    with torch.no_grad():
+        m.use_fused = True
+        r1 = m.render(o[None], d[None], staged=True, render_mask=True, perturb=False, **kw)
+        m.use_fused = False
+        with torch.autocast("cuda", dtype=torch.float16):
+            r0 = m.render(o[None], d[None], staged=True, render_mask=True, perturb=False, **kw)
+        m.use_fused = True
+    return r1, r0
+
+
+@pytest.mark.parametrize("K,density_scale", [(32, 1.0), (16, 25.0)])
+def test_render_fused_vs_reference_loop(cuda, K, density_scale):
+    """Whole-frame inference: the one-launch fused renderer against the reference's alive-ray loop
+    (mask_renderer.py:330-381) run on the op-level kernels.  North-star tolerance: maps within 1e-3."""
+    m, sc = build_model(cuda, K, density_scale=density_scale)
+    o, d = make_rays(sc, 96, 128)
+    o, d = o.to(cuda), d.to(cuda)
+    r1, r0 = _render_both(m, o, d, dt_gamma=1 / 128, max_steps=1024, T_thresh=1e-4)
+    for key in ("image", "depth"):
+        err = (r1[key] - r0[key]).abs()
+        assert err.max().item() < 1e-3, f"{key}: max err {err.max().item():.3e}"
+    p1 = torch.softmax(r1["instance_mask_logits"], -1)
+    p0 = torch.softmax(r0["instance_mask_logits"], -1)
+    assert (p1 - p0).abs().max().item() < 1e-3
+    assert r1["image"].shape == (1, 96 * 128, 3) and r1["instance_mask_logits"].shape == (1, 96 * 128, K)
+
+
+def test_render_fused_no_mask_and_misses(cuda):
+    m, sc = build_model(cuda, 32, density_scale=25.0)
+    o, d = make_rays(sc, 32, 32)
+    o = torch.cat([o, torch.tensor([[20.0, 20.0, 20.0]])]).to(cuda)      # a ray that misses the volume
+    d = torch.cat([d, torch.tensor([[0.0, 1.0, 0.0]])]).to(cuda)
+    with torch.no_grad():
+        r = m.render(o[None], d[None], staged=True, render_mask=False, perturb=False, dt_gamma=1 / 128, max_steps=1024, bg_color=1)
+        rm_ = m.render(o[None], d[None], staged=True, render_mask=True, perturb=False, dt_gamma=1 / 128, max_steps=1024, bg_color=1)
+    assert r["instance_mask_logits"] is None
+    torch.testing.assert_close(r["image"], rm_["image"], rtol=0, atol=1e-6)
+    assert torch.allclose(r["image"][0, -1], torch.ones(3, device=cuda))    # miss -> pure background
+    assert float(rm_["instance_mask_logits"][0, -1].abs().sum()) == 0.0

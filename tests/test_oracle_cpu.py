@@ -1,0 +1,183 @@
+"""CPU suite: pins the oracle (oracle/raymarch_oracle.c, oracle/field_oracle.py) against golden vectors produced by
+the reference itself -- tests/golden/ref_kernels.npz (the reference's CUDA kernels run on a B200,
+make_golden_gpu.py) and tests/golden/ref_run.npz (the reference's Python renderer, make_golden_cpu.py)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import bits_equal, scene_arrays
+from oracle import field_oracle as fo
+from oracle import raymarch_oracle as ro
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def gk():
+    return np.load(os.path.join(GOLD, "ref_kernels.npz"))
+
+
+@pytest.mark.parametrize("tag", ["b8", "b3"])
+def test_near_far_and_march_stream_bit_exact(gk, tag):
+    bound, dt_gamma, max_steps, cascade = gk[f"{tag}_cfg"]
+    bound, max_steps, cascade = float(bound), int(max_steps), int(cascade)
+    sc, c2, grid, bits = scene_arrays(16, bound, 0)
+    assert c2 == cascade
+    o, d = gk[f"{tag}_rays_o"], gk[f"{tag}_rays_d"]
+    aabb = np.array([-bound] * 3 + [bound] * 3, np.float32)
+    nears, fars = ro.near_far_from_aabb(o, d, aabb, 0.2)
+    assert bits_equal(nears, gk[f"{tag}_nears"]) and bits_equal(fars, gk[f"{tag}_fars"])
+    xyzs, dirs, deltas, rays, counter = ro.march_rays_train(o, d, bits, bound, float(dt_gamma), max_steps, cascade, 128, nears, fars,
+                                                           gk[f"{tag}_noises"])
+    assert np.array_equal(counter, gk[f"{tag}_counter"])
+    assert np.array_equal(rays, gk[f"{tag}_rays"])                       # (ray, offset, count): bit-exact
+    assert bits_equal(xyzs, gk[f"{tag}_xyzs"]) and bits_equal(deltas, gk[f"{tag}_deltas"])
+    # dirs are the ray direction repeated per sample
+    rep = np.repeat(d, rays[:, 2], axis=0)
+    assert bits_equal(dirs, rep)
+
+
+def test_march_budget_drops_tail_rays(gk):
+    bound, dt_gamma, max_steps, cascade = gk["b8_cfg"]
+    sc, _, grid, bits = scene_arrays(16, 8.0, 0)
+    o, d = gk["b8_rays_o"], gk["b8_rays_d"]
+    M = 1000
+    xyzs, dirs, deltas, rays, counter = ro.march_rays_train(o, d, bits, 8.0, float(dt_gamma), int(max_steps), int(cascade), 128, gk["b8_nears"],
+                                                           gk["b8_fars"], gk["b8_noises"], M=M)
+    kept = rays[:, 1] + rays[:, 2] <= M
+    full = gk["b8_xyzs"]
+    for (n, off, cnt), k in zip(rays, kept):
+        if cnt and k:
+            assert bits_equal(xyzs[off:off + cnt], full[off:off + cnt])
+        elif cnt and off < M:
+            assert not xyzs[off:min(off + cnt, M)].any()                 # dropped ray: rows stay zero (raymarching.cu:416)
+
+
+def test_march_rays_inference_bit_exact(gk):
+    bound, dt_gamma, max_steps, cascade = gk["b8_cfg"]
+    sc, _, grid, bits = scene_arrays(16, 8.0, 0)
+    alive = gk["inf_alive"]
+    x, dd, dl = ro.march_rays(alive.shape[0], 3, alive, gk["inf_rays_t"], gk["b8_rays_o"], gk["b8_rays_d"], 8.0, float(dt_gamma), int(max_steps),
+                              int(cascade), 128, bits, gk["b8_nears"], gk["b8_fars"], np.zeros(alive.shape[0], np.float32))
+    assert bits_equal(x, gk["inf_xyzs"]) and bits_equal(dl, gk["inf_deltas"])
+
+
+def test_morton_packbits(gk):
+    assert np.array_equal(ro.morton3D(gk["morton_coords"]), gk["morton_idx"])
+    assert np.array_equal(ro.morton3D_invert(gk["morton_idx"]), gk["morton_coords"])
+    assert ro.morton3D(np.array([[1, 0, 0], [0, 1, 0], [0, 0, 1]], np.int32)).tolist() == [1, 2, 4]      # known answers
+    ii = np.stack(np.meshgrid(*[np.arange(0, 128, 9)] * 3, indexing="ij"), -1).reshape(-1, 3).astype(np.int32)
+    assert np.array_equal(ro.morton3D_invert(ro.morton3D(ii)), ii)                                          # invert o encode = id
+    assert np.array_equal(ro.packbits(gk["pack_grid"], 5.0), gk["pack_bits"])
+
+
+def test_composite_forward_backward(gk):
+    """fp32 compositing: the device uses __expf (ex2.approx), the CPU expf -> tolerance 1e-5 (stated)."""
+    rays, deltas = gk["b8_rays"], gk["b8_deltas"]
+    sig, rgb, msk = gk["cmp_sig"], gk["cmp_rgb"], gk["cmp_msk"]
+    ws, depth, image, mask_out = ro.composite_rays_train_forward(sig, rgb, msk, deltas, rays, 1e-4)
+    np.testing.assert_allclose(ws, gk["cmp_ws"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(depth, gk["cmp_depth"], rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(image, gk["cmp_image"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(mask_out, gk["cmp_mask_out"], rtol=1e-5, atol=1e-5)
+    ws2, _, image2, _ = ro.composite_rays_train_forward(sig, rgb, None, deltas, rays, 1e-4)
+    np.testing.assert_allclose(ws2, gk["cmp_ws_plain"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(image2, gk["cmp_image_plain"], rtol=1e-5, atol=1e-6)
+    gs, gr, gm = ro.composite_rays_train_backward(gk["cmp_gws"], gk["cmp_gim"], gk["cmp_gmo"], sig, rgb, msk, deltas, rays, gk["cmp_ws"],
+                                                  gk["cmp_image"], gk["cmp_mask_out"], 1e-4)
+    np.testing.assert_allclose(gr, gk["cmp_gr"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(gm, gk["cmp_gm"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(gs, gk["cmp_gs"], rtol=2e-3, atol=2e-4)
+
+
+def test_composite_matches_autograd_of_segment_formulation(gk):
+    """Independent cross-check: w = alpha * cumprod(1 - alpha) with break-after-accumulate;
+    autograd of that formulation gives the backward."""
+    rays, deltas = gk["b8_rays"][:40], torch.from_numpy(gk["b8_deltas"])
+    sig = torch.from_numpy(gk["cmp_sig"]).double().requires_grad_(True)
+    rgb = torch.from_numpy(gk["cmp_rgb"]).double().requires_grad_(True)
+    gim = torch.from_numpy(gk["cmp_gim"]).double()
+    loss = 0
+    for n, off, cnt in rays:
+        if cnt == 0:
+            continue
+        a = 1 - torch.exp(-sig[off:off + cnt] * deltas[off:off + cnt, 0].double())
+        T = torch.cumprod(torch.cat([torch.ones(1, dtype=torch.double), 1 - a[:-1]]), 0)
+        T_after = T * (1 - a)
+        stop = torch.nonzero(T_after < 1e-4)
+        last = int(stop[0]) + 1 if len(stop) else cnt
+        w = (a * T)[:last]
+        loss = loss + ((w[:, None] * rgb[off:off + last]).sum(0) * gim[n]).sum()
+    loss.backward()
+    M = int(rays[-1, 1] + rays[-1, 2])
+    gs, gr, _ = ro.composite_rays_train_backward(np.zeros_like(gk["cmp_gws"]), gk["cmp_gim"], None, gk["cmp_sig"], gk["cmp_rgb"], None,
+                                                 gk["b8_deltas"], rays, gk["cmp_ws_plain"], gk["cmp_image_plain"], None, 1e-4)
+    np.testing.assert_allclose(gr[:M], rgb.grad.numpy()[:M], rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(gs[:M], sig.grad.numpy()[:M], rtol=2e-3, atol=2e-4)
+
+
+def test_grid_encode_and_sh_against_reference_kernels(gk):
+    offsets, pls = fo.level_offsets(desired_resolution=2048 * 2)
+    T = int(offsets[-1])
+    table = torch.rand(T, 2, generator=torch.Generator().manual_seed(int(gk["enc_table_seed"][0]))) - 0.5
+    x01 = torch.from_numpy(gk["enc_x01"])
+    out = fo.grid_encode(x01, table, offsets, pls, scales=gk["enc_scales_b2"])
+    # fp32, same operation order as the device (FMA emulated in double) -> agreement to the last bits
+    np.testing.assert_allclose(out.numpy(), gk["enc_out"], rtol=1e-6, atol=2e-7)
+    # with the host's own exp2 a few level scales differ by one ulp: still within 2e-4 (stated)
+    np.testing.assert_allclose(fo.grid_encode(x01, table, offsets, pls).numpy(), gk["enc_out"], rtol=0, atol=2e-4)
+    assert not out[2].any()                                              # out-of-range input -> zeros
+    gt = fo.grid_encode_backward(x01, torch.from_numpy(gk["enc_grad"]), T, offsets, pls, scales=gk["enc_scales_b2"])
+    rows = gk["enc_gtab_rows"]
+    np.testing.assert_allclose(gt[rows].numpy(), gk["enc_gtab_vals"], rtol=1e-4, atol=1e-6)
+    mask = np.ones(T, bool); mask[rows] = False
+    assert float(gt[mask].abs().sum()) == 0.0
+    sh = fo.sh_encode(torch.from_numpy(gk["sh_dirs"]), 4)
+    np.testing.assert_allclose(sh.numpy(), gk["sh_out"], rtol=1e-6, atol=1e-7)
+
+
+def test_grid_encode_constant_table_and_gradcheck():
+    """Analytic checks of SURVEY.md section 8c: constant table -> constant output; fp64 finite differences."""
+    offsets, pls = fo.level_offsets(num_levels=4, base_resolution=4, log2_hashmap_size=8, desired_resolution=32)
+    T = int(offsets[-1])
+    x01 = torch.rand(64, 3, generator=torch.Generator().manual_seed(0))
+    out = fo.grid_encode(x01, torch.full((T, 2), 0.25), offsets, pls, 4)
+    np.testing.assert_allclose(out.numpy(), 0.25, rtol=1e-6)
+    table = torch.randn(T, 2, generator=torch.Generator().manual_seed(1))
+    w = torch.randn(64, 8, generator=torch.Generator().manual_seed(2))
+    g = fo.grid_encode_backward(x01, w, T, offsets, pls, 4)
+    for r, c in [(0, 0), (5, 1), (40, 0), (T - 9, 1)]:
+        tp, tm = table.clone(), table.clone()
+        tp[r, c] += 1e-2; tm[r, c] -= 1e-2
+        fd = ((fo.grid_encode(x01, tp, offsets, pls, 4) * w).sum() - (fo.grid_encode(x01, tm, offsets, pls, 4) * w).sum()) / 2e-2
+        assert abs(fd.item() - g[r, c].item()) < 1e-3 * max(1, abs(fd.item()))
+
+
+def test_oracle_run_matches_reference_python_renderer():
+    g = np.load(os.path.join(GOLD, "ref_run.npz"))
+    K, bound, H, W, T, seed = g["cfg"]
+    K, T = int(K), int(T)
+    sd = {k[3:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("sd_")}
+    gen = torch.Generator().manual_seed(int(seed))
+    n_rows = int(sd["encoder.offsets"][-1])
+    for name in ("encoder.embeddings", "encoder_mask.embeddings"):
+        sd[name] = (torch.rand(n_rows, 2, generator=gen) * 2 - 1) * 0.5
+    field = fo.OracleField(sd, float(bound), K)
+    o, d = torch.from_numpy(g["rays_o"]), torch.from_numpy(g["rays_d"])
+    res = field.render(o[None], d[None], max_ray_batch=100, render_mask=True, num_steps=T, bg_color=1)
+    np.testing.assert_allclose(res["image"].numpy(), g["image"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(res["depth"].numpy(), g["depth"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(res["instance_mask_logits"].numpy(), g["logits"], rtol=1e-4, atol=1e-5)
+
+
+def test_update_grid_ema_restatement():
+    rng = np.random.RandomState(0)
+    grid = (rng.rand(2, 4096) * 30 - 3).astype(np.float32); grid[grid < -2] = -1
+    tmp = (rng.rand(2, 4096) * 40 - 8).astype(np.float32)
+    g, mean, bits = fo.update_grid_ema(grid, tmp, 0.95, 10.0)
+    valid = (grid >= 0) & (tmp >= 0)
+    assert np.array_equal(g[~valid], grid[~valid])
+    assert np.all(g[valid] >= tmp[valid]) and np.all(g[valid] >= grid[valid] * np.float32(0.95))
+    assert np.array_equal(bits, ro.packbits(g, min(mean, 10.0)))
