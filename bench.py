@@ -1,0 +1,340 @@
+#!/usr/bin/env python
+"""bench.py -- instance-field render throughput (BASELINE.json metric: Mrays/s) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--no-cpu-baseline]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+Workload (BASELINE.json configs[1], SURVEY.md section 8d "c2"): 640x480 frames (307 200 rays each) of the synthetic
+3D-FRONT-shaped room, bound 8 -> 4-cascade 128^3 occupancy grid, two 16-level 2^19-entry hash tables, 32 instance classes,
+dt_gamma 1/128, max_steps 1024, T_thresh 1e-4; seeded random weights / tables (no network, no dataset).
+
+A "step" = one frame rendered through NeRFNetwork.render (the call MaskTrainer.test_step makes, nerf/utils.py:1421): near/far
++ ONE fused launch (march + hash gathers x2 + tcgen05 MLP + composite) + the bg / depth tail.  Every step renders a different
+camera pose, and L2 (126 MB) is flushed between timed steps by writing a 512 MB buffer (outside the event pair).
+At N > 1 every rank renders its own frame each step (weak scaling, rays sharded by frame) and the finished tiles are
+gathered with ONE NCCL all_gather inside the timed step.
+
+Keys: value = device-timed Mrays/s with rays resident in HBM; e2e = same through the public API from pinned HOST rays to
+pinned HOST results (H2D + D2H inside the timed region); roofline = the fused kernel's algorithmic bytes / its own
+CUDA-event time vs the measured HBM peak; cpu_baseline = the CPU oracle port of the reference's PyTorch (non-cuda_ray)
+renderer on a bounded sample of the same frame, timed on this box's host cores.
+
+--impl reference runs ONLY that CPU path (the reference arm): no CUDA code of this repo is touched.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "instance_field_render_Mrays_per_s"
+UNIT = "Mrays/s"
+W_IMG, H_IMG, K_INST, BOUND = 640, 480, 32, 8.0
+DT_GAMMA, MAX_STEPS, T_THRESH = 1.0 / 128, 1024, 1e-4
+N_POSES = 16
+WORKLOAD = "c2: 640x480 instance-field render, 4x128^3 occupancy grid, 2x(16-level 2^19 hash grid), K=32, synthetic room"
+
+
+def build_scene_and_model(device=None):
+    import torch
+    from instance_nerf_b200 import synthetic
+    from instance_nerf_b200.nerf.network_mask import NeRFNetwork
+
+    torch.manual_seed(0)
+    model = NeRFNetwork(bound=BOUND, cuda_ray=True, num_instances=K_INST, density_scale=1, density_thresh=10)
+    synthetic.randomize_tables(model, 0)
+    scene = synthetic.RoomScene(K_INST, BOUND, 0)
+    synthetic.install_scene(model, scene)
+    poses = torch.from_numpy(synthetic.camera_poses(scene, N_POSES, 1))
+    if device is not None:
+        model = model.to(device)
+    return model.eval(), scene, poses
+
+
+def frame_rays(poses, i):
+    from instance_nerf_b200 import synthetic
+    r = synthetic.get_rays(poses[i:i + 1], synthetic.intrinsics(H_IMG, W_IMG), H_IMG, W_IMG)
+    return r["rays_o"].reshape(-1, 3).contiguous(), r["rays_d"].reshape(-1, 3).contiguous()
+
+
+# ------------------------------------------------------------------------------------------------ clocks --
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(self.idx)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        self.t.join(timeout=2)
+        sm = sorted(float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit())
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 9 for n, v in zip(names, r[5:9]) if v.lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------- CPU reference arm --
+def make_cpu_reference(n_rays: int, poses=None, model=None):
+    """The reference's PyTorch (non-cuda_ray) renderer -- NeRFMaskRenderer.run / staged render, mask_renderer.py:89-231,
+    565-584 -- as restated in oracle/field_oracle.py (pinned against the reference's own outputs, tests/golden/ref_run.npz),
+    set up on `n_rays` rays strided over frame 0 of the workload.  -> (render thunk, n_rays, cores)"""
+    import torch
+    from oracle import field_oracle as fo
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    if model is None:
+        model, _, poses = build_scene_and_model(None)
+    sd = {k: v.detach().float().cpu() for k, v in model.state_dict().items()}
+    field = fo.OracleField(sd, BOUND, K_INST, density_scale=1.0)
+    o, d = frame_rays(poses.cpu(), 0)
+    stride = max(1, o.shape[0] // n_rays)
+    o, d = o[::stride][:n_rays].contiguous(), d[::stride][:n_rays].contiguous()
+
+    def render():
+        return field.render(o[None], d[None], max_ray_batch=4096, render_mask=True, num_steps=128, bg_color=1)
+
+    return render, o.shape[0], cores
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    render, n_rays, cores = make_cpu_reference(8192)
+    for _ in range(args.warmup):
+        render()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        render()
+    total = time.perf_counter() - t0
+    value = n_rays * args.steps / total / 1e6
+    sample = f"{n_rays} rays strided over frame 0 per step, 128 uniform samples/ray (the reference's non-cuda_ray sampler), K=32"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": total / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": {"workload": WORKLOAD, "rays_per_step": n_rays, "samples_per_ray": 128},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------- GPU arm --
+def run_gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from instance_nerf_b200 import _lib
+    _lib.lib()  # fail loudly if libinerf_b200.so is missing
+
+    model, scene, poses = build_scene_and_model(dev)
+    N = H_IMG * W_IMG
+    K = K_INST
+    host_rays = []
+    for i in range(N_POSES):
+        o, d = frame_rays(poses, i)
+        host_rays.append((o.pin_memory(), d.pin_memory()))
+    dev_rays = [(o.to(dev), d.to(dev)) for o, d in host_rays]
+    kw = dict(staged=True, render_mask=True, perturb=False, dt_gamma=DT_GAMMA, max_steps=MAX_STEPS, T_thresh=T_THRESH, bg_color=1)
+    flush_buf = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    tile = torch.empty(N, 4 + K, dtype=torch.float32, device=dev)               # image 3 | depth 1 | logits K
+    gathered = torch.empty(world * N, 4 + K, dtype=torch.float32, device=dev) if world > 1 else None
+
+    # kernel-only timing hook around the fused launch (events on the launching stream)
+    kern_events, samples_seen = [], []
+    launches = {"n": 0}
+    fused = model._render_fused
+
+    def timed_fused(*a, **k):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = fused(*a, **k)
+        e1.record()
+        kern_events.append((e0, e1))
+        samples_seen.append(model._work_counter[2:4].clone())
+        launches["n"] += 2          # inerf_near_far_from_aabb + inerf_render_fused
+        return out
+
+    model._render_fused = timed_fused
+
+    def step(i, e2e=False, out_host=None):
+        p = (i * world + rank) % N_POSES
+        if e2e:
+            o = host_rays[p][0].to(dev, non_blocking=True)
+            d = host_rays[p][1].to(dev, non_blocking=True)
+        else:
+            o, d = dev_rays[p]
+        with torch.no_grad():
+            r = model.render(o[None], d[None], **kw)
+        tile[:, 0:3] = r["image"][0]
+        tile[:, 3] = r["depth"][0]
+        tile[:, 4:] = r["instance_mask_logits"][0]
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, tile)
+        if e2e:
+            out_host.copy_(gathered if world > 1 and rank == 0 else tile, non_blocking=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    kern_events.clear(); samples_seen.clear(); launches["n"] = 0
+
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+
+    # ---- device-resident timed region: K steps, L2 flushed between them -----------------------------------------
+    ev = []
+    barrier()
+    t_wall0 = time.perf_counter()
+    for i in range(args.steps):
+        flush_buf.fill_(i & 0xFF)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        step(args.warmup + i)
+        e1.record()
+        ev.append((e0, e1))
+    barrier()
+    wall_s = time.perf_counter() - t_wall0
+    total_ms = sum(a.elapsed_time(b) for a, b in ev)
+    kern_ms = [a.elapsed_time(b) for a, b in kern_events]
+    n_samples = [int(s.view(torch.int64).item()) for s in samples_seen]
+    gpu_launches = launches["n"]
+
+    # ---- end-to-end region: pinned host rays -> render -> pinned host results ----------------------------------------
+    out_host = torch.empty((world * N if (world > 1 and rank == 0) else N), 4 + K, dtype=torch.float32).pin_memory()
+    for i in range(min(2, args.warmup)):
+        step(i, True, out_host)
+    barrier()
+    ev2 = []
+    for i in range(args.steps):
+        flush_buf.fill_(i & 0xFF)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        step(args.warmup + i, True, out_host)
+        e1.record()
+        ev2.append((e0, e1))
+    barrier()
+    e2e_ms = sum(a.elapsed_time(b) for a, b in ev2)
+    clk = clocks.stop() if rank == 0 else None
+
+    if world > 1:
+        t = torch.tensor([total_ms, e2e_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms, e2e_ms = float(t[0]), float(t[1])
+
+    if rank == 0:
+        peaks = {}
+        ppath = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(ppath):
+            peaks = json.load(open(ppath))
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        # algorithmic bytes of the fused kernel (DESIGN.md "roofline"): per composited sample 2 tables x 16 levels x 8 corners x
+        # 4 B (fp16 pair) = 1024 B of gathers; per ray 32 B in (o, d, near, far) + (5 + K) * 4 B out.  Nothing else touches HBM.
+        avg_samples = sum(n_samples) / max(1, len(n_samples))
+        alg_bytes = avg_samples * 1024.0 + N * (32.0 + (5 + K) * 4.0)
+        avg_kern_ms = sum(kern_ms) / max(1, len(kern_ms))
+        achieved = alg_bytes / (avg_kern_ms * 1e-3) / 1e9
+        mlp_flops = avg_samples * (6144 + 12544 + 14208 + 128 * K)
+        ms_per_step = total_ms / args.steps
+        value = world * N / (ms_per_step * 1e-3) / 1e6
+        h2d = 2 * N * 3 * 4
+        d2h = out_host.numel() * 4
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16 operands / f32 accumulate",
+            "data": "synthetic",
+            "config": {"workload": WORKLOAD, "rays_per_step_per_gpu": N, "samples_per_ray": avg_samples / N, "l2": "flushed between timed steps (512 MB write)",
+                       "parallelism": f"frames sharded over {world} rank(s), all_gather of tiles" if world > 1 else "single GPU",
+                       "wall_s_timed_region_incl_flush": wall_s},
+            "e2e": {"value": world * N / (e2e_ms / args.steps * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": gpu_launches,
+            "roofline": {"kernel": "k_render_fused", "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                         "traffic": None, "peak_source": "MEASURED_PEAKS.json (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
+                         "kernel_ms": avg_kern_ms, "algorithmic_bytes_per_launch": alg_bytes,
+                         "mlp_tflops": mlp_flops / (avg_kern_ms * 1e-3) / 1e12},
+            "clocks": clk,
+        }
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            try:
+                line["roofline"]["traffic"] = json.load(open(tpath)).get("k_render_fused_dram_bytes_per_launch")
+            except Exception:
+                pass
+        if world == 1 and not args.no_cpu_baseline:
+            render, n_cpu, cores = make_cpu_reference(32768)
+            t0 = time.perf_counter()
+            render()
+            secs = time.perf_counter() - t0
+            v = n_cpu / secs / 1e6
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": f"{n_cpu} rays strided over frame 0, 128 uniform samples/ray (reference non-cuda_ray sampler), {secs:.1f} s"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -186,8 +186,9 @@ int inerf_sh_encode_backward(const float *grad, const float *inputs, uint32_t B,
  * the fp32 nn.Linear matrices ([out, in] row-major, network_mask.py:48,69,90).
  */
 typedef struct inerf_field_desc {
-    const void *table_sigma;   /* fp16 [offsets[L], 2]  encoder.embeddings      */
-    const void *table_mask;    /* fp16 [offsets[L], 2]  encoder_mask.embeddings */
+    const void *table_packed;  /* fp16 [offsets[L], 4]: (encoder.embeddings c0 c1, encoder_mask.embeddings c0 c1)
+                                  interleaved per entry by inerf_field_pack_tables: one 8-byte gather per corner
+                                  serves both encoders (they share level geometry, network_mask.py:34,76) */
     const int32_t *offsets;    /* int32 [L + 1] (shared by both encoders)      */
     const void *weights;       /* packed fp16 blob, inerf_field_weights_bytes(K) bytes */
     uint32_t L;                /* 16 */
@@ -198,6 +199,9 @@ typedef struct inerf_field_desc {
     float density_scale;       /* mask_renderer.py:273 */
 } inerf_field_desc;
 
+/* emb_sigma / emb_mask: device [n_entries, 2] of `dtype` (INERF_F32 parameters or INERF_F16) -> packed fp16 [n_entries, 4] */
+int inerf_field_pack_tables(const void *emb_sigma, const void *emb_mask, int dtype, uint64_t n_entries, void *packed,
+                            void *stream);
 size_t inerf_field_weights_bytes(uint32_t K);
 /* host-side packing (CPU pointers): w_* are fp32 row-major [out, in] */
 int inerf_field_pack_weights(const float *sigma0, const float *sigma1, const float *color0, const float *color1,
@@ -213,6 +217,9 @@ int inerf_field_forward(const inerf_field_desc *desc, const float *xyzs, const f
  * march -> encode -> MLP -> composite per 128-ray tile, ray state in registers,
  * no sample stream in HBM.  Outputs are the un-normalised accumulators the
  * reference loop produces before mask_renderer.py:376-377.
+ * `work_counter` is caller-owned scratch, int32[4], 8-byte aligned; the call
+ * zeroes it, uses [0] as the ray cursor and leaves the number of samples it
+ * composited in [2..3] (one uint64), which bench.py reads for the roofline.
  */
 int inerf_render_fused(const inerf_field_desc *desc, const float *rays_o, const float *rays_d, const float *nears,
                        const float *fars, const uint8_t *bitfield, uint32_t N, uint32_t C, uint32_t H,

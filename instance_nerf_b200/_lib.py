@@ -33,8 +33,7 @@ class FieldDesc(ctypes.Structure):
     """struct inerf_field_desc (include/inerf_b200.h)."""
 
     _fields_ = [
-        ("table_sigma", c_void_p),
-        ("table_mask", c_void_p),
+        ("table_packed", c_void_p),
         ("offsets", c_void_p),
         ("weights", c_void_p),
         ("L", c_uint32),
@@ -87,6 +86,7 @@ _PROTOS = {
     "inerf_occupancy_ema": [_P, _P, _U, _F, _P, _P],
     "inerf_occupancy_pack": [_P, _U, _P, _F, _P, _P, _P],
     "inerf_field_pack_weights": [_P] * 8 + [_U, _P],
+    "inerf_field_pack_tables": [_P, _P, _I, ctypes.c_uint64, _P, _P],
     "inerf_field_forward": [POINTER(FieldDesc), _P, _P, _U, _P, _P, _P, _P],
     "inerf_render_fused": [POINTER(FieldDesc), _P, _P, _P, _P, _P, _U, _U, _U, _F, _U, _F, _P, _P, _P, _P, _P, _P],
 }

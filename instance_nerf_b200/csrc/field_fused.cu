@@ -13,19 +13,43 @@ namespace {
 
 using namespace field;
 
+// shared-memory plan of k_field_forward (one operand stage)
+struct FSmem {
+    static constexpr uint32_t A_es = 0;
+    static constexpr uint32_t A_ci = A_es + kBytesEs;
+    static constexpr uint32_t A_mi = A_ci + kBytesCi;
+    static constexpr uint32_t A_h1 = A_mi + kBytesMi;
+    static constexpr uint32_t A_h2 = A_h1 + kBytesH;
+    static constexpr uint32_t W = A_h2 + kBytesH;
+    static __host__ __device__ uint32_t misc(uint32_t K) { return W + weight_layout(K).total; }
+    // misc: LevelGeom[16] | mbarrier (8 B) | tmem slot (4 B)
+    static __host__ __device__ uint32_t bytes(uint32_t K) { return misc(K) + 16 * sizeof(LevelGeom) + 64; }
+};
+
 __global__ void __launch_bounds__(kThreads, 2) k_field_forward(inerf_field_desc desc, const float* __restrict__ xyzs,
                                                                const float* __restrict__ dirs, uint32_t B, float* __restrict__ sigmas,
                                                                float* __restrict__ rgbs, float* __restrict__ masks) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    LevelGeom* lg;
-    uint64_t* bar;
-    const uint32_t tmem_base = cta_setup(smem, desc, lg, bar);
-    uint32_t phase = 0;
     const uint32_t K = desc.K, Kp = weight_layout(K).Kp;
+    const uint32_t misc = FSmem::misc(K);
+    LevelGeom* lg = reinterpret_cast<LevelGeom*>(smem + misc);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + misc + 16 * sizeof(LevelGeom));
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + misc + 16 * sizeof(LevelGeom) + 8);
+    load_weights(smem, FSmem::W, desc.weights, K);
+    init_levels(lg, desc.offsets, desc.L, desc.S, desc.H, threadIdx.x);
+    if (threadIdx.x == 0) { umma::mbar_init(bar, 1); umma::mbar_fence_init(); }
+    if (threadIdx.x < 32) umma::tmem_alloc<kTmemCols>(tmem_slot);
+    umma::fence_async_smem();
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+    const ChainBufs bufs{FSmem::A_es, FSmem::A_ci, FSmem::A_mi, FSmem::A_h1, FSmem::A_h2, FSmem::W};
+
+    uint32_t phase = 0;
     const bool with_masks = masks != nullptr;
     const float inv2b = __fdiv_rn(1.0f, __fmul_rn(2.0f, desc.bound));
-    const __half2* tab_s = reinterpret_cast<const __half2*>(desc.table_sigma);
-    const __half2* tab_m = reinterpret_cast<const __half2*>(desc.table_mask);
+    const uint2* table = reinterpret_cast<const uint2*>(desc.table_packed);
     const uint32_t num_tiles = (B + kTile - 1) / kTile;
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -42,23 +66,24 @@ __global__ void __launch_bounds__(kThreads, 2) k_field_forward(inerf_field_desc 
                 oob |= (x01[d] < 0.f || x01[d] > 1.f);
             }
         }
-        encode8(x01, oob, half * 8, lg, tab_s, tab_m, smem, row);
+        encode8(x01, oob, half * 8, lg, table, smem, bufs.a_es, bufs.a_mi, row);
         if (half == 0) {
             float dx = 0.f, dy = 0.f, dz = 0.f;
             if (s < B) { dx = __ldg(dirs + (size_t)s * 3); dy = __ldg(dirs + (size_t)s * 3 + 1); dz = __ldg(dirs + (size_t)s * 3 + 2); }
-            sh16_to_smem(dx, dy, dz, smem, row);
+            sh16_to_smem(dx, dy, dz, smem, bufs.a_ci, row);
         }
         umma::fence_async_smem();
         umma::fence_before_sync();
         __syncthreads();
 
-        const float sigma = mlp_chain(smem, tmem_base, bar, phase, K, desc.density_scale, with_masks, [](float) {});
+        const float sigma = mlp_chain(smem, bufs, tmem_base, bar, phase, K, desc.density_scale, with_masks, threadIdx.x, nullptr,
+                                      [] { __syncthreads(); }, [](float) {});
 
         // ---- output epilogue ----
         const uint32_t orow = tile * kTile + (warp & 3u) * 32u + lane;
         if (warp < 4) {
             float rgb[3];
-            epilogue_rgb(tmem_base, rgb);
+            epilogue_rgb(tmem_base, rgb, threadIdx.x);
             if (orow < B) {
                 sigmas[orow] = sigma;
                 rgbs[(size_t)orow * 3] = rgb[0]; rgbs[(size_t)orow * 3 + 1] = rgb[1]; rgbs[(size_t)orow * 3 + 2] = rgb[2];
@@ -82,7 +107,24 @@ __global__ void __launch_bounds__(kThreads, 2) k_field_forward(inerf_field_desc 
         umma::fence_before_sync();
         __syncthreads();  // TMEM / operand tiles are reused by the next tile
     }
-    cta_teardown(tmem_base);
+    umma::fence_before_sync();
+    __syncthreads();
+    if (threadIdx.x < 32) umma::tmem_dealloc<kTmemCols>(tmem_base);
+}
+
+// fp32 / fp16 embeddings of both encoders -> interleaved fp16 (sigma.c0, sigma.c1, mask.c0, mask.c1), one pass
+template <typename T>
+__global__ void k_pack_tables(const T* __restrict__ es, const T* __restrict__ em, uint64_t n, uint2* __restrict__ out) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        __half2 a, b;
+        if constexpr (std::is_same<T, float>::value) {
+            const float2 fa = reinterpret_cast<const float2*>(es)[i], fb = reinterpret_cast<const float2*>(em)[i];
+            a = __floats2half2_rn(fa.x, fa.y); b = __floats2half2_rn(fb.x, fb.y);
+        } else {
+            a = reinterpret_cast<const __half2*>(es)[i]; b = reinterpret_cast<const __half2*>(em)[i];
+        }
+        out[i] = make_uint2(h2_bits(a), h2_bits(b));
+    }
 }
 
 inline uint16_t f2h_bits(float f) {
@@ -105,9 +147,9 @@ void pack_layer(uint8_t* dst, const float* W, uint32_t n_out, uint32_t n_in, uin
 
 int validate_desc(const inerf_field_desc* d) {
     INERF_REQUIRE(d);
-    INERF_REQUIRE(d->table_sigma); INERF_REQUIRE(d->table_mask); INERF_REQUIRE(d->offsets); INERF_REQUIRE(d->weights);
+    INERF_REQUIRE(d->table_packed); INERF_REQUIRE(d->offsets); INERF_REQUIRE(d->weights);
     if (d->L != 16 || d->K == 0 || d->K > 64 || d->H == 0 || !(d->bound > 0.f)) return INERF_ERR_UNSUPPORTED;
-    if (((uintptr_t)d->weights & 15u) || ((uintptr_t)d->table_sigma & 3u) || ((uintptr_t)d->table_mask & 3u)) return INERF_ERR_ALIGN;
+    if (((uintptr_t)d->weights & 15u) || ((uintptr_t)d->table_packed & 7u)) return INERF_ERR_ALIGN;
     return INERF_OK;
 }
 
@@ -115,6 +157,19 @@ int validate_desc(const inerf_field_desc* d) {
 
 namespace field {
 int validate(const inerf_field_desc* d) { return validate_desc(d); }
+}
+
+extern "C" int inerf_field_pack_tables(const void* emb_sigma, const void* emb_mask, int dtype, uint64_t n_entries, void* packed,
+                                       void* stream) {
+    INERF_REQUIRE(emb_sigma); INERF_REQUIRE(emb_mask); INERF_REQUIRE(packed);
+    if (n_entries == 0) return INERF_OK;
+    if (((uintptr_t)packed & 7u) || ((uintptr_t)emb_sigma & 7u) || ((uintptr_t)emb_mask & 7u)) return INERF_ERR_ALIGN;
+    const unsigned grid = 8 * kNumSMs;
+    if (dtype == INERF_F32) k_pack_tables<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)emb_sigma, (const float*)emb_mask, n_entries, (uint2*)packed);
+    else if (dtype == INERF_F16) k_pack_tables<__half><<<grid, 256, 0, (cudaStream_t)stream>>>((const __half*)emb_sigma, (const __half*)emb_mask, n_entries, (uint2*)packed);
+    else return INERF_ERR_UNSUPPORTED;
+    INERF_LAUNCH_CHECK();
+    return INERF_OK;
 }
 
 extern "C" size_t inerf_field_weights_bytes(uint32_t K) { return (K == 0 || K > 64) ? 0 : field::weight_layout(K).total; }
@@ -144,7 +199,7 @@ extern "C" int inerf_field_forward(const inerf_field_desc* desc, const float* xy
     if (int e = validate_desc(desc)) return e;
     if (B == 0) return INERF_OK;
     INERF_REQUIRE(xyzs); INERF_REQUIRE(dirs); INERF_REQUIRE(sigmas); INERF_REQUIRE(rgbs);
-    const uint32_t smem_bytes = field::Smem::bytes(desc->K);
+    const uint32_t smem_bytes = FSmem::bytes(desc->K);
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(k_field_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);

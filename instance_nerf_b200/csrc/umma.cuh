@@ -54,6 +54,12 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 __device__ __forceinline__ void mbar_init(uint64_t* mbar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(mbar)), "r"(count) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* mbar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(mbar)) : "memory");
+}
+// barrier over a subset of the CTA's warps (id 1..15; id 0 is __syncthreads)
+template <uint32_t kId, uint32_t kThreads>
+__device__ __forceinline__ void named_sync() { asm volatile("bar.sync %0, %1;" :: "n"(kId), "n"(kThreads) : "memory"); }
 __device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* mbar, uint32_t parity) {
     uint32_t ok;

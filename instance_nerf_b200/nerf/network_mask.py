@@ -67,6 +67,7 @@ class NeRFNetwork(NeRFMaskRenderer):
 
         self.use_fused = True     # set False to force the modular operator sequence
         self._packed = None       # (key, fp16 weight blob on device)
+        self._tables = None       # (key, interleaved fp16 hash tables on device)
         self._work_counter = None
 
     # ---- fused path ------------------------------------------------------------------
@@ -96,14 +97,26 @@ class NeRFNetwork(NeRFMaskRenderer):
             self._packed = (key, blob.to(ws[0].device))
         return self._packed[1]
 
+    def _packed_tables(self) -> torch.Tensor:
+        """Interleaved fp16 copy of both hash tables, (sigma.c0, sigma.c1, mask.c0, mask.c1) per entry, refreshed only when
+        a parameter changes (the reference casts both whole tables to fp16 on EVERY encoder call, grid.py:43-44)."""
+        e, em = self.encoder.embeddings, self.encoder_mask.embeddings
+        key = (e.data_ptr(), e._version, em.data_ptr(), em._version, str(e.device))
+        if self._tables is None or self._tables[0] != key:
+            n = e.shape[0]
+            out = self._tables[1] if self._tables is not None and self._tables[1].shape[0] == n and self._tables[1].device == e.device \
+                else torch.empty(n, 4, dtype=torch.float16, device=e.device)
+            call("inerf_field_pack_tables", ptr(e.detach()), ptr(em.detach()), 0, n, ptr(out), stream_ptr(e.device))
+            self._tables = (key, out)
+        return self._tables[1]
+
     def _field_desc(self) -> FieldDesc:
-        e, em = self.encoder, self.encoder_mask
+        e = self.encoder
         d = FieldDesc()
-        self._keepalive = (e.half_table(), em.half_table(), self._packed_weights())
-        d.table_sigma = self._keepalive[0].data_ptr()
-        d.table_mask = self._keepalive[1].data_ptr()
+        self._keepalive = (self._packed_tables(), self._packed_weights())
+        d.table_packed = self._keepalive[0].data_ptr()
         d.offsets = e.offsets.data_ptr()
-        d.weights = self._keepalive[2].data_ptr()
+        d.weights = self._keepalive[1].data_ptr()
         d.L = e.num_levels
         d.H = e.base_resolution
         d.S = float(np.log2(e.per_level_scale))
@@ -134,7 +147,7 @@ class NeRFNetwork(NeRFMaskRenderer):
         image = torch.empty(N, 3, dtype=torch.float32, device=dev)
         mask_out = torch.empty(N, K, dtype=torch.float32, device=dev) if render_mask else None
         if self._work_counter is None or self._work_counter.device != dev:
-            self._work_counter = torch.zeros(1, dtype=torch.int32, device=dev)
+            self._work_counter = torch.zeros(4, dtype=torch.int32, device=dev)
         desc = self._field_desc()
         call("inerf_render_fused", ctypes.byref(desc), ptr(rays_o), ptr(rays_d), ptr(nears), ptr(fars), ptr(self.density_bitfield),
              N, self.cascade, self.grid_size, float(dt_gamma), int(max_steps), float(T_thresh), ptr(weights_sum), ptr(depth),

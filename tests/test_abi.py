@@ -1,0 +1,77 @@
+"""CPU suite: the C-ABI library loads without a GPU and exports every symbol include/inerf_b200.h declares;
+argument validation returns error codes instead of launching.  No compute calls here."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from instance_nerf_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def L():
+    if not os.path.exists(_lib.LIB_PATH):
+        _lib.build()
+    return _lib.lib()
+
+
+def test_header_symbols_all_exported(L):
+    hdr = open(os.path.join(ROOT, "include", "inerf_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = sorted(set(re.findall(r"\b(inerf_[A-Za-z0-9_]+)\s*\(", hdr)))
+    assert declared, "no declarations parsed"
+    missing = [s for s in declared if not hasattr(L, s)]
+    assert not missing, f"declared in the header but not exported: {missing}"
+    assert sorted(declared) == sorted(_lib.EXPORTED_SYMBOLS), "ctypes prototypes and the header disagree"
+
+
+def test_version_and_error_strings(L):
+    assert L.inerf_version() >= 1000
+    assert L.inerf_error_string(0) == b"ok"
+    for code in (-1, -2, -3, -4, -5):
+        assert L.inerf_error_string(code).startswith(b"inerf:")
+
+
+def test_bad_arguments_return_codes_without_a_gpu(L):
+    # NULL pointers / bad sizes are rejected before any launch (the reference's raymarching ops check nothing)
+    assert L.inerf_near_far_from_aabb(None, None, None, 4, 0.2, None, None, None) == -1
+    assert L.inerf_grid_encode_forward(None, None, None, None, 8, 3, 2, 16, 1.0, 16, None, 0, 0, 0, 0, 1, None) < 0
+    assert L.inerf_field_weights_bytes(0) == 0 and L.inerf_field_weights_bytes(65) == 0
+    assert L.inerf_field_weights_bytes(32) == (64 * 32 + 16 * 64 + 64 * 32 + 64 * 64 + 16 * 64 + 64 * 48 + 64 * 64 + 32 * 64) * 2
+    assert L.inerf_render_fused(None, None, None, None, None, None, 1, 4, 128, 0.0, 1024, 1e-4, None, None, None, None, None, None) < 0
+
+
+def test_pack_weights_layout_roundtrip(L):
+    """Host-side packing into the UMMA K-major core-matrix layout: element (n, k) of a layer lands at
+    (n%8)*16 + (n/8)*SBO + (k/8)*128 + (k%8)*2 with SBO = (Kpad/8)*128 (csrc/umma.cuh)."""
+    import numpy as np
+    K = 5
+    rng = np.random.RandomState(0)
+    shapes = [(64, 32), (16, 64), (64, 31), (64, 64), (3, 64), (64, 47), (64, 64), (K, 64)]
+    ws = [np.ascontiguousarray(rng.randn(*s).astype(np.float32)) for s in shapes]
+    n = L.inerf_field_weights_bytes(K)
+    blob = np.zeros(n, np.uint8)
+    rc = L.inerf_field_pack_weights(*[w.ctypes.data for w in ws], K, blob.ctypes.data)
+    assert rc == 0
+    h = blob.view(np.float16)
+    pads = [(64, 32), (16, 64), (64, 32), (64, 64), (16, 64), (64, 48), (64, 64), (16, 64)]
+    base = 0
+    for w, (Np, Kp) in zip(ws, pads):
+        sbo = (Kp // 8) * 128
+        for (r, c) in [(0, 0), (w.shape[0] - 1, w.shape[1] - 1), (w.shape[0] // 2, 7), (1, 8)]:
+            off = base + (r % 8) * 16 + (r // 8) * sbo + (c // 8) * 128 + (c % 8) * 2
+            assert h[off // 2] == np.float16(w[r, c])
+        base += Np * Kp * 2
+    assert base == n
+
+
+def test_product_path_has_no_cpu_fallback():
+    import torch
+    from instance_nerf_b200 import raymarching
+    if torch.cuda.is_available():
+        pytest.skip("CPU-only check")
+    with pytest.raises(Exception):
+        raymarching.composite_rays_train(torch.zeros(4), torch.zeros(4, 3), torch.zeros(4, 2), torch.zeros(1, 3, dtype=torch.int32))
