@@ -41,6 +41,23 @@ struct Walk {
     float bound, dt_gamma, dt_min, dt_max, rH, H3, Hf, Hm1, far;
     int C;
     const uint8_t* __restrict__ grid;
+    // render-kernel accelerators (results identical to reading grid[] directly):
+    //  * `coarse`: shared-memory bitmap, one bit per aligned 4x4x4 block of cells (= 64 consecutive Morton
+    //    indices = one 8-byte word of the bitfield), 0 = the whole block is empty -> no global load;
+    //  * the last 8-byte word read is kept in registers (consecutive samples mostly stay inside one block).
+    const uint32_t* coarse = nullptr;
+    unsigned long long cword = 0ull;
+    uint32_t cblk = 0xffffffffu;
+
+    __device__ __forceinline__ bool occupied_cached(uint32_t index) {
+        const uint32_t blk = index >> 6;
+        if (coarse != nullptr && !((coarse[blk >> 5] >> (blk & 31u)) & 1u)) return false;
+        if (blk != cblk) {
+            cword = __ldg(reinterpret_cast<const unsigned long long*>(grid) + blk);
+            cblk = blk;
+        }
+        return (cword >> (index & 63u)) & 1ull;
+    }
 
     __device__ __forceinline__ void init(const float* __restrict__ o, const float* __restrict__ d,
                                          const uint8_t* __restrict__ g, float bound_, float dt_gamma_,
@@ -56,6 +73,7 @@ struct Walk {
         dt_min = __fdiv_rn(2.0f * kSqrt3, (float)max_steps);                                   // :345
         dt_max = __fdiv_rn(__fmul_rn(2.0f * kSqrt3, (float)(1 << (C_ - 1))), Hf);              // :346
         far = far_; C = (int)C_; grid = g;
+        cblk = 0xffffffffu;
     }
     __device__ __forceinline__ float step_size(float t) const { return clampf(__fmul_rn(t, dt_gamma), dt_min, dt_max); }
 
@@ -109,9 +127,39 @@ struct Walk {
         return step;
     }
 
+    // ONE cell evaluation of the DDA at parameter t (used by the render kernel's per-lane state machine).
+    // Occupied: returns true with the sample (x, y, z, dt) and t advanced past it.  Empty: returns false with `tt` = the
+    // parameter at which the ray leaves this cell; the caller then does `do { t += step_size(t); } while (t < tt);`.
+    __device__ __forceinline__ bool eval_cell(float& t, float& x, float& y, float& z, float& dt, float& tt) {
+        x = clampf(__fmaf_rn(t, dx, ox), -bound, bound);
+        y = clampf(__fmaf_rn(t, dy, oy), -bound, bound);
+        z = clampf(__fmaf_rn(t, dz, oz), -bound, bound);
+        dt = step_size(t);
+        const float mx = fmaxf(fabsf(x), fmaxf(fabsf(y), fabsf(z)));
+        const float md = __fmul_rn(__fmul_rn(dt, Hf), 0.5f);
+        const int level = max(clamped_exponent(mx, C), clamped_exponent(md, C));
+        const float mip_bound = fminf(__uint_as_float((uint32_t)(127 + level) << 23), bound);
+        const float mip_rbound = __fdiv_rn(1.0f, mip_bound);
+        const float hH = __fmul_rn(0.5f, Hf);
+        const int nx = (int)clampf(__fmul_rn(__fmaf_rn(x, mip_rbound, 1.0f), hH), 0.0f, Hm1);
+        const int ny = (int)clampf(__fmul_rn(__fmaf_rn(y, mip_rbound, 1.0f), hH), 0.0f, Hm1);
+        const int nz = (int)clampf(__fmul_rn(__fmaf_rn(z, mip_rbound, 1.0f), hH), 0.0f, Hm1);
+        const uint32_t index = (uint32_t)__fmaf_rn((float)level, H3, (float)morton3D_enc(nx, ny, nz));
+        if (occupied_cached(index)) {
+            t = __fadd_rn(t, dt);
+            return true;
+        }
+        const float tx = __fmul_rn(__fmaf_rn(__fmaf_rn(__fmul_rn(__fadd_rn(__fadd_rn((float)nx, 0.5f), sx), rH), 2.0f, -1.0f), mip_bound, -x), rdx);
+        const float ty = __fmul_rn(__fmaf_rn(__fmaf_rn(__fmul_rn(__fadd_rn(__fadd_rn((float)ny, 0.5f), sy), rH), 2.0f, -1.0f), mip_bound, -y), rdy);
+        const float tz = __fmul_rn(__fmaf_rn(__fmaf_rn(__fmul_rn(__fadd_rn(__fadd_rn((float)nz, 0.5f), sz), rH), 2.0f, -1.0f), mip_bound, -z), rdz);
+        tt = __fadd_rn(t, fmaxf(0.0f, fminf(tx, fminf(ty, tz))));
+        return false;
+    }
+
     // Advance from `t` to the next occupied sample.  On success returns true with the sample position in
     // (x, y, z), its step in dt, and t advanced past it; on exhaustion (t >= far) returns false.
-    __device__ __forceinline__ bool next_sample(float& t, float& x, float& y, float& z, float& dt) const {
+    template <bool CACHED = false>
+    __device__ __forceinline__ bool next_sample(float& t, float& x, float& y, float& z, float& dt) {
         while (t < far) {
             x = clampf(__fmaf_rn(t, dx, ox), -bound, bound);
             y = clampf(__fmaf_rn(t, dy, oy), -bound, bound);
@@ -127,7 +175,8 @@ struct Walk {
             const int ny = (int)clampf(__fmul_rn(__fmaf_rn(y, mip_rbound, 1.0f), hH), 0.0f, Hm1);
             const int nz = (int)clampf(__fmul_rn(__fmaf_rn(z, mip_rbound, 1.0f), hH), 0.0f, Hm1);
             const uint32_t index = (uint32_t)__fmaf_rn((float)level, H3, (float)morton3D_enc(nx, ny, nz));
-            if (grid[index >> 3] & (1u << (index & 7u))) {
+            const bool occ = CACHED ? occupied_cached(index) : (grid[index >> 3] & (1u << (index & 7u))) != 0;
+            if (occ) {
                 t = __fadd_rn(t, dt);
                 return true;
             }

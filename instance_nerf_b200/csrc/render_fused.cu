@@ -31,8 +31,9 @@ using namespace field;
 
 constexpr uint32_t kChainT = 256, kGatherT = 256, kMarchT = 128;
 constexpr uint32_t kThreadsR = kChainT + kGatherT + kMarchT;
-constexpr uint32_t DQ = 4;   // sample FIFO depth (tiles)
-constexpr uint32_t DA = 2;   // gathered operand stages
+constexpr uint32_t RING = 8;  // samples queued per ray slot
+constexpr uint32_t DT = 4;    // tile descriptors in flight (gather may run DA tiles ahead of the chain)
+constexpr uint32_t DA = 2;    // gathered operand stages
 
 struct RenderParams {
     const float* rays_o;
@@ -47,21 +48,24 @@ struct RenderParams {
     float* image;
     float* mask_out;
     int32_t* work_counter;
+    uint32_t coarse_bytes;   // size of the shared-memory coarse occupancy bitmap (0 = disabled)
 };
 
-struct QStage {   // one FIFO stage: one sample per ray slot
-    float x[kTile], y[kTile], z[kTile], dt[kTile], d1[kTile], dx[kTile], dy[kTile], dz[kTile];
-    int32_t ray[kTile];   // -1 = no sample in this slot
-    int32_t end[kTile];   // 1 = last sample of its ray
+// Per-slot sample rings (SoA over the 128 ray slots).  dt == 0 marks an END entry (its ray has no more samples).
+struct Rings {
+    float x[RING][kTile], y[RING][kTile], z[RING][kTile], dt[RING][kTile], d1[RING][kTile];
+    int32_t ray[RING][kTile];
 };
 
 struct Ctrl {
-    uint64_t q_full[DQ], q_empty[DQ], a_full[DA], a_empty[DA], mma_bar;
+    uint64_t a_full[DA], a_empty[DA], mma_bar;
     uint32_t tmem_slot;
-    int32_t n_done;       // marchers that ran out of rays
-    int32_t last_tile;    // last tile holding a real sample (valid once n_done == 128)
-    int32_t a_flag[DA];   // 1 = terminal tile
-    int32_t kill[kTile];  // ray id terminated early by the compositor (marcher drops it)
+    int32_t n_done;               // marcher lanes that ran out of rays
+    int32_t a_flag[DA];           // 1 = terminal tile
+    uint32_t tail[kTile];         // entries produced per slot (marcher)
+    uint32_t chead[kTile];        // entries retired per slot (compositor)
+    int32_t kill[kTile];          // ray id terminated early by the compositor (marcher drops it)
+    int32_t tsel[DT][kTile];      // per tile: ring entry taken for each row, -1 = bubble
     float w_s[kTile];
     int32_t fin_s[kTile];
     LevelGeom lg[16];
@@ -73,123 +77,145 @@ struct RSmem {
     static constexpr uint32_t H2 = H1 + kBytesH;
     static constexpr uint32_t W = H2 + kBytesH;
     static __host__ __device__ uint32_t ctrl(uint32_t K) { return (W + weight_layout(K).total + 15u) & ~15u; }
-    static __host__ __device__ uint32_t queue(uint32_t K) { return (ctrl(K) + (uint32_t)sizeof(Ctrl) + 15u) & ~15u; }
-    static __host__ __device__ uint32_t bytes(uint32_t K) { return queue(K) + DQ * (uint32_t)sizeof(QStage); }
+    static __host__ __device__ uint32_t rings(uint32_t K) { return (ctrl(K) + (uint32_t)sizeof(Ctrl) + 15u) & ~15u; }
+    static __host__ __device__ uint32_t coarse(uint32_t K) { return rings(K) + (uint32_t)sizeof(Rings); }
+    // + coarse occupancy bitmap: C*H^3/64 bits
+    static __host__ __device__ uint32_t bytes(uint32_t K, uint32_t coarse_bytes) { return coarse(K) + coarse_bytes; }
 };
 
 __device__ __forceinline__ int32_t ld_vol(const int32_t* p) { return *reinterpret_cast<const volatile int32_t*>(p); }
+__device__ __forceinline__ uint32_t ld_vol(const uint32_t* p) { return *reinterpret_cast<const volatile uint32_t*>(p); }
 __device__ __forceinline__ void st_vol(int32_t* p, int32_t v) { *reinterpret_cast<volatile int32_t*>(p) = v; }
+__device__ __forceinline__ void st_vol(uint32_t* p, uint32_t v) { *reinterpret_cast<volatile uint32_t*>(p) = v; }
+// OR-reduction of a predicate over the kGatherT threads of the gather group (named barrier 2)
+__device__ __forceinline__ bool gather_any(bool pred) {
+    uint32_t r;
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\tsetp.ne.b32 q, %1, 0;\n\t"
+        "barrier.cta.red.or.pred p, 2, %2, q;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(r) : "r"((uint32_t)pred), "n"(kGatherT) : "memory");
+    return r != 0;
+}
 
 // ------------------------------------------------------------------------------------------------ march --
-__device__ __forceinline__ void march_role(const inerf_field_desc& desc, const RenderParams& p, Ctrl* ctl, QStage* q, uint32_t r) {
+// Per-lane state machine; every warp iteration each lane does ONE bounded unit of work (fetch a ray / evaluate one
+// occupancy cell / advance up to kSkipSteps steps through empty space), so a lane crossing a long empty stretch never
+// holds back the other 31.  The sample sequence per ray is the reference's (raymarching.cu:1008-1062).
+__device__ __forceinline__ void march_role(const inerf_field_desc& desc, const RenderParams& p, Ctrl* ctl, Rings* rg, const uint32_t* coarse,
+                                           uint32_t r) {
+    enum : int { NEED_RAY = 0, EVAL = 1, SKIP = 2, DONE = 3 };
+    constexpr int kSkipSteps = 6;
     march::Walk wk;
-    int32_t ray = -1, my_last = -1;
-    bool exhausted = false, have_pending = false;
-    uint32_t nsteps = 0;
-    float t = 0.f, last_t = 0.f, px = 0.f, py = 0.f, pz = 0.f, pdt = 0.f, pd1 = 0.f;
-    for (uint32_t tile = 0;; tile++) {
-        const uint32_t s = tile % DQ;
-        bool quit = false;
-        if (tile >= DQ) {
-            const uint32_t par = ((tile / DQ) - 1u) & 1u;
-            while (!umma::mbar_try_wait(&ctl->q_empty[s], par)) {
-                if (exhausted && ld_vol(&ctl->n_done) == (int32_t)kMarchT) {
-                    __threadfence_block();
-                    if ((int32_t)tile > ld_vol(&ctl->last_tile) + 1) { quit = true; break; }
-                }
-            }
-        }
-        if (!quit && exhausted && ld_vol(&ctl->n_done) == (int32_t)kMarchT) {
-            __threadfence_block();
-            if ((int32_t)tile > ld_vol(&ctl->last_tile) + 1) quit = true;
-        }
-        if (quit) break;
-
-        if (ray >= 0 && ld_vol(&ctl->kill[r]) == ray) { ray = -1; have_pending = false; }
-        if (!have_pending && !exhausted) {
-            while (true) {
-                const uint32_t idx = (uint32_t)atomicAdd(p.work_counter, 1);
-                if (idx >= p.N) { exhausted = true; break; }
+    wk.coarse = coarse;
+    int state = NEED_RAY;
+    int32_t ray = -1;
+    uint32_t nsteps = 0, tail = 0;
+    float t = 0.f, last_t = 0.f, tt = 0.f;
+    while (true) {
+        if (state != DONE && ray >= 0 && ld_vol(&ctl->kill[r]) == ray) { ray = -1; state = NEED_RAY; }
+        const bool room = tail - ld_vol(&ctl->chead[r]) < RING;
+        bool worked = false;
+        if (state == NEED_RAY) {
+            const uint32_t idx = (uint32_t)atomicAdd(p.work_counter, 1);
+            if (idx >= p.N) {
+                state = DONE;
+                atomicAdd(&ctl->n_done, 1);
+            } else {
                 wk.init(p.rays_o + (size_t)idx * 3, p.rays_d + (size_t)idx * 3, p.bitfield, desc.bound, p.dt_gamma, p.max_steps, p.C, p.H,
                         __ldg(p.fars + idx));
                 t = __ldg(p.nears + idx);
                 last_t = t;
-                if (wk.next_sample(t, px, py, pz, pdt)) {
-                    pd1 = __fsub_rn(t, last_t);
-                    last_t = t;
-                    nsteps = 1;
-                    ray = (int32_t)idx;
-                    have_pending = true;
-                    break;
+                nsteps = 0;
+                ray = (int32_t)idx;
+                state = EVAL;
+            }
+            worked = true;
+        } else if (state == EVAL) {
+            if (room) {
+                worked = true;
+                const uint32_t e = tail % RING;
+                if (!(t < wk.far) || nsteps >= p.max_steps) {
+                    if (nsteps > 0) {   // END marker; a ray without samples is never seen by the compositor (outputs pre-zeroed)
+                        rg->dt[e][r] = 0.f;
+                        rg->ray[e][r] = ray;
+                        __threadfence_block();
+                        st_vol(&ctl->tail[r], ++tail);
+                    }
+                    ray = -1;
+                    state = NEED_RAY;
+                } else {
+                    float x, y, z, dt;
+                    if (wk.eval_cell(t, x, y, z, dt, tt)) {
+                        rg->x[e][r] = x; rg->y[e][r] = y; rg->z[e][r] = z;
+                        rg->dt[e][r] = dt;
+                        rg->d1[e][r] = __fsub_rn(t, last_t);
+                        rg->ray[e][r] = ray;
+                        last_t = t;
+                        nsteps++;
+                        __threadfence_block();
+                        st_vol(&ctl->tail[r], ++tail);
+                    } else {
+                        t = __fadd_rn(t, wk.step_size(t));   // do { t += dt } while (t < tt): the first step is unconditional
+                        state = (t < tt) ? SKIP : EVAL;
+                    }
                 }
-                // no sample at all: the outputs of this ray stay at the zeros the host wrote
             }
-            if (exhausted) {
-                atomicMax(&ctl->last_tile, my_last);
-                __threadfence_block();
-                atomicAdd(&ctl->n_done, 1);
-            }
+        } else if (state == SKIP) {
+            worked = true;
+#pragma unroll 1
+            for (int i = 0; i < kSkipSteps && t < tt; i++) t = __fadd_rn(t, wk.step_size(t));
+            if (!(t < tt)) state = EVAL;
         }
-        QStage& qs = q[s];
-        if (have_pending) {
-            float nx = 0.f, ny = 0.f, nz = 0.f, ndt = 0.f;
-            const bool more = nsteps < p.max_steps && wk.next_sample(t, nx, ny, nz, ndt);   // look one sample ahead
-            qs.x[r] = px; qs.y[r] = py; qs.z[r] = pz; qs.dt[r] = pdt; qs.d1[r] = pd1;
-            qs.dx[r] = wk.dx; qs.dy[r] = wk.dy; qs.dz[r] = wk.dz;
-            qs.ray[r] = ray;
-            qs.end[r] = more ? 0 : 1;
-            my_last = (int32_t)tile;
-            if (more) {
-                pd1 = __fsub_rn(t, last_t);
-                last_t = t;
-                nsteps++;
-                px = nx; py = ny; pz = nz; pdt = ndt;
-            } else {
-                have_pending = false;
-                ray = -1;
-            }
-        } else {
-            qs.ray[r] = -1;
-        }
-        umma::mbar_arrive(&ctl->q_full[s]);
+        if (__all_sync(0xffffffffu, state == DONE)) break;
+        if (!__any_sync(0xffffffffu, worked)) __nanosleep(256);
     }
 }
 
 // ----------------------------------------------------------------------------------------------- gather --
-__device__ __forceinline__ void gather_role(const inerf_field_desc& desc, uint8_t* smem, Ctrl* ctl, QStage* q, uint32_t gt) {
+__device__ __forceinline__ void gather_role(const inerf_field_desc& desc, const RenderParams& p, uint8_t* smem, Ctrl* ctl, Rings* rg,
+                                            uint32_t gt) {
     const uint32_t row = gt & (kTile - 1), half = gt >> 7;
     const float inv2b = __fdiv_rn(1.0f, __fmul_rn(2.0f, desc.bound));
     const uint2* table = reinterpret_cast<const uint2*>(desc.table_packed);
+    uint32_t ghead = 0;   // entries of this row already handed to a tile (half-0 threads)
     for (uint32_t tile = 0;; tile++) {
-        const uint32_t sq = tile % DQ, sa = tile % DA;
-        umma::mbar_wait(&ctl->q_full[sq], (tile / DQ) & 1u);
-        const int32_t nd = ld_vol(&ctl->n_done);
-        __threadfence_block();
-        const int32_t lt = ld_vol(&ctl->last_tile);
-        const bool stop = nd == (int32_t)kMarchT && (int32_t)tile > lt;
-        const QStage& qs = q[sq];
-        int32_t ray = -1;
-        float x = 0.f, y = 0.f, z = 0.f, dx = 0.f, dy = 0.f, dz = 0.f;
-        if (!stop) {
-            ray = qs.ray[row];
-            if (ray >= 0) {
-                x = qs.x[row]; y = qs.y[row]; z = qs.z[row];
-                if (half == 0) { dx = qs.dx[row]; dy = qs.dy[row]; dz = qs.dz[row]; }
+        const uint32_t st = tile % DT, sa = tile % DA;
+        bool stop = false;
+        while (true) {   // assemble a tile: one queued sample from every slot that has one
+            int32_t sel = -1;
+            bool not_finished = false;
+            if (half == 0) {
+                const int32_t nd = ld_vol(&ctl->n_done);
+                __threadfence_block();
+                if (ld_vol(&ctl->tail[row]) != ghead) sel = (int32_t)(ghead % RING);
+                not_finished = sel >= 0 || nd != (int32_t)kMarchT;
+                ctl->tsel[st][row] = sel;
             }
+            if (!gather_any(not_finished)) { stop = true; break; }   // all marchers done and every ring drained
+            if (gather_any(sel >= 0)) { if (sel >= 0) ghead++; break; }
+            __nanosleep(128);
         }
-        umma::mbar_arrive(&ctl->q_empty[sq]);
         if (tile >= DA) umma::mbar_wait(&ctl->a_empty[sa], ((tile / DA) - 1u) & 1u);
         if (gt == 0) ctl->a_flag[sa] = stop ? 1 : 0;
         if (stop) { umma::mbar_arrive(&ctl->a_full[sa]); break; }
-        if (ray >= 0 && ld_vol(&ctl->kill[row]) != ray) {
-            const uint32_t a_es = RSmem::A + sa * kStageBytes, a_ci = a_es + kBytesEs, a_mi = a_ci + kBytesCi;
-            float x01[3];
-            x01[0] = __fmul_rn(__fadd_rn(x, desc.bound), inv2b);
-            x01[1] = __fmul_rn(__fadd_rn(y, desc.bound), inv2b);
-            x01[2] = __fmul_rn(__fadd_rn(z, desc.bound), inv2b);
-            const bool oob = x01[0] < 0.f || x01[0] > 1.f || x01[1] < 0.f || x01[1] > 1.f || x01[2] < 0.f || x01[2] > 1.f;
-            encode8(x01, oob, half * 8, ctl->lg, table, smem, a_es, a_mi, row);
-            if (half == 0) sh16_to_smem(dx, dy, dz, smem, a_ci, row);
+        const int32_t e = ctl->tsel[st][row];
+        if (e >= 0) {
+            __threadfence_block();
+            const int32_t ray = rg->ray[e][row];
+            if (rg->dt[e][row] != 0.f && ld_vol(&ctl->kill[row]) != ray) {
+                const uint32_t a_es = RSmem::A + sa * kStageBytes, a_ci = a_es + kBytesEs, a_mi = a_ci + kBytesCi;
+                float x01[3];
+                x01[0] = __fmul_rn(__fadd_rn(rg->x[e][row], desc.bound), inv2b);
+                x01[1] = __fmul_rn(__fadd_rn(rg->y[e][row], desc.bound), inv2b);
+                x01[2] = __fmul_rn(__fadd_rn(rg->z[e][row], desc.bound), inv2b);
+                const bool oob = x01[0] < 0.f || x01[0] > 1.f || x01[1] < 0.f || x01[1] > 1.f || x01[2] < 0.f || x01[2] > 1.f;
+                if (half == 0) {
+                    const float* d = p.rays_d + (size_t)ray * 3;
+                    sh16_to_smem(__ldg(d), __ldg(d + 1), __ldg(d + 2), smem, a_ci, row);
+                }
+                encode8(x01, oob, half * 8, ctl->lg, table, smem, a_es, a_mi, row);
+            }
         }
         umma::fence_async_smem();
         umma::mbar_arrive(&ctl->a_full[sa]);
@@ -198,7 +224,7 @@ __device__ __forceinline__ void gather_role(const inerf_field_desc& desc, uint8_
 
 // ------------------------------------------------------------------------------------------------ chain --
 template <int NCH>  // 16-column logit chunks owned per thread: 1 -> K <= 32, 2 -> K <= 64
-__device__ __forceinline__ void chain_role(const inerf_field_desc& desc, const RenderParams& p, uint8_t* smem, Ctrl* ctl, QStage* q,
+__device__ __forceinline__ void chain_role(const inerf_field_desc& desc, const RenderParams& p, uint8_t* smem, Ctrl* ctl, Rings* rg,
                                            uint32_t tmem_base, uint32_t ct) {
     const uint32_t K = desc.K, Kp = weight_layout(K).Kp;
     const bool with_masks = p.mask_out != nullptr;
@@ -209,7 +235,7 @@ __device__ __forceinline__ void chain_role(const inerf_field_desc& desc, const R
     const uint32_t c_begin = half ? (chunks + 1) / 2 : 0, c_end = half ? chunks : (chunks + 1) / 2;
     const bool vec_ok = (K & 3u) == 0;
 
-    uint32_t phase = 0, my_samples = 0;
+    uint32_t phase = 0, my_samples = 0, chead = 0;
     int32_t cur_ray = -1, dead = -1;
     float t_depth = 0.f, ws = 0.f, dep = 0.f, cr = 0.f, cg = 0.f, cb = 0.f;
     float macc[NCH][16];
@@ -221,7 +247,7 @@ __device__ __forceinline__ void chain_role(const inerf_field_desc& desc, const R
     auto chain_sync = [] { umma::named_sync<1, kChainT>(); };
 
     for (uint32_t tile = 0;; tile++) {
-        const uint32_t sq = tile % DQ, sa = tile % DA;
+        const uint32_t st = tile % DT, sa = tile % DA;
         umma::mbar_wait(&ctl->a_full[sa], (tile / DA) & 1u);
         if (ld_vol(&ctl->a_flag[sa])) break;
         const uint32_t a_es = RSmem::A + sa * kStageBytes;
@@ -230,28 +256,32 @@ __device__ __forceinline__ void chain_role(const inerf_field_desc& desc, const R
         mlp_chain(smem, bufs, tmem_base, &ctl->mma_bar, phase, K, desc.density_scale, with_masks, ct, &ctl->a_empty[sa], chain_sync,
                   [&](float sigma) {
                       if (owner) {
-                          const QStage& qs = q[sq];
-                          const int32_t ray = qs.ray[row];
+                          const int32_t e = ctl->tsel[st][row];
                           int32_t fin = -1;
-                          if (ray >= 0 && ray != dead) {
-                              if (ray != cur_ray) { cur_ray = ray; t_depth = __ldg(p.nears + ray); }
-                              const float dt = qs.dt[row], d1 = qs.d1[row];
-                              const int32_t endf = qs.end[row];
-                              const float alpha = 1.0f - __expf(-sigma * dt);
-                              const float T = 1.0f - ws;
-                              weight = alpha * T;
-                              ws += weight;
-                              t_depth += d1;
-                              dep = fmaf(weight, t_depth, dep);
-                              my_samples++;
-                              const bool term = T < p.T_thresh;
-                              if (term || endf) fin = ray;
-                              if (term) {
-                                  dead = ray;
-                                  if (!endf) st_vol(&ctl->kill[row], ray);
+                          if (e >= 0) {
+                              const int32_t ray = rg->ray[e][row];
+                              const float dt = rg->dt[e][row], d1 = rg->d1[e][row];
+                              st_vol(&ctl->chead[row], ++chead);   // entry retired: the marcher may reuse it
+                              if (ray != dead) {
+                                  if (dt == 0.f) {
+                                      if (ray == cur_ray) fin = ray;   // END marker: the ray is complete
+                                  } else {
+                                      if (ray != cur_ray) { cur_ray = ray; t_depth = __ldg(p.nears + ray); }
+                                      const float alpha = 1.0f - __expf(-sigma * dt);
+                                      const float T = 1.0f - ws;
+                                      weight = alpha * T;
+                                      ws += weight;
+                                      t_depth += d1;
+                                      dep = fmaf(weight, t_depth, dep);
+                                      my_samples++;
+                                      if (T < p.T_thresh) {   // raymarching.cu:1252: terminated, later samples of this ray are dropped
+                                          fin = ray;
+                                          dead = ray;
+                                          st_vol(&ctl->kill[row], ray);
+                                      }
+                                  }
                               }
                           }
-                          umma::mbar_arrive(&ctl->q_empty[sq]);
                           ctl->w_s[row] = weight;
                           ctl->fin_s[row] = fin;
                       }
@@ -282,6 +312,7 @@ __device__ __forceinline__ void chain_role(const inerf_field_desc& desc, const R
                 p.depth[fin] = dep;
                 p.image[(size_t)fin * 3] = cr; p.image[(size_t)fin * 3 + 1] = cg; p.image[(size_t)fin * 3 + 2] = cb;
                 ws = dep = cr = cg = cb = 0.f;
+                cur_ray = -1;
             }
             if (with_masks) {
 #pragma unroll
@@ -321,20 +352,28 @@ __global__ void __launch_bounds__(kThreadsR, 1) k_render_fused(inerf_field_desc 
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t K = desc.K;
     Ctrl* ctl = reinterpret_cast<Ctrl*>(smem + RSmem::ctrl(K));
-    QStage* q = reinterpret_cast<QStage*>(smem + RSmem::queue(K));
+    Rings* rg = reinterpret_cast<Rings*>(smem + RSmem::rings(K));
     const uint32_t tid = threadIdx.x;
 
     load_weights(smem, RSmem::W, desc.weights, K);
     init_levels(ctl->lg, desc.offsets, desc.L, desc.S, desc.H, tid);
     if (tid == 0) {
-        for (uint32_t i = 0; i < DQ; i++) { umma::mbar_init(&ctl->q_full[i], kMarchT); umma::mbar_init(&ctl->q_empty[i], kGatherT + kTile); }
         for (uint32_t i = 0; i < DA; i++) { umma::mbar_init(&ctl->a_full[i], kGatherT); umma::mbar_init(&ctl->a_empty[i], 1); ctl->a_flag[i] = 0; }
         umma::mbar_init(&ctl->mma_bar, 1);
         ctl->n_done = 0;
-        ctl->last_tile = -1;
         umma::mbar_fence_init();
     }
-    if (tid < kTile) ctl->kill[tid] = -1;
+    if (tid < kTile) { ctl->kill[tid] = -1; ctl->tail[tid] = 0; ctl->chead[tid] = 0; }
+    // coarse occupancy: bit b = (8-byte word b of the bitfield != 0), i.e. any of the 64 cells of that 4x4x4 block occupied
+    uint32_t* coarse = p.coarse_bytes ? reinterpret_cast<uint32_t*>(smem + RSmem::coarse(K)) : nullptr;
+    if (coarse) {
+        const uint32_t n_blocks = p.coarse_bytes * 8u;   // multiple of 32
+        const unsigned long long* words = reinterpret_cast<const unsigned long long*>(p.bitfield);
+        for (uint32_t base = (tid >> 5) * 32u; base < n_blocks; base += (kThreadsR / 32u) * 32u) {
+            const uint32_t bits = __ballot_sync(0xffffffffu, __ldg(words + base + (tid & 31u)) != 0ull);
+            if ((tid & 31u) == 0) coarse[base >> 5] = bits;
+        }
+    }
     if (tid < 32) umma::tmem_alloc<kTmemCols>(&ctl->tmem_slot);
     umma::fence_async_smem();
     umma::fence_before_sync();
@@ -342,9 +381,9 @@ __global__ void __launch_bounds__(kThreadsR, 1) k_render_fused(inerf_field_desc 
     umma::fence_after_sync();
     const uint32_t tmem_base = ctl->tmem_slot;
 
-    if (tid < kChainT) chain_role<NCH>(desc, p, smem, ctl, q, tmem_base, tid);
-    else if (tid < kChainT + kGatherT) gather_role(desc, smem, ctl, q, tid - kChainT);
-    else march_role(desc, p, ctl, q, tid - kChainT - kGatherT);
+    if (tid < kChainT) chain_role<NCH>(desc, p, smem, ctl, rg, tmem_base, tid);
+    else if (tid < kChainT + kGatherT) gather_role(desc, p, smem, ctl, rg, tid - kChainT);
+    else march_role(desc, p, ctl, rg, coarse, tid - kChainT - kGatherT);
 
     umma::fence_before_sync();
     __syncthreads();
@@ -362,7 +401,7 @@ extern "C" int inerf_render_fused(const inerf_field_desc* desc, const float* ray
     if (N == 0) return INERF_OK;
     INERF_REQUIRE(rays_o); INERF_REQUIRE(rays_d); INERF_REQUIRE(nears); INERF_REQUIRE(fars); INERF_REQUIRE(bitfield);
     INERF_REQUIRE(weights_sum); INERF_REQUIRE(depth); INERF_REQUIRE(image); INERF_REQUIRE(work_counter);
-    if ((uintptr_t)work_counter & 7u) return INERF_ERR_ALIGN;
+    if (((uintptr_t)work_counter & 7u) || ((uintptr_t)bitfield & 7u)) return INERF_ERR_ALIGN;
     if (mask_out && ((uintptr_t)mask_out & 15u)) return INERF_ERR_ALIGN;
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t ce = cudaMemsetAsync(work_counter, 0, 4 * sizeof(int32_t), st);
@@ -372,13 +411,17 @@ extern "C" int inerf_render_fused(const inerf_field_desc* desc, const float* ray
     if ((ce = cudaMemsetAsync(depth, 0, (size_t)N * 4, st)) != cudaSuccess) return (int)ce;
     if ((ce = cudaMemsetAsync(image, 0, (size_t)N * 12, st)) != cudaSuccess) return (int)ce;
     if (mask_out && (ce = cudaMemsetAsync(mask_out, 0, (size_t)N * desc->K * 4, st)) != cudaSuccess) return (int)ce;
-    RenderParams p{rays_o, rays_d, nears, fars, bitfield, N, C, H, max_steps, dt_gamma, T_thresh, weights_sum, depth, image, mask_out, work_counter};
-    const uint32_t smem_bytes = RSmem::bytes(desc->K);
+    // coarse bitmap: one bit per 64 cells; needs C*H^3 to be a multiple of 2048 and to fit the spare shared memory
+    const uint64_t cells = (uint64_t)C * H * H * H;
+    uint32_t coarse_bytes = 0;
+    if (cells % 2048 == 0 && cells / 512 <= 48 * 1024) coarse_bytes = (uint32_t)(cells / 512);
+    RenderParams p{rays_o, rays_d, nears, fars, bitfield, N, C, H, max_steps, dt_gamma, T_thresh, weights_sum, depth, image, mask_out, work_counter, coarse_bytes};
+    const uint32_t smem_bytes = RSmem::bytes(desc->K, coarse_bytes);
     static bool attr_set = false;
     if (!attr_set) {
-        ce = cudaFuncSetAttribute(k_render_fused<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        ce = cudaFuncSetAttribute(k_render_fused<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (ce != cudaSuccess) return (int)ce;
-        ce = cudaFuncSetAttribute(k_render_fused<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        ce = cudaFuncSetAttribute(k_render_fused<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (ce != cudaSuccess) return (int)ce;
         attr_set = true;
     }
