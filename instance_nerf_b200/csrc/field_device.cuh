@@ -45,7 +45,7 @@ struct LevelGeom {
     uint32_t r1;       // resolution + 1
     uint32_t offset;   // first entry of the level
     uint32_t size;     // entries in the level
-    uint32_t mode;     // 0 dense (index < size, no wrap), 1 hashed with power-of-two size, 2 hashed generic (%)
+    uint32_t mode;     // 0 dense (index < size, never wraps), 1 hashed with power-of-two size (mask), 2 hashed generic (%)
     uint32_t mask;     // size - 1 (mode 1)
     uint32_t r1sq;     // r1 * r1 (mode 0)
     uint32_t pad;
@@ -77,6 +77,13 @@ __device__ __forceinline__ uint32_t pack_half2(__half a, __half b) {
 __device__ __forceinline__ uint32_t h2_bits(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
 __device__ __forceinline__ __half2 bits_h2(uint32_t u) { return *reinterpret_cast<__half2*>(&u); }
 
+// (lo, hi) fp32 -> packed fp16x2, round-to-nearest-even, ReLU folded into the conversion (relu commutes with rounding)
+__device__ __forceinline__ uint32_t cvt_relu_f16x2(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+
 // level geometry exactly as the op-level kernel (gridencode.cu level_geom / gridencoder.cu:137-139)
 __device__ __forceinline__ void init_levels(LevelGeom* lg, const int32_t* __restrict__ offsets, uint32_t L, float S, uint32_t H,
                                             uint32_t tid) {
@@ -91,8 +98,7 @@ __device__ __forceinline__ void init_levels(LevelGeom* lg, const int32_t* __rest
         g.r1sq = g.r1 * g.r1;
         // gridencoder.cu:66-84: the dense stride survives all three dimensions iff r1^3 <= size
         const bool dense = (g.r1 <= g.size) && (g.r1sq <= g.size) && ((uint64_t)g.r1sq * g.r1 <= g.size);
-        const bool pow2 = (g.size & (g.size - 1)) == 0;
-        g.mode = dense ? 0u : (pow2 ? 1u : 2u);
+        g.mode = dense ? 0u : (((g.size & (g.size - 1)) == 0) ? 1u : 2u);
         g.mask = g.size - 1;
         g.pad = 0;
         lg[l] = g;
@@ -117,29 +123,33 @@ __device__ __forceinline__ void encode_level(const float x01[3], const LevelGeom
     const float wx[2] = {__fsub_rn(1.0f, fr[0]), fr[0]};
     const float wy[2] = {__fsub_rn(1.0f, fr[1]), fr[1]};
     const float wz[2] = {__fsub_rn(1.0f, fr[2]), fr[2]};
-    uint32_t ax[2], ay[2], az[2];
-    ax[0] = pg[0]; ax[1] = pg[0] + 1u;
+    // corner indices: one warp-uniform branch per level (dense levels never wrap, hashed levels have power-of-two sizes)
+    uint32_t idx[8];
     if (g.mode == 0) {
-        ay[0] = pg[1] * g.r1; ay[1] = ay[0] + g.r1;
-        az[0] = pg[2] * g.r1sq; az[1] = az[0] + g.r1sq;
+        const uint32_t y0 = pg[1] * g.r1, y1 = y0 + g.r1, z0 = pg[2] * g.r1sq, z1 = z0 + g.r1sq;
+        const uint32_t b00 = pg[0] + y0 + z0, b10 = pg[0] + y1 + z0, b01 = pg[0] + y0 + z1, b11 = pg[0] + y1 + z1;
+        idx[0] = b00; idx[1] = b00 + 1u; idx[2] = b10; idx[3] = b10 + 1u;
+        idx[4] = b01; idx[5] = b01 + 1u; idx[6] = b11; idx[7] = b11 + 1u;
     } else {
-        ay[0] = pg[1] * 2654435761u; ay[1] = ay[0] + 2654435761u;
-        az[0] = pg[2] * 805459861u; az[1] = az[0] + 805459861u;
+        const uint32_t x0 = pg[0], x1 = pg[0] + 1u;
+        const uint32_t y0 = pg[1] * 2654435761u, y1 = y0 + 2654435761u, z0 = pg[2] * 805459861u, z1 = z0 + 805459861u;
+        const uint32_t h00 = y0 ^ z0, h10 = y1 ^ z0, h01 = y0 ^ z1, h11 = y1 ^ z1;
+        idx[0] = (x0 ^ h00) & g.mask; idx[1] = (x1 ^ h00) & g.mask; idx[2] = (x0 ^ h10) & g.mask; idx[3] = (x1 ^ h10) & g.mask;
+        idx[4] = (x0 ^ h01) & g.mask; idx[5] = (x1 ^ h01) & g.mask; idx[6] = (x0 ^ h11) & g.mask; idx[7] = (x1 ^ h11) & g.mask;
+        if (g.mode == 2) {   // hashed level whose size is not a power of two (never produced by grid.py's level table; kept exact)
+            idx[0] = (x0 ^ h00) % g.size; idx[1] = (x1 ^ h00) % g.size; idx[2] = (x0 ^ h10) % g.size; idx[3] = (x1 ^ h10) % g.size;
+            idx[4] = (x0 ^ h01) % g.size; idx[5] = (x1 ^ h01) % g.size; idx[6] = (x0 ^ h11) % g.size; idx[7] = (x1 ^ h11) % g.size;
+        }
     }
     const uint2* base = table + g.offset;
     uint2 v[8];
-    float w[8];
 #pragma unroll
-    for (uint32_t c = 0; c < 8; c++) {
-        const uint32_t bx = c & 1u, by = (c >> 1) & 1u, bz = (c >> 2) & 1u;
-        uint32_t index;
-        if (g.mode == 0) index = ax[bx] + ay[by] + az[bz];
-        else {
-            index = ax[bx] ^ ay[by] ^ az[bz];
-            index = (g.mode == 1) ? (index & g.mask) : (index % g.size);
-        }
-        v[c] = __ldg(base + index);
-        w[c] = __fmul_rn(__fmul_rn(wx[bx], wy[by]), wz[bz]);
+    for (uint32_t c = 0; c < 8; c++) v[c] = __ldg(base + idx[c]);
+    float w[8];
+    {
+        const float w00 = __fmul_rn(wx[0], wy[0]), w10 = __fmul_rn(wx[1], wy[0]), w01 = __fmul_rn(wx[0], wy[1]), w11 = __fmul_rn(wx[1], wy[1]);
+        w[0] = __fmul_rn(w00, wz[0]); w[1] = __fmul_rn(w10, wz[0]); w[2] = __fmul_rn(w01, wz[0]); w[3] = __fmul_rn(w11, wz[0]);
+        w[4] = __fmul_rn(w00, wz[1]); w[5] = __fmul_rn(w10, wz[1]); w[6] = __fmul_rn(w01, wz[1]); w[7] = __fmul_rn(w11, wz[1]);
     }
     __half2 as = __float2half2_rn(0.f), am = as;
 #pragma unroll
@@ -168,6 +178,20 @@ __device__ __forceinline__ void encode8(const float x01[3], bool oob, uint32_t l
     *reinterpret_cast<uint4*>(smem + a_es + umma::tile_off(row, k0 + 8, kLBO, sbo_of(32))) = make_uint4(fs[4], fs[5], fs[6], fs[7]);
     *reinterpret_cast<uint4*>(smem + a_mi + umma::tile_off(row, k0, kLBO, sbo_of(48))) = make_uint4(fm[0], fm[1], fm[2], fm[3]);
     *reinterpret_cast<uint4*>(smem + a_mi + umma::tile_off(row, k0 + 8, kLBO, sbo_of(48))) = make_uint4(fm[4], fm[5], fm[6], fm[7]);
+}
+
+// Encode 4 consecutive levels [l0, l0+4) of one point: one 16-byte core-matrix row chunk per table.
+__device__ __forceinline__ void encode4(const float x01[3], bool oob, uint32_t l0, const LevelGeom* __restrict__ lg,
+                                        const uint2* __restrict__ table, uint8_t* smem, uint32_t a_es, uint32_t a_mi, uint32_t row) {
+    uint32_t fs[4], fm[4];
+#pragma unroll
+    for (uint32_t li = 0; li < 4; li++) {
+        encode_level(x01, lg[l0 + li], table, fs[li], fm[li]);
+        if (oob) { fs[li] = 0u; fm[li] = 0u; }
+    }
+    const uint32_t k0 = l0 * 2;
+    *reinterpret_cast<uint4*>(smem + a_es + umma::tile_off(row, k0, kLBO, sbo_of(32))) = make_uint4(fs[0], fs[1], fs[2], fs[3]);
+    *reinterpret_cast<uint4*>(smem + a_mi + umma::tile_off(row, k0, kLBO, sbo_of(48))) = make_uint4(fm[0], fm[1], fm[2], fm[3]);
 }
 
 // SH degree 4 (same polynomials as shencode.cu) rounded to fp16 into A_ci columns 0..15
@@ -225,7 +249,7 @@ __device__ __forceinline__ void epilogue_hidden(uint32_t tmem_d, uint8_t* smem, 
         uint32_t p[8];
 #pragma unroll
         for (int i = 0; i < 8; i++)
-            p[i] = h2_bits(__floats2half2_rn(fmaxf(__uint_as_float(v[h][2 * i]), 0.f), fmaxf(__uint_as_float(v[h][2 * i + 1]), 0.f)));
+            p[i] = cvt_relu_f16x2(__uint_as_float(v[h][2 * i]), __uint_as_float(v[h][2 * i + 1]));
         const uint32_t k = c0 + h * 16;
         *reinterpret_cast<uint4*>(smem + a_off + umma::tile_off(row, k, kLBO, sbo_of(64))) = make_uint4(p[0], p[1], p[2], p[3]);
         *reinterpret_cast<uint4*>(smem + a_off + umma::tile_off(row, k + 8, kLBO, sbo_of(64))) = make_uint4(p[4], p[5], p[6], p[7]);

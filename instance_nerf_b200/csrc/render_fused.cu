@@ -29,7 +29,9 @@ namespace {
 
 using namespace field;
 
-constexpr uint32_t kChainT = 256, kGatherT = 256, kMarchT = 128;
+constexpr uint32_t kChainT = 256, kGatherT = 512, kMarchT = 128;
+// register budget per role (setmaxnreg): 896 threads start at 72; 256*96 + 512*64 + 128*56 = 896*72
+constexpr uint32_t kRegsChain = 96, kRegsGather = 64, kRegsMarch = 56;
 constexpr uint32_t kThreadsR = kChainT + kGatherT + kMarchT;
 constexpr uint32_t RING = 8;  // samples queued per ray slot
 constexpr uint32_t DT = 4;    // tile descriptors in flight (gather may run DA tiles ahead of the chain)
@@ -175,17 +177,17 @@ __device__ __forceinline__ void march_role(const inerf_field_desc& desc, const R
 // ----------------------------------------------------------------------------------------------- gather --
 __device__ __forceinline__ void gather_role(const inerf_field_desc& desc, const RenderParams& p, uint8_t* smem, Ctrl* ctl, Rings* rg,
                                             uint32_t gt) {
-    const uint32_t row = gt & (kTile - 1), half = gt >> 7;
+    const uint32_t row = gt & (kTile - 1), quarter = gt >> 7;   // thread = (ray slot, 4 of the 16 levels)
     const float inv2b = __fdiv_rn(1.0f, __fmul_rn(2.0f, desc.bound));
     const uint2* table = reinterpret_cast<const uint2*>(desc.table_packed);
-    uint32_t ghead = 0;   // entries of this row already handed to a tile (half-0 threads)
+    uint32_t ghead = 0;   // entries of this row already handed to a tile (quarter-0 threads)
     for (uint32_t tile = 0;; tile++) {
         const uint32_t st = tile % DT, sa = tile % DA;
         bool stop = false;
         while (true) {   // assemble a tile: one queued sample from every slot that has one
             int32_t sel = -1;
             bool not_finished = false;
-            if (half == 0) {
+            if (quarter == 0) {
                 const int32_t nd = ld_vol(&ctl->n_done);
                 __threadfence_block();
                 if (ld_vol(&ctl->tail[row]) != ghead) sel = (int32_t)(ghead % RING);
@@ -210,11 +212,11 @@ __device__ __forceinline__ void gather_role(const inerf_field_desc& desc, const 
                 x01[1] = __fmul_rn(__fadd_rn(rg->y[e][row], desc.bound), inv2b);
                 x01[2] = __fmul_rn(__fadd_rn(rg->z[e][row], desc.bound), inv2b);
                 const bool oob = x01[0] < 0.f || x01[0] > 1.f || x01[1] < 0.f || x01[1] > 1.f || x01[2] < 0.f || x01[2] > 1.f;
-                if (half == 0) {
+                if (quarter == 0) {
                     const float* d = p.rays_d + (size_t)ray * 3;
                     sh16_to_smem(__ldg(d), __ldg(d + 1), __ldg(d + 2), smem, a_ci, row);
                 }
-                encode8(x01, oob, half * 8, ctl->lg, table, smem, a_es, a_mi, row);
+                encode4(x01, oob, quarter * 4, ctl->lg, table, smem, a_es, a_mi, row);
             }
         }
         umma::fence_async_smem();
@@ -290,7 +292,9 @@ __device__ __forceinline__ void chain_role(const inerf_field_desc& desc, const R
         if (owner) {
             float rgb[3];
             epilogue_rgb(tmem_base, rgb, ct);
-            cr = fmaf(weight, rgb[0], cr); cg = fmaf(weight, rgb[1], cg); cb = fmaf(weight, rgb[2], cb);
+            if (weight != 0.f) {   // bubble rows hold stale operands: never let them touch the accumulators
+                cr = fmaf(weight, rgb[0], cr); cg = fmaf(weight, rgb[1], cg); cb = fmaf(weight, rgb[2], cb);
+            }
         }
         if (with_masks) {
             const float wgt = ctl->w_s[row];
@@ -301,7 +305,10 @@ __device__ __forceinline__ void chain_role(const inerf_field_desc& desc, const R
                     umma::tmem_ld16(tmem_base + D_d + (((warp & 3u) * 32u) << 16) + (c_begin + c) * 16, v);
                     umma::tmem_ld_wait();
 #pragma unroll
-                    for (int i = 0; i < 16; i++) macc[c][i] = fmaf(wgt, __half2float(__float2half_rn(__uint_as_float(v[i]))), macc[c][i]);
+                    if (wgt != 0.f) {
+#pragma unroll
+                        for (int i = 0; i < 16; i++) macc[c][i] = fmaf(wgt, __half2float(__float2half_rn(__uint_as_float(v[i]))), macc[c][i]);
+                    }
                 }
             }
         }
@@ -355,6 +362,8 @@ __global__ void __launch_bounds__(kThreadsR, 1) k_render_fused(inerf_field_desc 
     Rings* rg = reinterpret_cast<Rings*>(smem + RSmem::rings(K));
     const uint32_t tid = threadIdx.x;
 
+    // operand tiles start as zeros: rows of a tile without a sample (bubbles) keep whatever was there last
+    for (uint32_t i = tid; i < RSmem::W / 16; i += kThreadsR) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
     load_weights(smem, RSmem::W, desc.weights, K);
     init_levels(ctl->lg, desc.offsets, desc.L, desc.S, desc.H, tid);
     if (tid == 0) {
@@ -381,9 +390,16 @@ __global__ void __launch_bounds__(kThreadsR, 1) k_render_fused(inerf_field_desc 
     umma::fence_after_sync();
     const uint32_t tmem_base = ctl->tmem_slot;
 
-    if (tid < kChainT) chain_role<NCH>(desc, p, smem, ctl, rg, tmem_base, tid);
-    else if (tid < kChainT + kGatherT) gather_role(desc, p, smem, ctl, rg, tid - kChainT);
-    else march_role(desc, p, ctl, rg, coarse, tid - kChainT - kGatherT);
+    if (tid < kChainT) {
+        umma::reg_alloc<kRegsChain>();
+        chain_role<NCH>(desc, p, smem, ctl, rg, tmem_base, tid);
+    } else if (tid < kChainT + kGatherT) {
+        umma::reg_dealloc<kRegsGather>();
+        gather_role(desc, p, smem, ctl, rg, tid - kChainT);
+    } else {
+        umma::reg_dealloc<kRegsMarch>();
+        march_role(desc, p, ctl, rg, coarse, tid - kChainT - kGatherT);
+    }
 
     umma::fence_before_sync();
     __syncthreads();

@@ -60,6 +60,11 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* mbar) {
 // barrier over a subset of the CTA's warps (id 1..15; id 0 is __syncthreads)
 template <uint32_t kId, uint32_t kThreads>
 __device__ __forceinline__ void named_sync() { asm volatile("bar.sync %0, %1;" :: "n"(kId), "n"(kThreads) : "memory"); }
+// Warpgroup-wide register re-budgeting (all 128 threads of an aligned warpgroup must execute it)
+template <uint32_t kRegs>
+__device__ __forceinline__ void reg_dealloc() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" :: "n"(kRegs)); }
+template <uint32_t kRegs>
+__device__ __forceinline__ void reg_alloc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" :: "n"(kRegs)); }
 __device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* mbar, uint32_t parity) {
     uint32_t ok;
