@@ -1,0 +1,165 @@
+"""Multi-GPU plumbing of the instance-field path: one process per GPU, torch.distributed
+(NCCL over NVLink on the B200 box; gloo in the CPU tests).  The reference has no reachable multi-GPU code on this path
+(its DDP branch is dead: nerf/utils.py:423-425 vs main_nerf_mask.py:165,207), so the design is ours:
+
+* rendering shards RAYS with no exchange inside the path; finished tiles `[n, 4 + K]` (image 3 | depth 1 | logits K) are
+  collected with ONE collective (`all_gather` or `gather`);
+* training shards the RAY BATCH; the only exchange is ONE `all_reduce(SUM)` per step over a flat fp32 bucket holding the
+  trainable hash-table gradient and the MLP gradients (53.4 MB at K = 32), then a division by the world size.
+
+Everything here is backend-agnostic host logic; the kernels are reached only through the `render_fn` / model passed in.
+"""
+from __future__ import annotations
+
+from typing import Callable, Iterable, Sequence
+
+import torch
+import torch.distributed as dist
+
+
+def _world():
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+# ----------------------------------------------------------------------------------------------- sharding --
+def shard_frames(n_frames: int, rank: int, world: int) -> list[int]:
+    """Whole frames per rank, round-robin (cost is proportional to marched samples, which varies smoothly along a camera
+    path: interleaving balances it better than contiguous blocks)."""
+    return list(range(rank, n_frames, world))
+
+
+def shard_rows(H: int, W: int, rank: int, world: int, block_rows: int = 8) -> torch.Tensor:
+    """Ray indices (row-major pixel ids) of one frame owned by `rank`: interleaved blocks of `block_rows` image rows."""
+    rows = torch.arange(H)
+    mine = rows[(rows // block_rows) % world == rank]
+    return (mine[:, None] * W + torch.arange(W)[None, :]).reshape(-1)
+
+
+def shard_batch(n_rays: int, rank: int, world: int) -> slice:
+    """Contiguous slice of a training ray batch (patch-major order is preserved inside a shard, nerf/utils.py:83-100)."""
+    per = (n_rays + world - 1) // world
+    return slice(min(rank * per, n_rays), min((rank + 1) * per, n_rays))
+
+
+# -------------------------------------------------------------------------------------------- render gather --
+def pack_tile(result: dict) -> torch.Tensor:
+    """{image [.., n, 3], depth [.., n], instance_mask_logits [.., n, K] | None} -> float32 [n, 4 + K]"""
+    image = result["image"].reshape(-1, 3).float()
+    depth = result["depth"].reshape(-1, 1).float()
+    parts = [image, depth]
+    if result.get("instance_mask_logits") is not None:
+        parts.append(result["instance_mask_logits"].reshape(image.shape[0], -1).float())
+    return torch.cat(parts, dim=-1).contiguous()
+
+
+def unpack_tile(tile: torch.Tensor) -> dict:
+    K = tile.shape[-1] - 4
+    return {"image": tile[..., 0:3], "depth": tile[..., 3], "instance_mask_logits": tile[..., 4:] if K > 0 else None}
+
+
+def gather_tiles(tile: torch.Tensor, counts: Sequence[int] | None = None, dst: int | None = None) -> list[torch.Tensor] | None:
+    """Collect every rank's `[n_r, C]` tile.  `counts` = rows per rank (None: all equal).  dst=None -> every rank gets the
+    list (all_gather), else only `dst` does (gather).  Ragged shards are padded to the largest one for the collective."""
+    rank, world = _world()
+    if world == 1:
+        return [tile]
+    counts = list(counts) if counts is not None else [tile.shape[0]] * world
+    n_max = max(counts)
+    buf = tile
+    if tile.shape[0] != n_max:
+        buf = tile.new_zeros(n_max, tile.shape[1])
+        buf[: tile.shape[0]] = tile
+    if dst is None:
+        out = tile.new_empty(world * n_max, tile.shape[1])
+        dist.all_gather_into_tensor(out, buf.contiguous())
+        return [out[r * n_max: r * n_max + counts[r]] for r in range(world)]
+    recv = [tile.new_empty(n_max, tile.shape[1]) for _ in range(world)] if rank == dst else None
+    dist.gather(buf.contiguous(), recv, dst=dst)
+    return [recv[r][: counts[r]] for r in range(world)] if rank == dst else None
+
+
+def render_frame_sharded(render_fn: Callable[[torch.Tensor, torch.Tensor], dict], rays_o: torch.Tensor, rays_d: torch.Tensor, H: int, W: int,
+                         block_rows: int = 8, dst: int | None = None) -> dict | None:
+    """Latency mode: ONE frame split over all ranks by interleaved row blocks.  `rays_o / rays_d` are the full `[H*W, 3]`
+    ray tensors (replicated: 24 B/ray); every rank renders its rows with `render_fn(o[1, n, 3], d[1, n, 3]) -> dict`
+    (e.g. `lambda o, d: model.render(o, d, staged=True, render_mask=True, ...)`) and the frame is re-assembled."""
+    rank, world = _world()
+    idx = [shard_rows(H, W, r, world, block_rows) for r in range(world)]
+    mine = idx[rank].to(rays_o.device)
+    res = render_fn(rays_o[mine][None], rays_d[mine][None])
+    tiles = gather_tiles(pack_tile(res), [int(i.numel()) for i in idx], dst)
+    if tiles is None:
+        return None
+    full = tiles[0].new_empty(H * W, tiles[0].shape[1])
+    for i, t in zip(idx, tiles):
+        full[i.to(full.device)] = t
+    return unpack_tile(full)
+
+
+def render_frames_sharded(render_fn: Callable[[int], dict], n_frames: int, dst: int | None = None) -> dict[int, dict] | None:
+    """Throughput mode (multi-view jobs, BASELINE config 4): whole frames round-robin over the ranks, one collective per
+    round of `world` frames.  `render_fn(frame_index) -> dict`; all frames must have the same ray count."""
+    rank, world = _world()
+    out: dict[int, dict] = {}
+    rounds = (n_frames + world - 1) // world
+    for k in range(rounds):
+        f = k * world + rank
+        have = f < n_frames
+        tile = pack_tile(render_fn(f if have else n_frames - 1))   # ranks past the end re-render the last frame to keep the collective uniform
+        tiles = gather_tiles(tile, None, dst)
+        if tiles is not None:
+            for r, t in enumerate(tiles):
+                if k * world + r < n_frames:
+                    out[k * world + r] = unpack_tile(t)
+    return out if (dst is None or rank == dst) else None
+
+
+# --------------------------------------------------------------------------------------- training all-reduce --
+class GradBucket:
+    """Flat fp32 bucket over the gradients of `params` (the instance stage trains `encoder_mask.embeddings` and
+    `mask_net.*.weight`): `sync()` = one all_reduce(SUM) + 1/world, written back into each `.grad` in place."""
+
+    def __init__(self, params: Iterable[torch.nn.Parameter]):
+        self.params = [p for p in params if p.requires_grad]
+        self.numel = sum(p.numel() for p in self.params)
+        self.flat = None
+
+    def sync(self) -> int:
+        """-> payload bytes that crossed the collective (0 when world == 1)"""
+        rank, world = _world()
+        if world == 1 or not self.params:
+            return 0
+        dev = self.params[0].device
+        if self.flat is None or self.flat.device != dev:
+            self.flat = torch.zeros(self.numel, dtype=torch.float32, device=dev)
+        off = 0
+        for p in self.params:
+            n = p.numel()
+            if p.grad is None:
+                self.flat[off: off + n].zero_()
+            else:
+                self.flat[off: off + n].copy_(p.grad.reshape(-1))
+            off += n
+        dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
+        self.flat.mul_(1.0 / world)
+        off = 0
+        for p in self.params:
+            n = p.numel()
+            g = self.flat[off: off + n].view_as(p)
+            if p.grad is None:
+                p.grad = g.clone()
+            else:
+                p.grad.copy_(g)
+            off += n
+        return self.numel * 4
+
+
+def broadcast_parameters(module: torch.nn.Module, src: int = 0) -> None:
+    """Replicate parameters and buffers (density grid, bitfield, step counter) from `src` before training starts."""
+    rank, world = _world()
+    if world == 1:
+        return
+    for t in list(module.parameters()) + list(module.buffers()):
+        dist.broadcast(t.data, src=src)
