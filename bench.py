@@ -321,6 +321,82 @@ def run_gpu_arm(args):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------- train arm --
+def run_train_arm(args):
+    """BASELINE.json configs[2] / [4]: instance-field training step (MaskTrainer.train_step + backward + Adam, nerf/utils.py:
+    929-936, 1287-1373), `--rays` rays per GPU per step as 8x8 patches, max_steps 1024, fp16 autocast (the `-O` preset).
+    At N > 1: data-parallel, one all_reduce of the mask-table + mask-net gradients per step."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from instance_nerf_b200 import synthetic
+    from instance_nerf_b200.nerf.trainer import MaskTrainStep
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    model, scene, poses = build_scene_and_model(dev)
+    n_rays = args.rays
+    trainer = MaskTrainStep(model, lr=1e-2, fp16=True, patch_size=8, label_regularization_weight=0.1, dt_gamma=DT_GAMMA, max_steps=MAX_STEPS,
+                            T_thresh=T_THRESH, data_parallel=world > 1)
+    intr = synthetic.intrinsics(H_IMG, W_IMG)
+    batches = []
+    for i in range(8):
+        g = torch.Generator().manual_seed(100 + i * world + rank)
+        r = synthetic.get_rays(poses[(i * world + rank) % N_POSES][None], intr, H_IMG, W_IMG, N=n_rays, patch_size=8, generator=g)
+        o, d = r["rays_o"].reshape(-1, 3).contiguous(), r["rays_d"].reshape(-1, 3).contiguous()
+        labels = torch.from_numpy(scene.first_hit_labels(o.numpy().astype(np.float64), d.numpy().astype(np.float64)))
+        batches.append({"rays_o": o[None].to(dev), "rays_d": d[None].to(dev), "masks": labels[None].to(dev)})
+    flush_buf = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        trainer.step(batches[i % 8])
+    barrier()
+    model.step_counter.zero_()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    ev = []
+    for i in range(args.steps):
+        flush_buf.fill_(i & 0xFF)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        loss = trainer.step(batches[(args.warmup + i) % 8])
+        e1.record()
+        ev.append((e0, e1))
+    barrier()
+    total_ms = sum(a.elapsed_time(b) for a, b in ev)
+    clk = clocks.stop() if rank == 0 else None
+    n_samples = float(model.step_counter[: min(16, args.steps), 0].float().mean().item())
+    if world > 1:
+        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t[0])
+    if rank == 0:
+        ms = total_ms / args.steps
+        line = {"metric": "instance_field_train_step_ms", "value": ms, "unit": "ms", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms, "higher_is_better": False, "scaling": "weak", "vs_baseline": None, "dtype": "f16 autocast / f32 params",
+                "data": "synthetic",
+                "config": {"workload": f"c3: instance-field training step, {n_rays} rays/GPU (8x8 patches) x max_steps 1024, K=32, hash+MLP backward, Adam",
+                           "rays_per_gpu": n_rays, "samples_per_step_per_gpu": n_samples, "l2": "flushed between timed steps (512 MB write)",
+                           "parallelism": f"dp{world}, flat-bucket all_reduce" if world > 1 else "single GPU"},
+                "rays_per_s": world * n_rays / (ms * 1e-3), "loss": float(loss.item()), "clocks": clk}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -328,10 +404,14 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="render", choices=["render", "train"], help="render = the headline metric (default); train = train-step ms")
+    ap.add_argument("--rays", type=int, default=4096, help="train workload: rays per GPU per step (4096 = config c3, 65536 = c5)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
         run_reference_arm(args)
+    elif args.workload == "train":
+        run_train_arm(args)
     else:
         run_gpu_arm(args)
 

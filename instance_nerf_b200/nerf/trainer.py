@@ -1,0 +1,82 @@
+"""Instance-stage training step (mirrors MaskTrainer of the reference: nerf/utils.py:1231-1373 train_step /
+label_regularization, and the step loop nerf/utils.py:919-939), reduced to what touches the hot path: freeze the RGB-sigma
+nets, render a ray batch with `render_mask=True`, cross-entropy on labelled pixels + depth-aware label smoothness on the
+8x8 patches, AMP backward, (optional data-parallel gradient all-reduce,) Adam.
+
+Data providers, logging, checkpoints and evaluation of the reference's Trainer are out of scope.
+"""
+from __future__ import annotations
+
+from types import SimpleNamespace
+
+import torch
+import torch.nn as nn
+
+from ..parallel import GradBucket
+
+
+class MaskTrainStep:
+    def __init__(self, model, lr=1e-2, fp16=True, patch_size=8, label_regularization_weight=0.0, dt_gamma=1 / 128, max_steps=1024,
+                 T_thresh=1e-4, data_parallel=False, fused_adam=True):
+        self.model = model
+        self.opt = SimpleNamespace(patch_size=patch_size, label_regularization_weight=label_regularization_weight)
+        self.render_kw = dict(dt_gamma=dt_gamma, max_steps=max_steps, T_thresh=T_thresh)
+        self.fp16 = fp16
+        self.num_instances = model.num_instances
+        # freeze rgb and density (nerf/utils.py:1242-1246)
+        model.encoder.requires_grad_(False)
+        model.sigma_net.requires_grad_(False)
+        model.encoder_dir.requires_grad_(False)
+        model.color_net.requires_grad_(False)
+        self.criterion = nn.CrossEntropyLoss(reduction="none")          # main_nerf_mask.py:177
+        params = [{"params": [p for p in g["params"] if p.requires_grad], "lr": g["lr"]} for g in model.get_params(lr)]
+        params = [g for g in params if g["params"]]
+        dev = next(model.parameters()).device
+        kw = dict(fused=True) if (fused_adam and dev.type == "cuda") else {}
+        self.optimizer = torch.optim.Adam(params, betas=(0.9, 0.99), eps=1e-15, **kw)   # main_nerf_mask.py:182
+        self.scaler = torch.amp.GradScaler("cuda", enabled=fp16 and dev.type == "cuda")
+        self.bucket = GradBucket([p for g in params for p in g["params"]]) if data_parallel else None
+        self.global_step = 0
+
+    def label_regularization(self, depth, pred_masks):
+        """nerf/utils.py:1262-1285: squared differences of neighbouring logits inside each patch, weighted by exp(-ddepth^2)."""
+        p = self.opt.patch_size
+        pm = pred_masks.view(-1, p, p, self.num_instances).permute(0, 3, 1, 2).contiguous()
+        diff_x = pm[:, :, :, 1:] - pm[:, :, :, :-1]
+        diff_y = pm[:, :, 1:, :] - pm[:, :, :-1, :]
+        depth = depth.view(-1, p, p)
+        ddx = depth[:, :, 1:] - depth[:, :, :-1]
+        ddy = depth[:, 1:, :] - depth[:, :-1, :]
+        wx = torch.exp(-(ddx * ddx)).unsqueeze(1).expand_as(diff_x)
+        wy = torch.exp(-(ddy * ddy)).unsqueeze(1).expand_as(diff_y)
+        return torch.sum(diff_x * diff_x * wx) / torch.sum(wx) + torch.sum(diff_y * diff_y * wy) / torch.sum(wy)
+
+    def train_step(self, data):
+        """nerf/utils.py:1287-1373 -> (pred_masks [B,N] argmax, gt_masks, loss)"""
+        rays_o, rays_d, gt_masks = data["rays_o"], data["rays_d"], data["masks"]
+        outputs = self.model.render(rays_o, rays_d, render_mask=True, staged=False, bg_color=1, perturb=True,
+                                    force_all_rays=self.opt.patch_size != 1, noises=data.get("noises"), **self.render_kw)
+        pred = outputs["instance_mask_logits"]
+        flat = pred.view(-1, self.num_instances)
+        gt = gt_masks.view(-1)
+        labeled = gt != -1
+        # same value as the reference's boolean-index form, without the host sync of `labeled.sum() > 0`
+        ce = self.criterion(flat.float(), torch.where(labeled, gt, torch.zeros_like(gt)))
+        loss = (ce * labeled).sum() / labeled.sum().clamp(min=1)
+        if self.opt.label_regularization_weight > 0:
+            loss = loss + self.label_regularization(outputs["depth"], pred) * self.opt.label_regularization_weight
+        return pred.argmax(dim=-1), gt_masks, loss
+
+    def step(self, data):
+        """One optimisation step (nerf/utils.py:929-936); returns the loss tensor (no host sync)."""
+        self.model.train()
+        self.global_step += 1
+        self.optimizer.zero_grad(set_to_none=False)
+        with torch.autocast("cuda", dtype=torch.float16, enabled=self.fp16):
+            _, _, loss = self.train_step(data)
+        self.scaler.scale(loss).backward()
+        if self.bucket is not None:
+            self.bucket.sync()
+        self.scaler.step(self.optimizer)
+        self.scaler.update()
+        return loss.detach()
