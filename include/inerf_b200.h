@@ -212,6 +212,33 @@ int inerf_field_forward(const inerf_field_desc *desc, const float *xyzs, const f
                         float *sigmas, float *rgbs, float *masks, void *stream);
 
 /*
+ * Training forward: inerf_field_forward that also keeps, per sample, the mask-net input row
+ * (32 mask-table features | 15 geo features | 0) as fp16 [B, 48] in `x0_save` (16-byte aligned) for the backward.
+ */
+int inerf_field_forward_train(const inerf_field_desc *desc, const float *xyzs, const float *dirs, uint32_t B,
+                              float *sigmas, float *rgbs, float *masks, void *x0_save, void *stream);
+/*
+ * Backward of the instance head in ONE launch (instance stage of MaskTrainer, nerf/utils.py:1242-1246: sigma / colour
+ * nets frozen).  Replaces autograd through mask_net (network_mask.py:150-154: 6 cuBLAS GEMMs + ReLU / cat backward)
+ * and kernel_grid_backward of encoder_mask (gridencoder.cu:245-337).
+ *   weights_bwd  packed fp16 blob from inerf_field_pack_weights_bwd (inerf_field_bwd_weights_bytes() bytes, device)
+ *   x0           fp16 [B, 48] saved by inerf_field_forward_train
+ *   grad_logits  float [B, K]  = dL/d(mask logits) per sample (output of composite_rays_with_masks_train_backward)
+ *   grad_table   float [offsets[L], 2], grad_w0 float [64, 47], grad_w1 float [64, 64], grad_w2 float [K, 64]:
+ *                ACCUMULATED into (atomics), so the caller zeroes them (or passes .grad buffers to accumulate).
+ */
+size_t inerf_field_bwd_weights_bytes(void);
+/* Same packing as inerf_field_pack_weights (+ _bwd when packed_bwd != NULL) from DEVICE fp32 matrices into DEVICE blobs,
+ * one launch on `stream`, no host round trip (the trainable weights change every optimizer step). */
+int inerf_field_pack_weights_device(const float *sigma0, const float *sigma1, const float *color0, const float *color1,
+                                    const float *color2, const float *mask0, const float *mask1, const float *mask2,
+                                    uint32_t K, void *packed_fwd, void *packed_bwd, void *stream);
+int inerf_field_pack_weights_bwd(const float *mask0, const float *mask1, const float *mask2, uint32_t K, void *packed_host);
+int inerf_field_backward_mask(const inerf_field_desc *desc, const void *weights_bwd, const float *xyzs, const void *x0,
+                              const float *grad_logits, uint32_t B, float *grad_table, float *grad_w0, float *grad_w1,
+                              float *grad_w2, void *stream);
+
+/*
  * Whole-frame inference render in ONE persistent launch, replacing the host
  * loop of NeRFMaskRenderer.run_cuda (nerf/mask_renderer.py:322-381):
  * march -> encode -> MLP -> composite per 128-ray tile, ray state in registers,

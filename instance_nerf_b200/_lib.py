@@ -88,12 +88,17 @@ _PROTOS = {
     "inerf_field_pack_weights": [_P] * 8 + [_U, _P],
     "inerf_field_pack_tables": [_P, _P, _I, ctypes.c_uint64, _P, _P],
     "inerf_field_forward": [POINTER(FieldDesc), _P, _P, _U, _P, _P, _P, _P],
+    "inerf_field_forward_train": [POINTER(FieldDesc), _P, _P, _U, _P, _P, _P, _P, _P],
+    "inerf_field_pack_weights_bwd": [_P, _P, _P, _U, _P],
+    "inerf_field_pack_weights_device": [_P] * 8 + [_U, _P, _P, _P],
+    "inerf_field_backward_mask": [POINTER(FieldDesc), _P, _P, _P, _P, _U, _P, _P, _P, _P, _P],
     "inerf_render_fused": [POINTER(FieldDesc), _P, _P, _P, _P, _P, _U, _U, _U, _F, _U, _F, _P, _P, _P, _P, _P, _P],
 }
 _SPECIAL = {
     "inerf_version": ([], c_int),
     "inerf_error_string": ([c_int], c_char_p),
     "inerf_field_weights_bytes": ([_U], c_size_t),
+    "inerf_field_bwd_weights_bytes": ([], c_size_t),
 }
 
 # Every symbol include/inerf_b200.h declares; tests check the .so exports all of them.
@@ -124,6 +129,24 @@ def lib() -> ctypes.CDLL:
             fn.restype = restype
         _lib = L
     return _lib
+
+
+# Derived device copies (fp16 tables, packed weight blobs) are cached and keyed on each parameter's version counter.
+# Fused / foreach optimizers update parameters WITHOUT bumping `_version` (measured: torch.optim.Adam(fused=True)), so a
+# global optimizer-step hook advances this epoch, which is part of every cache key.  After writing parameters through
+# `.data` by hand, call `invalidate_param_caches()`.
+PARAM_EPOCH = [0]
+
+
+def invalidate_param_caches(*_args, **_kwargs) -> None:
+    PARAM_EPOCH[0] += 1
+
+
+try:
+    from torch.optim.optimizer import register_optimizer_step_post_hook as _reg_hook
+    _reg_hook(invalidate_param_caches)
+except ImportError:  # very old torch: callers must invalidate by hand
+    pass
 
 
 def check(code: int, what: str = "") -> None:

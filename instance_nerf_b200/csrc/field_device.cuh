@@ -105,12 +105,9 @@ __device__ __forceinline__ void init_levels(LevelGeom* lg, const int32_t* __rest
     }
 }
 
-// One level of one point from the interleaved table: returns (sigma-table half2, mask-table half2) bit patterns.
-// Per corner: w fp32 = (wx * wy) * wz in the reference's order; product rounded to fp16; fp16 accumulation.
-// __hadd2 (one rounding of the exact sum) equals the reference's half(float(acc) + float(p)): fp32 carries
-// 24 >= 2*11+2 bits, so the double rounding is innocuous.
-__device__ __forceinline__ void encode_level(const float x01[3], const LevelGeom g, const uint2* __restrict__ table, uint32_t& out_s,
-                                             uint32_t& out_m) {
+// Corner indices (relative to the level's first entry) and trilinear weights of one point at one level.
+// w fp32 = (wx * wy) * wz in the reference's order (gridencoder.cu:161-185 / :283-301).
+__device__ __forceinline__ void level_corners(const float x01[3], const LevelGeom& g, uint32_t idx[8], float w[8]) {
     float fr[3];
     uint32_t pg[3];
 #pragma unroll
@@ -123,8 +120,7 @@ __device__ __forceinline__ void encode_level(const float x01[3], const LevelGeom
     const float wx[2] = {__fsub_rn(1.0f, fr[0]), fr[0]};
     const float wy[2] = {__fsub_rn(1.0f, fr[1]), fr[1]};
     const float wz[2] = {__fsub_rn(1.0f, fr[2]), fr[2]};
-    // corner indices: one warp-uniform branch per level (dense levels never wrap, hashed levels have power-of-two sizes)
-    uint32_t idx[8];
+    // one warp-uniform branch per level (dense levels never wrap, hashed levels have power-of-two sizes)
     if (g.mode == 0) {
         const uint32_t y0 = pg[1] * g.r1, y1 = y0 + g.r1, z0 = pg[2] * g.r1sq, z1 = z0 + g.r1sq;
         const uint32_t b00 = pg[0] + y0 + z0, b10 = pg[0] + y1 + z0, b01 = pg[0] + y0 + z1, b11 = pg[0] + y1 + z1;
@@ -141,16 +137,24 @@ __device__ __forceinline__ void encode_level(const float x01[3], const LevelGeom
             idx[4] = (x0 ^ h01) % g.size; idx[5] = (x1 ^ h01) % g.size; idx[6] = (x0 ^ h11) % g.size; idx[7] = (x1 ^ h11) % g.size;
         }
     }
+    const float w00 = __fmul_rn(wx[0], wy[0]), w10 = __fmul_rn(wx[1], wy[0]), w01 = __fmul_rn(wx[0], wy[1]), w11 = __fmul_rn(wx[1], wy[1]);
+    w[0] = __fmul_rn(w00, wz[0]); w[1] = __fmul_rn(w10, wz[0]); w[2] = __fmul_rn(w01, wz[0]); w[3] = __fmul_rn(w11, wz[0]);
+    w[4] = __fmul_rn(w00, wz[1]); w[5] = __fmul_rn(w10, wz[1]); w[6] = __fmul_rn(w01, wz[1]); w[7] = __fmul_rn(w11, wz[1]);
+}
+
+// One level of one point from the interleaved table: returns (sigma-table half2, mask-table half2) bit patterns.
+// Per corner: product rounded to fp16; fp16 accumulation.
+// __hadd2 (one rounding of the exact sum) equals the reference's half(float(acc) + float(p)): fp32 carries
+// 24 >= 2*11+2 bits, so the double rounding is innocuous.
+__device__ __forceinline__ void encode_level(const float x01[3], const LevelGeom g, const uint2* __restrict__ table, uint32_t& out_s,
+                                             uint32_t& out_m) {
+    uint32_t idx[8];
+    float w[8];
+    level_corners(x01, g, idx, w);
     const uint2* base = table + g.offset;
     uint2 v[8];
 #pragma unroll
     for (uint32_t c = 0; c < 8; c++) v[c] = __ldg(base + idx[c]);
-    float w[8];
-    {
-        const float w00 = __fmul_rn(wx[0], wy[0]), w10 = __fmul_rn(wx[1], wy[0]), w01 = __fmul_rn(wx[0], wy[1]), w11 = __fmul_rn(wx[1], wy[1]);
-        w[0] = __fmul_rn(w00, wz[0]); w[1] = __fmul_rn(w10, wz[0]); w[2] = __fmul_rn(w01, wz[0]); w[3] = __fmul_rn(w11, wz[0]);
-        w[4] = __fmul_rn(w00, wz[1]); w[5] = __fmul_rn(w10, wz[1]); w[6] = __fmul_rn(w01, wz[1]); w[7] = __fmul_rn(w11, wz[1]);
-    }
     __half2 as = __float2half2_rn(0.f), am = as;
 #pragma unroll
     for (uint32_t c = 0; c < 8; c++) {
@@ -231,6 +235,29 @@ __device__ __forceinline__ void issue_gemm(uint32_t smem_base, uint32_t a_off, u
         const uint64_t da = umma::make_desc(smem_base + a_off + k * 2 * kLBO, kLBO, sbo);
         const uint64_t db = umma::make_desc(smem_base + b_off + k * 2 * kLBO, kLBO, sbo);
         umma::mma_f16(tmem_d, da, db, idesc, k > 0);
+    }
+}
+
+// general form: separate core-matrix row-group strides for A and B (operands that are column ranges of wider tiles)
+__device__ __forceinline__ void issue_gemm2(uint32_t smem_base, uint32_t a_off, uint32_t sbo_a, uint32_t b_off, uint32_t sbo_b, uint32_t Kdim,
+                                            uint32_t N, uint32_t tmem_d) {
+    const uint32_t idesc = umma::make_idesc_f16(128, N);
+    for (uint32_t k = 0; k < Kdim / 16; k++) {
+        const uint64_t da = umma::make_desc(smem_base + a_off + k * 2 * kLBO, kLBO, sbo_a);
+        const uint64_t db = umma::make_desc(smem_base + b_off + k * 2 * kLBO, kLBO, sbo_b);
+        umma::mma_f16(tmem_d, da, db, idesc, k > 0);
+    }
+}
+// D[128 x N] (+)= A^T * B, the reduction running over the 128 ROWS (samples) of two K-major tiles: A is [128 x 128 cols]
+// (row-group stride sbo_a), B is [128 x N cols] (sbo_b).  The tiles are read as MN-major operands: same bytes, descriptor
+// LBO = row-group stride, SBO = 128 (validated by csrc/probe/umma_probe_t.cu).
+__device__ __forceinline__ void issue_gemm_tn(uint32_t smem_base, uint32_t a_off, uint32_t sbo_a, uint32_t b_off, uint32_t sbo_b, uint32_t N,
+                                              uint32_t tmem_d, bool accumulate) {
+    const uint32_t idesc = umma::make_idesc_f16(128, N) | (1u << 15) | (1u << 16);   // a_major = b_major = MN
+    for (uint32_t k = 0; k < kTile / 16; k++) {
+        const uint64_t da = umma::make_desc(smem_base + a_off + k * 2 * sbo_a, sbo_a, 128);
+        const uint64_t db = umma::make_desc(smem_base + b_off + k * 2 * sbo_b, sbo_b, 128);
+        umma::mma_f16(tmem_d, da, db, idesc, accumulate || k > 0);
     }
 }
 

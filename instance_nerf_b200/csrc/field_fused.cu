@@ -28,7 +28,8 @@ struct FSmem {
 
 __global__ void __launch_bounds__(kThreads, 2) k_field_forward(inerf_field_desc desc, const float* __restrict__ xyzs,
                                                                const float* __restrict__ dirs, uint32_t B, float* __restrict__ sigmas,
-                                                               float* __restrict__ rgbs, float* __restrict__ masks) {
+                                                               float* __restrict__ rgbs, float* __restrict__ masks,
+                                                               uint4* __restrict__ x0_save) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t K = desc.K, Kp = weight_layout(K).Kp;
     const uint32_t misc = FSmem::misc(K);
@@ -78,6 +79,14 @@ __global__ void __launch_bounds__(kThreads, 2) k_field_forward(inerf_field_desc 
 
         const float sigma = mlp_chain(smem, bufs, tmem_base, bar, phase, K, desc.density_scale, with_masks, threadIdx.x, nullptr,
                                       [] { __syncthreads(); }, [](float) {});
+        // training: keep the mask-net input row (32 mask-table features | 15 geo | 0, fp16) for the backward pass
+        if (x0_save != nullptr && s < B) {
+#pragma unroll
+            for (uint32_t c = 0; c < 3; c++) {
+                const uint32_t chunk = half * 3 + c;   // 6 chunks of 8 halves per row
+                x0_save[(size_t)s * 6 + chunk] = *reinterpret_cast<const uint4*>(smem + bufs.a_mi + umma::tile_off(row, chunk * 8, kLBO, sbo_of(48)));
+            }
+        }
 
         // ---- output epilogue ----
         const uint32_t orow = tile * kTile + (warp & 3u) * 32u + lane;
@@ -194,11 +203,12 @@ extern "C" int inerf_field_pack_weights(const float* sigma0, const float* sigma1
     return INERF_OK;
 }
 
-extern "C" int inerf_field_forward(const inerf_field_desc* desc, const float* xyzs, const float* dirs, uint32_t B, float* sigmas,
-                                   float* rgbs, float* masks, void* stream) {
+static int field_forward_impl(const inerf_field_desc* desc, const float* xyzs, const float* dirs, uint32_t B, float* sigmas, float* rgbs,
+                              float* masks, void* x0_save, void* stream) {
     if (int e = validate_desc(desc)) return e;
     if (B == 0) return INERF_OK;
     INERF_REQUIRE(xyzs); INERF_REQUIRE(dirs); INERF_REQUIRE(sigmas); INERF_REQUIRE(rgbs);
+    if (x0_save && (((uintptr_t)x0_save & 15u) || masks == nullptr)) return INERF_ERR_ALIGN;
     const uint32_t smem_bytes = FSmem::bytes(desc->K);
     static bool attr_set = false;
     if (!attr_set) {
@@ -208,7 +218,18 @@ extern "C" int inerf_field_forward(const inerf_field_desc* desc, const float* xy
     }
     const uint32_t num_tiles = (B + field::kTile - 1) / field::kTile;
     const uint32_t grid = num_tiles < 2u * kNumSMs ? num_tiles : 2u * kNumSMs;
-    k_field_forward<<<grid, field::kThreads, smem_bytes, (cudaStream_t)stream>>>(*desc, xyzs, dirs, B, sigmas, rgbs, masks);
+    k_field_forward<<<grid, field::kThreads, smem_bytes, (cudaStream_t)stream>>>(*desc, xyzs, dirs, B, sigmas, rgbs, masks, (uint4*)x0_save);
     INERF_LAUNCH_CHECK();
     return INERF_OK;
+}
+
+extern "C" int inerf_field_forward(const inerf_field_desc* desc, const float* xyzs, const float* dirs, uint32_t B, float* sigmas,
+                                   float* rgbs, float* masks, void* stream) {
+    return field_forward_impl(desc, xyzs, dirs, B, sigmas, rgbs, masks, nullptr, stream);
+}
+
+extern "C" int inerf_field_forward_train(const inerf_field_desc* desc, const float* xyzs, const float* dirs, uint32_t B, float* sigmas,
+                                         float* rgbs, float* masks, void* x0_save, void* stream) {
+    INERF_REQUIRE(x0_save);
+    return field_forward_impl(desc, xyzs, dirs, B, sigmas, rgbs, masks, x0_save, stream);
 }

@@ -1,0 +1,402 @@
+// inerf_field_backward_mask: backward of the instance head for the instance-field training stage, ONE persistent launch.
+//
+// In that stage (MaskTrainer, nerf/utils.py:1242-1246) the sigma / colour nets and their table are frozen; the trainable
+// part is mask_net (47->64->64->K, network_mask.py:84-92) and encoder_mask's hash table.  Given dL/dlogits per sample
+// (what composite_rays_with_masks_train_backward produces, raymarching.cu:828-940) the reference runs, through autograd,
+// 6 cuBLAS GEMMs + 2 ReLU-backward kernels + 1 cat-backward + kernel_grid_backward (gridencoder.cu:245-337) + a
+// whole-table zero + cast.  Here, per 128-sample tile and all on tcgen05 (fp16 operands, fp32 accumulators in TMEM):
+//
+//   recompute  H1 = relu(X0 W0^T), H2 = relu(H1 W1^T)          (X0 = saved mask-net input row, fp16 [.,48])
+//   dX chain   dH2 = (dY W2) . [H2>0],  dH1 = (dH2 W1) . [H1>0],  dF = dH1 W0[:, :32]
+//   dW         [dY|dH2]^T [H2|H1] -> dW2, dW1 ;  [dH1|0]^T X0 -> dW0    accumulated ACROSS tiles in TMEM (the operand tiles
+//              are read as MN-major, so no transposed copies are written); one atomicAdd pass per CTA at the end
+//   scatter    dF (32 feature grads / sample) -> 16 levels x 8 corners float2 atomics into the fp32 table gradient.
+//
+// Gradients w.r.t. the geo features (X0 columns 32..46) are not produced: sigma_net is frozen in this stage.
+#include <cstring>
+
+#include "field_device.cuh"
+
+namespace {
+
+using namespace field;
+
+struct BwdWeights {   // byte offsets inside the packed backward blob (all B operands, K-major)
+    static constexpr uint32_t w0 = 0;                  // [64 x 48]  W0[o][j]            (recompute layer 0)
+    static constexpr uint32_t w1 = w0 + 64 * 48 * 2;   // [64 x 64]  W1[o][j]            (recompute layer 1)
+    static constexpr uint32_t w2t = w1 + 64 * 64 * 2;  // [64 x 64]  (n=j, k=o) = W2[o][j], o >= K zero
+    static constexpr uint32_t w1t = w2t + 64 * 64 * 2; // [64 x 64]  (n=j, k=o) = W1[o][j]
+    static constexpr uint32_t w0t = w1t + 64 * 64 * 2; // [32 x 64]  (n=j, k=o) = W0[o][j], j < 32 (mask-table features only)
+    static constexpr uint32_t total = w0t + 32 * 64 * 2;
+};
+
+struct BSmem {
+    static constexpr uint32_t TG = 0;                      // [128 x 128]  dY (64, cols >= K zero) | dH2 (64)
+    static constexpr uint32_t TH = TG + kTile * 128 * 2;   // [128 x 128]  H2 (64) | H1 (64)
+    static constexpr uint32_t TG2 = TH + kTile * 128 * 2;  // [128 x 128]  dH1 (64) | zeros (64)
+    static constexpr uint32_t TX = TG2 + kTile * 128 * 2;  // [128 x 48]   X0
+    static constexpr uint32_t W = TX + kTile * 48 * 2;
+    static constexpr uint32_t MISC = W + BwdWeights::total;   // LevelGeom[16] | mbarrier | tmem slot
+    static constexpr uint32_t bytes = MISC + 16 * sizeof(LevelGeom) + 64;
+};
+constexpr uint32_t kSbo128 = sbo_of(128), kSbo64 = sbo_of(64), kSbo48 = sbo_of(48);
+// TMEM columns (512 allocated: one CTA per SM)
+constexpr uint32_t T_a = 0, T_b = 64, T_x = 128, T_w1 = 160, T_w0 = 288, kBwdTmemCols = 512;
+
+struct BwdParams {
+    const float* xyzs;          // [B, 3]
+    const uint4* x0;            // fp16 [B, 48] as 6 x 16 B per row
+    const float* grad_logits;   // [B, K]
+    uint32_t B;
+    float2* grad_table;         // fp32 [T, 2] (encoder_mask.embeddings.grad), accumulated
+    float* grad_w0;             // [64, 47]
+    float* grad_w1;             // [64, 64]
+    float* grad_w2;             // [K, 64]
+    const void* weights;        // packed backward blob
+};
+
+// 32 TMEM columns -> ReLU -> fp16 -> 4 chunks of a 128-column tile; returns the 32 "value > 0" bits
+__device__ __forceinline__ uint32_t epi_relu32(uint32_t taddr, uint8_t* smem, uint32_t tile_off0, uint32_t row, uint32_t col0) {
+    uint32_t v[2][16];
+    umma::tmem_ld16(taddr, v[0]);
+    umma::tmem_ld16(taddr + 16, v[1]);
+    umma::tmem_ld_wait();
+    uint32_t mask = 0;
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        uint32_t p[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            p[i] = cvt_relu_f16x2(__uint_as_float(v[h][2 * i]), __uint_as_float(v[h][2 * i + 1]));
+            mask |= ((p[i] & 0xffffu) ? 1u : 0u) << (h * 16 + 2 * i);
+            mask |= ((p[i] >> 16) ? 1u : 0u) << (h * 16 + 2 * i + 1);
+        }
+        const uint32_t k = col0 + h * 16;
+        *reinterpret_cast<uint4*>(smem + tile_off0 + umma::tile_off(row, k, kLBO, kSbo128)) = make_uint4(p[0], p[1], p[2], p[3]);
+        *reinterpret_cast<uint4*>(smem + tile_off0 + umma::tile_off(row, k + 8, kLBO, kSbo128)) = make_uint4(p[4], p[5], p[6], p[7]);
+    }
+    return mask;
+}
+
+// 32 TMEM columns . mask -> fp16 -> 4 chunks of a 128-column tile
+__device__ __forceinline__ void epi_masked32(uint32_t taddr, uint32_t mask, uint8_t* smem, uint32_t tile_off0, uint32_t row, uint32_t col0) {
+    uint32_t v[2][16];
+    umma::tmem_ld16(taddr, v[0]);
+    umma::tmem_ld16(taddr + 16, v[1]);
+    umma::tmem_ld_wait();
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        uint32_t p[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const float a = ((mask >> (h * 16 + 2 * i)) & 1u) ? __uint_as_float(v[h][2 * i]) : 0.f;
+            const float b = ((mask >> (h * 16 + 2 * i + 1)) & 1u) ? __uint_as_float(v[h][2 * i + 1]) : 0.f;
+            p[i] = h2_bits(__floats2half2_rn(a, b));
+        }
+        const uint32_t k = col0 + h * 16;
+        *reinterpret_cast<uint4*>(smem + tile_off0 + umma::tile_off(row, k, kLBO, kSbo128)) = make_uint4(p[0], p[1], p[2], p[3]);
+        *reinterpret_cast<uint4*>(smem + tile_off0 + umma::tile_off(row, k + 8, kLBO, kSbo128)) = make_uint4(p[4], p[5], p[6], p[7]);
+    }
+}
+
+__global__ void __launch_bounds__(kThreads, 1) k_field_backward_mask(inerf_field_desc desc, BwdParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const uint32_t K = desc.K, tid = threadIdx.x;
+    LevelGeom* lg = reinterpret_cast<LevelGeom*>(smem + BSmem::MISC);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + BSmem::MISC + 16 * sizeof(LevelGeom));
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + BSmem::MISC + 16 * sizeof(LevelGeom) + 8);
+
+    // zero the operand tiles once (TG2's right half and dY's padding columns stay zero for the whole launch)
+    for (uint32_t i = tid; i < BSmem::W / 16; i += kThreads) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
+    {
+        const uint4* wsrc = reinterpret_cast<const uint4*>(p.weights);
+        uint4* wdst = reinterpret_cast<uint4*>(smem + BSmem::W);
+        for (uint32_t i = tid; i < BwdWeights::total / 16; i += kThreads) wdst[i] = __ldg(wsrc + i);
+    }
+    init_levels(lg, desc.offsets, desc.L, desc.S, desc.H, tid);
+    if (tid == 0) { umma::mbar_init(bar, 1); umma::mbar_fence_init(); }
+    if (tid < 32) umma::tmem_alloc<kBwdTmemCols>(tmem_slot);
+    umma::fence_async_smem();
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t sbase = umma::smem_u32(smem);
+
+    const uint32_t warp = tid >> 5, lane = tid & 31;
+    const uint32_t row = tid & (kTile - 1), half = tid >> 7;
+    const uint32_t lane_base = ((warp & 3u) * 32u) << 16;
+    const float inv2b = __fdiv_rn(1.0f, __fmul_rn(2.0f, desc.bound));
+    const uint32_t num_tiles = (p.B + kTile - 1) / kTile;
+    uint32_t phase = 0, tiles_done = 0;
+    const bool issuer = tid == 0;
+
+    auto wait_mma = [&] {
+        __syncwarp();
+        umma::mbar_wait(bar, phase);
+        phase ^= 1u;
+        umma::fence_after_sync();
+    };
+    auto publish = [&] {   // generic-proxy tile writes -> visible to the next MMAs
+        umma::fence_async_smem();
+        umma::fence_before_sync();
+        __syncthreads();
+    };
+
+    for (uint32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, tiles_done++) {
+        const uint32_t s = tile * kTile + row;
+        const bool live = s < p.B;
+        // ---- S0: X0 and dY rows -> operand tiles --------------------------------------------------------------
+#pragma unroll
+        for (uint32_t c = 0; c < 3; c++) {
+            const uint32_t chunk = half * 3 + c;
+            const uint4 v = live ? __ldg(p.x0 + (size_t)s * 6 + chunk) : make_uint4(0u, 0u, 0u, 0u);
+            *reinterpret_cast<uint4*>(smem + BSmem::TX + umma::tile_off(row, chunk * 8, kLBO, kSbo48)) = v;
+        }
+        {
+            const float* g = p.grad_logits + (size_t)s * K;
+#pragma unroll
+            for (uint32_t c = 0; c < 4; c++) {
+                const uint32_t k0 = half * 32 + c * 8;
+                uint32_t q[4];
+#pragma unroll
+                for (uint32_t i = 0; i < 4; i++) {
+                    const uint32_t ka = k0 + 2 * i;
+                    const float a = (live && ka < K) ? __ldg(g + ka) : 0.f;
+                    const float b = (live && ka + 1 < K) ? __ldg(g + ka + 1) : 0.f;
+                    q[i] = h2_bits(__floats2half2_rn(a, b));
+                }
+                *reinterpret_cast<uint4*>(smem + BSmem::TG + umma::tile_off(row, k0, kLBO, kSbo128)) = make_uint4(q[0], q[1], q[2], q[3]);
+            }
+        }
+        publish();
+        // ---- S1: H1 pre-activation and dY W2 -----------------------------------------------------------------------
+        if (issuer) {
+            umma::fence_after_sync();
+            issue_gemm2(sbase, BSmem::TX, kSbo48, BSmem::W + BwdWeights::w0, kSbo48, 48, 64, tmem + T_a);
+            issue_gemm2(sbase, BSmem::TG, kSbo128, BSmem::W + BwdWeights::w2t, kSbo64, 64, 64, tmem + T_b);
+            umma::commit(bar);
+        }
+        wait_mma();
+        const uint32_t mask1 = epi_relu32(tmem + T_a + lane_base + half * 32, smem, BSmem::TH, row, 64 + half * 32);   // H1 -> TH[:, 64:128]
+        publish();
+        // ---- S2: H2 pre-activation; dH2 = (dY W2) . [H2 > 0] ---------------------------------------------------
+        if (issuer) {
+            umma::fence_after_sync();
+            issue_gemm2(sbase, BSmem::TH + 8 * kLBO, kSbo128, BSmem::W + BwdWeights::w1, kSbo64, 64, 64, tmem + T_a);
+            umma::commit(bar);
+        }
+        wait_mma();
+        const uint32_t mask2 = epi_relu32(tmem + T_a + lane_base + half * 32, smem, BSmem::TH, row, half * 32);        // H2 -> TH[:, 0:64]
+        epi_masked32(tmem + T_b + lane_base + half * 32, mask2, smem, BSmem::TG, row, 64 + half * 32);                 // dH2 -> TG[:, 64:128]
+        publish();
+        // ---- S3: dH1 = (dH2 W1) . [H1 > 0] --------------------------------------------------------------------------
+        if (issuer) {
+            umma::fence_after_sync();
+            issue_gemm2(sbase, BSmem::TG + 8 * kLBO, kSbo128, BSmem::W + BwdWeights::w1t, kSbo64, 64, 64, tmem + T_b);
+            umma::commit(bar);
+        }
+        wait_mma();
+        epi_masked32(tmem + T_b + lane_base + half * 32, mask1, smem, BSmem::TG2, row, half * 32);                     // dH1 -> TG2[:, 0:64]
+        publish();
+        // ---- S4: dF = dH1 W0[:, :32]; weight gradients accumulate across tiles ------------------------------------
+        if (issuer) {
+            umma::fence_after_sync();
+            issue_gemm2(sbase, BSmem::TG2, kSbo128, BSmem::W + BwdWeights::w0t, kSbo64, 64, 32, tmem + T_x);
+            issue_gemm_tn(sbase, BSmem::TG, kSbo128, BSmem::TH, kSbo128, 128, tmem + T_w1, tiles_done > 0);
+            issue_gemm_tn(sbase, BSmem::TG2, kSbo128, BSmem::TX, kSbo48, 48, tmem + T_w0, tiles_done > 0);
+            umma::commit(bar);
+        }
+        wait_mma();
+        // ---- scatter: 8 levels (16 feature gradients) per thread -> table gradient -------------------------------
+        {
+            uint32_t v[16];
+            umma::tmem_ld16(tmem + T_x + lane_base + half * 16, v);
+            umma::tmem_ld_wait();
+            if (live) {
+                float x01[3];
+#pragma unroll
+                for (int d = 0; d < 3; d++) x01[d] = __fmul_rn(__fadd_rn(__ldg(p.xyzs + (size_t)s * 3 + d), desc.bound), inv2b);
+                const bool oob = x01[0] < 0.f || x01[0] > 1.f || x01[1] < 0.f || x01[1] > 1.f || x01[2] < 0.f || x01[2] > 1.f;
+                if (!oob) {
+#pragma unroll
+                    for (uint32_t li = 0; li < 8; li++) {
+                        const float g0 = __uint_as_float(v[2 * li]), g1 = __uint_as_float(v[2 * li + 1]);
+                        if (g0 != 0.f || g1 != 0.f) {
+                            const LevelGeom g = lg[half * 8 + li];
+                            uint32_t idx[8];
+                            float w[8];
+                            level_corners(x01, g, idx, w);
+                            float2* base = p.grad_table + g.offset;
+#pragma unroll
+                            for (uint32_t c = 0; c < 8; c++) atomicAdd(base + idx[c], make_float2(__fmul_rn(w[c], g0), __fmul_rn(w[c], g1)));
+                        }
+                    }
+                }
+            }
+        }
+        umma::fence_before_sync();
+        __syncthreads();   // TMEM accumulators T_a/T_b/T_x and the operand tiles are reused by the next tile
+    }
+
+    // ---- weight gradients of this CTA: TMEM -> global (fp32 atomics) ------------------------------------------------
+    {
+        const uint32_t q = warp & 3u, m = q * 32u + lane;   // TMEM lane = row of [dY|dH2]^T resp. [dH1|0]^T
+        if (q < 2 && half == 0) {            // dW2[o = m][j], lanes 0..63, columns 0..63 of T_w1
+            for (uint32_t c = 0; c < 64; c += 16) {
+                uint32_t v[16];
+                umma::tmem_ld16(tmem + T_w1 + lane_base + c, v);
+                umma::tmem_ld_wait();
+                if (m < K)
+#pragma unroll
+                    for (int j = 0; j < 16; j++) atomicAdd(p.grad_w2 + (size_t)m * 64 + c + j, __uint_as_float(v[j]));
+            }
+        } else if (q >= 2 && half == 1) {    // dW1[o = m - 64][j], lanes 64..127, columns 64..127 of T_w1
+            for (uint32_t c = 0; c < 64; c += 16) {
+                uint32_t v[16];
+                umma::tmem_ld16(tmem + T_w1 + lane_base + 64 + c, v);
+                umma::tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 16; j++) atomicAdd(p.grad_w1 + (size_t)(m - 64) * 64 + c + j, __uint_as_float(v[j]));
+            }
+        }
+        if (q < 2) {                         // dW0[o = m][j], lanes 0..63, columns 0..47 of T_w0 (j = 47 is X0's zero padding)
+            const uint32_t c_begin = half ? 32u : 0u, c_end = half ? 48u : 32u;
+            for (uint32_t c = c_begin; c < c_end; c += 16) {
+                uint32_t v[16];
+                umma::tmem_ld16(tmem + T_w0 + lane_base + c, v);
+                umma::tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 16; j++)
+                    if (c + j < 47) atomicAdd(p.grad_w0 + (size_t)m * 47 + c + j, __uint_as_float(v[j]));
+            }
+        }
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    if (tid < 32) umma::tmem_dealloc<kBwdTmemCols>(tmem);
+}
+
+inline uint16_t f2h(float f) {
+    const __half h = __float2half_rn(f);
+    uint16_t b;
+    memcpy(&b, &h, 2);
+    return b;
+}
+// element (n, k) of a [Npad x Kpad] K-major B-operand tile
+inline void put(uint8_t* dst, uint32_t n, uint32_t k, uint32_t Kpad, float v) {
+    const uint16_t b = f2h(v);
+    memcpy(dst + umma::tile_off(n, k, kLBO, sbo_of(Kpad)), &b, 2);
+}
+
+}  // namespace
+
+namespace {
+// ---- on-device weight packing (no host round trip: the trainable weights change every optimizer step) ----------
+struct PackJob {
+    const float* W;        // fp32 [n_out, n_in] row-major (nn.Linear layout)
+    uint32_t n_out, n_in;  // logical shape of W
+    uint32_t Npad, Kpad;   // operand tile shape [Npad x Kpad]
+    uint32_t dst;          // byte offset inside the blob
+    uint32_t transpose;    // 0: (n, k) = W[n][k]; 1: (n, k) = W[k][n]
+    uint32_t n_lim;        // rows of the tile that carry data (others zero)
+};
+struct PackJobs {
+    PackJob j[13];
+    uint32_t n;
+};
+__global__ void k_pack_weights(PackJobs jobs, uint8_t* fwd, uint8_t* bwd, uint32_t n_fwd) {
+    for (uint32_t ji = blockIdx.y; ji < jobs.n; ji += gridDim.y) {
+        const PackJob J = jobs.j[ji];
+        uint8_t* out = (ji < n_fwd ? fwd : bwd) + J.dst;
+        const uint32_t total = J.Npad * J.Kpad;
+        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+            const uint32_t n = i / J.Kpad, k = i % J.Kpad;
+            float v = 0.f;
+            if (!J.transpose) { if (n < J.n_out && k < J.n_in) v = J.W[(size_t)n * J.n_in + k]; }
+            else if (k < J.n_out && n < J.n_in && n < J.n_lim) v = J.W[(size_t)k * J.n_in + n];
+            *reinterpret_cast<__half*>(out + umma::tile_off(n, k, kLBO, sbo_of(J.Kpad))) = __float2half_rn(v);
+        }
+    }
+}
+}  // namespace
+
+// Device-side equivalent of inerf_field_pack_weights (+ inerf_field_pack_weights_bwd when packed_bwd != NULL):
+// all pointers are DEVICE pointers, one launch, no synchronisation.
+extern "C" int inerf_field_pack_weights_device(const float* sigma0, const float* sigma1, const float* color0, const float* color1,
+                                               const float* color2, const float* mask0, const float* mask1, const float* mask2, uint32_t K,
+                                               void* packed_fwd, void* packed_bwd, void* stream) {
+    if (K == 0 || K > 64) return INERF_ERR_SIZE;
+    INERF_REQUIRE(sigma0); INERF_REQUIRE(sigma1); INERF_REQUIRE(color0); INERF_REQUIRE(color1); INERF_REQUIRE(color2);
+    INERF_REQUIRE(mask0); INERF_REQUIRE(mask1); INERF_REQUIRE(mask2); INERF_REQUIRE(packed_fwd);
+    const WeightLayout wl = weight_layout(K);
+    PackJobs jobs{};
+    uint32_t n = 0;
+    auto add = [&](const float* W, uint32_t n_out, uint32_t n_in, uint32_t Npad, uint32_t Kpad, uint32_t dst, uint32_t tr, uint32_t n_lim) {
+        jobs.j[n++] = PackJob{W, n_out, n_in, Npad, Kpad, dst, tr, n_lim};
+    };
+    add(sigma0, 64, 32, 64, 32, wl.s0, 0, 64);
+    add(sigma1, 16, 64, 16, 64, wl.s1, 0, 16);
+    add(color0, 64, 31, 64, 32, wl.c0, 0, 64);
+    add(color1, 64, 64, 64, 64, wl.c1, 0, 64);
+    add(color2, 3, 64, 16, 64, wl.c2, 0, 16);
+    add(mask0, 64, 47, 64, 48, wl.m0, 0, 64);
+    add(mask1, 64, 64, 64, 64, wl.m1, 0, 64);
+    add(mask2, K, 64, wl.Kp, 64, wl.m2, 0, wl.Kp);
+    const uint32_t n_fwd = n;
+    if (packed_bwd) {
+        add(mask0, 64, 47, 64, 48, BwdWeights::w0, 0, 64);
+        add(mask1, 64, 64, 64, 64, BwdWeights::w1, 0, 64);
+        add(mask2, K, 64, 64, 64, BwdWeights::w2t, 1, 64);
+        add(mask1, 64, 64, 64, 64, BwdWeights::w1t, 1, 64);
+        add(mask0, 64, 47, 32, 64, BwdWeights::w0t, 1, 32);
+    }
+    jobs.n = n;
+    k_pack_weights<<<dim3(4, n), 256, 0, (cudaStream_t)stream>>>(jobs, (uint8_t*)packed_fwd, (uint8_t*)packed_bwd, n_fwd);
+    INERF_LAUNCH_CHECK();
+    return INERF_OK;
+}
+
+extern "C" size_t inerf_field_bwd_weights_bytes(void) { return BwdWeights::total; }
+
+extern "C" int inerf_field_pack_weights_bwd(const float* mask0, const float* mask1, const float* mask2, uint32_t K, void* packed_host) {
+    if (K == 0 || K > 64) return INERF_ERR_SIZE;
+    INERF_REQUIRE(mask0); INERF_REQUIRE(mask1); INERF_REQUIRE(mask2); INERF_REQUIRE(packed_host);
+    uint8_t* p = static_cast<uint8_t*>(packed_host);
+    memset(p, 0, BwdWeights::total);
+    for (uint32_t o = 0; o < 64; o++)
+        for (uint32_t j = 0; j < 47; j++) {
+            put(p + BwdWeights::w0, o, j, 48, mask0[o * 47 + j]);
+            if (j < 32) put(p + BwdWeights::w0t, j, o, 64, mask0[o * 47 + j]);
+        }
+    for (uint32_t o = 0; o < 64; o++)
+        for (uint32_t j = 0; j < 64; j++) {
+            put(p + BwdWeights::w1, o, j, 64, mask1[o * 64 + j]);
+            put(p + BwdWeights::w1t, j, o, 64, mask1[o * 64 + j]);
+        }
+    for (uint32_t o = 0; o < K; o++)
+        for (uint32_t j = 0; j < 64; j++) put(p + BwdWeights::w2t, j, o, 64, mask2[o * 64 + j]);
+    return INERF_OK;
+}
+
+extern "C" int inerf_field_backward_mask(const inerf_field_desc* desc, const void* weights_bwd, const float* xyzs, const void* x0,
+                                         const float* grad_logits, uint32_t B, float* grad_table, float* grad_w0, float* grad_w1,
+                                         float* grad_w2, void* stream) {
+    if (int e = field::validate(desc)) return e;
+    if (B == 0) return INERF_OK;
+    INERF_REQUIRE(weights_bwd); INERF_REQUIRE(xyzs); INERF_REQUIRE(x0); INERF_REQUIRE(grad_logits);
+    INERF_REQUIRE(grad_table); INERF_REQUIRE(grad_w0); INERF_REQUIRE(grad_w1); INERF_REQUIRE(grad_w2);
+    if (((uintptr_t)weights_bwd & 15u) || ((uintptr_t)x0 & 15u) || ((uintptr_t)grad_table & 7u)) return INERF_ERR_ALIGN;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(k_field_backward_mask, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BSmem::bytes);
+        if (e != cudaSuccess) return (int)e;
+        attr_set = true;
+    }
+    BwdParams p{xyzs, (const uint4*)x0, grad_logits, B, (float2*)grad_table, grad_w0, grad_w1, grad_w2, weights_bwd};
+    const uint32_t num_tiles = (B + kTile - 1) / kTile;
+    const uint32_t grid = num_tiles < (uint32_t)kNumSMs ? num_tiles : (uint32_t)kNumSMs;
+    k_field_backward_mask<<<grid, kThreads, BSmem::bytes, (cudaStream_t)stream>>>(*desc, p);
+    INERF_LAUNCH_CHECK();
+    return INERF_OK;
+}

@@ -16,7 +16,7 @@ import torch
 import torch.nn as nn
 from torch.autograd import Function
 
-from .._lib import call, ptr, stream_ptr
+from .._lib import PARAM_EPOCH, call, ptr, stream_ptr
 
 _gridtype_to_id = {"hash": 0, "tiled": 1}
 _interp_to_id = {"linear": 0, "smoothstep": 1}
@@ -114,7 +114,7 @@ class GridEncoder(nn.Module):
     def half_table(self) -> torch.Tensor:
         """Persistent fp16 shadow of `embeddings`, refreshed when the parameter changes."""
         e = self.embeddings
-        key = (e.data_ptr(), e._version, e.device)
+        key = (e.data_ptr(), e._version, e.device, PARAM_EPOCH[0])
         if self._lowp is None or self._lowp_key != key:
             self._lowp = e.detach().to(torch.half).contiguous()
             self._lowp_key = key

@@ -20,10 +20,49 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from .._lib import FieldDesc, call, lib, ptr, stream_ptr
+from .._lib import PARAM_EPOCH, FieldDesc, call, lib, ptr, stream_ptr
 from ..activation import trunc_exp
 from ..encoding import get_encoder
 from .renderer import NeRFMaskRenderer
+
+
+class _FusedInstanceField(torch.autograd.Function):
+    """Whole field forward (inerf_field_forward_train) / instance-head backward (inerf_field_backward_mask), one launch each.
+    The table gradient (13.3 M fp32 entries) is accumulated straight into `encoder_mask.embeddings.grad` by the kernel's
+    atomics -- no zero-filled temporary, no extra pass to add it -- so `None` is returned for that input."""
+
+    @staticmethod
+    def forward(ctx, model, x, d, table_mask, w0, w1, w2):
+        B, K, dev = x.shape[0], model.num_instances, x.device
+        sigmas = torch.empty(B, dtype=torch.float32, device=dev)
+        rgbs = torch.empty(B, 3, dtype=torch.float32, device=dev)
+        masks = torch.empty(B, K, dtype=torch.float32, device=dev)
+        x0 = torch.empty(B, 48, dtype=torch.float16, device=dev)
+        desc = model._field_desc()
+        call("inerf_field_forward_train", ctypes.byref(desc), ptr(x), ptr(d), B, ptr(sigmas), ptr(rgbs), ptr(masks), ptr(x0), stream_ptr(dev))
+        ctx.model = model
+        ctx.save_for_backward(x, x0)
+        ctx.mark_non_differentiable(sigmas, rgbs)
+        return sigmas, rgbs, masks
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g_sigmas, g_rgbs, g_masks):
+        x, x0 = ctx.saved_tensors
+        model = ctx.model
+        B, K, dev = x.shape[0], model.num_instances, x.device
+        table = model.encoder_mask.embeddings
+        if table.grad is None:
+            table.grad = torch.zeros_like(table)
+        gw0 = torch.zeros(64, 47, dtype=torch.float32, device=dev)
+        gw1 = torch.zeros(64, 64, dtype=torch.float32, device=dev)
+        gw2 = torch.zeros(K, 64, dtype=torch.float32, device=dev)
+        if B > 0:
+            desc = model._field_desc()
+            _, wb = model._packed_weights(want_bwd=True)
+            call("inerf_field_backward_mask", ctypes.byref(desc), ptr(wb), ptr(x), ptr(x0), ptr(g_masks.float().contiguous()), B,
+                 ptr(table.grad), ptr(gw0), ptr(gw1), ptr(gw2), stream_ptr(dev))
+        return None, None, None, None, gw0, gw1, gw2
 
 
 class NeRFNetwork(NeRFMaskRenderer):
@@ -66,7 +105,7 @@ class NeRFNetwork(NeRFMaskRenderer):
             self.bg_net = None
 
         self.use_fused = True     # set False to force the modular operator sequence
-        self._packed = None       # (key, fp16 weight blob on device)
+        self._packed = None       # (key, forward fp16 weight blob, backward blob | None) on device
         self._tables = None       # (key, interleaved fp16 hash tables on device)
         self._work_counter = None
 
@@ -85,23 +124,28 @@ class NeRFNetwork(NeRFMaskRenderer):
     def fused_render_available(self, render_mask: bool) -> bool:
         return self.fused_available() and self.bg_radius <= 0 and hasattr(lib(), "inerf_render_fused")
 
-    def _packed_weights(self) -> torch.Tensor:
+    def _packed_weights(self, want_bwd: bool = False):
+        """fp16 operand blobs for the tcgen05 kernels, re-packed ON THE DEVICE (one launch, no host round trip) whenever a
+        weight's version counter changes -- every optimizer step while mask_net trains.  -> forward blob (, backward blob)"""
         ws = [m.weight for m in (*self.sigma_net, *self.color_net, *self.mask_net)]
-        key = tuple((w.data_ptr(), w._version) for w in ws) + (str(ws[0].device),)
-        if self._packed is None or self._packed[0] != key:
+        dev = ws[0].device
+        key = tuple((w.data_ptr(), w._version) for w in ws) + (str(dev), PARAM_EPOCH[0])
+        if self._packed is None or self._packed[0] != key or (want_bwd and self._packed[2] is None):
             K = self.num_instances
-            nbytes = lib().inerf_field_weights_bytes(K)
-            host = [w.detach().float().cpu().contiguous() for w in ws]
-            blob = torch.empty(nbytes, dtype=torch.uint8).pin_memory() if torch.cuda.is_available() else torch.empty(nbytes, dtype=torch.uint8)
-            call("inerf_field_pack_weights", *[h.data_ptr() for h in host], K, blob.data_ptr())
-            self._packed = (key, blob.to(ws[0].device))
-        return self._packed[1]
+            fwd = self._packed[1] if self._packed is not None and self._packed[1].device == dev else \
+                torch.empty(lib().inerf_field_weights_bytes(K), dtype=torch.uint8, device=dev)
+            bwd = self._packed[2] if self._packed is not None and self._packed[2] is not None and self._packed[2].device == dev else None
+            if want_bwd and bwd is None:
+                bwd = torch.empty(lib().inerf_field_bwd_weights_bytes(), dtype=torch.uint8, device=dev)
+            call("inerf_field_pack_weights_device", *[ptr(w.detach()) for w in ws], K, ptr(fwd), ptr(bwd), stream_ptr(dev))
+            self._packed = (key, fwd, bwd)
+        return (self._packed[1], self._packed[2]) if want_bwd else self._packed[1]
 
     def _packed_tables(self) -> torch.Tensor:
         """Interleaved fp16 copy of both hash tables, (sigma.c0, sigma.c1, mask.c0, mask.c1) per entry, refreshed only when
         a parameter changes (the reference casts both whole tables to fp16 on EVERY encoder call, grid.py:43-44)."""
         e, em = self.encoder.embeddings, self.encoder_mask.embeddings
-        key = (e.data_ptr(), e._version, em.data_ptr(), em._version, str(e.device))
+        key = (e.data_ptr(), e._version, em.data_ptr(), em._version, str(e.device), PARAM_EPOCH[0])
         if self._tables is None or self._tables[0] != key:
             n = e.shape[0]
             out = self._tables[1] if self._tables is not None and self._tables[1].shape[0] == n and self._tables[1].device == e.device \
@@ -138,6 +182,23 @@ class NeRFNetwork(NeRFMaskRenderer):
         call("inerf_field_forward", ctypes.byref(desc), ptr(x), ptr(d), B, ptr(sigmas), ptr(rgbs), ptr(masks), stream_ptr(dev))
         return sigmas, rgbs, masks
 
+    def fused_train_available(self, x, d) -> bool:
+        """Instance stage (MaskTrainer, nerf/utils.py:1242-1246): RGB-sigma nets frozen, instance head trainable, fp16 autocast
+        (the `-O` preset) -> forward and backward of the whole field are ONE launch each."""
+        if not (self.fused_available() and x.is_cuda and torch.is_autocast_enabled() and not x.requires_grad and not d.requires_grad):
+            return False
+        if not hasattr(lib(), "inerf_field_backward_mask"):
+            return False
+        frozen = (self.encoder, self.sigma_net, self.encoder_dir, self.color_net)
+        if any(p.requires_grad for m in frozen for p in m.parameters()):
+            return False
+        return self.encoder_mask.embeddings.requires_grad and all(l.weight.requires_grad for l in self.mask_net)
+
+    def forward_fused_train(self, x, d):
+        x = x.float().contiguous().view(-1, 3)
+        d = d.float().contiguous().view(-1, 3)
+        return _FusedInstanceField.apply(self, x, d, self.encoder_mask.embeddings, *[l.weight for l in self.mask_net])
+
     def _render_fused(self, rays_o, rays_d, nears, fars, render_mask, dt_gamma, max_steps, T_thresh):
         N = rays_o.shape[0]
         dev = rays_o.device
@@ -167,6 +228,8 @@ class NeRFNetwork(NeRFMaskRenderer):
         """x [N,3] in [-bound,bound], d [N,3] unit -> (sigma [N], rgb [N,3], mask_logits [N,K])"""
         if not torch.is_grad_enabled() and x.is_cuda and self.fused_available():
             return self.forward_fused(x, d)
+        if torch.is_grad_enabled() and self.fused_train_available(x, d):
+            return self.forward_fused_train(x, d)
         h = self._mlp(self.sigma_net, self.encoder(x, bound=self.bound))
         sigma = trunc_exp(h[..., 0])
         geo_feat = h[..., 1:]

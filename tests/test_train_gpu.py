@@ -1,0 +1,86 @@
+"""GPU parity of the fused instance-stage training path (inerf_field_forward_train + inerf_field_backward_mask, tcgen05)
+against the reference operator sequence (network_mask.py:119-158 through autograd: grid-encode kernels + nn.Linear), and an
+end-to-end training step (MaskTrainer.train_step semantics, nerf/utils.py:1287-1373)."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import scene_arrays
+from test_field_gpu import build_model
+
+pytestmark = pytest.mark.gpu
+
+
+def _freeze(m):
+    for mod in (m.encoder, m.sigma_net, m.encoder_dir, m.color_net):
+        mod.requires_grad_(False)
+
+
+def _rel(a, b):
+    return float((a - b).norm() / b.norm().clamp(min=1e-12))
+
+
+@pytest.mark.parametrize("K,B", [(32, 128 * 9 + 17), (16, 128 * 3), (5, 77)])
+def test_fused_backward_matches_autograd(cuda, K, B):
+    m, _ = build_model(cuda, K)
+    m.train()
+    _freeze(m)
+    g = torch.Generator().manual_seed(3)
+    x = ((torch.rand(B, 3, generator=g) * 2 - 1) * 7.5).to(cuda)
+    d = torch.nn.functional.normalize(torch.randn(B, 3, generator=g), dim=-1).to(cuda)
+    G = torch.randn(B, K, generator=g).to(cuda)
+    params = [m.encoder_mask.embeddings, *[l.weight for l in m.mask_net]]
+
+    def grads(use_fused, autocast):
+        for p in params:
+            p.grad = None
+        m.use_fused = use_fused
+        with torch.autocast("cuda", dtype=torch.float16, enabled=autocast):
+            assert m.fused_train_available(x, d) == (use_fused and autocast)
+            s, c, k = m(x, d)
+            loss = (k.float() * G).sum()
+        loss.backward()
+        m.use_fused = True
+        return [p.grad.detach().float().clone() for p in params], (s.detach().float(), c.detach().float(), k.detach().float())
+
+    g_fused, out_fused = grads(True, True)
+    g_amp, out_amp = grads(False, True)       # the reference's fp16 autocast sequence (fp16 GEMM outputs, fp16 table atomics)
+    g_fp32, _ = grads(False, False)           # fp32 reference of the same op sequence
+    torch.testing.assert_close(out_fused[2], out_amp[2], rtol=2e-2, atol=2e-2)
+    names = ["table", "w0", "w1", "w2"]
+    for n, a, b, c in zip(names, g_fused, g_amp, g_fp32):
+        e_fused, e_amp = _rel(a, c), _rel(b, c)
+        # the fused path keeps fp32 accumulators where autocast rounds to fp16: it must be at least as close to fp32 as autocast is
+        assert e_fused < max(2e-2, 1.5 * e_amp), f"{n}: fused vs fp32 {e_fused:.3e}, autocast vs fp32 {e_amp:.3e}"
+    # table gradient support is identical (same corners touched)
+    nz_f, nz_r = g_fused[0].abs().sum(1) > 0, g_fp32[0].abs().sum(1) > 0
+    assert float((nz_f ^ nz_r).float().mean()) < 1e-3
+
+
+def test_train_step_runs_fused_and_learns(cuda):
+    from instance_nerf_b200 import synthetic
+    from instance_nerf_b200.nerf.trainer import MaskTrainStep
+    K = 16
+    m, sc = build_model(cuda, K, density_scale=10.0)
+    H, W = 96, 128
+    poses = torch.from_numpy(synthetic.camera_poses(sc, 1, 1))
+    r = synthetic.get_rays(poses, synthetic.intrinsics(H, W), H, W, N=1024, patch_size=8, generator=torch.Generator().manual_seed(0))
+    o, d = r["rays_o"].reshape(-1, 3).contiguous(), r["rays_d"].reshape(-1, 3).contiguous()
+    labels = torch.from_numpy(sc.first_hit_labels(o.numpy().astype(np.float64), d.numpy().astype(np.float64)))
+    data = {"rays_o": o[None].to(cuda), "rays_d": d[None].to(cuda), "masks": labels[None].to(cuda),
+            "noises": torch.rand(o.shape[0], generator=torch.Generator().manual_seed(1)).to(cuda)}
+    tr = MaskTrainStep(m, lr=1e-2, fp16=True, label_regularization_weight=0.1)
+    # first-step loss: fused vs modular forward on identical weights
+    m.train()
+    with torch.no_grad():
+        pass
+    with torch.autocast("cuda", dtype=torch.float16):
+        _, _, l_fused = tr.train_step(data)
+        m.use_fused = False
+        _, _, l_mod = tr.train_step(data)
+        m.use_fused = True
+    assert abs(float(l_fused) - float(l_mod)) < 2e-2 * max(1.0, abs(float(l_mod)))
+    losses = [float(tr.step(data)) for _ in range(40)]
+    assert np.isfinite(losses).all()
+    assert np.mean(losses[-5:]) < 0.6 * np.mean(losses[:3]), losses
+    assert m.encoder_mask.embeddings.grad is not None and float(m.encoder_mask.embeddings.grad.abs().sum()) > 0
