@@ -253,6 +253,22 @@ int inerf_render_fused(const inerf_field_desc *desc, const float *rays_o, const 
                        float dt_gamma, uint32_t max_steps, float T_thresh, float *weights_sum, float *depth,
                        float *image, float *mask_out, int32_t *work_counter, void *stream);
 
+/* --------------------------------------------------------------- loss tail -- */
+
+/*
+ * MaskTrainer.train_step's loss on the composited maps (nerf/utils.py:1310-1314 cross-entropy over labelled pixels,
+ * label -1 = unlabelled; nerf/utils.py:1262-1285 depth-aware label smoothness on patch x patch pixel blocks, batch order
+ * patch-major as produced by get_rays, nerf/utils.py:83-100).  logits float [N, K], depth float [N], labels int64 [N],
+ * N a multiple of patch^2 (patch = 1: cross-entropy only).  acc6 = 6 floats of caller-owned scratch kept for the backward.
+ * Backward writes grad_logits [N, K] = upstream[0] * dloss/dlogits (upstream NULL = 1); no gradient goes to depth
+ * (the compositor drops grad_depth, raymarching.py:342).
+ */
+int inerf_mask_loss(const float *logits, const float *depth, const long long *labels, uint32_t N, uint32_t K,
+                    uint32_t patch, float reg_weight, float *acc6, float *loss_out, void *stream);
+int inerf_mask_loss_backward(const float *logits, const float *depth, const long long *labels, uint32_t N, uint32_t K,
+                             uint32_t patch, float reg_weight, const float *acc6, const float *upstream,
+                             float *grad_logits, void *stream);
+
 /* ------------------------------------------------------ occupancy grid EMA -- */
 
 /*

@@ -83,6 +83,8 @@ _PROTOS = {
     "inerf_grid_encode_backward": [_P, _P, _P, _P, _P, _U, _U, _U, _U, _F, _U, _P, _P, _U, _I, _U, _I, _I, _P],
     "inerf_sh_encode_forward": [_P, _P, _U, _U, _U, _P, _P],
     "inerf_sh_encode_backward": [_P, _P, _U, _U, _U, _P, _P, _P],
+    "inerf_mask_loss": [_P, _P, _P, _U, _U, _U, _F, _P, _P, _P],
+    "inerf_mask_loss_backward": [_P, _P, _P, _U, _U, _U, _F, _P, _P, _P, _P],
     "inerf_occupancy_ema": [_P, _P, _U, _F, _P, _P],
     "inerf_occupancy_pack": [_P, _U, _P, _F, _P, _P, _P],
     "inerf_field_pack_weights": [_P] * 8 + [_U, _P],

@@ -1,0 +1,155 @@
+// Instance-stage loss tail in two launches: MaskTrainer.train_step's cross-entropy on
+// labelled pixels (nerf/utils.py:1310-1314, criterion = CrossEntropyLoss(reduction='none'), main_nerf_mask.py:177) plus the
+// depth-aware label smoothness on p x p patches (label_regularization, nerf/utils.py:1262-1285), forward and gradient.
+// The reference spends ~150 tiny elementwise / reduction launches on these [N, K] tensors.
+//
+//   loss = sum_{labelled n} (logsumexp(x_n) - x_n[gt_n]) / n_labelled
+//        + reg_w * ( sum diff_x^2 w_x / (K sum w_x) + sum diff_y^2 w_y / (K sum w_y) ),   w = exp(-(ddepth)^2)
+//   (the reference divides by torch.sum(weight.expand_as(diff)), i.e. K times the per-pixel-pair sum)
+// No gradient flows to depth: the compositor drops grad_depth (raymarching.py:342).
+#include "common.cuh"
+
+namespace {
+
+struct LossAcc {   // accumulated by k_loss_reduce, consumed by k_loss_grad
+    float ce_sum, n_lab, sx, wx, sy, wy;
+};
+
+__device__ __forceinline__ float block_sum(float v, float* red) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = (blockDim.x + 31) >> 5;
+    __syncthreads();
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    float t = 0.f;
+    for (int i = 0; i < nw; i++) t += red[i];
+    return t;
+}
+
+// one block per patch, one thread per pixel of the patch
+__global__ void k_loss_reduce(const float* __restrict__ logits, const float* __restrict__ depth, const long long* __restrict__ labels, uint32_t K,
+                              uint32_t p, int use_reg, LossAcc* __restrict__ acc) {
+    __shared__ float red[32];
+    const uint32_t pp = p * p, t = threadIdx.x;
+    const uint32_t n = blockIdx.x * pp + t;
+    const uint32_t i = t / p, j = t % p;
+    const float* x = logits + (size_t)n * K;
+    float ce = 0.f, lab = 0.f;
+    const long long gt = labels[n];
+    if (gt >= 0) {
+        float m = -INFINITY;
+        for (uint32_t k = 0; k < K; k++) m = fmaxf(m, x[k]);
+        float s = 0.f;
+        for (uint32_t k = 0; k < K; k++) s += expf(x[k] - m);
+        ce = logf(s) + m - x[gt];
+        lab = 1.f;
+    }
+    float sx = 0.f, wx = 0.f, sy = 0.f, wy = 0.f;
+    if (use_reg) {
+        if (j + 1 < p) {
+            const float dd = depth[n + 1] - depth[n];
+            wx = expf(-(dd * dd));
+            const float* xr = x + K;
+            float a = 0.f;
+            for (uint32_t k = 0; k < K; k++) { const float df = xr[k] - x[k]; a = fmaf(df, df, a); }
+            sx = a * wx;
+        }
+        if (i + 1 < p) {
+            const float dd = depth[n + p] - depth[n];
+            wy = expf(-(dd * dd));
+            const float* xd = x + (size_t)p * K;
+            float a = 0.f;
+            for (uint32_t k = 0; k < K; k++) { const float df = xd[k] - x[k]; a = fmaf(df, df, a); }
+            sy = a * wy;
+        }
+    }
+    ce = block_sum(ce, red); lab = block_sum(lab, red);
+    sx = block_sum(sx, red); wx = block_sum(wx, red); sy = block_sum(sy, red); wy = block_sum(wy, red);
+    if (t == 0) {
+        atomicAdd(&acc->ce_sum, ce); atomicAdd(&acc->n_lab, lab);
+        atomicAdd(&acc->sx, sx); atomicAdd(&acc->wx, wx); atomicAdd(&acc->sy, sy); atomicAdd(&acc->wy, wy);
+    }
+}
+
+// loss value (block 0, thread 0) and d loss / d logits * upstream
+__global__ void k_loss_grad(const float* __restrict__ logits, const float* __restrict__ depth, const long long* __restrict__ labels, uint32_t K,
+                            uint32_t p, float reg_w, const LossAcc* __restrict__ acc, const float* __restrict__ upstream, float* __restrict__ loss_out,
+                            float* __restrict__ grad) {
+    const uint32_t pp = p * p, t = threadIdx.x;
+    const uint32_t n = blockIdx.x * pp + t;
+    const uint32_t i = t / p, j = t % p;
+    const LossAcc A = *acc;
+    const float n_lab = fmaxf(A.n_lab, 1.f);
+    const float Wx = (float)K * A.wx, Wy = (float)K * A.wy;
+    if (loss_out != nullptr && blockIdx.x == 0 && t == 0) {
+        float l = A.ce_sum / n_lab;
+        if (reg_w > 0.f) l += reg_w * (A.sx / Wx + A.sy / Wy);
+        loss_out[0] = l;
+    }
+    if (grad == nullptr) return;
+    const float up = upstream ? upstream[0] : 1.f;
+    const float* x = logits + (size_t)n * K;
+    float* g = grad + (size_t)n * K;
+    const long long gt = labels[n];
+    float m = -INFINITY, inv = 0.f;
+    if (gt >= 0) {
+        for (uint32_t k = 0; k < K; k++) m = fmaxf(m, x[k]);
+        float s = 0.f;
+        for (uint32_t k = 0; k < K; k++) s += expf(x[k] - m);
+        inv = 1.f / s;
+    }
+    float wl = 0.f, wr = 0.f, wu = 0.f, wd = 0.f;   // pair weights to the left / right / up / down neighbour
+    if (reg_w > 0.f) {
+        const float d0 = depth[n];
+        if (j > 0) { const float dd = d0 - depth[n - 1]; wl = expf(-(dd * dd)); }
+        if (j + 1 < p) { const float dd = depth[n + 1] - d0; wr = expf(-(dd * dd)); }
+        if (i > 0) { const float dd = d0 - depth[n - p]; wu = expf(-(dd * dd)); }
+        if (i + 1 < p) { const float dd = depth[n + p] - d0; wd = expf(-(dd * dd)); }
+    }
+    const float cx = reg_w > 0.f ? 2.f * reg_w / Wx : 0.f, cy = reg_w > 0.f ? 2.f * reg_w / Wy : 0.f;
+    for (uint32_t k = 0; k < K; k++) {
+        float v = 0.f;
+        if (gt >= 0) v = (expf(x[k] - m) * inv - (k == (uint32_t)gt ? 1.f : 0.f)) / n_lab;
+        if (reg_w > 0.f) {
+            const float xc = x[k];
+            float r = 0.f;
+            if (j > 0) r += cx * wl * (xc - x[(long long)k - (long long)K]);
+            if (j + 1 < p) r -= cx * wr * (x[k + K] - xc);
+            if (i > 0) r += cy * wu * (xc - x[(long long)k - (long long)p * K]);
+            if (i + 1 < p) r -= cy * wd * (x[k + (size_t)p * K] - xc);
+            v += r;
+        }
+        g[k] = v * up;
+    }
+}
+
+}  // namespace
+
+extern "C" int inerf_mask_loss(const float* logits, const float* depth, const long long* labels, uint32_t N, uint32_t K, uint32_t patch,
+                               float reg_weight, float* acc6, float* loss_out, void* stream) {
+    INERF_REQUIRE(logits); INERF_REQUIRE(labels); INERF_REQUIRE(acc6); INERF_REQUIRE(loss_out);
+    if (reg_weight > 0.f) INERF_REQUIRE(depth);
+    if (patch == 0 || patch > 32 || K == 0 || N == 0 || N % (patch * patch)) return INERF_ERR_SIZE;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(acc6, 0, sizeof(LossAcc), st);
+    if (e != cudaSuccess) return (int)e;
+    const uint32_t pp = patch * patch;
+    k_loss_reduce<<<N / pp, pp, 0, st>>>(logits, depth, labels, K, patch, reg_weight > 0.f, (LossAcc*)acc6);
+    INERF_LAUNCH_CHECK();
+    k_loss_grad<<<1, 1, 0, st>>>(logits, depth, labels, K, patch, reg_weight, (const LossAcc*)acc6, nullptr, loss_out, nullptr);
+    INERF_LAUNCH_CHECK();
+    return INERF_OK;
+}
+
+extern "C" int inerf_mask_loss_backward(const float* logits, const float* depth, const long long* labels, uint32_t N, uint32_t K, uint32_t patch,
+                                        float reg_weight, const float* acc6, const float* upstream, float* grad_logits, void* stream) {
+    INERF_REQUIRE(logits); INERF_REQUIRE(labels); INERF_REQUIRE(acc6); INERF_REQUIRE(grad_logits);
+    if (reg_weight > 0.f) INERF_REQUIRE(depth);
+    if (patch == 0 || patch > 32 || K == 0 || N == 0 || N % (patch * patch)) return INERF_ERR_SIZE;
+    const uint32_t pp = patch * patch;
+    k_loss_grad<<<N / pp, pp, 0, (cudaStream_t)stream>>>(logits, depth, labels, K, patch, reg_weight, (const LossAcc*)acc6, upstream, nullptr,
+                                                          grad_logits);
+    INERF_LAUNCH_CHECK();
+    return INERF_OK;
+}

@@ -213,25 +213,53 @@ __global__ void __launch_bounds__(kThreads, 1) k_field_backward_mask(inerf_field
             uint32_t v[16];
             umma::tmem_ld16(tmem + T_x + lane_base + half * 16, v);
             umma::tmem_ld_wait();
+            // Consecutive rows of a tile are consecutive samples of the same ray (the stream is sorted by ray and by t), so on the
+            // coarse levels whole runs of lanes fall into the SAME cell: left alone, their atomics serialise on a handful of
+            // addresses in L2.  Levels 0..7 (threads of half 0) therefore reduce each run inside the warp first -- segmented
+            // reduction towards the run's first lane, bounded by the next run head -- and only run heads issue atomics.
+            float x01[3] = {2.f, 2.f, 2.f};
             if (live) {
-                float x01[3];
 #pragma unroll
                 for (int d = 0; d < 3; d++) x01[d] = __fmul_rn(__fadd_rn(__ldg(p.xyzs + (size_t)s * 3 + d), desc.bound), inv2b);
-                const bool oob = x01[0] < 0.f || x01[0] > 1.f || x01[1] < 0.f || x01[1] > 1.f || x01[2] < 0.f || x01[2] > 1.f;
-                if (!oob) {
+            }
+            const bool ok = live && !(x01[0] < 0.f || x01[0] > 1.f || x01[1] < 0.f || x01[1] > 1.f || x01[2] < 0.f || x01[2] > 1.f);
 #pragma unroll
-                    for (uint32_t li = 0; li < 8; li++) {
-                        const float g0 = __uint_as_float(v[2 * li]), g1 = __uint_as_float(v[2 * li + 1]);
-                        if (g0 != 0.f || g1 != 0.f) {
-                            const LevelGeom g = lg[half * 8 + li];
-                            uint32_t idx[8];
-                            float w[8];
-                            level_corners(x01, g, idx, w);
-                            float2* base = p.grad_table + g.offset;
+            for (uint32_t li = 0; li < 8; li++) {
+                float g0 = ok ? __uint_as_float(v[2 * li]) : 0.f, g1 = ok ? __uint_as_float(v[2 * li + 1]) : 0.f;
+                const LevelGeom g = lg[half * 8 + li];
+                uint32_t idx[8];
+                float w[8];
+                float xs[3] = {ok ? x01[0] : 0.f, ok ? x01[1] : 0.f, ok ? x01[2] : 0.f};
+                level_corners(xs, g, idx, w);
+                float2* base = p.grad_table + g.offset;
+                if (half == 0) {
+                    // run heads: first lane, or a lane whose cell differs from the previous lane's (corner 0 and corner 7
+                    // together identify the cell; a hash collision only splits or merges runs of identical addresses)
+                    const uint32_t p0 = __shfl_up_sync(0xffffffffu, idx[0], 1), p7 = __shfl_up_sync(0xffffffffu, idx[7], 1);
+                    const bool head = lane == 0 || p0 != idx[0] || p7 != idx[7];
+                    const uint32_t heads = __ballot_sync(0xffffffffu, head);
+                    const uint32_t after = lane == 31 ? 0u : (heads >> (lane + 1));
+                    const uint32_t next_head = after ? (lane + 1 + (uint32_t)__ffs(after) - 1u) : 32u;
+                    float a0[8], a1[8];
 #pragma unroll
-                            for (uint32_t c = 0; c < 8; c++) atomicAdd(base + idx[c], make_float2(__fmul_rn(w[c], g0), __fmul_rn(w[c], g1)));
+                    for (uint32_t c = 0; c < 8; c++) { a0[c] = __fmul_rn(w[c], g0); a1[c] = __fmul_rn(w[c], g1); }
+#pragma unroll
+                    for (uint32_t off = 1; off < 32; off <<= 1) {
+                        const bool take = lane + off < next_head;
+#pragma unroll
+                        for (uint32_t c = 0; c < 8; c++) {
+                            const float o0 = __shfl_down_sync(0xffffffffu, a0[c], off), o1 = __shfl_down_sync(0xffffffffu, a1[c], off);
+                            if (take) { a0[c] += o0; a1[c] += o1; }
                         }
                     }
+                    if (head) {
+#pragma unroll
+                        for (uint32_t c = 0; c < 8; c++)
+                            if (a0[c] != 0.f || a1[c] != 0.f) atomicAdd(base + idx[c], make_float2(a0[c], a1[c]));
+                    }
+                } else if (g0 != 0.f || g1 != 0.f) {
+#pragma unroll
+                    for (uint32_t c = 0; c < 8; c++) atomicAdd(base + idx[c], make_float2(__fmul_rn(w[c], g0), __fmul_rn(w[c], g1)));
                 }
             }
         }

@@ -12,16 +12,47 @@ from types import SimpleNamespace
 import torch
 import torch.nn as nn
 
+from .._lib import call, ptr, stream_ptr
 from ..parallel import GradBucket
+
+
+class _MaskLoss(torch.autograd.Function):
+    """Cross-entropy on labelled pixels + depth-aware label smoothness, value and gradient in 3 launches
+    (inerf_mask_loss / inerf_mask_loss_backward) instead of ~150 elementwise / reduction kernels."""
+
+    @staticmethod
+    def forward(ctx, logits, depth, labels, patch, reg_weight):
+        logits = logits.float().contiguous()
+        N, K = logits.shape
+        depth = depth.detach().float().contiguous().view(-1)
+        labels = labels.contiguous().view(-1).long()
+        acc = torch.empty(6, dtype=torch.float32, device=logits.device)
+        loss = torch.empty(1, dtype=torch.float32, device=logits.device)
+        call("inerf_mask_loss", ptr(logits), ptr(depth), ptr(labels), N, K, int(patch), float(reg_weight), ptr(acc), ptr(loss),
+             stream_ptr(logits.device))
+        ctx.save_for_backward(logits, depth, labels, acc)
+        ctx.cfg = (N, K, int(patch), float(reg_weight))
+        return loss[0]
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        logits, depth, labels, acc = ctx.saved_tensors
+        N, K, patch, reg_weight = ctx.cfg
+        grad = torch.empty_like(logits)
+        call("inerf_mask_loss_backward", ptr(logits), ptr(depth), ptr(labels), N, K, patch, reg_weight, ptr(acc),
+             ptr(g.float().contiguous().view(1)), ptr(grad), stream_ptr(logits.device))
+        return grad, None, None, None, None
 
 
 class MaskTrainStep:
     def __init__(self, model, lr=1e-2, fp16=True, patch_size=8, label_regularization_weight=0.0, dt_gamma=1 / 128, max_steps=1024,
-                 T_thresh=1e-4, data_parallel=False, fused_adam=True):
+                 T_thresh=1e-4, data_parallel=False, fused_adam=True, fused_loss=True):
         self.model = model
         self.opt = SimpleNamespace(patch_size=patch_size, label_regularization_weight=label_regularization_weight)
         self.render_kw = dict(dt_gamma=dt_gamma, max_steps=max_steps, T_thresh=T_thresh)
         self.fp16 = fp16
+        self.fused_loss = fused_loss
         self.num_instances = model.num_instances
         # freeze rgb and density (nerf/utils.py:1242-1246)
         model.encoder.requires_grad_(False)
@@ -59,6 +90,10 @@ class MaskTrainStep:
         pred = outputs["instance_mask_logits"]
         flat = pred.view(-1, self.num_instances)
         gt = gt_masks.view(-1)
+        p = self.opt.patch_size
+        if self.fused_loss and flat.is_cuda and flat.shape[0] % (p * p) == 0:
+            loss = _MaskLoss.apply(flat, outputs["depth"], gt, p, self.opt.label_regularization_weight)
+            return pred.argmax(dim=-1), gt_masks, loss
         labeled = gt != -1
         # same value as the reference's boolean-index form, without the host sync of `labeled.sum() > 0`
         ce = self.criterion(flat.float(), torch.where(labeled, gt, torch.zeros_like(gt)))

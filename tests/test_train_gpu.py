@@ -84,3 +84,26 @@ def test_train_step_runs_fused_and_learns(cuda):
     assert np.isfinite(losses).all()
     assert np.mean(losses[-5:]) < 0.6 * np.mean(losses[:3]), losses
     assert m.encoder_mask.embeddings.grad is not None and float(m.encoder_mask.embeddings.grad.abs().sum()) > 0
+
+
+@pytest.mark.parametrize("K,reg", [(32, 0.1), (7, 0.0), (16, 1.0)])
+def test_fused_loss_tail_matches_torch(cuda, K, reg):
+    """inerf_mask_loss(+_backward) against the reference formulation written in torch (nerf/utils.py:1262-1285, 1310-1314)."""
+    from instance_nerf_b200.nerf.trainer import MaskTrainStep, _MaskLoss
+    g = torch.Generator().manual_seed(0)
+    N, p = 64 * 12, 8
+    logits = (torch.randn(N, K, generator=g) * 3).to(cuda).requires_grad_(True)
+    depth = torch.rand(N, generator=g).to(cuda)
+    labels = torch.randint(-1, K, (N,), generator=g).to(cuda)
+    stub = MaskTrainStep.__new__(MaskTrainStep)
+    stub.opt = type("o", (), {"patch_size": p, "label_regularization_weight": reg})()
+    stub.num_instances = K
+    lab = labels != -1
+    ce = torch.nn.functional.cross_entropy(logits[lab], labels[lab], reduction="none").mean()
+    ref = ce + (stub.label_regularization(depth, logits) * reg if reg > 0 else 0)
+    ref.backward()
+    g_ref = logits.grad.clone(); logits.grad = None
+    out = _MaskLoss.apply(logits, depth, labels, p, reg)
+    (out * 3.0).backward()
+    torch.testing.assert_close(out, ref.detach(), rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(logits.grad / 3.0, g_ref, rtol=1e-4, atol=1e-7)
