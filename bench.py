@@ -12,7 +12,8 @@ A "step" = one frame rendered through NeRFNetwork.render (the call MaskTrainer.t
 + ONE fused launch (march + hash gathers x2 + tcgen05 MLP + composite) + the bg / depth tail.  Every step renders a different
 camera pose, and L2 (126 MB) is flushed between timed steps by writing a 512 MB buffer (outside the event pair).
 At N > 1 every rank renders its own frame each step (weak scaling, rays sharded by frame) and the finished tiles are
-gathered with ONE NCCL all_gather inside the timed step.
+gathered with ONE NCCL all_gather per step, issued asynchronously so it overlaps the next frame's render (the last
+step waits for its gather inside the timed region).
 
 Keys: value = device-timed Mrays/s with rays resident in HBM; e2e = same through the public API from pinned HOST rays to
 pinned HOST results (H2D + D2H inside the timed region); roofline = the fused kernel's algorithmic bytes / its own
@@ -179,8 +180,10 @@ def run_gpu_arm(args):
     dev_rays = [(o.to(dev), d.to(dev)) for o, d in host_rays]
     kw = dict(staged=True, render_mask=True, perturb=False, dt_gamma=DT_GAMMA, max_steps=MAX_STEPS, T_thresh=T_THRESH, bg_color=1)
     flush_buf = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device=dev)
-    tile = torch.empty(N, 4 + K, dtype=torch.float32, device=dev)               # image 3 | depth 1 | logits K
-    gathered = torch.empty(world * N, 4 + K, dtype=torch.float32, device=dev) if world > 1 else None
+    # image 3 | depth 1 | logits K; double buffered so the NCCL gather of frame i overlaps the render of frame i + 1
+    tiles = [torch.empty(N, 4 + K, dtype=torch.float32, device=dev) for _ in range(2)]
+    gathered = [torch.empty(world * N, 4 + K, dtype=torch.float32, device=dev) for _ in range(2)] if world > 1 else None
+    handles = [None, None]
 
     # kernel-only timing hook around the fused launch (events on the launching stream)
     kern_events, samples_seen = [], []
@@ -206,15 +209,27 @@ def run_gpu_arm(args):
             d = host_rays[p][1].to(dev, non_blocking=True)
         else:
             o, d = dev_rays[p]
+        b = i & 1
+        if handles[b] is not None:        # the gather that last used this buffer pair must have finished (stream-side wait)
+            handles[b].wait()
+            handles[b] = None
+        tile = tiles[b]
         with torch.no_grad():
             r = model.render(o[None], d[None], **kw)
         tile[:, 0:3] = r["image"][0]
         tile[:, 3] = r["depth"][0]
         tile[:, 4:] = r["instance_mask_logits"][0]
         if world > 1:
-            dist.all_gather_into_tensor(gathered, tile)
+            handles[b] = dist.all_gather_into_tensor(gathered[b], tile, async_op=True)
         if e2e:
-            out_host.copy_(gathered if world > 1 and rank == 0 else tile, non_blocking=True)
+            drain()
+            out_host.copy_(gathered[b] if world > 1 and rank == 0 else tile, non_blocking=True)
+
+    def drain():
+        for b in range(2):
+            if handles[b] is not None:
+                handles[b].wait()
+                handles[b] = None
 
     def barrier():
         if world > 1:
@@ -223,6 +238,7 @@ def run_gpu_arm(args):
 
     for i in range(args.warmup):
         step(i)
+    drain()
     barrier()
     kern_events.clear(); samples_seen.clear(); launches["n"] = 0
 
@@ -239,6 +255,8 @@ def run_gpu_arm(args):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         step(args.warmup + i)
+        if i == args.steps - 1:
+            drain()
         e1.record()
         ev.append((e0, e1))
     barrier()
@@ -292,7 +310,7 @@ def run_gpu_arm(args):
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16 operands / f32 accumulate",
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "rays_per_step_per_gpu": N, "samples_per_ray": avg_samples / N, "l2": "flushed between timed steps (512 MB write)",
-                       "parallelism": f"frames sharded over {world} rank(s), all_gather of tiles" if world > 1 else "single GPU",
+                       "parallelism": f"frames sharded over {world} rank(s), async all_gather of tiles overlapped with the next frame" if world > 1 else "single GPU",
                        "wall_s_timed_region_incl_flush": wall_s},
             "e2e": {"value": world * N / (e2e_ms / args.steps * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": gpu_launches,
@@ -308,6 +326,11 @@ def run_gpu_arm(args):
                 line["roofline"]["traffic"] = json.load(open(tpath)).get("k_render_fused_dram_bytes_per_launch")
             except Exception:
                 pass
+        if world == 1 and not args.no_train:
+            # second half of BASELINE.json's metric ("train-step ms @ 4096 rays"), measured in the same run (config c3)
+            tr = measure_train(dev, 0, 1, 20, 5, 4096, model, scene, poses)
+            line["train_step"] = {"ms": tr["ms"], "ms_median": tr["ms_median"], "unit": "ms", "rays": 4096, "samples": tr["samples"],
+                                  "workload": "c3: 4096 rays (8x8 patches) x max_steps 1024, K=32, fp16 autocast, CE + label smoothness, backward, Adam"}
         if world == 1 and not args.no_cpu_baseline:
             render, n_cpu, cores = make_cpu_reference(32768)
             t0 = time.perf_counter()
@@ -322,27 +345,17 @@ def run_gpu_arm(args):
 
 
 # ------------------------------------------------------------------------------------------- train arm --
-def run_train_arm(args):
-    """BASELINE.json configs[2] / [4]: instance-field training step (MaskTrainer.train_step + backward + Adam, nerf/utils.py:
-    929-936, 1287-1373), `--rays` rays per GPU per step as 8x8 patches, max_steps 1024, fp16 autocast (the `-O` preset).
-    At N > 1: data-parallel, one all_reduce of the mask-table + mask-net gradients per step."""
+def measure_train(dev, rank, world, steps, warmup, n_rays, model=None, scene=None, poses=None):
+    """Times `steps` full optimisation steps (MaskTrainStep.step: render -> loss -> backward -> [all_reduce] -> Adam) with CUDA
+    events, L2 flushed between steps.  -> dict(ms, samples, loss, clocks)"""
     import numpy as np
     import torch
     import torch.distributed as dist
     from instance_nerf_b200 import synthetic
     from instance_nerf_b200.nerf.trainer import MaskTrainStep
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    model, scene, poses = build_scene_and_model(dev)
-    n_rays = args.rays
+    if model is None:
+        model, scene, poses = build_scene_and_model(dev)
     trainer = MaskTrainStep(model, lr=1e-2, fp16=True, patch_size=8, label_regularization_weight=0.1, dt_gamma=DT_GAMMA, max_steps=MAX_STEPS,
                             T_thresh=T_THRESH, data_parallel=world > 1)
     intr = synthetic.intrinsics(H_IMG, W_IMG)
@@ -360,38 +373,64 @@ def run_train_arm(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for i in range(args.warmup):
+    for i in range(warmup):
         trainer.step(batches[i % 8])
     barrier()
     model.step_counter.zero_()
-    clocks = ClockSampler(local_rank)
+    model.local_step = 0
+    clocks = ClockSampler(dev.index or 0)
     if rank == 0:
         clocks.start()
     ev = []
-    for i in range(args.steps):
+    for i in range(steps):
         flush_buf.fill_(i & 0xFF)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        loss = trainer.step(batches[(args.warmup + i) % 8])
+        loss = trainer.step(batches[(warmup + i) % 8])
         e1.record()
         ev.append((e0, e1))
     barrier()
-    total_ms = sum(a.elapsed_time(b) for a, b in ev)
+    times = sorted(a.elapsed_time(b) for a, b in ev)
+    total_ms = sum(times)
     clk = clocks.stop() if rank == 0 else None
-    n_samples = float(model.step_counter[: min(16, args.steps), 0].float().mean().item())
+    n_samples = float(model.step_counter[: min(16, steps), 0].float().mean().item())
     if world > 1:
         t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms = float(t[0])
+    model.eval()
+    for p in model.parameters():
+        p.requires_grad_(True)
+    return {"ms": total_ms / steps, "ms_median": times[len(times) // 2], "samples": n_samples, "loss": float(loss.item()), "clocks": clk}
+
+
+def run_train_arm(args):
+    """BASELINE.json configs[2] / [4]: instance-field training step (MaskTrainer.train_step + backward + Adam, nerf/utils.py:
+    929-936, 1287-1373), `--rays` rays per GPU per step as 8x8 patches, max_steps 1024, fp16 autocast (the `-O` preset).
+    At N > 1: data-parallel, one all_reduce of the mask-table + mask-net gradients per step."""
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n_rays = args.rays
+    r = measure_train(dev, rank, world, args.steps, args.warmup, n_rays)
     if rank == 0:
-        ms = total_ms / args.steps
+        ms = r["ms"]
         line = {"metric": "instance_field_train_step_ms", "value": ms, "unit": "ms", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms, "higher_is_better": False, "scaling": "weak", "vs_baseline": None, "dtype": "f16 autocast / f32 params",
                 "data": "synthetic",
                 "config": {"workload": f"c3: instance-field training step, {n_rays} rays/GPU (8x8 patches) x max_steps 1024, K=32, hash+MLP backward, Adam",
-                           "rays_per_gpu": n_rays, "samples_per_step_per_gpu": n_samples, "l2": "flushed between timed steps (512 MB write)",
+                           "rays_per_gpu": n_rays, "samples_per_step_per_gpu": r["samples"], "l2": "flushed between timed steps (512 MB write)",
                            "parallelism": f"dp{world}, flat-bucket all_reduce" if world > 1 else "single GPU"},
-                "rays_per_s": world * n_rays / (ms * 1e-3), "loss": float(loss.item()), "clocks": clk}
+                "ms_per_step_median": r["ms_median"], "rays_per_s": world * n_rays / (ms * 1e-3), "loss": r["loss"], "clocks": r["clocks"]}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -404,6 +443,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the train-step figure appended to the render line at N = 1")
     ap.add_argument("--workload", default="render", choices=["render", "train"], help="render = the headline metric (default); train = train-step ms")
     ap.add_argument("--rays", type=int, default=4096, help="train workload: rays per GPU per step (4096 = config c3, 65536 = c5)")
     args = ap.parse_args()

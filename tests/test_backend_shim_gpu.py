@@ -86,18 +86,21 @@ def test_raymarching_prototypes(both, cuda):
         alive1, rt1 = alive0.clone(), nears.clone()
         for it in range(2):
             n_step = 4
-            x, dd, dl2 = torch.zeros(N * n_step, 3, device=cuda), torch.zeros(N * n_step, 3, device=cuda), torch.zeros(N * n_step, 2, device=cuda)
-            mod.march_rays(N, n_step, alive, rt, o, d, bound, dt_gamma, max_steps, C, 128, bits, nears, fars, x, dd, dl2, torch.zeros(N, device=cuda))
+            na = alive.shape[0]
+            x, dd, dl2 = torch.zeros(na * n_step, 3, device=cuda), torch.zeros(na * n_step, 3, device=cuda), torch.zeros(na * n_step, 2, device=cuda)
+            mod.march_rays(na, n_step, alive, rt, o, d, bound, dt_gamma, max_steps, C, 128, bits, nears, fars, x, dd, dl2, torch.zeros(na, device=cuda))
             gg = torch.Generator().manual_seed(10 + it)
-            s2 = torch.exp(torch.randn(N * n_step, generator=gg) + 2.5).to(cuda)
-            c2 = torch.rand(N * n_step, 3, generator=gg).to(cuda)
-            m2 = torch.randn(N * n_step, K, generator=gg).to(cuda)
+            s2 = torch.exp(torch.randn(na * n_step, generator=gg) + 2.5).to(cuda)
+            c2 = torch.rand(na * n_step, 3, generator=gg).to(cuda)
+            m2 = torch.randn(na * n_step, K, generator=gg).to(cuda)
             if it == 0:
                 fin[name + "_x"] = (x.clone(), dl2.clone())
-            rt1.copy_(rt); alive1.copy_(alive)
-            mod.composite_rays_with_masks(N, n_step, K, 1e-2, alive, rt, s2, c2, m2, dl2, ws, dp, im, mo)
-            mod.composite_rays(N, n_step, 1e-2, alive1, rt1, s2, c2, dl2, ws1, dp1, im1)
-        fin[name] = (alive.clone(), rt.clone(), ws, dp, im, mo, alive1.clone(), ws1, im1)
+            rt1.copy_(rt); alive1 = alive.clone()
+            mod.composite_rays_with_masks(na, n_step, K, 1e-2, alive, rt, s2, c2, m2, dl2, ws, dp, im, mo)
+            mod.composite_rays(na, n_step, 1e-2, alive1, rt1, s2, c2, dl2, ws1, dp1, im1)
+            last = (alive.clone(), alive1.clone())
+            alive = alive[alive >= 0].contiguous()      # the reference loop compacts between iterations (mask_renderer.py:370)
+        fin[name] = (last[0], rt.clone(), ws, dp, im, mo, last[1], ws1, im1)
     assert bits_equal(fin["ref_x"][0], fin["ours_x"][0]) and bits_equal(fin["ref_x"][1], fin["ours_x"][1])
     assert torch.equal(fin["ref"][0], fin["ours"][0]) and torch.equal(fin["ref"][6], fin["ours"][6])
     for a, b in zip(fin["ref"][1:6] + fin["ref"][7:], fin["ours"][1:6] + fin["ours"][7:]):
