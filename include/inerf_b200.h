@@ -48,6 +48,15 @@ const char *inerf_error_string(int code);
 /* raymarching/src/raymarching.h:7  near_far_from_aabb (kernel raymarching.cu:91-145) */
 int inerf_near_far_from_aabb(const float *rays_o, const float *rays_d, const float *aabb, uint32_t N,
                              float min_near, float *nears, float *fars, void *stream);
+/*
+ * nerf/utils.py:56-140 get_rays (Python / ~10 torch kernels in the reference; no FFI function there):
+ * poses [B,4,4] row-major cam2world, intrinsics (fx, fy, cx, cy), image H x W.  `inds` = int64 [N] flat pixel indices
+ * (row*W + col) shared by every pose, or NULL with N == H*W for the full frame.  Writes rays_o, rays_d [B,N,3].
+ * With aabb != NULL the slab test of near_far_from_aabb is fused: nears, fars [B*N] (bit-identical to a separate call).
+ */
+int inerf_get_rays(const float *poses, uint32_t B, float fx, float fy, float cx, float cy, uint32_t H, uint32_t W,
+                   const long long *inds, uint32_t N, float *rays_o, float *rays_d, const float *aabb, float min_near,
+                   float *nears, float *fars, void *stream);
 /* raymarching.h:8  sph_from_ray (raymarching.cu:162-198) */
 int inerf_sph_from_ray(const float *rays_o, const float *rays_d, float radius, uint32_t N, float *coords,
                        void *stream);

@@ -19,7 +19,8 @@ from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int32, c_size_
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libinerf_b200.so")
+# INERF_B200_LIB: development override (A/B builds of the same library, csrc/Makefile VARIANT=); never a fallback
+LIB_PATH = os.environ.get("INERF_B200_LIB") or os.path.join(_HERE, "libinerf_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
 
 _lib = None
@@ -79,6 +80,7 @@ _PROTOS = {
     "inerf_composite_rays": [_U, _U, _F, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "inerf_composite_rays_with_masks": [_U, _U, _U, _F, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "inerf_compact_alive": [_P, _U, _P, _P, _P],
+    "inerf_get_rays": [_P, _U, _F, _F, _F, _F, _U, _U, _P, _U, _P, _P, _P, _F, _P, _P, _P],
     "inerf_grid_encode_forward": [_P, _P, _P, _P, _U, _U, _U, _U, _F, _U, _P, _U, _I, _U, _I, _I, _P],
     "inerf_grid_encode_backward": [_P, _P, _P, _P, _P, _U, _U, _U, _U, _F, _U, _P, _P, _U, _I, _U, _I, _I, _P],
     "inerf_sh_encode_forward": [_P, _P, _U, _U, _U, _P, _P],

@@ -26,7 +26,14 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
+// Rows of the [M, K] logit stream in flight per warp: the recurrence (phase A) never waits on them, so phase B issues
+// kRowsInFlight independent 128-byte row loads back to back (64 warps/SM x 8 x 128 B = 64 KB in flight per SM).
+constexpr int kRowsInFlight = 8;
+
 // ---- training forward (K == 0: plain, raymarching.cu:500-577; K > 0: :705-799) ----
+// Per 32-sample chunk: phase A = the T recurrence / colour / depth sums in the reference's order (every lane redundantly,
+// shuffles only), leaving w_j in lane j and the number m of samples that contribute (early stop included);
+// phase B = macc[k] += w_j * logits[j, k] for j < m in the same order, as a pure stream.
 template <int KPL>
 __global__ void __launch_bounds__(256) k_composite_train_fwd(
     const float* __restrict__ sigmas, const float* __restrict__ rgbs, const float* __restrict__ masks,
@@ -56,25 +63,41 @@ __global__ void __launch_bounds__(256) k_composite_train_fwd(
                 cr = __ldg(rgbs + (size_t)s * 3); cg = __ldg(rgbs + (size_t)s * 3 + 1); cb = __ldg(rgbs + (size_t)s * 3 + 2);
             }
             const uint32_t cnt = min(32u, num_steps - base);
+            uint32_t m = cnt;
+            float my_w = 0.f;
             for (uint32_t j = 0; j < cnt; j++) {
                 const float a = __shfl_sync(kFull, alpha, j);
                 const float weight = a * T;
                 r = fmaf(weight, __shfl_sync(kFull, cr, j), r);
                 g = fmaf(weight, __shfl_sync(kFull, cg, j), g);
                 b = fmaf(weight, __shfl_sync(kFull, cb, j), b);
-                if (KPL > 0) {
-                    const float* mrow = masks + (size_t)(offset + base + j) * K;
-#pragma unroll
-                    for (int i = 0; i < KPL; i++) {
-                        const uint32_t k = lane + 32u * i;
-                        if (k < K) macc[i] = fmaf(weight, __ldg(mrow + k), macc[i]);
-                    }
-                }
                 t += __shfl_sync(kFull, d1, j);
                 d = fmaf(weight, t, d);
                 ws += weight;
                 T *= 1.0f - a;
-                if (T < T_thresh) { done = true; break; }
+                if (lane == j) my_w = weight;
+                if (T < T_thresh) { done = true; m = j + 1; break; }
+            }
+            if (KPL > 0) {
+                const float* mbase = masks + (size_t)(offset + base) * K;
+                for (uint32_t j0 = 0; j0 < m; j0 += kRowsInFlight) {
+                    float v[kRowsInFlight][KPL > 0 ? KPL : 1];
+#pragma unroll
+                    for (int u = 0; u < kRowsInFlight; u++)
+#pragma unroll
+                        for (int i = 0; i < KPL; i++) {
+                            const uint32_t k = lane + 32u * i;
+                            v[u][i] = (j0 + u < m && k < K) ? __ldg(mbase + (size_t)(j0 + u) * K + k) : 0.f;
+                        }
+#pragma unroll
+                    for (int u = 0; u < kRowsInFlight; u++) {
+                        if (j0 + u < m) {   // warp-uniform
+                            const float weight = __shfl_sync(kFull, my_w, j0 + u);
+#pragma unroll
+                            for (int i = 0; i < KPL; i++) macc[i] = fmaf(weight, v[u][i], macc[i]);
+                        }
+                    }
+                }
             }
         }
     }
@@ -93,6 +116,8 @@ __global__ void __launch_bounds__(256) k_composite_train_fwd(
 }
 
 // ---- training backward (K == 0: raymarching.cu:601-682; K > 0: :828-940) ----
+// Same two phases.  Phase A leaves in lane j: w_j, T_j (after sample j) and the colour / weights_sum part of grad_sigma_j.
+// Phase B streams the logit rows: macc, grad_masks = g_m * w_j, and the K-term sum of grad_sigma_j (warp reduce per row).
 template <int KPL>
 __global__ void __launch_bounds__(256) k_composite_train_bwd(
     const float* __restrict__ grad_weights_sum, const float* __restrict__ grad_image, const float* __restrict__ grad_mask_out,
@@ -129,9 +154,9 @@ __global__ void __launch_bounds__(256) k_composite_train_bwd(
             alpha = 1.0f - __expf(-__ldg(sigmas + s) * d0);
             cr = __ldg(rgbs + (size_t)s * 3); cg = __ldg(rgbs + (size_t)s * 3 + 1); cb = __ldg(rgbs + (size_t)s * 3 + 2);
         }
-        float my_w = 0.f, my_gs = 0.f;  // lane j keeps the results of sample base + j
-        bool my_written = false;
+        float my_w = 0.f, my_T = 0.f, my_gs = 0.f;  // lane j keeps the results of sample base + j
         const uint32_t cnt = min(32u, num_steps - base);
+        uint32_t m = cnt;
         bool done = false;
         for (uint32_t j = 0; j < cnt; j++) {
             const float a = __shfl_sync(kFull, alpha, j);
@@ -141,26 +166,44 @@ __global__ void __launch_bounds__(256) k_composite_train_bwd(
             g = fmaf(weight, gj, g);
             b = fmaf(weight, bj, b);
             T *= 1.0f - a;
-            float part = 0.f;
-            if (KPL > 0) {
-                const size_t row = (size_t)(offset + base + j) * K;
+            const float gs = gr * (T * rj - (r_final - r)) + gg * (T * gj - (g_final - g)) + gb * (T * bj - (b_final - b)) + ws_term;
+            if (lane == j) { my_w = weight; my_T = T; my_gs = gs; }
+            if (T < T_thresh) { done = true; m = j + 1; break; }
+        }
+        if (KPL > 0) {
+            const size_t row0 = (size_t)(offset + base) * K;
+            float my_part = 0.f;
+            for (uint32_t j0 = 0; j0 < m; j0 += kRowsInFlight) {
+                float v[kRowsInFlight][KPL > 0 ? KPL : 1];
 #pragma unroll
-                for (int i = 0; i < KPL; i++) {
-                    const uint32_t k = lane + 32u * i;
-                    if (k < K) {
-                        const float m = __ldg(masks + row + k);
-                        macc[i] = fmaf(weight, m, macc[i]);
-                        grad_masks[row + k] = gm[i] * weight;
-                        part += gm[i] * (T * m - (mfin[i] - macc[i]));
+                for (int u = 0; u < kRowsInFlight; u++)
+#pragma unroll
+                    for (int i = 0; i < KPL; i++) {
+                        const uint32_t k = lane + 32u * i;
+                        v[u][i] = (j0 + u < m && k < K) ? __ldg(masks + row0 + (size_t)(j0 + u) * K + k) : 0.f;
+                    }
+#pragma unroll
+                for (int u = 0; u < kRowsInFlight; u++) {
+                    if (j0 + u < m) {   // warp-uniform
+                        const float weight = __shfl_sync(kFull, my_w, j0 + u), Tj = __shfl_sync(kFull, my_T, j0 + u);
+                        float part = 0.f;
+#pragma unroll
+                        for (int i = 0; i < KPL; i++) {
+                            const uint32_t k = lane + 32u * i;
+                            if (k < K) {
+                                macc[i] = fmaf(weight, v[u][i], macc[i]);
+                                grad_masks[row0 + (size_t)(j0 + u) * K + k] = gm[i] * weight;
+                                part += gm[i] * (Tj * v[u][i] - (mfin[i] - macc[i]));
+                            }
+                        }
+                        part = warp_sum(part);
+                        if (lane == j0 + u) my_part = part;
                     }
                 }
-                part = warp_sum(part);
             }
-            const float gs = gr * (T * rj - (r_final - r)) + gg * (T * gj - (g_final - g)) + gb * (T * bj - (b_final - b)) + ws_term + part;
-            if (lane == j) { my_w = weight; my_gs = gs; my_written = true; }
-            if (T < T_thresh) { done = true; break; }
+            my_gs += my_part;
         }
-        if (my_written) {
+        if (lane < m) {
             grad_sigmas[s] = d0 * my_gs;
             grad_rgbs[(size_t)s * 3] = gr * my_w; grad_rgbs[(size_t)s * 3 + 1] = gg * my_w; grad_rgbs[(size_t)s * 3 + 2] = gb * my_w;
         }

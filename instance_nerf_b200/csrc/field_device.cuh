@@ -153,8 +153,16 @@ __device__ __forceinline__ void encode_level(const float x01[3], const LevelGeom
     level_corners(x01, g, idx, w);
     const uint2* base = table + g.offset;
     uint2 v[8];
+#ifdef INERF_DBG_NO_GATHER_LOADS   // dev experiment (scripts/gpu_ab.sh): index math kept alive, no table traffic
+#pragma unroll
+    for (uint32_t c = 0; c < 8; c++) v[c] = make_uint2(idx[c] * 0x9E3779B1u, idx[c]);
+    (void)base;
+#else
+    // One 8-byte gather per corner.  (Tried and rejected on B200: fetching the x-neighbour with one aligned 16-byte gather when
+    // it is entry a^1 -- 23 % fewer L1 sectors but LDG.128 scatters cost as many data-pipe wavefronts, +6 % time)
 #pragma unroll
     for (uint32_t c = 0; c < 8; c++) v[c] = __ldg(base + idx[c]);
+#endif
     __half2 as = __float2half2_rn(0.f), am = as;
 #pragma unroll
     for (uint32_t c = 0; c < 8; c++) {
@@ -333,6 +341,13 @@ __device__ __forceinline__ float mlp_chain(uint8_t* smem, const ChainBufs& b, ui
     const uint32_t sbase = umma::smem_u32(smem);
     const WeightLayout wl = weight_layout(K);
     const bool issuer = tid == 0;
+#ifdef INERF_DBG_NO_MLP   // dev experiment: the chain only releases the operand stage and composites a constant density
+    if (issuer && release_bar) { umma::fence_after_sync(); umma::commit(release_bar); }
+    __syncwarp();
+    on_sigma(0.05f);
+    sync();
+    return 0.05f;
+#endif
     // sigma layer 0
     if (issuer) {
         umma::fence_after_sync();

@@ -17,29 +17,75 @@ using namespace march;
 
 // ---- utils -------------------------------------------------------------------
 
-__global__ void k_near_far_from_aabb(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
-                                     const float* __restrict__ aabb, uint32_t N, float min_near,
-                                     float* __restrict__ nears, float* __restrict__ fars) {
-    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= N) return;
-    const float ox = rays_o[n * 3], oy = rays_o[n * 3 + 1], oz = rays_o[n * 3 + 2];
-    const float rdx = __fdiv_rn(1.0f, rays_d[n * 3]), rdy = __fdiv_rn(1.0f, rays_d[n * 3 + 1]), rdz = __fdiv_rn(1.0f, rays_d[n * 3 + 2]);
+// slab test of raymarching.cu:91-145; a miss at the y or z stage returns near = far = FLT_MAX
+__device__ __forceinline__ void near_far_one(float ox, float oy, float oz, float dx, float dy, float dz, const float* __restrict__ aabb,
+                                             float min_near, float& near_out, float& far_out) {
+    const float rdx = __fdiv_rn(1.0f, dx), rdy = __fdiv_rn(1.0f, dy), rdz = __fdiv_rn(1.0f, dz);
     const float kMax = 3.402823466e+38f;
     float near = __fmul_rn(__fsub_rn(aabb[0], ox), rdx), far = __fmul_rn(__fsub_rn(aabb[3], ox), rdx), tmp;
     if (near > far) { tmp = near; near = far; far = tmp; }
     float near_y = __fmul_rn(__fsub_rn(aabb[1], oy), rdy), far_y = __fmul_rn(__fsub_rn(aabb[4], oy), rdy);
     if (near_y > far_y) { tmp = near_y; near_y = far_y; far_y = tmp; }
-    if (near > far_y || near_y > far) { nears[n] = kMax; fars[n] = kMax; return; }
+    if (near > far_y || near_y > far) { near_out = kMax; far_out = kMax; return; }
     if (near_y > near) near = near_y;
     if (far_y < far) far = far_y;
     float near_z = __fmul_rn(__fsub_rn(aabb[2], oz), rdz), far_z = __fmul_rn(__fsub_rn(aabb[5], oz), rdz);
     if (near_z > far_z) { tmp = near_z; near_z = far_z; far_z = tmp; }
-    if (near > far_z || near_z > far) { nears[n] = kMax; fars[n] = kMax; return; }
+    if (near > far_z || near_z > far) { near_out = kMax; far_out = kMax; return; }
     if (near_z > near) near = near_z;
     if (far_z < far) far = far_z;
     if (near < min_near) near = min_near;
+    near_out = near;
+    far_out = far;
+}
+
+__global__ void k_near_far_from_aabb(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                                     const float* __restrict__ aabb, uint32_t N, float min_near,
+                                     float* __restrict__ nears, float* __restrict__ fars) {
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    float near, far;
+    near_far_one(rays_o[n * 3], rays_o[n * 3 + 1], rays_o[n * 3 + 2], rays_d[n * 3], rays_d[n * 3 + 1], rays_d[n * 3 + 2], aabb, min_near,
+                 near, far);
     nears[n] = near;
     fars[n] = far;
+}
+
+// nerf/utils.py:56-140 get_rays: pixel centre (+0.5), camera direction ((i-cx)/fx, (j-cy)/fy, 1) normalised, rotated by the
+// pose; rays_o = camera centre.  One thread per (pose, ray); `inds` (int64 [N], shared by every pose: utils.py:104,108)
+// selects pixels, NULL = all H*W pixels in row-major order.  The reference builds the full H*W meshgrid and ~10 torch
+// kernels even for 4096 rays.  With `aabb` the slab test of near_far_from_aabb runs in the same thread on the same
+// fp32 values (bit-identical to calling it afterwards).  Divisions / sqrt are IEEE round-to-nearest, the 3x3 rotation is
+// a plain multiply-add chain in k order (torch's matmul may order / contract differently: parity to ~1 ulp, tests/).
+__global__ void k_get_rays(const float* __restrict__ poses, float fx, float fy, float cx, float cy, uint32_t W, uint32_t N, uint32_t B,
+                           const long long* __restrict__ inds, float* __restrict__ rays_o, float* __restrict__ rays_d,
+                           const float* __restrict__ aabb, float min_near, float* __restrict__ nears, float* __restrict__ fars) {
+    const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= (uint64_t)N * B) return;
+    const uint32_t b = (uint32_t)(g / N), n = (uint32_t)(g - (uint64_t)b * N);
+    const uint32_t pix = inds ? (uint32_t)inds[n] : n;
+    const uint32_t row = pix / W, col = pix - row * W;
+    const float* P = poses + (size_t)b * 16;
+    const float xs = __fdiv_rn(__fsub_rn(__fadd_rn((float)col, 0.5f), cx), fx);
+    const float ys = __fdiv_rn(__fsub_rn(__fadd_rn((float)row, 0.5f), cy), fy);
+    const float nrm = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(xs, xs), __fmul_rn(ys, ys)), 1.0f));
+    const float vx = __fdiv_rn(xs, nrm), vy = __fdiv_rn(ys, nrm), vz = __fdiv_rn(1.0f, nrm);
+    float dxyz[3], oxyz[3];
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+        dxyz[r] = __fadd_rn(__fadd_rn(__fmul_rn(vx, P[r * 4]), __fmul_rn(vy, P[r * 4 + 1])), __fmul_rn(vz, P[r * 4 + 2]));
+        oxyz[r] = P[r * 4 + 3];
+    }
+    float* po = rays_o + g * 3;
+    float* pd = rays_d + g * 3;
+    po[0] = oxyz[0]; po[1] = oxyz[1]; po[2] = oxyz[2];
+    pd[0] = dxyz[0]; pd[1] = dxyz[1]; pd[2] = dxyz[2];
+    if (aabb) {
+        float near, far;
+        near_far_one(oxyz[0], oxyz[1], oxyz[2], dxyz[0], dxyz[1], dxyz[2], aabb, min_near, near, far);
+        nears[g] = near;
+        fars[g] = far;
+    }
 }
 
 // raymarching.cu:162-198
@@ -239,6 +285,20 @@ extern "C" int inerf_near_far_from_aabb(const float* rays_o, const float* rays_d
     if (N == 0) return INERF_OK;
     INERF_REQUIRE(rays_o); INERF_REQUIRE(rays_d); INERF_REQUIRE(aabb); INERF_REQUIRE(nears); INERF_REQUIRE(fars);
     k_near_far_from_aabb<<<div_up(N, 256), 256, 0, (cudaStream_t)stream>>>(rays_o, rays_d, aabb, N, min_near, nears, fars);
+    INERF_LAUNCH_CHECK();
+    return INERF_OK;
+}
+
+extern "C" int inerf_get_rays(const float* poses, uint32_t B, float fx, float fy, float cx, float cy, uint32_t H, uint32_t W,
+                              const long long* inds, uint32_t N, float* rays_o, float* rays_d, const float* aabb, float min_near,
+                              float* nears, float* fars, void* stream) {
+    if (H == 0 || W == 0 || (uint64_t)H * W > 0x7fffffffull || fx == 0.f || fy == 0.f) return INERF_ERR_SIZE;
+    if (inds == nullptr && N != H * W) return INERF_ERR_SIZE;
+    if ((uint64_t)N * B == 0) return INERF_OK;
+    INERF_REQUIRE(poses); INERF_REQUIRE(rays_o); INERF_REQUIRE(rays_d);
+    if (aabb) { INERF_REQUIRE(nears); INERF_REQUIRE(fars); }
+    k_get_rays<<<div_up((uint64_t)N * B, 256), 256, 0, (cudaStream_t)stream>>>(poses, fx, fy, cx, cy, W, N, B, inds, rays_o, rays_d, aabb,
+                                                                              min_near, nears, fars);
     INERF_LAUNCH_CHECK();
     return INERF_OK;
 }

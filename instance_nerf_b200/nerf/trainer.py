@@ -115,3 +115,55 @@ class MaskTrainStep:
         self.scaler.step(self.optimizer)
         self.scaler.update()
         return loss.detach()
+
+
+class RGBTrainStep:
+    """Stage-1 RGB-sigma training step (mirrors Trainer.train_step, nerf/utils.py:536-632, and the step loop :919-939):
+    render a ray batch, MSE against the ground-truth colours (alpha-blended onto a random per-pixel background when the
+    images carry alpha), AMP backward through compositing, both MLPs, SH and the sigma hash table, Adam.  The LPIPS patch
+    term, CLIP loss and the error-map resampling of the reference's Trainer are outside the hot path."""
+
+    def __init__(self, model, lr=1e-2, fp16=True, patch_size=1, dt_gamma=1 / 128, max_steps=1024, T_thresh=1e-4, data_parallel=False,
+                 fused_adam=True):
+        self.model = model
+        self.opt = SimpleNamespace(patch_size=patch_size)
+        self.render_kw = dict(dt_gamma=dt_gamma, max_steps=max_steps, T_thresh=T_thresh)
+        self.fp16 = fp16
+        self.criterion = nn.MSELoss(reduction="none")                                   # main_nerf.py:104
+        params = [{"params": list(g["params"]), "lr": g["lr"]} for g in model.get_params(lr)]
+        params = [g for g in params if g["params"]]
+        dev = next(model.parameters()).device
+        kw = dict(fused=True) if (fused_adam and dev.type == "cuda") else {}
+        self.optimizer = torch.optim.Adam(params, betas=(0.9, 0.99), eps=1e-15, **kw)   # main_nerf.py:120
+        self.scaler = torch.amp.GradScaler("cuda", enabled=fp16 and dev.type == "cuda")
+        self.bucket = GradBucket([p for g in params for p in g["params"]]) if data_parallel else None
+        self.global_step = 0
+
+    def train_step(self, data):
+        """-> (pred_rgb [B,N,3], gt_rgb [B,N,3], loss)"""
+        rays_o, rays_d, images = data["rays_o"], data["rays_d"], data["images"]
+        C = images.shape[-1]
+        if C == 3 or self.model.bg_radius > 0:
+            bg_color = 1
+        else:
+            bg_color = data["bg_color"] if "bg_color" in data else torch.rand_like(images[..., :3])
+        gt_rgb = images[..., :3] * images[..., 3:] + bg_color * (1 - images[..., 3:]) if C == 4 else images
+        bg = bg_color if isinstance(bg_color, int) else bg_color.reshape(-1, 3)
+        outputs = self.model.render(rays_o, rays_d, staged=False, bg_color=bg, perturb=True, force_all_rays=self.opt.patch_size != 1,
+                                    noises=data.get("noises"), **self.render_kw)
+        pred_rgb = outputs["image"]
+        loss = self.criterion(pred_rgb, gt_rgb).mean(-1).mean()
+        return pred_rgb, gt_rgb, loss
+
+    def step(self, data):
+        self.model.train()
+        self.global_step += 1
+        self.optimizer.zero_grad(set_to_none=False)
+        with torch.autocast("cuda", dtype=torch.float16, enabled=self.fp16):
+            _, _, loss = self.train_step(data)
+        self.scaler.scale(loss).backward()
+        if self.bucket is not None:
+            self.bucket.sync()
+        self.scaler.step(self.optimizer)
+        self.scaler.update()
+        return loss.detach()
