@@ -196,7 +196,7 @@ def run_gpu_arm(args):
         out = fused(*a, **k)
         e1.record()
         kern_events.append((e0, e1))
-        samples_seen.append(model._work_counter[2:4].clone())
+        samples_seen.append(model._work_counter.clone())
         launches["n"] += 2          # inerf_near_far_from_aabb + inerf_render_fused
         return out
 
@@ -263,7 +263,8 @@ def run_gpu_arm(args):
     wall_s = time.perf_counter() - t_wall0
     total_ms = sum(a.elapsed_time(b) for a, b in ev)
     kern_ms = [a.elapsed_time(b) for a, b in kern_events]
-    n_samples = [int(s.view(torch.int64).item()) for s in samples_seen]
+    n_samples = [int(s[2:4].view(torch.int64).item()) for s in samples_seen]
+    n_tiles = [int(s[1].item()) for s in samples_seen]
     gpu_launches = launches["n"]
 
     # ---- end-to-end region: pinned host rays -> render -> pinned host results ----------------------------------------
@@ -309,7 +310,8 @@ def run_gpu_arm(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16 operands / f32 accumulate",
             "data": "synthetic",
-            "config": {"workload": WORKLOAD, "rays_per_step_per_gpu": N, "samples_per_ray": avg_samples / N, "l2": "flushed between timed steps (512 MB write)",
+            "config": {"workload": WORKLOAD, "rays_per_step_per_gpu": N, "samples_per_ray": avg_samples / N,
+                       "tile_fill": (sum(n_samples) / max(1, 128 * sum(n_tiles))), "l2": "flushed between timed steps (512 MB write)",
                        "parallelism": f"frames sharded over {world} rank(s), async all_gather of tiles overlapped with the next frame" if world > 1 else "single GPU",
                        "wall_s_timed_region_incl_flush": wall_s},
             "e2e": {"value": world * N / (e2e_ms / args.steps * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},

@@ -254,8 +254,9 @@ int inerf_field_backward_mask(const inerf_field_desc *desc, const void *weights_
  * no sample stream in HBM.  Outputs are the un-normalised accumulators the
  * reference loop produces before mask_renderer.py:376-377.
  * `work_counter` is caller-owned scratch, int32[4], 8-byte aligned; the call
- * zeroes it, uses [0] as the ray cursor and leaves the number of samples it
- * composited in [2..3] (one uint64), which bench.py reads for the roofline.
+ * zeroes it, uses [0] as the ray cursor and leaves the number of 128-row tiles
+ * it evaluated in [1] and the number of samples it composited in [2..3] (one
+ * uint64), which bench.py reads for the roofline and the tile fill rate.
  */
 int inerf_render_fused(const inerf_field_desc *desc, const float *rays_o, const float *rays_d, const float *nears,
                        const float *fars, const uint8_t *bitfield, uint32_t N, uint32_t C, uint32_t H,

@@ -14,6 +14,10 @@
 #include "common.cuh"
 #include "umma.cuh"
 
+#ifndef INERF_FMUL2
+#define INERF_FMUL2 0
+#endif
+
 namespace field {
 
 constexpr int kTile = 128;        // samples per tile = TMEM lanes = UMMA M
@@ -168,8 +172,15 @@ __device__ __forceinline__ void encode_level(const float x01[3], const LevelGeom
     for (uint32_t c = 0; c < 8; c++) {
         const float2 fs = __half22float2(bits_h2(v[c].x));
         const float2 fm = __half22float2(bits_h2(v[c].y));
+#if INERF_FMUL2   // packed fp32 multiply (FMUL2, sm_100): same round-to-nearest products, half the multiply issue slots
+        const float2 ww = make_float2(w[c], w[c]);
+        const float2 ps = __fmul2_rn(ww, fs), pm = __fmul2_rn(ww, fm);
+        as = __hadd2(as, __floats2half2_rn(ps.x, ps.y));
+        am = __hadd2(am, __floats2half2_rn(pm.x, pm.y));
+#else
         as = __hadd2(as, __floats2half2_rn(__fmul_rn(w[c], fs.x), __fmul_rn(w[c], fs.y)));
         am = __hadd2(am, __floats2half2_rn(__fmul_rn(w[c], fm.x), __fmul_rn(w[c], fm.y)));
+#endif
     }
     out_s = h2_bits(as);
     out_m = h2_bits(am);

@@ -22,6 +22,7 @@
 // Per-ray sample positions equal the reference's for a continuous march from `near`; the reference re-derives t
 // from the composited depth deltas between its n_step-sized chunks, which can differ in the last ulp after long
 // empty-space skips (maps agree to the 1e-3 tolerance of the north star).
+#include <cstdio>
 #include "field_device.cuh"
 #include "march_device.cuh"
 
@@ -33,9 +34,18 @@ constexpr uint32_t kChainT = 256, kGatherT = 512, kMarchT = 128;
 // register budget per role (setmaxnreg): 896 threads start at 72; 256*96 + 512*64 + 128*56 = 896*72
 constexpr uint32_t kRegsChain = 96, kRegsGather = 64, kRegsMarch = 56;
 constexpr uint32_t kThreadsR = kChainT + kGatherT + kMarchT;
-constexpr uint32_t RING = 8;  // samples queued per ray slot
+#ifndef INERF_RING
+#define INERF_RING 8
+#endif
+constexpr uint32_t RING = INERF_RING;  // samples queued per ray slot
 constexpr uint32_t DT = 4;    // tile descriptors in flight (gather may run DA tiles ahead of the chain)
 constexpr uint32_t DA = 2;    // gathered operand stages
+#ifndef INERF_SKIP_STEPS
+#define INERF_SKIP_STEPS 6    // empty-space steps a marcher lane advances per warp iteration
+#endif
+#ifndef INERF_RAY_PATCH
+#define INERF_RAY_PATCH 1     // 1: marcher warps take 32 consecutive rays at a time (coherent gathers); 0: one ray per free lane
+#endif
 
 struct RenderParams {
     const float* rays_o;
@@ -71,6 +81,10 @@ struct Ctrl {
     float w_s[kTile];
     int32_t fin_s[kTile];
     LevelGeom lg[16];
+#ifdef INERF_DBG_BUBBLES
+    int32_t mstate[kTile];        // marcher state per slot (0 idle, 1 eval, 2 skip, 3 done, 4 eval blocked on ring room)
+    unsigned long long bub[8];    // bubble rows by marcher state at tile assembly, [5] = polls that found nothing, [6] = tiles
+#endif
 };
 
 struct RSmem {
@@ -107,7 +121,7 @@ __device__ __forceinline__ bool gather_any(bool pred) {
 __device__ __forceinline__ void march_role(const inerf_field_desc& desc, const RenderParams& p, Ctrl* ctl, Rings* rg, const uint32_t* coarse,
                                            uint32_t r) {
     enum : int { NEED_RAY = 0, EVAL = 1, SKIP = 2, DONE = 3 };
-    constexpr int kSkipSteps = 6;
+    constexpr int kSkipSteps = INERF_SKIP_STEPS;
     march::Walk wk;
     wk.coarse = coarse;
     int state = NEED_RAY;
@@ -118,9 +132,28 @@ __device__ __forceinline__ void march_role(const inerf_field_desc& desc, const R
         if (state != DONE && ray >= 0 && ld_vol(&ctl->kill[r]) == ray) { ray = -1; state = NEED_RAY; }
         const bool room = tail - ld_vol(&ctl->chead[r]) < RING;
         bool worked = false;
+#ifdef INERF_DBG_BUBBLES
+        st_vol(&ctl->mstate[r], (state == EVAL && !room) ? 4 : state);
+#endif
+#if INERF_RAY_PATCH
+        // Rays are taken 32 at a time: a warp's lanes always march 32 CONSECUTIVE rays (neighbouring pixels), sample for
+        // sample in step, so the gather warp that consumes these 32 slots reads neighbouring cells -- one L1 sector serves
+        // several lanes at the coarse and middle levels (measured 87 -> ~30 sectors per sample).  A lane
+        // whose ray ends early idles until its 31 neighbours have finished marching (not compositing): ~5 % bubble rows.
+        const bool acquire = __all_sync(0xffffffffu, state == NEED_RAY || state == DONE) && state == NEED_RAY;
+        if (state == NEED_RAY && acquire) {
+            uint32_t base = 0;
+            const uint32_t takers = __activemask();
+            const uint32_t leader = __ffs(takers) - 1u;
+            if ((r & 31u) == leader) base = (uint32_t)atomicAdd(p.work_counter, 32);
+            base = __shfl_sync(takers, base, leader);
+            const uint32_t idx = base + (r & 31u);
+            if (idx >= p.N) {
+#else
         if (state == NEED_RAY) {
             const uint32_t idx = (uint32_t)atomicAdd(p.work_counter, 1);
             if (idx >= p.N) {
+#endif
                 state = DONE;
                 atomicAdd(&ctl->n_done, 1);
             } else {
@@ -195,7 +228,17 @@ __device__ __forceinline__ void gather_role(const inerf_field_desc& desc, const 
                 ctl->tsel[st][row] = sel;
             }
             if (!gather_any(not_finished)) { stop = true; break; }   // all marchers done and every ring drained
-            if (gather_any(sel >= 0)) { if (sel >= 0) ghead++; break; }
+            if (gather_any(sel >= 0)) {
+#ifdef INERF_DBG_BUBBLES
+                if (quarter == 0 && sel < 0) atomicAdd(&ctl->bub[ld_vol(&ctl->mstate[row])], 1ull);
+                if (gt == 0) atomicAdd(&ctl->bub[6], 1ull);
+#endif
+                if (sel >= 0) ghead++;
+                break;
+            }
+#ifdef INERF_DBG_BUBBLES
+            if (gt == 0) atomicAdd(&ctl->bub[5], 1ull);
+#endif
             __nanosleep(128);
         }
         if (tile >= DA) umma::mbar_wait(&ctl->a_empty[sa], ((tile / DA) - 1u) & 1u);
@@ -248,9 +291,11 @@ __device__ __forceinline__ void chain_role(const inerf_field_desc& desc, const R
 
     auto chain_sync = [] { umma::named_sync<1, kChainT>(); };
 
+    uint32_t tile_count = 0;
     for (uint32_t tile = 0;; tile++) {
         const uint32_t st = tile % DT, sa = tile % DA;
         umma::mbar_wait(&ctl->a_full[sa], (tile / DA) & 1u);
+        tile_count = tile;
         if (ld_vol(&ctl->a_flag[sa])) break;
         const uint32_t a_es = RSmem::A + sa * kStageBytes;
         const ChainBufs bufs{a_es, a_es + kBytesEs, a_es + kBytesEs + kBytesCi, RSmem::H1, RSmem::H2, RSmem::W};
@@ -345,6 +390,8 @@ __device__ __forceinline__ void chain_role(const inerf_field_desc& desc, const R
         umma::fence_before_sync();
         chain_sync();   // TMEM, the chain's operand tiles and w_s / fin_s are reused by the next tile
     }
+    // tiles evaluated by this CTA -> work_counter[1] (rows = 128 x tiles; rows / samples = 1 + bubble share)
+    if (ct == 0) atomicAdd(p.work_counter + 1, (int32_t)tile_count);
     // samples composited by this launch -> work_counter[2..3] (u64), one atomic per owner warp
     if (owner) {
         uint32_t tot = my_samples;
@@ -373,6 +420,10 @@ __global__ void __launch_bounds__(kThreadsR, 1) k_render_fused(inerf_field_desc 
         umma::mbar_fence_init();
     }
     if (tid < kTile) { ctl->kill[tid] = -1; ctl->tail[tid] = 0; ctl->chead[tid] = 0; }
+#ifdef INERF_DBG_BUBBLES
+    if (tid < kTile) ctl->mstate[tid] = 0;
+    if (tid < 8) ctl->bub[tid] = 0ull;
+#endif
     // coarse occupancy: bit b = (8-byte word b of the bitfield != 0), i.e. any of the 64 cells of that 4x4x4 block occupied
     uint32_t* coarse = p.coarse_bytes ? reinterpret_cast<uint32_t*>(smem + RSmem::coarse(K)) : nullptr;
     if (coarse) {
@@ -403,6 +454,11 @@ __global__ void __launch_bounds__(kThreadsR, 1) k_render_fused(inerf_field_desc 
 
     umma::fence_before_sync();
     __syncthreads();
+#ifdef INERF_DBG_BUBBLES
+    if (tid == 0 && (blockIdx.x == 0 || blockIdx.x == 77))
+        printf("[bubbles cta %u] tiles %llu empty-polls %llu | bubble rows: idle %llu eval %llu skip %llu done %llu eval-noroom %llu\n", blockIdx.x,
+               ctl->bub[6], ctl->bub[5], ctl->bub[0], ctl->bub[1], ctl->bub[2], ctl->bub[3], ctl->bub[4]);
+#endif
     if (tid < 32) umma::tmem_dealloc<kTmemCols>(tmem_base);
 }
 

@@ -9,6 +9,6 @@ for v in "$@"; do
 import json
 j=json.load(open("gpurun_out/ab_${v}.json"))
 spr=j["config"]["samples_per_ray"]; k=j["roofline"]["kernel_ms"]
-print("   ms/frame %.3f  kernel_ms %.3f  samples/ray %.1f  ns/ksample %.2f  Mrays/s %.2f  frac %.3f  train_ms %.3f (median %.3f)" % (j["ms_per_step"], k, spr, k*1e6/(spr*307200)*1e3/1e3, j["value"], j["roofline"]["frac"], j["train_step"]["ms"], j["train_step"]["ms_median"]))
+print("   fill %.3f ms/frame %.3f  kernel_ms %.3f  samples/ray %.1f  ns/ksample %.2f  Mrays/s %.2f  frac %.3f  train_ms %.3f (median %.3f)" % (j["config"].get("tile_fill",0), j["ms_per_step"], k, spr, k*1e6/(spr*307200)*1e3/1e3, j["value"], j["roofline"]["frac"], j["train_step"]["ms"], j["train_step"]["ms_median"]))
 PY
 done
