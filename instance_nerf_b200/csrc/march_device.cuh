@@ -39,6 +39,8 @@ struct Walk {
     float ox, oy, oz, dx, dy, dz, rdx, rdy, rdz;
     float sx, sy, sz;  // 0.5 * sign(d)
     float bound, dt_gamma, dt_min, dt_max, rH, H3, Hf, Hm1, far;
+    float rbound;      // 1 / bound (for the cascade whose extent is clipped to `bound`)
+    uint32_t H3i;      // H^3; 0 = the cell index does not fit a float exactly (C * H^3 > 2^24): keep the float expression
     int C;
     const uint8_t* __restrict__ grid;
     // render-kernel accelerators (results identical to reading grid[] directly):
@@ -73,6 +75,8 @@ struct Walk {
         dt_min = __fdiv_rn(2.0f * kSqrt3, (float)max_steps);                                   // :345
         dt_max = __fdiv_rn(__fmul_rn(2.0f * kSqrt3, (float)(1 << (C_ - 1))), Hf);              // :346
         far = far_; C = (int)C_; grid = g;
+        rbound = __fdiv_rn(1.0f, bound_);
+        H3i = ((uint64_t)C_ * H * H * H <= (1ull << 24)) ? H * H * H : 0u;
         cblk = 0xffffffffu;
     }
     __device__ __forceinline__ float step_size(float t) const { return clampf(__fmul_rn(t, dt_gamma), dt_min, dt_max); }
@@ -130,6 +134,9 @@ struct Walk {
     // ONE cell evaluation of the DDA at parameter t (used by the render kernel's per-lane state machine).
     // Occupied: returns true with the sample (x, y, z, dt) and t advanced past it.  Empty: returns false with `tt` = the
     // parameter at which the ray leaves this cell; the caller then does `do { t += step_size(t); } while (t < tt);`.
+    // Same values as run() / the reference, with two latency cuts that are exact: 1 / mip_bound is a power of two (exponent
+    // arithmetic) unless the cascade is clipped to `bound` (precomputed quotient), and level * H^3 + morton is formed in
+    // integers whenever the reference's float expression (raymarching.cu:1033) is exact, i.e. C * H^3 <= 2^24.
     __device__ __forceinline__ bool eval_cell(float& t, float& x, float& y, float& z, float& dt, float& tt) {
         x = clampf(__fmaf_rn(t, dx, ox), -bound, bound);
         y = clampf(__fmaf_rn(t, dy, oy), -bound, bound);
@@ -138,13 +145,16 @@ struct Walk {
         const float mx = fmaxf(fabsf(x), fmaxf(fabsf(y), fabsf(z)));
         const float md = __fmul_rn(__fmul_rn(dt, Hf), 0.5f);
         const int level = max(clamped_exponent(mx, C), clamped_exponent(md, C));
-        const float mip_bound = fminf(__uint_as_float((uint32_t)(127 + level) << 23), bound);
-        const float mip_rbound = __fdiv_rn(1.0f, mip_bound);
+        const float pow2 = __uint_as_float((uint32_t)(127 + level) << 23);
+        const bool clipped = !(pow2 <= bound);   // fminf(2^level, bound) picks bound
+        const float mip_bound = clipped ? bound : pow2;
+        const float mip_rbound = clipped ? rbound : __uint_as_float((uint32_t)(127 - level) << 23);
         const float hH = __fmul_rn(0.5f, Hf);
         const int nx = (int)clampf(__fmul_rn(__fmaf_rn(x, mip_rbound, 1.0f), hH), 0.0f, Hm1);
         const int ny = (int)clampf(__fmul_rn(__fmaf_rn(y, mip_rbound, 1.0f), hH), 0.0f, Hm1);
         const int nz = (int)clampf(__fmul_rn(__fmaf_rn(z, mip_rbound, 1.0f), hH), 0.0f, Hm1);
-        const uint32_t index = (uint32_t)__fmaf_rn((float)level, H3, (float)morton3D_enc(nx, ny, nz));
+        const uint32_t index = H3i ? (uint32_t)level * H3i + morton3D_enc(nx, ny, nz)
+                                   : (uint32_t)__fmaf_rn((float)level, H3, (float)morton3D_enc(nx, ny, nz));
         if (occupied_cached(index)) {
             t = __fadd_rn(t, dt);
             return true;

@@ -43,6 +43,12 @@ constexpr uint32_t DA = 2;    // gathered operand stages
 #ifndef INERF_SKIP_STEPS
 #define INERF_SKIP_STEPS 6    // empty-space steps a marcher lane advances per warp iteration
 #endif
+#ifndef INERF_MARCH_CELLS
+#define INERF_MARCH_CELLS 8   // occupancy cells a marcher lane may evaluate per warp iteration (1 = one cell, skip steps as their own state)
+#endif
+#ifndef INERF_MARCH_MULTI
+#define INERF_MARCH_MULTI 1   // 1: a lane may queue several samples per warp iteration (as many as its ring has room for)
+#endif
 #ifndef INERF_RAY_PATCH
 #define INERF_RAY_PATCH 1     // 1: marcher warps take 32 consecutive rays at a time (coherent gathers); 0: one ray per free lane
 #endif
@@ -122,6 +128,8 @@ __device__ __forceinline__ void march_role(const inerf_field_desc& desc, const R
                                            uint32_t r) {
     enum : int { NEED_RAY = 0, EVAL = 1, SKIP = 2, DONE = 3 };
     constexpr int kSkipSteps = INERF_SKIP_STEPS;
+    constexpr int kCells = INERF_MARCH_CELLS;
+    constexpr bool kMulti = INERF_MARCH_MULTI != 0;
     march::Walk wk;
     wk.coarse = coarse;
     int state = NEED_RAY;
@@ -130,7 +138,8 @@ __device__ __forceinline__ void march_role(const inerf_field_desc& desc, const R
     float t = 0.f, last_t = 0.f, tt = 0.f;
     while (true) {
         if (state != DONE && ray >= 0 && ld_vol(&ctl->kill[r]) == ray) { ray = -1; state = NEED_RAY; }
-        const bool room = tail - ld_vol(&ctl->chead[r]) < RING;
+        const uint32_t chead_seen = ld_vol(&ctl->chead[r]);
+        const bool room = tail - chead_seen < RING;
         bool worked = false;
 #ifdef INERF_DBG_BUBBLES
         st_vol(&ctl->mstate[r], (state == EVAL && !room) ? 4 : state);
@@ -169,17 +178,24 @@ __device__ __forceinline__ void march_role(const inerf_field_desc& desc, const R
         } else if (state == EVAL) {
             if (room) {
                 worked = true;
-                const uint32_t e = tail % RING;
-                if (!(t < wk.far) || nsteps >= p.max_steps) {
-                    if (nsteps > 0) {   // END marker; a ray without samples is never seen by the compositor (outputs pre-zeroed)
-                        rg->dt[e][r] = 0.f;
-                        rg->ray[e][r] = ray;
-                        __threadfence_block();
-                        st_vol(&ctl->tail[r], ++tail);
+                // up to kCells occupancy cells per warp iteration (the loop's vote / ring bookkeeping is paid once), emitting a
+                // sample for every occupied one while the ring has room: every lane with a ray does the same amount of work per
+                // iteration whether it is crossing empty space or a solid
+                uint32_t free_entries = kMulti ? RING - (tail - chead_seen) : 1u;
+#pragma unroll 1
+                for (int c = 0; c < kCells && free_entries; c++) {
+                    const uint32_t e = tail % RING;
+                    if (!(t < wk.far) || nsteps >= p.max_steps) {
+                        if (nsteps > 0) {   // END marker; a ray without samples is never seen by the compositor (outputs pre-zeroed)
+                            rg->dt[e][r] = 0.f;
+                            rg->ray[e][r] = ray;
+                            __threadfence_block();
+                            st_vol(&ctl->tail[r], ++tail);
+                        }
+                        ray = -1;
+                        state = NEED_RAY;
+                        break;
                     }
-                    ray = -1;
-                    state = NEED_RAY;
-                } else {
                     float x, y, z, dt;
                     if (wk.eval_cell(t, x, y, z, dt, tt)) {
                         rg->x[e][r] = x; rg->y[e][r] = y; rg->z[e][r] = z;
@@ -190,9 +206,14 @@ __device__ __forceinline__ void march_role(const inerf_field_desc& desc, const R
                         nsteps++;
                         __threadfence_block();
                         st_vol(&ctl->tail[r], ++tail);
-                    } else {
-                        t = __fadd_rn(t, wk.step_size(t));   // do { t += dt } while (t < tt): the first step is unconditional
+                        free_entries--;
+                        continue;
+                    }
+                    t = __fadd_rn(t, wk.step_size(t));   // do { t += dt } while (t < tt): the first step is unconditional
+                    if (kCells == 1) {
                         state = (t < tt) ? SKIP : EVAL;
+                    } else {
+                        while (t < tt) t = __fadd_rn(t, wk.step_size(t));
                     }
                 }
             }
