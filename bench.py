@@ -201,7 +201,7 @@ def run_gpu_arm(args):
         e1.record()
         kern_events.append((e0, e1))
         samples_seen.append(model._work_counter.clone())
-        launches["n"] += 2          # inerf_near_far_from_aabb + inerf_render_fused
+        launches["n"] += 3          # inerf_near_far_from_aabb + k_first_hit + k_render_fused
         return out
 
     model._render_fused = timed_fused
@@ -393,7 +393,9 @@ def measure_train(dev, rank, world, steps, warmup, n_rays, model=None, scene=Non
             dist.barrier()
         torch.cuda.synchronize()
 
-    for i in range(warmup):
+    # every distinct batch goes through once before timing: the sample count differs per batch, and the first time a larger
+    # sample stream shows up the caching allocator grows (cudaMalloc + sync) -- steady-state training never sees that
+    for i in range(max(warmup, len(batches))):
         trainer.step(batches[i % 8])
     barrier()
     model.step_counter.zero_()

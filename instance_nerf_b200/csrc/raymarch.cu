@@ -219,6 +219,92 @@ __global__ void __launch_bounds__(128) k_march_write(const float* __restrict__ r
     w.run<true>(t0, num_steps, xyzs + (size_t)offset * 3, dirs + (size_t)offset * 3, deltas + (size_t)offset * 2);
 }
 
+// ---- training marching, one WARP per ray (small batches) -------------------------------------------------------------
+// With a few thousand rays the thread-per-ray kernels above run one serial chain of ~4*10^4 dependent instructions per
+// ray on a fraction of a warp slot per SM (c3: 4096 rays = 128 warps on 148 SMs, 120-150 us per pass).  Here the 32
+// lanes of a warp share one ray.  The reference's walk visits a SUBSEQUENCE of the fixed step sequence
+// t_{n+1} = t_n + clamp(t_n * dt_gamma, dt_min, dt_max) (both the sample step and the empty-space skip use it,
+// raymarching.cu:373-398): a sample is taken at an evaluation point whose cell is occupied, an empty cell moves the
+// evaluation point to the first t_m >= its exit parameter.  So every lane takes one candidate t_{n+lane}, evaluates its
+// cell (occupancy, exit parameter) in parallel, and the warp then replays the reference's pointer chase over the 32
+// results with ballots.  Same samples bit for bit (tests/test_ops_vs_ref_gpu.py); writes are coalesced.
+template <bool WRITE>
+__global__ void __launch_bounds__(256) k_march_train_warp(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                                                          const uint8_t* __restrict__ grid, float bound, float dt_gamma, uint32_t max_steps,
+                                                          uint32_t N, uint32_t C, uint32_t H, uint32_t M, const float* __restrict__ nears,
+                                                          const float* __restrict__ fars, const float* __restrict__ noises,
+                                                          int32_t* __restrict__ rays, float* __restrict__ xyzs, float* __restrict__ dirs,
+                                                          float* __restrict__ deltas) {
+    const uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
+    if (n >= N) return;
+    uint32_t limit = max_steps, offset = 0;
+    if (WRITE) {
+        offset = (uint32_t)rays[n * 3 + 1];
+        limit = (uint32_t)rays[n * 3 + 2];
+        if (limit == 0 || offset + limit > M) return;  // :415-416
+    }
+    Walk w;
+    w.init(rays_o + (size_t)n * 3, rays_d + (size_t)n * 3, grid, bound, dt_gamma, max_steps, C, H, fars[n]);
+    float t = nears[n];
+    t = __fmaf_rn(w.step_size(t), noises[n], t);  // :351
+    float last_t = t;                               // t after the previous sample (warp-uniform)
+    for (uint32_t j = 0; j < lane; j++) t = __fadd_rn(t, w.step_size(t));   // lane j holds candidate t_{n0 + j}
+    uint32_t count = 0;
+    float pending = -1.0f;                          // exit parameter of an empty cell whose target lies in a later batch
+    bool have_pending = false;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    while (true) {
+        // ---- every lane: its cell ----
+        float tn = t, x, y, z, dt, tt = 0.f;
+        const bool in_range = t < w.far;
+        bool occ = false;
+        if (in_range) occ = w.eval_cell(tn, x, y, z, dt, tt);   // occupied: tn = t + dt
+        const uint32_t occ_b = __ballot_sync(0xffffffffu, occ);
+        const uint32_t in_b = __ballot_sync(0xffffffffu, in_range);
+        // ---- replay the reference's walk over the 32 candidates ----
+        uint32_t cur = 0, emit = 0;
+        bool done = false;
+        if (have_pending) {
+            const uint32_t ge = __ballot_sync(0xffffffffu, !(t < pending));
+            if (ge) { cur = __ffs(ge) - 1u; have_pending = false; } else cur = 32u;
+        }
+        while (cur < 32u) {
+            if (!((in_b >> cur) & 1u) || count >= limit) { done = true; break; }
+            if ((occ_b >> cur) & 1u) {
+                emit |= 1u << cur;
+                count++;
+                cur++;
+            } else {
+                const float ttc = __shfl_sync(0xffffffffu, tt, cur);
+                const uint32_t ge = __ballot_sync(0xffffffffu, !(t < ttc)) & ~((2u << cur) - 1u);   // lanes above cur
+                if (ge) cur = __ffs(ge) - 1u;
+                else { pending = ttc; have_pending = true; cur = 32u; }
+            }
+        }
+        // ---- emit ----
+        if (WRITE && emit) {
+            // deltas[1] = (t after this sample) - (t after the previous one); the previous one is the next lower emitting lane
+            const uint32_t below = emit & lt_mask;
+            const int src = below ? 31 - __clz(below) : 0;
+            const float prev_next = __shfl_sync(0xffffffffu, tn, src);
+            if ((emit >> lane) & 1u) {
+                const float lt = below ? prev_next : last_t;
+                const size_t s = (size_t)offset + (count - __popc(emit)) + __popc(below);
+                xyzs[s * 3] = x; xyzs[s * 3 + 1] = y; xyzs[s * 3 + 2] = z;
+                dirs[s * 3] = w.dx; dirs[s * 3 + 1] = w.dy; dirs[s * 3 + 2] = w.dz;
+                deltas[s * 2] = dt;
+                deltas[s * 2 + 1] = __fsub_rn(tn, lt);
+            }
+        }
+        if (emit) last_t = __shfl_sync(0xffffffffu, tn, 31 - __clz(emit));
+        if (done || !(in_b >> 31)) break;   // the walk ended, or candidates past this batch are all beyond `far`
+        // ---- next batch: every lane advances 32 steps ----
+#pragma unroll 4
+        for (int j = 0; j < 32; j++) t = __fadd_rn(t, w.step_size(t));
+    }
+    if (!WRITE && lane == 0) rays[n * 3 + 2] = (int32_t)count;
+}
+
 // ---- inference marching (raymarching.cu:958-1063) -------------------------------
 
 __global__ void __launch_bounds__(128) k_march_rays(uint32_t n_alive, uint32_t n_step, const int32_t* __restrict__ rays_alive,
@@ -337,6 +423,16 @@ extern "C" int inerf_packbits(const float* grid, uint32_t N, float density_thres
     return INERF_OK;
 }
 
+// One warp per ray pays off while thread-per-ray cannot fill the machine (a serial walk per thread); it evaluates every
+// step of the empty stretches instead of one per cell, so the thread-per-ray kernels win once there are enough rays.
+// The warp kernel reads the bitfield as 8-byte words (Walk::occupied_cached).
+#ifndef INERF_WARP_MARCH_MAX_RAYS
+#define INERF_WARP_MARCH_MAX_RAYS 24576u
+#endif
+static bool use_warp_march(uint32_t N, const uint8_t* grid, uint32_t C, uint32_t H) {
+    return N <= INERF_WARP_MARCH_MAX_RAYS && ((uintptr_t)grid & 7u) == 0 && ((uint64_t)C * H * H * H) % 64u == 0;
+}
+
 static int check_march_args(uint32_t C, uint32_t H, uint32_t max_steps) {
     if (C == 0 || C > 16 || H == 0 || H > 1024 || max_steps == 0) return INERF_ERR_SIZE;
     if (H & (H - 1)) return INERF_ERR_UNSUPPORTED;  // the float rewrite of the double sub-expression needs H = 2^k
@@ -352,8 +448,12 @@ extern "C" int inerf_march_rays_train_count(const float* rays_o, const float* ra
     if (N == 0) return INERF_OK;
     INERF_REQUIRE(rays_o); INERF_REQUIRE(rays_d); INERF_REQUIRE(grid); INERF_REQUIRE(nears); INERF_REQUIRE(fars);
     INERF_REQUIRE(rays); INERF_REQUIRE(noises);
-    k_march_count<<<div_up(N, 128), 128, 0, (cudaStream_t)stream>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H,
-                                                                  nears, fars, noises, rays);
+    if (use_warp_march(N, grid, C, H))
+        k_march_train_warp<false><<<div_up(N, 8), 256, 0, (cudaStream_t)stream>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, 0,
+                                                                                nears, fars, noises, rays, nullptr, nullptr, nullptr);
+    else
+        k_march_count<<<div_up(N, 128), 128, 0, (cudaStream_t)stream>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H,
+                                                                      nears, fars, noises, rays);
     INERF_LAUNCH_CHECK();
     k_march_scan<<<1, 1024, 0, (cudaStream_t)stream>>>(rays, N, counter);
     INERF_LAUNCH_CHECK();
@@ -368,8 +468,12 @@ extern "C" int inerf_march_rays_train_write(const float* rays_o, const float* ra
     if (N == 0 || M == 0) return INERF_OK;
     INERF_REQUIRE(rays_o); INERF_REQUIRE(rays_d); INERF_REQUIRE(grid); INERF_REQUIRE(nears); INERF_REQUIRE(fars);
     INERF_REQUIRE(rays); INERF_REQUIRE(noises); INERF_REQUIRE(xyzs); INERF_REQUIRE(dirs); INERF_REQUIRE(deltas);
-    k_march_write<<<div_up(N, 128), 128, 0, (cudaStream_t)stream>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, M,
-                                                                  nears, fars, noises, rays, xyzs, dirs, deltas);
+    if (use_warp_march(N, grid, C, H))
+        k_march_train_warp<true><<<div_up(N, 8), 256, 0, (cudaStream_t)stream>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, M,
+                                                                               nears, fars, noises, const_cast<int32_t*>(rays), xyzs, dirs, deltas);
+    else
+        k_march_write<<<div_up(N, 128), 128, 0, (cudaStream_t)stream>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, M,
+                                                                      nears, fars, noises, rays, xyzs, dirs, deltas);
     INERF_LAUNCH_CHECK();
     return INERF_OK;
 }

@@ -35,7 +35,7 @@ constexpr uint32_t kChainT = 256, kGatherT = 512, kMarchT = 128;
 constexpr uint32_t kRegsChain = 96, kRegsGather = 64, kRegsMarch = 56;
 constexpr uint32_t kThreadsR = kChainT + kGatherT + kMarchT;
 #ifndef INERF_RING
-#define INERF_RING 8
+#define INERF_RING 14   // 14 x 3 KB of rings keeps the CTA inside the 196 KB shared-memory carve-out at K <= 32 (60 KB of L1 left)
 #endif
 constexpr uint32_t RING = INERF_RING;  // samples queued per ray slot
 constexpr uint32_t DT = 4;    // tile descriptors in flight (gather may run DA tiles ahead of the chain)
@@ -48,6 +48,9 @@ constexpr uint32_t DA = 2;    // gathered operand stages
 #endif
 #ifndef INERF_MARCH_MULTI
 #define INERF_MARCH_MULTI 1   // 1: a lane may queue several samples per warp iteration (as many as its ring has room for)
+#endif
+#ifndef INERF_FIRST_HIT
+#define INERF_FIRST_HIT 1      // 1: leading empty space of every ray is walked by a full-occupancy pre-pass (k_first_hit)
 #endif
 #ifndef INERF_RAY_PATCH
 #define INERF_RAY_PATCH 1     // 1: marcher warps take 32 consecutive rays at a time (coherent gathers); 0: one ray per free lane
@@ -168,8 +171,15 @@ __device__ __forceinline__ void march_role(const inerf_field_desc& desc, const R
             } else {
                 wk.init(p.rays_o + (size_t)idx * 3, p.rays_d + (size_t)idx * 3, p.bitfield, desc.bound, p.dt_gamma, p.max_steps, p.C, p.H,
                         __ldg(p.fars + idx));
+#if INERF_FIRST_HIT
+                // k_first_hit already walked this ray's leading empty space (same DDA, same t sequence): resume at the first
+                // occupied cell.  The value travels in depth[idx], which goes back to 0 (the output of a ray with no sample).
+                t = *reinterpret_cast<const volatile float*>(p.depth + idx);
+                p.depth[idx] = 0.f;
+#else
                 t = __ldg(p.nears + idx);
-                last_t = t;
+#endif
+                last_t = __ldg(p.nears + idx);
                 nsteps = 0;
                 ray = (int32_t)idx;
                 state = EVAL;
@@ -422,6 +432,26 @@ __device__ __forceinline__ void chain_role(const inerf_field_desc& desc, const R
     }
 }
 
+// Pre-pass: walk every ray from `near` through its leading empty space to the first occupied cell, one thread per ray at
+// full occupancy (the walk is a serial chain of ~10^4 dependent instructions per ray; inside the persistent kernel it
+// would run on 4 marcher warps per SM and starve the gather / MLP pipeline at every ray start: 12 % bubble rows at c2).
+// t_first[i] = parameter at which the render kernel's marcher resumes (same eval_cell / step sequence, so the samples
+// are unchanged); >= far when the ray never meets an occupied cell.
+__global__ void __launch_bounds__(256) k_first_hit(RenderParams p, float bound, float* __restrict__ t_first) {
+    const uint32_t idx = blockIdx.x * 256u + threadIdx.x;
+    if (idx >= p.N) return;
+    march::Walk wk;
+    wk.init(p.rays_o + (size_t)idx * 3, p.rays_d + (size_t)idx * 3, p.bitfield, bound, p.dt_gamma, p.max_steps, p.C, p.H, __ldg(p.fars + idx));
+    float t = __ldg(p.nears + idx), tt = 0.f;
+    while (t < wk.far) {
+        const float t0 = t;
+        float x, y, z, dt;
+        if (wk.eval_cell(t, x, y, z, dt, tt)) { t = t0; break; }
+        do { t = __fadd_rn(t, wk.step_size(t)); } while (t < tt);
+    }
+    t_first[idx] = t;
+}
+
 template <int NCH>
 __global__ void __launch_bounds__(kThreadsR, 1) k_render_fused(inerf_field_desc desc, RenderParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -501,13 +531,17 @@ extern "C" int inerf_render_fused(const inerf_field_desc* desc, const float* ray
     if (ce != cudaSuccess) return (int)ce;
     // rays without a single sample are never touched by the kernel: their outputs are these zeros
     if ((ce = cudaMemsetAsync(weights_sum, 0, (size_t)N * 4, st)) != cudaSuccess) return (int)ce;
+#if !INERF_FIRST_HIT
     if ((ce = cudaMemsetAsync(depth, 0, (size_t)N * 4, st)) != cudaSuccess) return (int)ce;
+#endif
     if ((ce = cudaMemsetAsync(image, 0, (size_t)N * 12, st)) != cudaSuccess) return (int)ce;
     if (mask_out && (ce = cudaMemsetAsync(mask_out, 0, (size_t)N * desc->K * 4, st)) != cudaSuccess) return (int)ce;
     // coarse bitmap: one bit per 64 cells; needs C*H^3 to be a multiple of 2048 and to fit the spare shared memory
     const uint64_t cells = (uint64_t)C * H * H * H;
     uint32_t coarse_bytes = 0;
+#ifndef INERF_NO_COARSE
     if (cells % 2048 == 0 && cells / 512 <= 48 * 1024) coarse_bytes = (uint32_t)(cells / 512);
+#endif
     RenderParams p{rays_o, rays_d, nears, fars, bitfield, N, C, H, max_steps, dt_gamma, T_thresh, weights_sum, depth, image, mask_out, work_counter, coarse_bytes};
     const uint32_t smem_bytes = RSmem::bytes(desc->K, coarse_bytes);
     static bool attr_set = false;
@@ -518,6 +552,10 @@ extern "C" int inerf_render_fused(const inerf_field_desc* desc, const float* ray
         if (ce != cudaSuccess) return (int)ce;
         attr_set = true;
     }
+#if INERF_FIRST_HIT
+    k_first_hit<<<(N + 255u) / 256u, 256, 0, st>>>(p, desc->bound, depth);   // depth[] carries t_first into the render kernel
+    INERF_LAUNCH_CHECK();
+#endif
     const uint32_t want = (N + field::kTile - 1) / field::kTile;
     const uint32_t grid = want < (uint32_t)kNumSMs ? want : (uint32_t)kNumSMs;
     if (desc->K <= 32) k_render_fused<1><<<grid, kThreadsR, smem_bytes, st>>>(*desc, p);

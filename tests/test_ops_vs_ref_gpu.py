@@ -85,11 +85,16 @@ def _march_both(ref, cuda, o, d, bits, bound, cascade, dt_gamma, max_steps, pert
     dict(bound=3.0, dt_gamma=1 / 128, max_steps=1024, seed=4),   # non power-of-two bound: mip_rbound = 1/3 is inexact
     dict(bound=2.0, dt_gamma=1 / 256, max_steps=256, seed=5),
     dict(bound=1.0, dt_gamma=0.0, max_steps=128, seed=6),
+    dict(bound=8.0, dt_gamma=1 / 128, max_steps=1024, seed=7, big=True),
+    dict(bound=3.0, dt_gamma=1 / 128, max_steps=64, seed=8, big=True),
+    dict(bound=8.0, dt_gamma=1 / 128, max_steps=37, seed=9),      # max_steps cuts rays short inside a 32-candidate batch
 ])
 def test_march_rays_train_bit_exact(ref, cuda, cfg):
+    """12 288 + adversarial rays -> the one-warp-per-ray kernels (k_march_train_warp); with cfg["big"] 30 720 rays -> the
+    thread-per-ray kernels (raymarch.cu use_warp_march)."""
     bound = cfg["bound"]
     sc, cascade, grid, bits = scene_arrays(16, bound, 0)
-    o, d = make_rays(sc, 96, 128)
+    o, d = make_rays(sc, *((160, 192) if cfg.get("big") else (96, 128)))
     ao, ad = adversarial_rays(bound)
     o, d = _dev(torch.cat([o, ao]), torch.cat([d, ad]), device=cuda)
     bits_t = torch.from_numpy(bits).to(cuda)
