@@ -350,7 +350,8 @@ def run_gpu_arm(args):
             # second half of BASELINE.json's metric ("train-step ms @ 4096 rays"), measured in the same run (config c3)
             tr = measure_train(dev, 0, 1, 20, 5, 4096, model, scene, poses)
             line["train_step"] = {"ms": tr["ms"], "ms_median": tr["ms_median"], "unit": "ms", "rays": 4096, "samples": tr["samples"],
-                                  "workload": "c3: 4096 rays (8x8 patches) x max_steps 1024, K=32, fp16 autocast, CE + label smoothness, backward, Adam"}
+                                  "workload": "c3: 4096 rays (8x8 patches) x max_steps 1024, K=32, fp16 autocast, CE + label smoothness, backward, Adam",
+                                  "cuda_graph": tr["cuda_graph"], "graph_replays": tr["graph_replays"], "graph_captures": tr["graph_captures"]}
         if world == 1 and not args.no_cpu_baseline:
             render, n_cpu, cores = make_cpu_reference(32768)
             t0 = time.perf_counter()
@@ -377,7 +378,7 @@ def measure_train(dev, rank, world, steps, warmup, n_rays, model=None, scene=Non
     if model is None:
         model, scene, poses = build_scene_and_model(dev)
     trainer = MaskTrainStep(model, lr=1e-2, fp16=True, patch_size=8, label_regularization_weight=0.1, dt_gamma=DT_GAMMA, max_steps=MAX_STEPS,
-                            T_thresh=T_THRESH, data_parallel=world > 1)
+                            T_thresh=T_THRESH, data_parallel=world > 1, cuda_graph=(world == 1 and not os.environ.get("INERF_NO_GRAPH")))
     intr = synthetic.intrinsics(H_IMG, W_IMG)
     batches = []
     for i in range(8):
@@ -395,7 +396,7 @@ def measure_train(dev, rank, world, steps, warmup, n_rays, model=None, scene=Non
 
     # every distinct batch goes through once before timing: the sample count differs per batch, and the first time a larger
     # sample stream shows up the caching allocator grows (cudaMalloc + sync) -- steady-state training never sees that
-    for i in range(max(warmup, len(batches))):
+    for i in range(max(warmup, 2 * len(batches))):   # two passes: the second one replays a graph whose budget fits every batch
         trainer.step(batches[i % 8])
     barrier()
     model.step_counter.zero_()
@@ -403,7 +404,7 @@ def measure_train(dev, rank, world, steps, warmup, n_rays, model=None, scene=Non
     clocks = ClockSampler(dev.index or 0)
     if rank == 0:
         clocks.start()
-    ev = []
+    ev, totals = [], []
     for i in range(steps):
         flush_buf.fill_(i & 0xFF)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -411,11 +412,14 @@ def measure_train(dev, rank, world, steps, warmup, n_rays, model=None, scene=Non
         loss = trainer.step(batches[(warmup + i) % 8])
         e1.record()
         ev.append((e0, e1))
+        totals.append(trainer.last_total)
     barrier()
     times = sorted(a.elapsed_time(b) for a, b in ev)
     total_ms = sum(times)
     clk = clocks.stop() if rank == 0 else None
     n_samples = float(model.step_counter[: min(16, steps), 0].float().mean().item())
+    if trainer.cuda_graph and trainer.graph_replays:
+        n_samples = float(sum(totals)) / max(1, len(totals))
     if world > 1:
         t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -423,7 +427,8 @@ def measure_train(dev, rank, world, steps, warmup, n_rays, model=None, scene=Non
     model.eval()
     for p in model.parameters():
         p.requires_grad_(True)
-    return {"ms": total_ms / steps, "ms_median": times[len(times) // 2], "samples": n_samples, "loss": float(loss.item()), "clocks": clk}
+    return {"ms": total_ms / steps, "ms_median": times[len(times) // 2], "samples": n_samples, "loss": float(loss.item()), "clocks": clk,
+            "cuda_graph": bool(trainer.cuda_graph), "graph_captures": trainer.graph_captures, "graph_replays": trainer.graph_replays}
 
 
 def run_train_arm(args):

@@ -206,6 +206,8 @@ typedef struct inerf_field_desc {
     float bound;               /* scene bound: x01 = (x + bound) / (2 bound) */
     uint32_t K;                /* num_instances, 1..64 */
     float density_scale;       /* mask_renderer.py:273 */
+    const int32_t *n_valid;    /* optional device int32: rows >= *n_valid of a sample stream are padding and are not
+                                  evaluated (fixed-size streams of a CUDA-graph-captured training step); NULL = all B rows */
 } inerf_field_desc;
 
 /* emb_sigma / emb_mask: device [n_entries, 2] of `dtype` (INERF_F32 parameters or INERF_F16) -> packed fp16 [n_entries, 4] */

@@ -43,6 +43,7 @@ class FieldDesc(ctypes.Structure):
         ("bound", c_float),
         ("K", c_uint32),
         ("density_scale", c_float),
+        ("n_valid", c_void_p),
     ]
 
 

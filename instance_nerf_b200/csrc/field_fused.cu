@@ -27,7 +27,7 @@ struct FSmem {
 };
 
 __global__ void __launch_bounds__(kThreads, 2) k_field_forward(inerf_field_desc desc, const float* __restrict__ xyzs,
-                                                               const float* __restrict__ dirs, uint32_t B, float* __restrict__ sigmas,
+                                                               const float* __restrict__ dirs, uint32_t B_rows, float* __restrict__ sigmas,
                                                                float* __restrict__ rgbs, float* __restrict__ masks,
                                                                uint4* __restrict__ x0_save) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -51,6 +51,8 @@ __global__ void __launch_bounds__(kThreads, 2) k_field_forward(inerf_field_desc 
     const bool with_masks = masks != nullptr;
     const float inv2b = __fdiv_rn(1.0f, __fmul_rn(2.0f, desc.bound));
     const uint2* table = reinterpret_cast<const uint2*>(desc.table_packed);
+    // rows past *n_valid (device-side count, e.g. the marcher's total) are padding of a fixed-size stream: not evaluated
+    const uint32_t B = desc.n_valid ? min(B_rows, (uint32_t)max(0, __ldg(desc.n_valid))) : B_rows;
     const uint32_t num_tiles = (B + kTile - 1) / kTile;
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 

@@ -127,7 +127,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_field_backward_mask(inerf_field
     const uint32_t row = tid & (kTile - 1), half = tid >> 7;
     const uint32_t lane_base = ((warp & 3u) * 32u) << 16;
     const float inv2b = __fdiv_rn(1.0f, __fmul_rn(2.0f, desc.bound));
-    const uint32_t num_tiles = (p.B + kTile - 1) / kTile;
+    const uint32_t B_eff = desc.n_valid ? min(p.B, (uint32_t)max(0, __ldg(desc.n_valid))) : p.B;   // rows past *n_valid are padding
+    const uint32_t num_tiles = (B_eff + kTile - 1) / kTile;
     uint32_t phase = 0, tiles_done = 0;
     const bool issuer = tid == 0;
 
@@ -145,7 +146,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_field_backward_mask(inerf_field
 
     for (uint32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, tiles_done++) {
         const uint32_t s = tile * kTile + row;
-        const bool live = s < p.B;
+        const bool live = s < B_eff;
         // ---- S0: X0 and dY rows -> operand tiles --------------------------------------------------------------
 #pragma unroll
         for (uint32_t c = 0; c < 3; c++) {

@@ -39,6 +39,8 @@ class _FusedInstanceField(torch.autograd.Function):
         masks = torch.empty(B, K, dtype=torch.float32, device=dev)
         x0 = torch.empty(B, 48, dtype=torch.float16, device=dev)
         desc = model._field_desc()
+        desc.n_valid = model._n_valid_ptr   # fixed-size (graph-captured) streams: rows past the marcher's device-side total are padding
+        ctx.n_valid = model._n_valid_ptr
         call("inerf_field_forward_train", ctypes.byref(desc), ptr(x), ptr(d), B, ptr(sigmas), ptr(rgbs), ptr(masks), ptr(x0), stream_ptr(dev))
         ctx.model = model
         ctx.save_for_backward(x, x0)
@@ -59,6 +61,7 @@ class _FusedInstanceField(torch.autograd.Function):
         gw2 = torch.zeros(K, 64, dtype=torch.float32, device=dev)
         if B > 0:
             desc = model._field_desc()
+            desc.n_valid = ctx.n_valid
             _, wb = model._packed_weights(want_bwd=True)
             call("inerf_field_backward_mask", ctypes.byref(desc), ptr(wb), ptr(x), ptr(x0), ptr(g_masks.float().contiguous()), B,
                  ptr(table.grad), ptr(gw0), ptr(gw1), ptr(gw2), stream_ptr(dev))
@@ -108,6 +111,7 @@ class NeRFNetwork(NeRFMaskRenderer):
         self._packed = None       # (key, forward fp16 weight blob, backward blob | None) on device
         self._tables = None       # (key, interleaved fp16 hash tables on device)
         self._work_counter = None
+        self._n_valid_ptr = None  # device address of the live sample count while a fixed-size training stream is in use
 
     # ---- fused path ------------------------------------------------------------------
     def _standard_arch(self) -> bool:

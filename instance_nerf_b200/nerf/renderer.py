@@ -234,9 +234,20 @@ class NeRFRenderer(nn.Module):
             counter = self.step_counter[self.local_step % 16]
             counter.zero_()
             self.local_step += 1
-            xyzs, dirs, deltas, rays = raymarching.march_rays_train(
-                rays_o, rays_d, self.bound, self.density_bitfield, self.cascade, self.grid_size, nears, fars, counter,
-                self.mean_count, perturb, 128, force_all_rays, dt_gamma, max_steps, noises=kwargs.get("noises"))
+            budget = int(getattr(self, "sample_budget", 0) or 0)
+            if budget > 0:
+                # fixed-size sample stream (CUDA-graph-captured training step, nerf/trainer.py): `budget` rows, no host read of
+                # the marched total; the field kernels stop at the device-side total (counter[0]), rows beyond it are padding.
+                # The caller guarantees budget >= total (and checks counter[0] afterwards), so no ray is dropped.
+                xyzs, dirs, deltas, rays = raymarching.march_rays_train(
+                    rays_o, rays_d, self.bound, self.density_bitfield, self.cascade, self.grid_size, nears, fars, counter,
+                    budget, perturb, -1, False, dt_gamma, max_steps, noises=kwargs.get("noises"))
+                self._n_valid_ptr = counter.data_ptr()
+            else:
+                xyzs, dirs, deltas, rays = raymarching.march_rays_train(
+                    rays_o, rays_d, self.bound, self.density_bitfield, self.cascade, self.grid_size, nears, fars, counter,
+                    self.mean_count, perturb, 128, force_all_rays, dt_gamma, max_steps, noises=kwargs.get("noises"))
+                self._n_valid_ptr = None
             sigmas, rgbs, masks = self._field(xyzs, dirs, render_mask)
             sigmas = self.density_scale * sigmas
             if not render_mask:

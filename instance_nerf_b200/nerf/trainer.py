@@ -47,7 +47,7 @@ class _MaskLoss(torch.autograd.Function):
 
 class MaskTrainStep:
     def __init__(self, model, lr=1e-2, fp16=True, patch_size=8, label_regularization_weight=0.0, dt_gamma=1 / 128, max_steps=1024,
-                 T_thresh=1e-4, data_parallel=False, fused_adam=True, fused_loss=True):
+                 T_thresh=1e-4, data_parallel=False, fused_adam=True, fused_loss=True, cuda_graph=False):
         self.model = model
         self.opt = SimpleNamespace(patch_size=patch_size, label_regularization_weight=label_regularization_weight)
         self.render_kw = dict(dt_gamma=dt_gamma, max_steps=max_steps, T_thresh=T_thresh)
@@ -63,11 +63,23 @@ class MaskTrainStep:
         params = [{"params": [p for p in g["params"] if p.requires_grad], "lr": g["lr"]} for g in model.get_params(lr)]
         params = [g for g in params if g["params"]]
         dev = next(model.parameters()).device
+        # cuda_graph: the whole step (march -> field -> composite -> loss -> backward -> Adam) replays as ONE CUDA graph; at
+        # 4096 rays the eager step is bound by ~60 launches of host work, not by the GPU
+        self.cuda_graph = bool(cuda_graph and dev.type == "cuda" and not data_parallel and fused_adam and fused_loss)
         kw = dict(fused=True) if (fused_adam and dev.type == "cuda") else {}
+        if self.cuda_graph:
+            kw["capturable"] = True
         self.optimizer = torch.optim.Adam(params, betas=(0.9, 0.99), eps=1e-15, **kw)   # main_nerf_mask.py:182
         self.scaler = torch.amp.GradScaler("cuda", enabled=fp16 and dev.type == "cuda")
         self.bucket = GradBucket([p for g in params for p in g["params"]]) if data_parallel else None
         self.global_step = 0
+        self._graph = None          # (torch.cuda.CUDAGraph, static inputs, static loss, budget, counter view)
+        self._graph_key = None
+        self._samples_seen = 0      # largest marched total of any batch so far
+        self._eager_steps = 0
+        self.graph_replays = 0
+        self.last_total = 0         # marched samples of the last replayed step
+        self.graph_captures = 0
 
     def label_regularization(self, depth, pred_masks):
         """nerf/utils.py:1262-1285: squared differences of neighbouring logits inside each patch, weighted by exp(-ddepth^2)."""
@@ -103,18 +115,103 @@ class MaskTrainStep:
         return pred.argmax(dim=-1), gt_masks, loss
 
     def step(self, data):
-        """One optimisation step (nerf/utils.py:929-936); returns the loss tensor (no host sync)."""
+        """One optimisation step (nerf/utils.py:929-936); returns the loss tensor (no host sync in the eager path)."""
+        if self.cuda_graph:
+            return self._step_graphed(data)
+        return self._step_eager(data)
+
+    def _step_eager(self, data, guard=None):
         self.model.train()
         self.global_step += 1
         self.optimizer.zero_grad(set_to_none=False)
         with torch.autocast("cuda", dtype=torch.float16, enabled=self.fp16):
             _, _, loss = self.train_step(data)
+        if guard is not None:
+            loss = guard(loss)
         self.scaler.scale(loss).backward()
         if self.bucket is not None:
             self.bucket.sync()
         self.scaler.step(self.optimizer)
         self.scaler.update()
         return loss.detach()
+
+    # ---- CUDA-graph replay of the whole step -------------------------------------------------------------------------
+    # The sample stream of a step has a data-dependent length (the marched total M).  The graph is captured with a FIXED
+    # stream of `budget` rows (model.sample_budget -> march_rays_train's no-sync budget mode); the marcher leaves the real
+    # total in step_counter[slot][0] on the device, the field forward / backward kernels stop there (inerf_field_desc.n_valid)
+    # and the compositing kernels only touch rows that rays reference, so padding costs nothing and no ray is dropped while
+    # M <= budget.  If a batch ever marches more than `budget` samples, a device-side guard turns that step's loss into +inf:
+    # GradScaler sees non-finite gradients and skips the optimizer step, so a truncated batch never updates the parameters;
+    # the host reads the total after every replay (the one sync of the step, where the reference reads loss.item(),
+    # nerf/utils.py:937), re-runs that batch eagerly and re-captures with a larger budget.
+    GRAPH_WARMUP_STEPS = 3
+    GRAPH_HEADROOM = 1.125
+
+    def _counter_slot(self):
+        # run_cuda uses step_counter[local_step % 16] and then increments local_step; the captured graph keeps ONE slot
+        return self.model.step_counter[self.model.local_step % 16]
+
+    def _capture(self, data):
+        from .._lib import PARAM_EPOCH
+        model = self.model
+        budget = int(self._samples_seen * self.GRAPH_HEADROOM) + 4096
+        budget += (-budget) % 4096
+        static = {k: v.clone() for k, v in data.items() if torch.is_tensor(v)}
+        counter = self._counter_slot()
+        limit = torch.tensor(budget, dtype=torch.int32, device=counter.device)
+        inf = torch.tensor(float("inf"), dtype=torch.float32, device=counter.device)
+        one = torch.ones((), dtype=torch.float32, device=counter.device)
+
+        def guard(loss):   # x inf, not where(.., inf, loss): the GRADIENTS must turn non-finite for GradScaler to skip the step
+            return loss.float() * torch.where(counter[0] > limit, inf, one)
+
+        model.sample_budget = budget
+        PARAM_EPOCH[0] += 1                       # the packed fp16 tables / weight blobs must be rebuilt INSIDE the graph
+        slot = model.local_step
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        try:
+            with torch.cuda.graph(g):
+                loss = self._step_eager(static, guard)
+        finally:
+            model.sample_budget = 0
+            model._n_valid_ptr = None
+        model.local_step = slot                   # capture advanced it; replays always use the captured slot
+        self.global_step -= 1
+        self._graph = (g, static, loss, budget, counter)
+        self._graph_key = tuple((k, tuple(v.shape), v.dtype) for k, v in static.items())
+        self.graph_captures += 1
+
+    def _step_graphed(self, data):
+        from .._lib import PARAM_EPOCH
+        tensors = {k: v for k, v in data.items() if torch.is_tensor(v)}
+        key = tuple((k, tuple(v.shape), v.dtype) for k, v in tensors.items())
+        if self._graph is not None and key != self._graph_key:
+            self._graph = None
+        if self._graph is None:
+            if self._eager_steps < self.GRAPH_WARMUP_STEPS or key != self._graph_key:
+                slot = self._counter_slot()
+                loss = self._step_eager(data)
+                self._samples_seen = max(self._samples_seen, int(slot[0].item()))
+                self._eager_steps += 1
+                self._graph_key = key
+                return loss
+            self._capture(data)
+        g, static, loss, budget, counter = self._graph
+        for k, v in tensors.items():
+            static[k].copy_(v, non_blocking=True)
+        g.replay()
+        self.global_step += 1
+        self.graph_replays += 1
+        PARAM_EPOCH[0] += 1                       # parameters changed without their version counters moving
+        total = int(counter[0].item())
+        self.last_total = total
+        self._samples_seen = max(self._samples_seen, total)
+        if total > budget:                        # the guard skipped this step on the device: redo it exactly, then re-capture
+            self._graph = None
+            self.global_step -= 1
+            return self._step_eager(data)
+        return loss
 
 
 class RGBTrainStep:

@@ -107,3 +107,63 @@ def test_fused_loss_tail_matches_torch(cuda, K, reg):
     (out * 3.0).backward()
     torch.testing.assert_close(out, ref.detach(), rtol=1e-5, atol=1e-6)
     torch.testing.assert_close(logits.grad / 3.0, g_ref, rtol=1e-4, atol=1e-7)
+
+
+def _train_setup(cuda, K=16, n_rays=1024, seed=0):
+    from instance_nerf_b200 import synthetic
+    m, sc = build_model(cuda, K, density_scale=10.0)
+    H, W = 96, 128
+    poses = torch.from_numpy(synthetic.camera_poses(sc, 1, 1))
+    r = synthetic.get_rays(poses, synthetic.intrinsics(H, W), H, W, N=n_rays, patch_size=8, generator=torch.Generator().manual_seed(seed))
+    o, d = r["rays_o"].reshape(-1, 3).contiguous(), r["rays_d"].reshape(-1, 3).contiguous()
+    labels = torch.from_numpy(sc.first_hit_labels(o.numpy().astype(np.float64), d.numpy().astype(np.float64)))
+    data = {"rays_o": o[None].to(cuda), "rays_d": d[None].to(cuda), "masks": labels[None].to(cuda),
+            "noises": torch.rand(o.shape[0], generator=torch.Generator().manual_seed(1)).to(cuda)}
+    return m, data
+
+
+def test_graphed_train_step_matches_eager(cuda):
+    """MaskTrainStep(cuda_graph=True): the whole step replayed as one CUDA graph over a fixed-size sample stream gives the
+    same losses / parameters as the eager step (hash-table gradients are float atomics: compared with a tolerance), and a
+    batch that marches more samples than the captured budget is NOT applied from the truncated stream: the device-side
+    guard skips it, the host redoes it eagerly and re-captures."""
+    from instance_nerf_b200.nerf.trainer import MaskTrainStep
+    m_e, data = _train_setup(cuda)
+    m_g, _ = _train_setup(cuda)
+    tr_e = MaskTrainStep(m_e, lr=1e-2, fp16=True, label_regularization_weight=0.1)
+    tr_g = MaskTrainStep(m_g, lr=1e-2, fp16=True, label_regularization_weight=0.1, cuda_graph=True)
+    assert tr_g.cuda_graph
+    le = [float(tr_e.step(data)) for _ in range(12)]
+    lg = [float(tr_g.step(data)) for _ in range(12)]
+    assert tr_g.graph_captures == 1 and tr_g.graph_replays == 12 - MaskTrainStep.GRAPH_WARMUP_STEPS
+    np.testing.assert_allclose(lg, le, rtol=2e-3, atol=2e-4)
+    for pe, pg in zip(m_e.mask_net.parameters(), m_g.mask_net.parameters()):
+        torch.testing.assert_close(pg, pe, rtol=2e-2, atol=2e-4)
+    # table gradients are float atomics in a nondeterministic order and Adam (eps 1e-15) turns a sign flip of a ~0 gradient into
+    # a full lr-sized step: all but a handful of the 13.3 M entries agree
+    te, tg = m_e.encoder_mask.embeddings.detach(), m_g.encoder_mask.embeddings.detach()
+    bad = ((tg - te).abs() > 2e-4 + 2e-2 * te.abs()).float().mean().item()
+    assert bad < 1e-5, bad
+    # inference after graph replays sees the replayed parameters (packed fp16 copies are refreshed)
+    m_e.eval(); m_g.eval()
+    with torch.no_grad():
+        kw = dict(staged=True, render_mask=True, perturb=False, dt_gamma=1 / 128, max_steps=1024, T_thresh=1e-4, bg_color=1)
+        re_, rg_ = m_e.render(data["rays_o"], data["rays_d"], **kw), m_g.render(data["rays_o"], data["rays_d"], **kw)
+    torch.testing.assert_close(rg_["instance_mask_logits"], re_["instance_mask_logits"], rtol=5e-2, atol=5e-3)
+
+    # ---- overflow: shrink the budget below the marched total and re-capture ----
+    total = tr_g._samples_seen
+    tr_g._graph = None
+    tr_g._samples_seen = total // 4
+    before = [p.detach().clone() for p in m_g.mask_net.parameters()]
+    caps = tr_g.graph_captures
+    l1 = float(tr_g.step(data))          # captures with a too-small budget, replays (guard trips), redoes the batch eagerly
+    le1 = float(tr_e.step(data))
+    assert tr_g.graph_captures == caps + 1 and tr_g._graph is None and tr_g._samples_seen == total
+    assert abs(l1 - le1) < 2e-3 * max(1.0, abs(le1))
+    assert any(float((a - b).abs().max()) > 0 for a, b in zip(before, m_g.mask_net.parameters()))
+    for pe, pg in zip(m_e.mask_net.parameters(), m_g.mask_net.parameters()):
+        torch.testing.assert_close(pg, pe, rtol=2e-2, atol=3e-4)
+    l2, le2 = float(tr_g.step(data)), float(tr_e.step(data))   # re-captured with a sufficient budget
+    assert tr_g.graph_captures == caps + 2 and tr_g._graph is not None
+    assert abs(l2 - le2) < 2e-3 * max(1.0, abs(le2))
