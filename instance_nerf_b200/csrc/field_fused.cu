@@ -9,6 +9,10 @@
 
 #include "field_device.cuh"
 
+#ifndef INERF_FIELD_WS
+#define INERF_FIELD_WS 1   // 1: warp-specialised forward kernel (k_field_forward_ws); 0: two lock-step CTAs per SM (k_field_forward)
+#endif
+
 namespace {
 
 using namespace field;
@@ -123,6 +127,142 @@ __global__ void __launch_bounds__(kThreads, 2) k_field_forward(inerf_field_desc 
     if (threadIdx.x < 32) umma::tmem_dealloc<kTmemCols>(tmem_base);
 }
 
+// ---- warp-specialised variant (default): gather and MLP chain as concurrent roles of ONE CTA per SM ------------------------
+// Same tiles, same arithmetic, same outputs as k_field_forward; the structure is the render kernel's (render_fused.cu)
+// without its marcher and compositor: 16 gather warps (thread = sample row x 4 of the 16 levels, 64 registers) fill one of
+// two operand stages while 8 chain warps (96 registers) run the tcgen05 chain of the previous tile and write sigma / rgb /
+// logits (and the saved mask-net input row).  The two-CTA kernel above overlaps gathers and MMAs only across CTAs and
+// keeps 8 gather warps per SM in flight; here 16 gather warps never wait for an epilogue.
+constexpr uint32_t kWsChainT = 256, kWsGatherT = 512, kWsThreads = kWsChainT + kWsGatherT, kWsStages = 2;
+
+struct WsCtrl {
+    uint64_t a_full[kWsStages], a_empty[kWsStages], mma_bar;
+    uint32_t tmem_slot;
+    LevelGeom lg[16];
+};
+struct WsSmem {
+    static constexpr uint32_t A = 0;
+    static constexpr uint32_t H1 = A + kWsStages * kStageBytes;
+    static constexpr uint32_t H2 = H1 + kBytesH;
+    static constexpr uint32_t W = H2 + kBytesH;
+    static __host__ __device__ uint32_t ctrl(uint32_t K) { return (W + weight_layout(K).total + 15u) & ~15u; }
+    static __host__ __device__ uint32_t bytes(uint32_t K) { return ctrl(K) + (uint32_t)sizeof(WsCtrl) + 16u; }
+};
+
+__global__ void __launch_bounds__(kWsThreads, 1) k_field_forward_ws(inerf_field_desc desc, const float* __restrict__ xyzs,
+                                                                    const float* __restrict__ dirs, uint32_t B_rows,
+                                                                    float* __restrict__ sigmas, float* __restrict__ rgbs,
+                                                                    float* __restrict__ masks, uint4* __restrict__ x0_save) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const uint32_t K = desc.K, Kp = weight_layout(K).Kp;
+    WsCtrl* ctl = reinterpret_cast<WsCtrl*>(smem + WsSmem::ctrl(K));
+    const uint32_t tid = threadIdx.x;
+    load_weights(smem, WsSmem::W, desc.weights, K);
+    init_levels(ctl->lg, desc.offsets, desc.L, desc.S, desc.H, tid);
+    if (tid == 0) {
+        for (uint32_t i = 0; i < kWsStages; i++) { umma::mbar_init(&ctl->a_full[i], kWsGatherT); umma::mbar_init(&ctl->a_empty[i], 1); }
+        umma::mbar_init(&ctl->mma_bar, 1);
+        umma::mbar_fence_init();
+    }
+    if (tid < 32) umma::tmem_alloc<kTmemCols>(&ctl->tmem_slot);
+    umma::fence_async_smem();
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tmem_base = ctl->tmem_slot;
+    const uint32_t B = desc.n_valid ? min(B_rows, (uint32_t)max(0, __ldg(desc.n_valid))) : B_rows;   // rows past *n_valid: padding
+    const uint32_t num_tiles = (B + kTile - 1) / kTile;
+    const bool with_masks = masks != nullptr;
+
+    if (tid < kWsChainT) {
+        // ------------------------------------------------------------------------------------------------ chain --
+        umma::reg_alloc<96>();
+        const uint32_t warp = tid >> 5, lane = tid & 31;
+        uint32_t phase = 0, it = 0;
+        auto chain_sync = [] { umma::named_sync<1, kWsChainT>(); };
+        for (uint32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, it++) {
+            const uint32_t sa = it % kWsStages;
+            umma::mbar_wait(&ctl->a_full[sa], (it / kWsStages) & 1u);
+            const uint32_t a_es = WsSmem::A + sa * kStageBytes;
+            const ChainBufs bufs{a_es, a_es + kBytesEs, a_es + kBytesEs + kBytesCi, WsSmem::H1, WsSmem::H2, WsSmem::W};
+            const uint32_t orow = tile * kTile + (warp & 3u) * 32u + lane;
+            const float sigma = mlp_chain(smem, bufs, tmem_base, &ctl->mma_bar, phase, K, desc.density_scale, with_masks, tid, &ctl->a_empty[sa],
+                                          chain_sync, [&](float) {
+                // training: keep the mask-net input row (32 mask-table features | 15 geo | 0, fp16) for the backward pass.  The row's
+                // owner wrote the geo columns itself a moment ago, and the stage is only released after the layer-0 MMAs.
+                if (x0_save != nullptr && warp < 4 && orow < B) {
+#pragma unroll
+                    for (uint32_t c = 0; c < 6; c++)
+                        x0_save[(size_t)orow * 6 + c] =
+                            *reinterpret_cast<const uint4*>(smem + bufs.a_mi + umma::tile_off(tid, c * 8, kLBO, sbo_of(48)));
+                }
+            });
+            if (warp < 4) {
+                float rgb[3];
+                epilogue_rgb(tmem_base, rgb, tid);
+                if (orow < B) {
+                    sigmas[orow] = sigma;
+                    rgbs[(size_t)orow * 3] = rgb[0]; rgbs[(size_t)orow * 3 + 1] = rgb[1]; rgbs[(size_t)orow * 3 + 2] = rgb[2];
+                }
+            }
+            if (with_masks) {
+                const uint32_t chunks = Kp / 16, c_begin = (warp >> 2) ? (chunks + 1) / 2 : 0, c_end = (warp >> 2) ? chunks : (chunks + 1) / 2;
+                for (uint32_t c = c_begin; c < c_end; c++) {
+                    uint32_t v[16];
+                    umma::tmem_ld16(tmem_base + D_d + (((warp & 3u) * 32u) << 16) + c * 16, v);
+                    umma::tmem_ld_wait();
+                    if (orow < B) {
+                        float* out = masks + (size_t)orow * K + c * 16;
+                        if ((K & 3u) == 0 && c * 16 + 16 <= K) {
+#pragma unroll
+                            for (int i = 0; i < 4; i++)
+                                reinterpret_cast<float4*>(out)[i] = make_float4(__half2float(__float2half_rn(__uint_as_float(v[4 * i]))),
+                                                                                __half2float(__float2half_rn(__uint_as_float(v[4 * i + 1]))),
+                                                                                __half2float(__float2half_rn(__uint_as_float(v[4 * i + 2]))),
+                                                                                __half2float(__float2half_rn(__uint_as_float(v[4 * i + 3]))));
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 16; i++)
+                                if (c * 16 + i < K) out[i] = __half2float(__float2half_rn(__uint_as_float(v[i])));
+                        }
+                    }
+                }
+            }
+            umma::fence_before_sync();
+            chain_sync();   // TMEM and the chain's hidden tiles are reused by the next tile
+        }
+    } else {
+        // ----------------------------------------------------------------------------------------------- gather --
+        umma::reg_dealloc<64>();
+        const uint32_t gt = tid - kWsChainT, row = gt & (kTile - 1), quarter = gt >> 7;
+        const float inv2b = __fdiv_rn(1.0f, __fmul_rn(2.0f, desc.bound));
+        const uint2* table = reinterpret_cast<const uint2*>(desc.table_packed);
+        uint32_t it = 0;
+        for (uint32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, it++) {
+            const uint32_t sa = it % kWsStages;
+            if (it >= kWsStages) umma::mbar_wait(&ctl->a_empty[sa], ((it / kWsStages) - 1u) & 1u);
+            const uint32_t s = tile * kTile + row;
+            if (s < B) {   // rows past the end keep stale operands: their outputs are never stored
+                const uint32_t a_es = WsSmem::A + sa * kStageBytes, a_ci = a_es + kBytesEs, a_mi = a_ci + kBytesCi;
+                float x01[3];
+                bool oob = false;
+#pragma unroll
+                for (int d = 0; d < 3; d++) {
+                    x01[d] = __fmul_rn(__fadd_rn(__ldg(xyzs + (size_t)s * 3 + d), desc.bound), inv2b);  // grid.py:149
+                    oob |= (x01[d] < 0.f || x01[d] > 1.f);
+                }
+                if (quarter == 0) sh16_to_smem(__ldg(dirs + (size_t)s * 3), __ldg(dirs + (size_t)s * 3 + 1), __ldg(dirs + (size_t)s * 3 + 2), smem, a_ci, row);
+                encode4(x01, oob, quarter * 4, ctl->lg, table, smem, a_es, a_mi, row);
+            }
+            umma::fence_async_smem();
+            umma::mbar_arrive(&ctl->a_full[sa]);
+        }
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    if (tid < 32) umma::tmem_dealloc<kTmemCols>(tmem_base);
+}
+
 // fp32 / fp16 embeddings of both encoders -> interleaved fp16 (sigma.c0, sigma.c1, mask.c0, mask.c1), one pass
 template <typename T>
 __global__ void k_pack_tables(const T* __restrict__ es, const T* __restrict__ em, uint64_t n, uint2* __restrict__ out) {
@@ -219,6 +359,21 @@ static int field_forward_impl(const inerf_field_desc* desc, const float* xyzs, c
         attr_set = true;
     }
     const uint32_t num_tiles = (B + field::kTile - 1) / field::kTile;
+#if INERF_FIELD_WS
+    {
+        static bool ws_attr_set = false;
+        if (!ws_attr_set) {
+            cudaError_t e = cudaFuncSetAttribute(k_field_forward_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+            if (e != cudaSuccess) return (int)e;
+            ws_attr_set = true;
+        }
+        const uint32_t grid_ws = num_tiles < (uint32_t)kNumSMs ? num_tiles : (uint32_t)kNumSMs;
+        k_field_forward_ws<<<grid_ws, kWsThreads, WsSmem::bytes(desc->K), (cudaStream_t)stream>>>(*desc, xyzs, dirs, B, sigmas, rgbs, masks,
+                                                                                                 (uint4*)x0_save);
+        INERF_LAUNCH_CHECK();
+        return INERF_OK;
+    }
+#endif
     const uint32_t grid = num_tiles < 2u * kNumSMs ? num_tiles : 2u * kNumSMs;
     k_field_forward<<<grid, field::kThreads, smem_bytes, (cudaStream_t)stream>>>(*desc, xyzs, dirs, B, sigmas, rgbs, masks, (uint4*)x0_save);
     INERF_LAUNCH_CHECK();
