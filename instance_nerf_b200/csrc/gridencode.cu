@@ -12,6 +12,7 @@
 // every product rounded to half, accumulated in half (c10::Half `+=`):
 // gridencoder.cu:161-185.  Results are bit-identical for both dtypes.
 #include "common.cuh"
+#include "field_device.cuh"   // level geometry / corner indices shared with the fused kernels (bit-identical to grid_index below)
 
 namespace {
 
@@ -217,6 +218,145 @@ __global__ void __launch_bounds__(256) k_grid_bwd(const T* __restrict__ grad, co
     }
 }
 
+// ---- fast path: D = 3, C = 2, hash grid, linear interpolation, [B, L*C] layout, L % 4 == 0 (the configuration of every
+// encoder on the instance-field path, network_mask.py:34,76) ------------------------------------------------------------
+// Thread = (sample, 4 consecutive levels); the 32 lanes of a warp hold 32 CONSECUTIVE samples at the same levels.  The
+// sample stream is sorted by ray and by t, so neighbouring lanes read neighbouring cells and one L1 sector serves several
+// lanes on the coarse and middle levels (the generic kernels above put the 16 levels of two samples in one warp: every
+// lane of a load hits a different table).  Table entries are read as one 4-byte (fp16) / 8-byte (fp32) word per corner,
+// a thread's 4 levels x 2 channels leave as one (fp16) or two (fp32) 16-byte stores.  Same arithmetic, same bits.
+constexpr uint32_t kFastSamples = 64;   // samples per 256-thread CTA (x 4 level quarters)
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_grid_fwd3x2(const float* __restrict__ inputs, const T* __restrict__ grid,
+                                                     const int32_t* __restrict__ offsets, T* __restrict__ outputs, uint32_t B, uint32_t L,
+                                                     float S, uint32_t H) {
+    __shared__ field::LevelGeom lg[64];
+    field::init_levels(lg, offsets, L, S, H, threadIdx.x);
+    __syncthreads();
+    const uint32_t LQ = L / 4, quarter = threadIdx.x / kFastSamples;
+    const uint32_t b = blockIdx.x * kFastSamples + (threadIdx.x % kFastSamples);
+    if (b >= B) return;
+    float x[3];
+    bool oob = false;
+#pragma unroll
+    for (uint32_t d = 0; d < 3; d++) { x[d] = __ldg(inputs + (size_t)b * 3 + d); oob |= (x[d] < 0 || x[d] > 1); }
+    T* out = outputs + ((size_t)b * L + quarter * LQ) * 2;
+    for (uint32_t l0 = 0; l0 < LQ; l0 += 4) {
+        T res[8];
+#pragma unroll
+        for (uint32_t li = 0; li < 4; li++) {
+            uint32_t idx[8];
+            float w[8];
+            const field::LevelGeom g = lg[quarter * LQ + l0 + li];
+            const float xs[3] = {oob ? 0.f : x[0], oob ? 0.f : x[1], oob ? 0.f : x[2]};
+            field::level_corners(xs, g, idx, w);
+            if constexpr (sizeof(T) == 2) {
+                const uint32_t* base = reinterpret_cast<const uint32_t*>(grid) + g.offset;
+                uint32_t v[8];
+#pragma unroll
+                for (uint32_t c = 0; c < 8; c++) v[c] = __ldg(base + idx[c]);
+                __half2 acc = __float2half2_rn(0.f);
+#pragma unroll
+                for (uint32_t c = 0; c < 8; c++) {   // product rounded to half, accumulated in half (gridencoder.cu:161-185)
+                    const float2 f = __half22float2(field::bits_h2(v[c]));
+                    acc = __hadd2(acc, __floats2half2_rn(__fmul_rn(w[c], f.x), __fmul_rn(w[c], f.y)));
+                }
+                if (oob) acc = __float2half2_rn(0.f);
+                res[2 * li] = __low2half(acc); res[2 * li + 1] = __high2half(acc);
+            } else {
+                const float2* base = reinterpret_cast<const float2*>(grid) + g.offset;
+                float2 v[8];
+#pragma unroll
+                for (uint32_t c = 0; c < 8; c++) v[c] = __ldg(base + idx[c]);
+                float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+                for (uint32_t c = 0; c < 8; c++) { a0 = fmaf(w[c], v[c].x, a0); a1 = fmaf(w[c], v[c].y, a1); }
+                res[2 * li] = oob ? 0.f : a0; res[2 * li + 1] = oob ? 0.f : a1;
+            }
+        }
+        if constexpr (sizeof(T) == 2) {
+            *reinterpret_cast<uint4*>(out + l0 * 2) = *reinterpret_cast<const uint4*>(res);
+        } else {
+            reinterpret_cast<float4*>(out + l0 * 2)[0] = reinterpret_cast<const float4*>(res)[0];
+            reinterpret_cast<float4*>(out + l0 * 2)[1] = reinterpret_cast<const float4*>(res)[1];
+        }
+    }
+}
+
+// Backward fast path, same mapping.  On levels whose resolution is at most kRunRes consecutive samples of a ray mostly fall
+// into the SAME cell: their atomics would serialise on a handful of L2 addresses (the generic kernel: 4 % of HBM peak).
+// Those levels reduce each run of equal cells inside the warp first (segmented shuffle reduction in fp32 towards the run's
+// first lane) and only run heads issue atomics; the fp16 table gradient then receives ONE rounding of the run's fp32 sum
+// instead of a sum of individually rounded halves (closer to the exact gradient than the reference's own ordering noise).
+constexpr float kRunRes = 512.0f;
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_grid_bwd3x2(const T* __restrict__ grad, const float* __restrict__ inputs,
+                                                     const int32_t* __restrict__ offsets, T* __restrict__ grad_grid, uint32_t B, uint32_t L,
+                                                     float S, uint32_t H) {
+    __shared__ field::LevelGeom lg[64];
+    field::init_levels(lg, offsets, L, S, H, threadIdx.x);
+    __syncthreads();
+    const uint32_t LQ = L / 4, quarter = threadIdx.x / kFastSamples, lane = threadIdx.x & 31u;
+    const uint32_t b = blockIdx.x * kFastSamples + (threadIdx.x % kFastSamples);
+    float x[3] = {0.f, 0.f, 0.f};
+    bool ok = b < B;
+    if (ok) {
+#pragma unroll
+        for (uint32_t d = 0; d < 3; d++) { x[d] = __ldg(inputs + (size_t)b * 3 + d); ok &= !(x[d] < 0 || x[d] > 1); }
+    }
+    if (!ok) { x[0] = x[1] = x[2] = 0.f; }
+    const T* g_row = grad + ((size_t)(b < B ? b : 0) * L + quarter * LQ) * 2;
+    for (uint32_t li = 0; li < LQ; li++) {
+        const field::LevelGeom g = lg[quarter * LQ + li];
+        float g0 = 0.f, g1 = 0.f;
+        if (ok) { g0 = (float)g_row[2 * li]; g1 = (float)g_row[2 * li + 1]; }
+        uint32_t idx[8];
+        float w[8];
+        field::level_corners(x, g, idx, w);
+        float a0[8], a1[8];
+#pragma unroll
+        for (uint32_t c = 0; c < 8; c++) { a0[c] = __fmul_rn(w[c], g0); a1[c] = __fmul_rn(w[c], g1); }
+        bool head = true;
+        if (g.scale <= kRunRes) {   // warp-uniform: every lane of a warp works on the same level
+            const uint32_t p0 = __shfl_up_sync(0xffffffffu, idx[0], 1), p7 = __shfl_up_sync(0xffffffffu, idx[7], 1);
+            head = lane == 0 || p0 != idx[0] || p7 != idx[7];
+            const uint32_t heads = __ballot_sync(0xffffffffu, head);
+            const uint32_t after = lane == 31 ? 0u : (heads >> (lane + 1));
+            const uint32_t next_head = after ? (lane + 1 + (uint32_t)__ffs(after) - 1u) : 32u;
+#pragma unroll
+            for (uint32_t off = 1; off < 32; off <<= 1) {
+                const bool take = lane + off < next_head;
+#pragma unroll
+                for (uint32_t c = 0; c < 8; c++) {
+                    const float o0 = __shfl_down_sync(0xffffffffu, a0[c], off), o1 = __shfl_down_sync(0xffffffffu, a1[c], off);
+                    if (take) { a0[c] += o0; a1[c] += o1; }
+                }
+            }
+        }
+        if (head) {
+#pragma unroll
+            for (uint32_t c = 0; c < 8; c++) {
+                if (a0[c] == 0.f && a1[c] == 0.f) continue;
+                if constexpr (sizeof(T) == 2)
+                    atomicAdd(reinterpret_cast<__half2*>(grad_grid) + g.offset + idx[c], __floats2half2_rn(a0[c], a1[c]));
+                else
+                    atomicAdd(reinterpret_cast<float2*>(grad_grid) + g.offset + idx[c], make_float2(a0[c], a1[c]));
+            }
+        }
+    }
+}
+
+template <typename T>
+bool fast_path_ok(uint32_t D, uint32_t C, uint32_t L, uint32_t gridtype, bool ac, uint32_t interp, int layout, const void* table, const void* act) {
+#ifdef INERF_NO_GRID_FAST
+    return false;
+#endif
+    return D == 3 && C == 2 && L % 4 == 0 && L <= 64 && gridtype == 0 && !ac && interp == 0 && layout == 1 &&
+           ((uintptr_t)table & (2 * sizeof(T) - 1)) == 0 && ((uintptr_t)act & 15u) == 0 && ((L / 4) * 2 * sizeof(T)) % 16 == 0;
+}
+
 // gridencoder.cu:340-366
 template <typename T>
 __global__ void k_input_bwd(const T* __restrict__ grad, const T* __restrict__ dy_dx, T* __restrict__ grad_inputs, uint32_t B, uint32_t D,
@@ -266,6 +406,11 @@ int launch_bwd_c(const T* grad, const float* inputs, const int32_t* offsets, T* 
 template <typename T>
 int fwd_t(const float* inputs, const void* emb, const int32_t* offsets, void* out, uint32_t B, uint32_t D, uint32_t C, uint32_t L, float S,
           uint32_t H, void* dy_dx, uint32_t gridtype, bool ac, uint32_t interp, int layout, cudaStream_t st) {
+    if (dy_dx == nullptr && fast_path_ok<T>(D, C, L, gridtype, ac, interp, layout, emb, out)) {
+        k_grid_fwd3x2<T><<<div_up(B, kFastSamples), 256, 0, st>>>(inputs, (const T*)emb, offsets, (T*)out, B, L, S, H);
+        INERF_LAUNCH_CHECK();
+        return INERF_OK;
+    }
     switch (D) {
         case 2: return launch_fwd_c<T, 2>(inputs, (const T*)emb, offsets, (T*)out, B, C, L, S, H, (T*)dy_dx, gridtype, ac, interp, layout, st);
         case 3: return launch_fwd_c<T, 3>(inputs, (const T*)emb, offsets, (T*)out, B, C, L, S, H, (T*)dy_dx, gridtype, ac, interp, layout, st);
@@ -276,6 +421,11 @@ template <typename T>
 int bwd_t(const void* grad, const float* inputs, const int32_t* offsets, void* gg, uint32_t B, uint32_t D, uint32_t C, uint32_t L, float S,
           uint32_t H, const void* dy_dx, void* grad_inputs, uint32_t gridtype, bool ac, uint32_t interp, int layout, cudaStream_t st) {
     int e;
+    if (fast_path_ok<T>(D, C, L, gridtype, ac, interp, layout, gg, grad)) {
+        k_grid_bwd3x2<T><<<div_up(B, kFastSamples), 256, 0, st>>>((const T*)grad, inputs, offsets, (T*)gg, B, L, S, H);
+        e = INERF_OK;
+        INERF_LAUNCH_CHECK();
+    } else
     switch (D) {
         case 2: e = launch_bwd_c<T, 2>((const T*)grad, inputs, offsets, (T*)gg, B, C, L, S, H, gridtype, ac, interp, layout, st); break;
         case 3: e = launch_bwd_c<T, 3>((const T*)grad, inputs, offsets, (T*)gg, B, C, L, S, H, gridtype, ac, interp, layout, st); break;
