@@ -152,7 +152,7 @@ def run_reference_arm(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # --------------------------------------------------------------------------------------------- GPU arm --
@@ -175,10 +175,24 @@ def run_gpu_arm(args):
     model, scene, poses = build_scene_and_model(dev)
     N = H_IMG * W_IMG
     K = K_INST
+    # Work units of one step = `world` whole frames.  Rank r renders the row blocks r, r + world, ... of EVERY frame of the step
+    # (H / world rows of each), not one frame of its own: cost is proportional to marched samples, which vary by +-25 % from
+    # pose to pose, and the per-step tile gather is a synchronisation point -- interleaved rows give every rank the same mix
+    # (SURVEY.md section 8e).  Rows stay whole, so the marcher's 32-ray patches remain runs of neighbouring pixels.
+    from instance_nerf_b200 import parallel
+    block_rows = 4
+    if H_IMG % (world * block_rows):
+        raise SystemExit(f"bench.py: {H_IMG} rows do not split into {block_rows}-row blocks over {world} ranks")
+    mine = parallel.shard_rows(H_IMG, W_IMG, rank, world, block_rows=block_rows)    # this rank's pixel ids inside a frame
+    n_groups = max(1, N_POSES // world)
     host_rays = []
-    for i in range(N_POSES):
-        o, d = frame_rays(poses, i)
-        host_rays.append((o.pin_memory(), d.pin_memory()))
+    for g in range(n_groups):
+        os_, ds_ = [], []
+        for j in range(world):
+            o, d = frame_rays(poses, (g * world + j) % N_POSES)
+            os_.append(o[mine])
+            ds_.append(d[mine])
+        host_rays.append((torch.cat(os_).contiguous().pin_memory(), torch.cat(ds_).contiguous().pin_memory()))
     dev_rays = [(o.to(dev), d.to(dev)) for o, d in host_rays]
     kw = dict(staged=True, render_mask=True, perturb=False, dt_gamma=DT_GAMMA, max_steps=MAX_STEPS, T_thresh=T_THRESH, bg_color=1)
     flush_buf = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device=dev)
@@ -207,7 +221,7 @@ def run_gpu_arm(args):
     model._render_fused = timed_fused
 
     def step(i, e2e=False, out_host=None):
-        p = (i * world + rank) % N_POSES
+        p = i % n_groups
         if e2e:
             o = host_rays[p][0].to(dev, non_blocking=True)
             d = host_rays[p][1].to(dev, non_blocking=True)
@@ -330,7 +344,8 @@ def run_gpu_arm(args):
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "rays_per_step_per_gpu": N, "samples_per_ray": avg_samples / N,
                        "tile_fill": (sum(n_samples) / max(1, 128 * sum(n_tiles))), "l2": "flushed between timed steps (512 MB write)",
-                       "parallelism": f"frames sharded over {world} rank(s), async all_gather of tiles overlapped with the next frame" if world > 1 else "single GPU",
+                       "parallelism": (f"{world} frames per step, every frame's rows interleaved over {world} ranks (balanced by samples), async NCCL "
+                                       f"all_gather of the finished row blocks overlapped with the next step") if world > 1 else "single GPU",
                        "wall_s_timed_region_incl_flush": wall_s},
             "e2e": {"value": world * N / (e2e_ms / args.steps * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": gpu_launches,
@@ -360,7 +375,7 @@ def run_gpu_arm(args):
             v = n_cpu / secs / 1e6
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": f"{n_cpu} rays strided over frame 0, 128 uniform samples/ray (reference non-cuda_ray sampler), {secs:.1f} s"}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -458,12 +473,31 @@ def run_train_arm(args):
                            "rays_per_gpu": n_rays, "samples_per_step_per_gpu": r["samples"], "l2": "flushed between timed steps (512 MB write)",
                            "parallelism": f"dp{world}, flat-bucket all_reduce" if world > 1 else "single GPU"},
                 "ms_per_step_median": r["ms_median"], "rays_per_s": world * n_rays / (ms * 1e-3), "loss": r["loss"], "clocks": r["clocks"]}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+def _claim_stdout():
+    """The contract is ONE JSON line on stdout.  NCCL / CUDA libraries print banners ("NCCL version ...") straight to fd 1, so
+    fd 1 is pointed at stderr for the life of the process and the JSON line goes out through a private duplicate."""
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+_JSON_OUT = None
+
+
+def emit(line: dict):
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
