@@ -15,6 +15,10 @@
 //     `T < T_thresh` is warp-uniform and matches the reference sample for sample.
 #include "common.cuh"
 
+#ifndef INERF_COMPOSITE_SCAN
+#define INERF_COMPOSITE_SCAN 1   // 1: scan formulation of the training kernels (default); 0: per-sample replay in every lane
+#endif
+
 namespace {
 
 constexpr int kMaxKPL = 4;  // classes per lane -> K <= 128
@@ -211,6 +215,196 @@ __global__ void __launch_bounds__(256) k_composite_train_bwd(
     }
 }
 
+// ---- training forward / backward, scan formulation (default) -------------------------------------------------------------
+// The kernels above replay the reference's per-sample recurrence in every lane and broadcast each sample with shuffles:
+// 5-11 SHFL per sample, and the shuffle unit retires one warp instruction per clock per SM -- that, not HBM, bounds them
+// (forward 0.45, backward 0.38 of HBM peak at K = 32).  Here lane j of a 32-sample chunk owns sample j:
+//   T_j      = T_carry * prod_{i<=j}(1 - alpha_i)          one inclusive product scan (5 SHFL per CHUNK)
+//   stop     = first j with T_j < T_thresh                  one ballot; samples after it get weight 0 (raymarching.cu:573)
+//   w_j      = alpha_j * T_{j-1},  t_j = t_carry + sum_{i<=j} delta1_i   (one add scan)
+//   sums     per-lane partials of w, w*rgb, w*t across the chunks of a ray, ONE warp reduction per ray
+// and in the backward the two "what is still to come" terms of grad_sigma become scans as well:
+//   sum_c g_c (T_j c_jc - (C_c - Crun_jc)) = T_j q_j - (Q - Qrun_j),   q_j = g . rgb_j,        Qrun = scan(w q)
+//   sum_k g_k (T_j m_jk - (M_k - Mrun_jk)) = T_j p_j - (G - Prun_j),   p_j = g_mask . logits_j, Prun = scan(w p)
+// with p_j formed by the lane that owns row j from its own 4K-byte row (no per-row warp reduction, no broadcast).
+// Same mathematics as the reference; sums are re-associated (differences ~1e-7 relative, tests/test_ops_vs_ref_gpu.py).
+__device__ __forceinline__ float scan_mul(float v, uint32_t lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const float u = __shfl_up_sync(kFull, v, o); if (lane >= (uint32_t)o) v *= u; }
+    return v;
+}
+__device__ __forceinline__ float scan_add(float v, uint32_t lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const float u = __shfl_up_sync(kFull, v, o); if (lane >= (uint32_t)o) v += u; }
+    return v;
+}
+
+template <int KPL>
+__global__ void __launch_bounds__(256) k_composite_train_fwd_scan(
+    const float* __restrict__ sigmas, const float* __restrict__ rgbs, const float* __restrict__ masks,
+    const float* __restrict__ deltas, const int32_t* __restrict__ rays, uint32_t M, uint32_t N, uint32_t K,
+    float T_thresh, float* __restrict__ weights_sum, float* __restrict__ depth, float* __restrict__ image,
+    float* __restrict__ mask_out) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (n >= N) return;
+    const uint32_t index = (uint32_t)rays[n * 3], offset = (uint32_t)rays[n * 3 + 1], num_steps = (uint32_t)rays[n * 3 + 2];
+    float macc[KPL > 0 ? KPL : 1];
+#pragma unroll
+    for (int i = 0; i < (KPL > 0 ? KPL : 1); i++) macc[i] = 0.f;
+    float pr = 0.f, pg = 0.f, pb = 0.f, pd = 0.f, pws = 0.f;   // per-lane partial sums
+    float Tc = 1.0f, tc = 0.f;
+    if (num_steps != 0 && offset + num_steps <= M) {
+        for (uint32_t base = 0; base < num_steps; base += 32) {
+            const uint32_t s = offset + base + lane;
+            const bool valid = base + lane < num_steps;
+            float alpha = 0.f, d1 = 0.f, cr = 0.f, cg = 0.f, cb = 0.f;
+            if (valid) {
+                const float2 dl = __ldg(reinterpret_cast<const float2*>(deltas) + s);
+                alpha = 1.0f - __expf(-__ldg(sigmas + s) * dl.x);
+                d1 = dl.y;
+                cr = __ldg(rgbs + (size_t)s * 3); cg = __ldg(rgbs + (size_t)s * 3 + 1); cb = __ldg(rgbs + (size_t)s * 3 + 2);
+            }
+            const float P = scan_mul(1.0f - alpha, lane);
+            const float Pex = __shfl_up_sync(kFull, P, 1);
+            const float T_after = Tc * P, T_before = lane == 0 ? Tc : Tc * Pex;
+            const uint32_t cnt = min(32u, num_steps - base);
+            const uint32_t term = __ballot_sync(kFull, valid && T_after < T_thresh);
+            const uint32_t m = term ? (uint32_t)__ffs(term) : cnt;      // samples of this chunk that contribute
+            const float my_w = lane < m ? alpha * T_before : 0.f;
+            const float t = tc + scan_add(d1, lane);
+            pws += my_w;
+            pr = fmaf(my_w, cr, pr); pg = fmaf(my_w, cg, pg); pb = fmaf(my_w, cb, pb);
+            pd = fmaf(my_w, t, pd);
+            if (KPL > 0) {
+                const float* mbase = masks + (size_t)(offset + base) * K;
+                for (uint32_t j0 = 0; j0 < m; j0 += kRowsInFlight) {
+                    float v[kRowsInFlight][KPL > 0 ? KPL : 1];
+#pragma unroll
+                    for (int u = 0; u < kRowsInFlight; u++)
+#pragma unroll
+                        for (int i = 0; i < KPL; i++) {
+                            const uint32_t k = lane + 32u * i;
+                            v[u][i] = (j0 + u < m && k < K) ? __ldg(mbase + (size_t)(j0 + u) * K + k) : 0.f;
+                        }
+#pragma unroll
+                    for (int u = 0; u < kRowsInFlight; u++) {
+                        if (j0 + u < m) {   // warp-uniform
+                            const float weight = __shfl_sync(kFull, my_w, j0 + u);
+#pragma unroll
+                            for (int i = 0; i < KPL; i++) macc[i] = fmaf(weight, v[u][i], macc[i]);
+                        }
+                    }
+                }
+            }
+            if (term) break;
+            Tc = __shfl_sync(kFull, T_after, 31);
+            tc = __shfl_sync(kFull, t, 31);
+        }
+    }
+    const float ws = warp_sum(pws), d = warp_sum(pd), r = warp_sum(pr), g = warp_sum(pg), b = warp_sum(pb);
+    if (lane == 0) {
+        weights_sum[index] = ws;
+        depth[index] = d;
+        image[(size_t)index * 3] = r; image[(size_t)index * 3 + 1] = g; image[(size_t)index * 3 + 2] = b;
+    }
+    if (KPL > 0) {
+#pragma unroll
+        for (int i = 0; i < KPL; i++) {
+            const uint32_t k = lane + 32u * i;
+            if (k < K) mask_out[(size_t)index * K + k] = macc[i];
+        }
+    }
+}
+
+template <int KPL>   // K <= 32 * KPL, KPL <= 2: every lane keeps the ray's K logit gradients in registers
+__global__ void __launch_bounds__(256) k_composite_train_bwd_scan(
+    const float* __restrict__ grad_weights_sum, const float* __restrict__ grad_image, const float* __restrict__ grad_mask_out,
+    const float* __restrict__ sigmas, const float* __restrict__ rgbs, const float* __restrict__ masks,
+    const float* __restrict__ deltas, const int32_t* __restrict__ rays, const float* __restrict__ weights_sum,
+    const float* __restrict__ image, const float* __restrict__ mask_out, uint32_t M, uint32_t N, uint32_t K, float T_thresh,
+    float* __restrict__ grad_sigmas, float* __restrict__ grad_rgbs, float* __restrict__ grad_masks) {
+    constexpr int KMAX = KPL > 0 ? 32 * KPL : 1;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (n >= N) return;
+    const uint32_t index = (uint32_t)rays[n * 3], offset = (uint32_t)rays[n * 3 + 1], num_steps = (uint32_t)rays[n * 3 + 2];
+    if (num_steps == 0 || offset + num_steps > M) return;
+
+    const float gr = grad_image[(size_t)index * 3], gg = grad_image[(size_t)index * 3 + 1], gb = grad_image[(size_t)index * 3 + 2];
+    const float Qfin = gr * image[(size_t)index * 3] + gg * image[(size_t)index * 3 + 1] + gb * image[(size_t)index * 3 + 2];
+    const float ws_term = grad_weights_sum[index] * (1 - weights_sum[index]);
+    float gm[KMAX];
+    float Gfin = 0.f;
+    if (KPL > 0) {
+#pragma unroll
+        for (int k = 0; k < KMAX; k++) {
+            gm[k] = (uint32_t)k < K ? __ldg(grad_mask_out + (size_t)index * K + k) : 0.f;
+            Gfin = fmaf(gm[k], (uint32_t)k < K ? __ldg(mask_out + (size_t)index * K + k) : 0.f, Gfin);
+        }
+    }
+    const bool vec = KPL > 0 && (K & 3u) == 0 && (((uintptr_t)masks | (uintptr_t)grad_masks) & 15u) == 0;
+    float Tc = 1.0f, Qc = 0.f, Pc = 0.f;
+
+    for (uint32_t base = 0; base < num_steps; base += 32) {
+        const uint32_t s = offset + base + lane;
+        const bool valid = base + lane < num_steps;
+        float alpha = 0.f, d0 = 0.f, cr = 0.f, cg = 0.f, cb = 0.f;
+        if (valid) {
+            d0 = __ldg(deltas + (size_t)s * 2);
+            alpha = 1.0f - __expf(-__ldg(sigmas + s) * d0);
+            cr = __ldg(rgbs + (size_t)s * 3); cg = __ldg(rgbs + (size_t)s * 3 + 1); cb = __ldg(rgbs + (size_t)s * 3 + 2);
+        }
+        const float P = scan_mul(1.0f - alpha, lane);
+        const float Pex = __shfl_up_sync(kFull, P, 1);
+        const float T_after = Tc * P, T_before = lane == 0 ? Tc : Tc * Pex;
+        const uint32_t cnt = min(32u, num_steps - base);
+        const uint32_t term = __ballot_sync(kFull, valid && T_after < T_thresh);
+        const uint32_t m = term ? (uint32_t)__ffs(term) : cnt;
+        const bool inc = lane < m;
+        const float w = inc ? alpha * T_before : 0.f;
+        const float q = gr * cr + gg * cg + gb * cb;
+        const float Qrun = Qc + scan_add(w * q, lane);
+        float gs = T_after * q - (Qfin - Qrun) + ws_term;
+        if (KPL > 0) {
+            float p = 0.f;
+            if (inc) {
+                const float* mrow = masks + (size_t)s * K;
+                float* grow = grad_masks + (size_t)s * K;
+                if (vec) {
+#pragma unroll
+                    for (int k4 = 0; k4 < KMAX / 4; k4++) {
+                        if ((uint32_t)k4 * 4u < K) {
+                            const float4 v = __ldg(reinterpret_cast<const float4*>(mrow) + k4);
+                            p = fmaf(gm[4 * k4], v.x, p); p = fmaf(gm[4 * k4 + 1], v.y, p);
+                            p = fmaf(gm[4 * k4 + 2], v.z, p); p = fmaf(gm[4 * k4 + 3], v.w, p);
+                            reinterpret_cast<float4*>(grow)[k4] = make_float4(gm[4 * k4] * w, gm[4 * k4 + 1] * w, gm[4 * k4 + 2] * w, gm[4 * k4 + 3] * w);
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < KMAX; k++) {
+                        if ((uint32_t)k < K) {
+                            p = fmaf(gm[k], __ldg(mrow + k), p);
+                            grow[k] = gm[k] * w;
+                        }
+                    }
+                }
+            }
+            const float Prun = Pc + scan_add(w * p, lane);
+            gs += T_after * p - (Gfin - Prun);
+            Pc = __shfl_sync(kFull, Prun, 31);
+        }
+        if (inc) {
+            grad_sigmas[s] = d0 * gs;
+            grad_rgbs[(size_t)s * 3] = gr * w; grad_rgbs[(size_t)s * 3 + 1] = gg * w; grad_rgbs[(size_t)s * 3 + 2] = gb * w;
+        }
+        if (term) break;
+        Tc = __shfl_sync(kFull, T_after, 31);
+        Qc = __shfl_sync(kFull, Qrun, 31);
+    }
+}
+
 // ---- inference (K == 0: raymarching.cu:1076-1163; K > 0: :1175-1271) ----
 template <int KPL>
 __global__ void __launch_bounds__(256) k_composite_infer(
@@ -301,6 +495,12 @@ int composite_train_fwd(const float* sigmas, const float* rgbs, const float* mas
     if (K) { INERF_REQUIRE(mask_out); if (M) INERF_REQUIRE(masks); }
     if ((uintptr_t)deltas & 7u) return INERF_ERR_ALIGN;
     return dispatch_kpl(K, [&](auto kpl) {
+#if INERF_COMPOSITE_SCAN
+        k_composite_train_fwd_scan<decltype(kpl)::value><<<div_up((unsigned long long)N * 32, 256), 256, 0, (cudaStream_t)stream>>>(
+            sigmas, rgbs, masks, deltas, rays, M, N, K, T_thresh, weights_sum, depth, image, mask_out);
+        INERF_LAUNCH_CHECK();
+        return (int)INERF_OK;
+#endif
         k_composite_train_fwd<decltype(kpl)::value><<<div_up((unsigned long long)N * 32, 256), 256, 0, (cudaStream_t)stream>>>(
             sigmas, rgbs, masks, deltas, rays, M, N, K, T_thresh, weights_sum, depth, image, mask_out);
         INERF_LAUNCH_CHECK();
@@ -317,6 +517,15 @@ int composite_train_bwd(const float* grad_weights_sum, const float* grad_image, 
     INERF_REQUIRE(rays); INERF_REQUIRE(weights_sum); INERF_REQUIRE(image); INERF_REQUIRE(grad_sigmas); INERF_REQUIRE(grad_rgbs);
     if (K) { INERF_REQUIRE(grad_mask_out); INERF_REQUIRE(masks); INERF_REQUIRE(mask_out); INERF_REQUIRE(grad_masks); }
     return dispatch_kpl(K, [&](auto kpl) {
+#if INERF_COMPOSITE_SCAN
+        if constexpr (decltype(kpl)::value <= 2) {   // K <= 64: the ray's logit gradients fit in registers
+            k_composite_train_bwd_scan<decltype(kpl)::value><<<div_up((unsigned long long)N * 32, 256), 256, 0, (cudaStream_t)stream>>>(
+                grad_weights_sum, grad_image, grad_mask_out, sigmas, rgbs, masks, deltas, rays, weights_sum, image, mask_out, M, N, K,
+                T_thresh, grad_sigmas, grad_rgbs, grad_masks);
+            INERF_LAUNCH_CHECK();
+            return (int)INERF_OK;
+        }
+#endif
         k_composite_train_bwd<decltype(kpl)::value><<<div_up((unsigned long long)N * 32, 256), 256, 0, (cudaStream_t)stream>>>(
             grad_weights_sum, grad_image, grad_mask_out, sigmas, rgbs, masks, deltas, rays, weights_sum, image, mask_out, M, N, K,
             T_thresh, grad_sigmas, grad_rgbs, grad_masks);
