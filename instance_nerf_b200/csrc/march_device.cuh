@@ -51,7 +51,10 @@ struct Walk {
     unsigned long long cword = 0ull;
     uint32_t cblk = 0xffffffffu;
 
+    bool words = true;   // the bitfield may be read as aligned 8-byte words (set by init)
+
     __device__ __forceinline__ bool occupied_cached(uint32_t index) {
+        if (!words) return (grid[index >> 3] >> (index & 7u)) & 1u;
         const uint32_t blk = index >> 6;
         if (coarse != nullptr && !((coarse[blk >> 5] >> (blk & 31u)) & 1u)) return false;
         if (blk != cblk) {
@@ -77,42 +80,23 @@ struct Walk {
         far = far_; C = (int)C_; grid = g;
         rbound = __fdiv_rn(1.0f, bound_);
         H3i = ((uint64_t)C_ * H * H * H <= (1ull << 24)) ? H * H * H : 0u;
+        words = (((uintptr_t)g & 7u) == 0) && (((uint64_t)C_ * H * H * H) & 63u) == 0;
         cblk = 0xffffffffu;
     }
     __device__ __forceinline__ float step_size(float t) const { return clampf(__fmul_rn(t, dt_gamma), dt_min, dt_max); }
 
-    // One DDA walk (raymarching.cu:359-400 / :427-479 / :1008-1062).
+    // One DDA walk (raymarching.cu:359-400 / :427-479 / :1008-1062): the reference's loop, one eval_cell per visited cell.
     template <bool WRITE>
     __device__ __forceinline__ uint32_t run(float t, uint32_t limit, float* __restrict__ xyzs, float* __restrict__ dirs,
-                                            float* __restrict__ deltas) const {
+                                            float* __restrict__ deltas) {
         uint32_t step = 0;
         float last_t = t;
         while (t < far && step < limit) {
-            const float x = clampf(__fmaf_rn(t, dx, ox), -bound, bound);
-            const float y = clampf(__fmaf_rn(t, dy, oy), -bound, bound);
-            const float z = clampf(__fmaf_rn(t, dz, oz), -bound, bound);
-            const float dt = step_size(t);
-            // mip level: max(mip_from_pos, mip_from_dt)
-            const float mx = fmaxf(fabsf(x), fmaxf(fabsf(y), fabsf(z)));
-            const float md = __fmul_rn(__fmul_rn(dt, Hf), 0.5f);
-            const int level = max(clamped_exponent(mx, C), clamped_exponent(md, C));
-            const float mip_bound = fminf(__uint_as_float((uint32_t)(127 + level) << 23), bound);
-            const float mip_rbound = __fdiv_rn(1.0f, mip_bound);
-            // (x * mip_rbound + 1) is one float FMA in the reference; the * 0.5 * H that follows is done in
-            // double there and is exact for H a power of two, so a float multiply by 0.5 * H gives the same bits.
-            const float hH = __fmul_rn(0.5f, Hf);
-            const int nx = (int)clampf(__fmul_rn(__fmaf_rn(x, mip_rbound, 1.0f), hH), 0.0f, Hm1);
-            const int ny = (int)clampf(__fmul_rn(__fmaf_rn(y, mip_rbound, 1.0f), hH), 0.0f, Hm1);
-            const int nz = (int)clampf(__fmul_rn(__fmaf_rn(z, mip_rbound, 1.0f), hH), 0.0f, Hm1);
-            const uint32_t index = (uint32_t)__fmaf_rn((float)level, H3, (float)morton3D_enc(nx, ny, nz));
-            const bool occ = grid[index >> 3] & (1u << (index & 7u));
-            if (occ) {
+            float x, y, z, dt, tt;
+            if (eval_cell(t, x, y, z, dt, tt)) {   // occupied: t has been advanced past the sample
                 if (WRITE) {
                     xyzs[0] = x; xyzs[1] = y; xyzs[2] = z;
                     dirs[0] = dx; dirs[1] = dy; dirs[2] = dz;
-                }
-                t = __fadd_rn(t, dt);
-                if (WRITE) {
                     deltas[0] = dt;
                     deltas[1] = __fsub_rn(t, last_t);
                     last_t = t;
@@ -120,11 +104,6 @@ struct Walk {
                 }
                 step++;
             } else {
-                // distance to the next voxel face along each axis (:390-394)
-                const float tx = __fmul_rn(__fmaf_rn(__fmaf_rn(__fmul_rn(__fadd_rn(__fadd_rn((float)nx, 0.5f), sx), rH), 2.0f, -1.0f), mip_bound, -x), rdx);
-                const float ty = __fmul_rn(__fmaf_rn(__fmaf_rn(__fmul_rn(__fadd_rn(__fadd_rn((float)ny, 0.5f), sy), rH), 2.0f, -1.0f), mip_bound, -y), rdy);
-                const float tz = __fmul_rn(__fmaf_rn(__fmaf_rn(__fmul_rn(__fadd_rn(__fadd_rn((float)nz, 0.5f), sz), rH), 2.0f, -1.0f), mip_bound, -z), rdz);
-                const float tt = __fadd_rn(t, fmaxf(0.0f, fminf(tx, fminf(ty, tz))));
                 do { t = __fadd_rn(t, step_size(t)); } while (t < tt);
             }
         }

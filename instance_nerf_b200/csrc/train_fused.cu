@@ -36,9 +36,11 @@ struct BSmem {
     static constexpr uint32_t TG2 = TH + kTile * 128 * 2;  // [128 x 128]  dH1 (64) | zeros (64)
     static constexpr uint32_t TX = TG2 + kTile * 128 * 2;  // [128 x 48]   X0
     static constexpr uint32_t W = TX + kTile * 48 * 2;
-    static constexpr uint32_t MISC = W + BwdWeights::total;   // LevelGeom[16] | mbarrier | tmem slot
+    static constexpr uint32_t DF = W + BwdWeights::total;      // 2 x [128 x 32] fp32: dF handed from the chain to the scatter warps
+    static constexpr uint32_t MISC = DF + 2 * kTile * 32 * 4; // LevelGeom[16] | mbarrier | tmem slot | df_full[2] | df_empty[2]
     static constexpr uint32_t bytes = MISC + 16 * sizeof(LevelGeom) + 64;
 };
+constexpr uint32_t kBwdChainT = 256, kBwdScatterT = 256, kBwdThreads = kBwdChainT + kBwdScatterT;
 constexpr uint32_t kSbo128 = sbo_of(128), kSbo64 = sbo_of(64), kSbo48 = sbo_of(48);
 // TMEM columns (512 allocated: one CTA per SM)
 constexpr uint32_t T_a = 0, T_b = 64, T_x = 128, T_w1 = 160, T_w0 = 288, kBwdTmemCols = 512;
@@ -99,22 +101,32 @@ __device__ __forceinline__ void epi_masked32(uint32_t taddr, uint32_t mask, uint
     }
 }
 
-__global__ void __launch_bounds__(kThreads, 1) k_field_backward_mask(inerf_field_desc desc, BwdParams p) {
+// Two roles per CTA: the CHAIN warps (threads 0..255) run the tcgen05 recompute / dX / dW chain of tile i + 1 while the SCATTER
+// warps (threads 256..511) push tile i's feature gradients into the table gradient.  The scatter is bound by the rate at
+// which an SM retires RED lanes (~1 per clock); run back to back with the chain (the first version of this kernel) it left
+// the tensor pipe and the LSU idle in turns.  dF travels through a double-buffered fp32 tile in shared memory.
+__global__ void __launch_bounds__(kBwdThreads, 1) k_field_backward_mask(inerf_field_desc desc, BwdParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t K = desc.K, tid = threadIdx.x;
     LevelGeom* lg = reinterpret_cast<LevelGeom*>(smem + BSmem::MISC);
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + BSmem::MISC + 16 * sizeof(LevelGeom));
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + BSmem::MISC + 16 * sizeof(LevelGeom) + 8);
+    uint64_t* df_full = reinterpret_cast<uint64_t*>(smem + BSmem::MISC + 16 * sizeof(LevelGeom) + 16);    // [2]
+    uint64_t* df_empty = df_full + 2;                                                                       // [2]
 
     // zero the operand tiles once (TG2's right half and dY's padding columns stay zero for the whole launch)
-    for (uint32_t i = tid; i < BSmem::W / 16; i += kThreads) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (uint32_t i = tid; i < BSmem::W / 16; i += kBwdThreads) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
     {
         const uint4* wsrc = reinterpret_cast<const uint4*>(p.weights);
         uint4* wdst = reinterpret_cast<uint4*>(smem + BSmem::W);
-        for (uint32_t i = tid; i < BwdWeights::total / 16; i += kThreads) wdst[i] = __ldg(wsrc + i);
+        for (uint32_t i = tid; i < BwdWeights::total / 16; i += kBwdThreads) wdst[i] = __ldg(wsrc + i);
     }
     init_levels(lg, desc.offsets, desc.L, desc.S, desc.H, tid);
-    if (tid == 0) { umma::mbar_init(bar, 1); umma::mbar_fence_init(); }
+    if (tid == 0) {
+        umma::mbar_init(bar, 1);
+        for (int i = 0; i < 2; i++) { umma::mbar_init(&df_full[i], kBwdChainT); umma::mbar_init(&df_empty[i], kBwdScatterT); }
+        umma::mbar_fence_init();
+    }
     if (tid < 32) umma::tmem_alloc<kBwdTmemCols>(tmem_slot);
     umma::fence_async_smem();
     umma::fence_before_sync();
@@ -123,8 +135,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_field_backward_mask(inerf_field
     const uint32_t tmem = *tmem_slot;
     const uint32_t sbase = umma::smem_u32(smem);
 
-    const uint32_t warp = tid >> 5, lane = tid & 31;
-    const uint32_t row = tid & (kTile - 1), half = tid >> 7;
+    const bool chain_role = tid < kBwdChainT;
+    const uint32_t rt = chain_role ? tid : tid - kBwdChainT;      // thread index inside the role
+    const uint32_t warp = rt >> 5, lane = rt & 31;
+    const uint32_t row = rt & (kTile - 1), half = rt >> 7;
     const uint32_t lane_base = ((warp & 3u) * 32u) << 16;
     const float inv2b = __fdiv_rn(1.0f, __fmul_rn(2.0f, desc.bound));
     const uint32_t B_eff = desc.n_valid ? min(p.B, (uint32_t)max(0, __ldg(desc.n_valid))) : p.B;   // rows past *n_valid are padding
@@ -138,12 +152,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_field_backward_mask(inerf_field
         phase ^= 1u;
         umma::fence_after_sync();
     };
-    auto publish = [&] {   // generic-proxy tile writes -> visible to the next MMAs
+    auto publish = [&] {   // generic-proxy tile writes -> visible to the next MMAs (barrier over the chain role only)
         umma::fence_async_smem();
         umma::fence_before_sync();
-        __syncthreads();
+        umma::named_sync<1, kBwdChainT>();
     };
 
+    if (chain_role) {
     for (uint32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, tiles_done++) {
         const uint32_t s = tile * kTile + row;
         const bool live = s < B_eff;
@@ -209,11 +224,71 @@ __global__ void __launch_bounds__(kThreads, 1) k_field_backward_mask(inerf_field
             umma::commit(bar);
         }
         wait_mma();
-        // ---- scatter: 8 levels (16 feature gradients) per thread -> table gradient -------------------------------
+        // ---- hand dF (32 feature gradients / sample, fp32, [column][row] so that neither side has bank conflicts) to the scatter warps
         {
+            const uint32_t db = tiles_done & 1u;
+            if (tiles_done >= 2) umma::mbar_wait(&df_empty[db], ((tiles_done >> 1) - 1u) & 1u);
             uint32_t v[16];
             umma::tmem_ld16(tmem + T_x + lane_base + half * 16, v);
             umma::tmem_ld_wait();
+            float* dst = reinterpret_cast<float*>(smem + BSmem::DF) + db * (kTile * 32) + (half * 16) * kTile + row;
+#pragma unroll
+            for (int i = 0; i < 16; i++) dst[i * kTile] = __uint_as_float(v[i]);
+            umma::mbar_arrive(&df_full[db]);
+        }
+        umma::fence_before_sync();
+        umma::named_sync<1, kBwdChainT>();   // TMEM accumulators T_a/T_b/T_x and the operand tiles are reused by the next tile
+    }
+
+    // ---- weight gradients of this CTA: TMEM -> global (fp32 atomics) ------------------------------------------------
+    {
+        const uint32_t q = warp & 3u, m = q * 32u + lane;   // TMEM lane = row of [dY|dH2]^T resp. [dH1|0]^T
+        if (q < 2 && half == 0) {            // dW2[o = m][j], lanes 0..63, columns 0..63 of T_w1
+            for (uint32_t c = 0; c < 64; c += 16) {
+                uint32_t v[16];
+                umma::tmem_ld16(tmem + T_w1 + lane_base + c, v);
+                umma::tmem_ld_wait();
+                if (m < K)
+#pragma unroll
+                    for (int j = 0; j < 16; j++) atomicAdd(p.grad_w2 + (size_t)m * 64 + c + j, __uint_as_float(v[j]));
+            }
+        } else if (q >= 2 && half == 1) {    // dW1[o = m - 64][j], lanes 64..127, columns 64..127 of T_w1
+            for (uint32_t c = 0; c < 64; c += 16) {
+                uint32_t v[16];
+                umma::tmem_ld16(tmem + T_w1 + lane_base + 64 + c, v);
+                umma::tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 16; j++) atomicAdd(p.grad_w1 + (size_t)(m - 64) * 64 + c + j, __uint_as_float(v[j]));
+            }
+        }
+        if (q < 2) {                         // dW0[o = m][j], lanes 0..63, columns 0..47 of T_w0 (j = 47 is X0's zero padding)
+            const uint32_t c_begin = half ? 32u : 0u, c_end = half ? 48u : 32u;
+            for (uint32_t c = c_begin; c < c_end; c += 16) {
+                uint32_t v[16];
+                umma::tmem_ld16(tmem + T_w0 + lane_base + c, v);
+                umma::tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 16; j++)
+                    if (c + j < 47) atomicAdd(p.grad_w0 + (size_t)m * 47 + c + j, __uint_as_float(v[j]));
+            }
+        }
+    }
+    } else {
+    // ------------------------------------------------------------------------------------------------ scatter role --
+    uint32_t it = 0;
+    for (uint32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, it++) {
+        const uint32_t s = tile * kTile + row;
+        const bool live = s < B_eff;
+        const uint32_t db = it & 1u;
+        umma::mbar_wait(&df_full[db], (it >> 1) & 1u);
+        uint32_t v[16];
+        {
+            const float* src = reinterpret_cast<const float*>(smem + BSmem::DF) + db * (kTile * 32) + (half * 16) * kTile + row;
+#pragma unroll
+            for (int i = 0; i < 16; i++) v[i] = __float_as_uint(src[i * kTile]);
+        }
+        umma::mbar_arrive(&df_empty[db]);   // the values are in registers: the chain may refill this buffer
+        {
             // Consecutive rows of a tile are consecutive samples of the same ray (the stream is sorted by ray and by t), so on the
             // coarse levels whole runs of lanes fall into the SAME cell: left alone, their atomics serialise on a handful of
             // addresses in L2.  Levels 0..7 (threads of half 0) therefore reduce each run inside the warp first -- segmented
@@ -264,43 +339,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_field_backward_mask(inerf_field
                 }
             }
         }
-        umma::fence_before_sync();
-        __syncthreads();   // TMEM accumulators T_a/T_b/T_x and the operand tiles are reused by the next tile
+    }
     }
 
-    // ---- weight gradients of this CTA: TMEM -> global (fp32 atomics) ------------------------------------------------
-    {
-        const uint32_t q = warp & 3u, m = q * 32u + lane;   // TMEM lane = row of [dY|dH2]^T resp. [dH1|0]^T
-        if (q < 2 && half == 0) {            // dW2[o = m][j], lanes 0..63, columns 0..63 of T_w1
-            for (uint32_t c = 0; c < 64; c += 16) {
-                uint32_t v[16];
-                umma::tmem_ld16(tmem + T_w1 + lane_base + c, v);
-                umma::tmem_ld_wait();
-                if (m < K)
-#pragma unroll
-                    for (int j = 0; j < 16; j++) atomicAdd(p.grad_w2 + (size_t)m * 64 + c + j, __uint_as_float(v[j]));
-            }
-        } else if (q >= 2 && half == 1) {    // dW1[o = m - 64][j], lanes 64..127, columns 64..127 of T_w1
-            for (uint32_t c = 0; c < 64; c += 16) {
-                uint32_t v[16];
-                umma::tmem_ld16(tmem + T_w1 + lane_base + 64 + c, v);
-                umma::tmem_ld_wait();
-#pragma unroll
-                for (int j = 0; j < 16; j++) atomicAdd(p.grad_w1 + (size_t)(m - 64) * 64 + c + j, __uint_as_float(v[j]));
-            }
-        }
-        if (q < 2) {                         // dW0[o = m][j], lanes 0..63, columns 0..47 of T_w0 (j = 47 is X0's zero padding)
-            const uint32_t c_begin = half ? 32u : 0u, c_end = half ? 48u : 32u;
-            for (uint32_t c = c_begin; c < c_end; c += 16) {
-                uint32_t v[16];
-                umma::tmem_ld16(tmem + T_w0 + lane_base + c, v);
-                umma::tmem_ld_wait();
-#pragma unroll
-                for (int j = 0; j < 16; j++)
-                    if (c + j < 47) atomicAdd(p.grad_w0 + (size_t)m * 47 + c + j, __uint_as_float(v[j]));
-            }
-        }
-    }
     umma::fence_before_sync();
     __syncthreads();
     if (tid < 32) umma::tmem_dealloc<kBwdTmemCols>(tmem);
@@ -425,7 +466,7 @@ extern "C" int inerf_field_backward_mask(const inerf_field_desc* desc, const voi
     BwdParams p{xyzs, (const uint4*)x0, grad_logits, B, (float2*)grad_table, grad_w0, grad_w1, grad_w2, weights_bwd};
     const uint32_t num_tiles = (B + kTile - 1) / kTile;
     const uint32_t grid = num_tiles < (uint32_t)kNumSMs ? num_tiles : (uint32_t)kNumSMs;
-    k_field_backward_mask<<<grid, kThreads, BSmem::bytes, (cudaStream_t)stream>>>(*desc, p);
+    k_field_backward_mask<<<grid, kBwdThreads, BSmem::bytes, (cudaStream_t)stream>>>(*desc, p);
     INERF_LAUNCH_CHECK();
     return INERF_OK;
 }
