@@ -217,6 +217,53 @@ __device__ __forceinline__ void encode4(const float x01[3], bool oob, uint32_t l
     *reinterpret_cast<uint4*>(smem + a_mi + umma::tile_off(row, k0, kLBO, sbo_of(48))) = make_uint4(fm[0], fm[1], fm[2], fm[3]);
 }
 
+// Software-pipelined encode4: the 8 gathers of level l + 1 are issued BEFORE level l's values are blended, so a thread keeps 16
+// table loads in flight instead of 8 (the straightforward loop above compiles to load-8 / wait / blend per level, and the
+// gather warps spend most of their time on the long-scoreboard of those loads).  Same arithmetic.
+__device__ __forceinline__ void blend_level(const uint2 (&v)[8], const float (&w)[8], uint32_t& out_s, uint32_t& out_m) {
+    __half2 as = __float2half2_rn(0.f), am = as;
+#pragma unroll
+    for (uint32_t c = 0; c < 8; c++) {
+        const float2 fs = __half22float2(bits_h2(v[c].x));
+        const float2 fm = __half22float2(bits_h2(v[c].y));
+        const float2 ww = make_float2(w[c], w[c]);
+        const float2 ps = __fmul2_rn(ww, fs), pm = __fmul2_rn(ww, fm);
+        as = __hadd2(as, __floats2half2_rn(ps.x, ps.y));
+        am = __hadd2(am, __floats2half2_rn(pm.x, pm.y));
+    }
+    out_s = h2_bits(as);
+    out_m = h2_bits(am);
+}
+__device__ __forceinline__ void encode4_pipelined(const float x01[3], bool oob, uint32_t l0, const LevelGeom* __restrict__ lg,
+                                                  const uint2* __restrict__ table, uint8_t* smem, uint32_t a_es, uint32_t a_mi, uint32_t row) {
+    uint32_t fs[4], fm[4];
+    uint2 v[2][8];
+    float w[2][8];
+    {
+        uint32_t idx[8];
+        const LevelGeom g = lg[l0];
+        level_corners(x01, g, idx, w[0]);
+#pragma unroll
+        for (uint32_t c = 0; c < 8; c++) v[0][c] = __ldg(table + g.offset + idx[c]);
+    }
+#pragma unroll
+    for (uint32_t li = 0; li < 4; li++) {
+        const uint32_t cur = li & 1u, nxt = cur ^ 1u;
+        if (li + 1 < 4) {
+            uint32_t idx[8];
+            const LevelGeom g = lg[l0 + li + 1];
+            level_corners(x01, g, idx, w[nxt]);
+#pragma unroll
+            for (uint32_t c = 0; c < 8; c++) v[nxt][c] = __ldg(table + g.offset + idx[c]);
+        }
+        blend_level(v[cur], w[cur], fs[li], fm[li]);
+        if (oob) { fs[li] = 0u; fm[li] = 0u; }
+    }
+    const uint32_t k0 = l0 * 2;
+    *reinterpret_cast<uint4*>(smem + a_es + umma::tile_off(row, k0, kLBO, sbo_of(32))) = make_uint4(fs[0], fs[1], fs[2], fs[3]);
+    *reinterpret_cast<uint4*>(smem + a_mi + umma::tile_off(row, k0, kLBO, sbo_of(48))) = make_uint4(fm[0], fm[1], fm[2], fm[3]);
+}
+
 // SH degree 4 (same polynomials as shencode.cu) rounded to fp16 into A_ci columns 0..15
 __device__ __forceinline__ void sh16_to_smem(float x, float y, float z, uint8_t* smem, uint32_t a_ci, uint32_t row) {
     float o[16];

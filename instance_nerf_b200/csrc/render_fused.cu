@@ -32,7 +32,15 @@ using namespace field;
 
 constexpr uint32_t kChainT = 256, kGatherT = 512, kMarchT = 128;
 // register budget per role (setmaxnreg): 896 threads start at 72; 256*96 + 512*64 + 128*56 = 896*72
-constexpr uint32_t kRegsChain = 96, kRegsGather = 64, kRegsMarch = 56;
+#ifndef INERF_GATHER_PIPE
+#define INERF_GATHER_PIPE 0
+#endif
+#ifndef INERF_REGS_CHAIN
+#define INERF_REGS_CHAIN 96
+#define INERF_REGS_GATHER 64
+#endif
+constexpr uint32_t kRegsChain = INERF_REGS_CHAIN, kRegsGather = INERF_REGS_GATHER, kRegsMarch = 56;
+static_assert(kChainT * kRegsChain + kGatherT * kRegsGather + kMarchT * kRegsMarch <= 65536, "register budget of the three roles");
 constexpr uint32_t kThreadsR = kChainT + kGatherT + kMarchT;
 #ifndef INERF_RING
 #define INERF_RING 14   // 14 x 3 KB of rings keeps the CTA inside the 196 KB shared-memory carve-out at K <= 32 (60 KB of L1 left)
@@ -290,7 +298,11 @@ __device__ __forceinline__ void gather_role(const inerf_field_desc& desc, const 
                     const float* d = p.rays_d + (size_t)ray * 3;
                     sh16_to_smem(__ldg(d), __ldg(d + 1), __ldg(d + 2), smem, a_ci, row);
                 }
+#if INERF_GATHER_PIPE
+                encode4_pipelined(x01, oob, quarter * 4, ctl->lg, table, smem, a_es, a_mi, row);
+#else
                 encode4(x01, oob, quarter * 4, ctl->lg, table, smem, a_es, a_mi, row);
+#endif
             }
         }
         umma::fence_async_smem();
