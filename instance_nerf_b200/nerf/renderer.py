@@ -372,10 +372,18 @@ class NeRFRenderer(nn.Module):
             for xs in X:
                 for ys in X:
                     for zs in X:
-                        xx, yy, zz = custom_meshgrid(xs, ys, zs)
-                        coords = torch.cat([xx.reshape(-1, 1), yy.reshape(-1, 1), zz.reshape(-1, 1)], dim=-1)
-                        indices = raymarching.morton3D(coords).long()
-                        xyzs = 2 * coords.float() / (G - 1) - 1
+                        # block geometry is a constant of (G, S): built once per device instead of on every update
+                        ck = (str(dev), G, S, int(xs[0]), int(ys[0]), int(zs[0])) if len(X) == 1 else None
+                        cache = getattr(self, "_sweep_cache", None)
+                        if ck is not None and cache is not None and cache[0] == ck:
+                            indices, xyzs = cache[1], cache[2]
+                        else:
+                            xx, yy, zz = custom_meshgrid(xs, ys, zs)
+                            coords = torch.cat([xx.reshape(-1, 1), yy.reshape(-1, 1), zz.reshape(-1, 1)], dim=-1)
+                            indices = raymarching.morton3D(coords).long()
+                            xyzs = 2 * coords.float() / (G - 1) - 1
+                            if ck is not None:
+                                self._sweep_cache = (ck, indices, xyzs)
                         for cas in range(self.cascade):
                             bound = min(2 ** cas, self.bound)
                             half_grid_size = bound / G

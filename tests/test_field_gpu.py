@@ -125,3 +125,37 @@ def test_render_fused_full_size_split_invariance(cuda, H, W):
         assert torch.equal(full[key], torch.cat([a[key], b[key]], dim=1)), key
     assert torch.isfinite(full["image"]).all() and torch.isfinite(full["instance_mask_logits"]).all()
     assert float(full["image"].min()) >= 0.0 and float(full["image"].max()) <= 1.0 + 1e-5
+
+
+def test_update_extra_state_full_sweep_vs_oracle(cuda):
+    """the full-sweep branch of update_extra_state (mask_renderer.py:466-495 -> EMA -> mean ->
+    threshold -> packbits) with injected jitter, against the CPU restatement: a sample of cells per cascade is recomputed
+    on the host (query point from the Morton index and the cell's row of the jitter block, fp32 field) and the whole
+    grid -> (mean, bitfield) tail is recomputed from the GPU grid with the numpy EMA / packbits restatement (bit-exact)."""
+    from oracle import field_oracle as fo
+    m, _ = build_model(cuda, 8, density_scale=1.0)
+    m.train()
+    m.reset_extra_state()
+    G, C = m.grid_size, m.cascade
+    g = torch.Generator().manual_seed(5)
+    noises = [torch.rand(G ** 3, 3, generator=g) for _ in range(C)]
+    with torch.autocast("cuda", dtype=torch.float16):
+        m.update_extra_state(decay=0.95, noises=[n.to(cuda) for n in noises])
+    torch.cuda.synchronize()
+    grid = m.density_grid.detach().cpu().numpy()
+    assert m.iter_density == 1 and np.isfinite(grid).all() and (grid >= 0).all()
+
+    field = fo.OracleField({k: v.detach().cpu() for k, v in m.state_dict().items()}, m.bound, m.num_instances, density_scale=m.density_scale)
+    rng = np.random.RandomState(0)
+    for cas in range(C):
+        cells = rng.randint(0, G ** 3, size=20000)
+        x = fo.extra_state_sweep_points(cells, cas, G, m.bound, noises[cas].numpy())
+        with torch.no_grad():
+            sig = field.density(torch.from_numpy(x))["sigma"].numpy() * m.density_scale
+        # first update from an all-zero grid: grid = max(0 * decay, sigma) = sigma; fp16 autocast MLP on the device vs fp32 here
+        np.testing.assert_allclose(grid[cas, cells], sig, rtol=2e-2, atol=1e-3)
+    # the EMA -> mean -> threshold -> packbits tail, recomputed from the device grid: identity EMA (tmp == grid), bit-exact bits
+    g2, mean, bits = fo.update_grid_ema(np.zeros_like(grid), grid, 0.95, m.density_thresh)
+    assert np.array_equal(g2, grid)
+    assert abs(float(m.mean_density) - mean) < 1e-5 * max(1.0, mean)
+    assert np.array_equal(m.density_bitfield.cpu().numpy(), bits)
