@@ -91,6 +91,21 @@ int inerf_march_rays_train_write(const float *rays_o, const float *rays_d, const
                                  float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M,
                                  const float *nears, const float *fars, float *xyzs, float *dirs, float *deltas,
                                  const int32_t *rays, const float *noises, void *stream);
+/*
+ * Single-walk variant: the caller passes a float scratch of inerf_march_scratch_floats(N, max_steps) elements
+ * ([N, max_steps], uninitialised) to
+ * inerf_march_rays_train_count_t, which also records the parameter t of every sample, and replaces the _write call by
+ * inerf_march_rays_train_expand (one warp per ray, no second walk, coalesced stores).  Same stream, bit for bit.
+ */
+size_t inerf_march_scratch_floats(uint32_t N, uint32_t max_steps);
+int inerf_march_rays_train_count_t(const float *rays_o, const float *rays_d, const uint8_t *grid, float bound,
+                                   float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H,
+                                   const float *nears, const float *fars, int32_t *rays, int32_t *counter,
+                                   const float *noises, float *t_scratch, void *stream);
+int inerf_march_rays_train_expand(const float *rays_o, const float *rays_d, float bound, float dt_gamma, uint32_t max_steps,
+                                  uint32_t N, uint32_t C, uint32_t H, uint32_t M, const float *nears, float *xyzs, float *dirs,
+                                  float *deltas, const int32_t *rays, const float *noises, const float *t_scratch,
+                                  void *stream);
 int inerf_march_rays_train(const float *rays_o, const float *rays_d, const uint8_t *grid, float bound, float dt_gamma,
                            uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M, const float *nears,
                            const float *fars, float *xyzs, float *dirs, float *deltas, int32_t *rays,

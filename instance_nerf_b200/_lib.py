@@ -73,6 +73,8 @@ _PROTOS = {
     "inerf_march_rays_train_count": [_P, _P, _P, _F, _F, _U, _U, _U, _U, _P, _P, _P, _P, _P, _P],
     "inerf_march_rays_train_write": [_P, _P, _P, _F, _F, _U, _U, _U, _U, _U, _P, _P, _P, _P, _P, _P, _P, _P],
     "inerf_march_rays_train": [_P, _P, _P, _F, _F, _U, _U, _U, _U, _U, _P, _P, _P, _P, _P, _P, _P, _P, _P],
+    "inerf_march_rays_train_count_t": [_P, _P, _P, _F, _F, _U, _U, _U, _U, _P, _P, _P, _P, _P, _P, _P],
+    "inerf_march_rays_train_expand": [_P, _P, _F, _F, _U, _U, _U, _U, _U, _P, _P, _P, _P, _P, _P, _P, _P],
     "inerf_composite_rays_train_forward": [_P, _P, _P, _P, _U, _U, _F, _P, _P, _P, _P],
     "inerf_composite_rays_train_backward": [_P, _P, _P, _P, _P, _P, _P, _P, _U, _U, _F, _P, _P, _P],
     "inerf_composite_rays_with_masks_train_forward": [_P, _P, _P, _P, _P, _U, _U, _U, _F, _P, _P, _P, _P, _P],
@@ -104,6 +106,7 @@ _SPECIAL = {
     "inerf_error_string": ([c_int], c_char_p),
     "inerf_field_weights_bytes": ([_U], c_size_t),
     "inerf_field_bwd_weights_bytes": ([], c_size_t),
+    "inerf_march_scratch_floats": ([_U, _U], c_size_t),
 }
 
 # Every symbol include/inerf_b200.h declares; tests check the .so exports all of them.

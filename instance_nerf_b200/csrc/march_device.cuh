@@ -86,14 +86,18 @@ struct Walk {
     __device__ __forceinline__ float step_size(float t) const { return clampf(__fmul_rn(t, dt_gamma), dt_min, dt_max); }
 
     // One DDA walk (raymarching.cu:359-400 / :427-479 / :1008-1062): the reference's loop, one eval_cell per visited cell.
+    // WRITE: false = count only, true = write samples.  `ts` (optional, count pass): the parameter t of every sample is
+    // recorded there, so that the samples can later be expanded in parallel without a second walk.
     template <bool WRITE>
     __device__ __forceinline__ uint32_t run(float t, uint32_t limit, float* __restrict__ xyzs, float* __restrict__ dirs,
-                                            float* __restrict__ deltas) {
+                                            float* __restrict__ deltas, float* __restrict__ ts = nullptr) {
         uint32_t step = 0;
         float last_t = t;
         while (t < far && step < limit) {
             float x, y, z, dt, tt;
+            const float t_sample = t;
             if (eval_cell(t, x, y, z, dt, tt)) {   // occupied: t has been advanced past the sample
+                if (ts) ts[step] = t_sample;
                 if (WRITE) {
                     xyzs[0] = x; xyzs[1] = y; xyzs[2] = z;
                     dirs[0] = dx; dirs[1] = dy; dirs[2] = dz;

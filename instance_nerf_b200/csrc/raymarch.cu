@@ -153,14 +153,52 @@ __global__ void __launch_bounds__(128) k_march_count(const float* __restrict__ r
                                                      const uint8_t* __restrict__ grid, float bound, float dt_gamma,
                                                      uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H,
                                                      const float* __restrict__ nears, const float* __restrict__ fars,
-                                                     const float* __restrict__ noises, int32_t* __restrict__ rays) {
+                                                     const float* __restrict__ noises, int32_t* __restrict__ rays,
+                                                     float* __restrict__ t_scratch) {
     const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= N) return;
     Walk w;
     w.init(rays_o + (size_t)n * 3, rays_d + (size_t)n * 3, grid, bound, dt_gamma, max_steps, C, H, fars[n]);
     float t0 = nears[n];
     t0 = __fmaf_rn(w.step_size(t0), noises[n], t0);  // :351
-    rays[n * 3 + 2] = (int32_t)w.run<false>(t0, max_steps, nullptr, nullptr, nullptr);
+    rays[n * 3 + 2] = (int32_t)w.run<false>(t0, max_steps, nullptr, nullptr, nullptr, t_scratch ? t_scratch + (size_t)n * max_steps : nullptr);
+}
+
+// Second phase when the count pass recorded every sample's t (t_scratch [N, max_steps]): no second walk.  One warp per ray,
+// lane j rebuilds sample j from t_j alone -- position, dt = step(t_j), and delta1 = (t_j + dt_j) - (t_{j-1} + dt_{j-1}), the
+// very expressions of the walk (raymarching.cu:373-389) -- and the 32 B / sample leave as coalesced stores.
+__global__ void __launch_bounds__(256) k_march_expand(const float* __restrict__ rays_o, const float* __restrict__ rays_d, float bound,
+                                                      float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M,
+                                                      const float* __restrict__ nears, const float* __restrict__ noises,
+                                                      const int32_t* __restrict__ rays, const float* __restrict__ t_scratch,
+                                                      float* __restrict__ xyzs, float* __restrict__ dirs, float* __restrict__ deltas) {
+    const uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
+    if (n >= N) return;
+    const uint32_t offset = (uint32_t)rays[n * 3 + 1], num = (uint32_t)rays[n * 3 + 2];
+    if (num == 0 || offset + num > M) return;  // :415-416
+    Walk w;
+    w.init(rays_o + (size_t)n * 3, rays_d + (size_t)n * 3, nullptr, bound, dt_gamma, max_steps, C, H, 0.f);
+    float last = nears[n];
+    last = __fmaf_rn(w.step_size(last), noises[n], last);   // last_t starts at the (jittered) start parameter
+    const float* ts = t_scratch + (size_t)n * max_steps;
+    for (uint32_t base = 0; base < num; base += 32) {
+        const uint32_t j = base + lane;
+        const bool valid = j < num;
+        const float t = valid ? ts[j] : 0.f;
+        const float dt = w.step_size(t);
+        const float tn = __fadd_rn(t, dt);
+        const float up = __shfl_up_sync(0xffffffffu, tn, 1);
+        const float lt = lane == 0 ? last : up;
+        if (valid) {
+            const size_t s = (size_t)offset + j;
+            xyzs[s * 3] = clampf(__fmaf_rn(t, w.dx, w.ox), -bound, bound);
+            xyzs[s * 3 + 1] = clampf(__fmaf_rn(t, w.dy, w.oy), -bound, bound);
+            xyzs[s * 3 + 2] = clampf(__fmaf_rn(t, w.dz, w.oz), -bound, bound);
+            dirs[s * 3] = w.dx; dirs[s * 3 + 1] = w.dy; dirs[s * 3 + 2] = w.dz;
+            reinterpret_cast<float2*>(deltas)[s] = make_float2(dt, __fsub_rn(tn, lt));
+        }
+        last = __shfl_sync(0xffffffffu, tn, min(31u, num - base - 1u));
+    }
 }
 
 // Single-CTA exclusive scan of the counts (N is at most a few million rays; the
@@ -234,9 +272,10 @@ __global__ void __launch_bounds__(256) k_march_train_warp(const float* __restric
                                                           uint32_t N, uint32_t C, uint32_t H, uint32_t M, const float* __restrict__ nears,
                                                           const float* __restrict__ fars, const float* __restrict__ noises,
                                                           int32_t* __restrict__ rays, float* __restrict__ xyzs, float* __restrict__ dirs,
-                                                          float* __restrict__ deltas) {
+                                                          float* __restrict__ deltas, float* __restrict__ t_scratch) {
     const uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
     if (n >= N) return;
+    float* ts = (!WRITE && t_scratch) ? t_scratch + (size_t)n * max_steps : nullptr;   // count pass: record t per sample
     uint32_t limit = max_steps, offset = 0;
     if (WRITE) {
         offset = (uint32_t)rays[n * 3 + 1];
@@ -296,6 +335,7 @@ __global__ void __launch_bounds__(256) k_march_train_warp(const float* __restric
                 deltas[s * 2 + 1] = __fsub_rn(tn, lt);
             }
         }
+        if (ts && ((emit >> lane) & 1u)) ts[(count - __popc(emit)) + __popc(emit & lt_mask)] = t;
         if (emit) last_t = __shfl_sync(0xffffffffu, tn, 31 - __clz(emit));
         if (done || !(in_b >> 31)) break;   // the walk ended, or candidates past this batch are all beyond `far`
         // ---- next batch: every lane advances 32 steps ----
@@ -439,10 +479,49 @@ static int check_march_args(uint32_t C, uint32_t H, uint32_t max_steps) {
     return INERF_OK;
 }
 
+extern "C" size_t inerf_march_scratch_floats(uint32_t N, uint32_t max_steps) {
+    // both count kernels (one warp per ray for small batches, one thread per ray for large ones) can record t per sample
+    return (size_t)N * max_steps;
+}
+
+static int march_count_impl(const float* rays_o, const float* rays_d, const uint8_t* grid, float bound,
+                            float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H,
+                            const float* nears, const float* fars, int32_t* rays, int32_t* counter,
+                            const float* noises, float* t_scratch, void* stream);
+
 extern "C" int inerf_march_rays_train_count(const float* rays_o, const float* rays_d, const uint8_t* grid, float bound,
                                             float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H,
                                             const float* nears, const float* fars, int32_t* rays, int32_t* counter,
                                             const float* noises, void* stream) {
+    return march_count_impl(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, nears, fars, rays, counter, noises, nullptr, stream);
+}
+
+extern "C" int inerf_march_rays_train_count_t(const float* rays_o, const float* rays_d, const uint8_t* grid, float bound,
+                                              float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H,
+                                              const float* nears, const float* fars, int32_t* rays, int32_t* counter,
+                                              const float* noises, float* t_scratch, void* stream) {
+    return march_count_impl(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, nears, fars, rays, counter, noises, t_scratch, stream);
+}
+
+extern "C" int inerf_march_rays_train_expand(const float* rays_o, const float* rays_d, float bound, float dt_gamma, uint32_t max_steps,
+                                             uint32_t N, uint32_t C, uint32_t H, uint32_t M, const float* nears, float* xyzs, float* dirs,
+                                             float* deltas, const int32_t* rays, const float* noises, const float* t_scratch,
+                                             void* stream) {
+    if (int e = check_march_args(C, H, max_steps)) return e;
+    if (N == 0 || M == 0) return INERF_OK;
+    INERF_REQUIRE(rays_o); INERF_REQUIRE(rays_d); INERF_REQUIRE(nears); INERF_REQUIRE(rays); INERF_REQUIRE(noises);
+    INERF_REQUIRE(xyzs); INERF_REQUIRE(dirs); INERF_REQUIRE(deltas); INERF_REQUIRE(t_scratch);
+    if ((uintptr_t)deltas & 7u) return INERF_ERR_ALIGN;
+    k_march_expand<<<div_up(N, 8), 256, 0, (cudaStream_t)stream>>>(rays_o, rays_d, bound, dt_gamma, max_steps, N, C, H, M, nears, noises, rays,
+                                                                 t_scratch, xyzs, dirs, deltas);
+    INERF_LAUNCH_CHECK();
+    return INERF_OK;
+}
+
+static int march_count_impl(const float* rays_o, const float* rays_d, const uint8_t* grid, float bound,
+                            float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H,
+                            const float* nears, const float* fars, int32_t* rays, int32_t* counter,
+                            const float* noises, float* t_scratch, void* stream) {
     if (int e = check_march_args(C, H, max_steps)) return e;
     INERF_REQUIRE(counter);
     if (N == 0) return INERF_OK;
@@ -450,10 +529,10 @@ extern "C" int inerf_march_rays_train_count(const float* rays_o, const float* ra
     INERF_REQUIRE(rays); INERF_REQUIRE(noises);
     if (use_warp_march(N, grid, C, H))
         k_march_train_warp<false><<<div_up(N, 8), 256, 0, (cudaStream_t)stream>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, 0,
-                                                                                nears, fars, noises, rays, nullptr, nullptr, nullptr);
+                                                                                nears, fars, noises, rays, nullptr, nullptr, nullptr, t_scratch);
     else
         k_march_count<<<div_up(N, 128), 128, 0, (cudaStream_t)stream>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H,
-                                                                      nears, fars, noises, rays);
+                                                                      nears, fars, noises, rays, t_scratch);
     INERF_LAUNCH_CHECK();
     k_march_scan<<<1, 1024, 0, (cudaStream_t)stream>>>(rays, N, counter);
     INERF_LAUNCH_CHECK();
@@ -470,7 +549,7 @@ extern "C" int inerf_march_rays_train_write(const float* rays_o, const float* ra
     INERF_REQUIRE(rays); INERF_REQUIRE(noises); INERF_REQUIRE(xyzs); INERF_REQUIRE(dirs); INERF_REQUIRE(deltas);
     if (use_warp_march(N, grid, C, H))
         k_march_train_warp<true><<<div_up(N, 8), 256, 0, (cudaStream_t)stream>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, M,
-                                                                               nears, fars, noises, const_cast<int32_t*>(rays), xyzs, dirs, deltas);
+                                                                               nears, fars, noises, const_cast<int32_t*>(rays), xyzs, dirs, deltas, nullptr);
     else
         k_march_write<<<div_up(N, 128), 128, 0, (cudaStream_t)stream>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, M,
                                                                       nears, fars, noises, rays, xyzs, dirs, deltas);

@@ -89,12 +89,22 @@ def main():
     print(f"# {N} rays, {M} samples ({M / N:.1f}/ray), K={K}", flush=True)
     rays_w = torch.empty_like(rays)
 
-    def ours_march():
+    from instance_nerf_b200._lib import lib
+    n_scr = int(lib().inerf_march_scratch_floats(N, bench.MAX_STEPS))
+    t_scr = torch.empty(n_scr, dtype=torch.float32, device=dev) if n_scr else None
+
+    def ours_march():   # what raymarching.march_rays_train issues for this batch size (large batch: count + record t, scan, expand)
         counter.zero_()
-        call("inerf_march_rays_train_count", ptr(o), ptr(d), ptr(bits), bound, bench.DT_GAMMA, bench.MAX_STEPS, N, C, H, ptr(nears), ptr(fars),
-             ptr(rays_w), ptr(counter), ptr(noises), st)
-        call("inerf_march_rays_train_write", ptr(o), ptr(d), ptr(bits), bound, bench.DT_GAMMA, bench.MAX_STEPS, N, C, H, M, ptr(nears), ptr(fars),
-             ptr(xyzs), ptr(dirs), ptr(deltas), ptr(rays_w), ptr(noises), st)
+        if t_scr is not None:
+            call("inerf_march_rays_train_count_t", ptr(o), ptr(d), ptr(bits), bound, bench.DT_GAMMA, bench.MAX_STEPS, N, C, H, ptr(nears),
+                 ptr(fars), ptr(rays_w), ptr(counter), ptr(noises), ptr(t_scr), st)
+            call("inerf_march_rays_train_expand", ptr(o), ptr(d), bound, bench.DT_GAMMA, bench.MAX_STEPS, N, C, H, M, ptr(nears), ptr(xyzs),
+                 ptr(dirs), ptr(deltas), ptr(rays_w), ptr(noises), ptr(t_scr), st)
+        else:
+            call("inerf_march_rays_train_count", ptr(o), ptr(d), ptr(bits), bound, bench.DT_GAMMA, bench.MAX_STEPS, N, C, H, ptr(nears), ptr(fars),
+                 ptr(rays_w), ptr(counter), ptr(noises), st)
+            call("inerf_march_rays_train_write", ptr(o), ptr(d), ptr(bits), bound, bench.DT_GAMMA, bench.MAX_STEPS, N, C, H, M, ptr(nears), ptr(fars),
+                 ptr(xyzs), ptr(dirs), ptr(deltas), ptr(rays_w), ptr(noises), st)
 
     rx = torch.empty(M, 3, device=dev); rd = torch.empty(M, 3, device=dev); rl = torch.empty(M, 2, device=dev)
     rrays = torch.empty(N, 3, dtype=torch.int32, device=dev); rcounter = torch.zeros(2, dtype=torch.int32, device=dev)
@@ -103,7 +113,7 @@ def main():
         rx.zero_(); rd.zero_(); rl.zero_(); rcounter.zero_()
         ref.raymarching.march_rays_train(o, d, bits, bound, bench.DT_GAMMA, bench.MAX_STEPS, N, C, H, M, nears, fars, rx, rd, rl, rrays, rcounter, noises)
 
-    row("march_rays_train (count+scan+write)", "sample", M, 32, timeit(ours_march), timeit(ref_march), extra_bytes=N * 48,
+    row("march_rays_train (count+scan+expand)", "sample", M, 32, timeit(ours_march), timeit(ref_march), extra_bytes=N * 48,
         note="ref zero-fills exactly M rows here; its wrapper zero-fills N*max_steps rows")
 
     # ---------------------------------------------------------------- grid encode fwd / bwd -----------------------
