@@ -308,6 +308,21 @@ int inerf_occupancy_ema(float *density_grid, const float *tmp_grid, uint32_t n_c
 int inerf_occupancy_pack(const float *density_grid, uint32_t n_cells, const double *sum_in, float density_thresh,
                          uint8_t *bitfield, float *mean_out, void *stream);
 
+/* ------------------------------------------------------------- optimizer -- */
+
+/*
+ * The Adam step the reference trainer takes on the trainable parameters (main_nerf_mask.py:182,
+ * torch.optim.Adam(betas=(0.9, 0.99), eps=1e-15); no weight decay / amsgrad), fused with the AMP unscale and with
+ * clearing the gradient: one pass over param / grad / exp_avg / exp_avg_sq (fp32 [n], 16-byte aligned) instead of
+ * zero_grad + unscale + Adam.  `step` is a device float holding the number of steps taken so far; grad_scale and
+ * found_inf are GradScaler's device scalars (NULL = 1 / 0).  found_inf != 0 leaves parameters and moments unchanged
+ * (the gradient is cleared either way).  Call inerf_adam_advance(step, found_inf) once after all tensors of a step.
+ */
+int inerf_adam_step(float *param, float *grad, float *exp_avg, float *exp_avg_sq, uint64_t n, float lr, float beta1,
+                    float beta2, float eps, const float *step, const float *grad_scale, const float *found_inf,
+                    void *stream);
+int inerf_adam_advance(float *step, const float *found_inf, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

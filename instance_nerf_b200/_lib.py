@@ -99,6 +99,8 @@ _PROTOS = {
     "inerf_field_pack_weights_bwd": [_P, _P, _P, _U, _P],
     "inerf_field_pack_weights_device": [_P] * 8 + [_U, _P, _P, _P],
     "inerf_field_backward_mask": [POINTER(FieldDesc), _P, _P, _P, _P, _U, _P, _P, _P, _P, _P],
+    "inerf_adam_step": [_P, _P, _P, _P, ctypes.c_uint64, _F, _F, _F, _F, _P, _P, _P, _P],
+    "inerf_adam_advance": [_P, _P, _P],
     "inerf_render_fused": [POINTER(FieldDesc), _P, _P, _P, _P, _P, _U, _U, _U, _F, _U, _F, _P, _P, _P, _P, _P, _P],
 }
 _SPECIAL = {

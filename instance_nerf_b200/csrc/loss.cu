@@ -153,3 +153,67 @@ extern "C" int inerf_mask_loss_backward(const float* logits, const float* depth,
     INERF_LAUNCH_CHECK();
     return INERF_OK;
 }
+
+
+// ---- Adam step of the trainable parameters (main_nerf_mask.py:182: torch.optim.Adam(betas=(0.9, 0.99), eps=1e-15)), one pass ----
+// What torch runs per step on the 13.3 M-entry table: zero_grad (write g), the AMP finite check (read + write g), fused Adam
+// (read p g m v, write p m v) = 9 passes over 53 MB.  Here: read p g m v, write p m v and g = 0 in ONE kernel (the finite check
+// stays with GradScaler).  Arithmetic is torch's `adam_math` (fused_adam_utils.cuh) for amsgrad = maximize = weight_decay = 0:
+//   g /= grad_scale;  m = lerp(m, g, 1 - b1);  v = b2 v + (1 - b2) g g;  p -= (lr / (1 - b1^t)) * m / (sqrt(v) / sqrt(1 - b2^t) + eps)
+// `step` is a device float (t - 1 on entry), so the launch can live in a CUDA graph; inerf_adam_advance bumps it afterwards.
+// found_inf != 0 (non-finite gradients somewhere in the model): parameters and moments are left alone, g is still cleared.
+namespace {
+__global__ void __launch_bounds__(256) k_adam_step(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                                                   uint64_t n, float lr, float b1, float b2, float eps, const float* __restrict__ step,
+                                                   const float* __restrict__ grad_scale, const float* __restrict__ found_inf) {
+    const bool skip = found_inf != nullptr && *found_inf != 0.f;
+    const float t = *step + 1.0f;
+    const float bc1 = 1.0f - (float)pow((double)b1, (double)t), bc2 = 1.0f - (float)pow((double)b2, (double)t);
+    const float step_size = lr / bc1, bc2_sqrt = sqrtf(bc2);
+    const float scale = grad_scale ? *grad_scale : 1.0f;
+    const uint64_t n4 = n >> 2, stride = (uint64_t)gridDim.x * blockDim.x;
+    auto upd = [&](float& pp, float gg, float& mm, float& vv) {
+        gg = gg / scale;
+        mm = mm + (1.0f - b1) * (gg - mm);                    // lerp(m, g, 1 - b1), weight < 0.5
+        vv = b2 * vv + (1.0f - b2) * gg * gg;
+        const float denom = sqrtf(vv) / bc2_sqrt + eps;
+        pp -= step_size * mm / denom;
+    };
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        const float4 g4 = reinterpret_cast<const float4*>(g)[i];
+        if (!skip) {
+            float4 p4 = reinterpret_cast<float4*>(p)[i], m4 = reinterpret_cast<float4*>(m)[i], v4 = reinterpret_cast<float4*>(v)[i];
+            upd(p4.x, g4.x, m4.x, v4.x); upd(p4.y, g4.y, m4.y, v4.y); upd(p4.z, g4.z, m4.z, v4.z); upd(p4.w, g4.w, m4.w, v4.w);
+            reinterpret_cast<float4*>(p)[i] = p4; reinterpret_cast<float4*>(m)[i] = m4; reinterpret_cast<float4*>(v)[i] = v4;
+        }
+        reinterpret_cast<float4*>(g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    for (uint64_t i = (n4 << 2) + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const float gg = g[i];
+        if (!skip) { float pp = p[i], mm = m[i], vv = v[i]; upd(pp, gg, mm, vv); p[i] = pp; m[i] = mm; v[i] = vv; }
+        g[i] = 0.f;
+    }
+}
+__global__ void k_adam_advance(float* __restrict__ step, const float* __restrict__ found_inf) {
+    if (found_inf == nullptr || *found_inf == 0.f) *step += 1.0f;
+}
+}  // namespace
+
+extern "C" int inerf_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, uint64_t n, float lr, float beta1, float beta2,
+                               float eps, const float* step, const float* grad_scale, const float* found_inf, void* stream) {
+    if (n == 0) return INERF_OK;
+    INERF_REQUIRE(param); INERF_REQUIRE(grad); INERF_REQUIRE(exp_avg); INERF_REQUIRE(exp_avg_sq); INERF_REQUIRE(step);
+    if ((((uintptr_t)param | (uintptr_t)grad | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq) & 15u) != 0) return INERF_ERR_ALIGN;
+    const uint64_t want = ((n >> 2) + 255) / 256;
+    const unsigned int blocks = (unsigned int)(want < 1 ? 1 : (want > (uint64_t)kNumSMs * 16 ? (uint64_t)kNumSMs * 16 : want));
+    k_adam_step<<<blocks, 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, step, grad_scale, found_inf);
+    INERF_LAUNCH_CHECK();
+    return INERF_OK;
+}
+
+extern "C" int inerf_adam_advance(float* step, const float* found_inf, void* stream) {
+    INERF_REQUIRE(step);
+    k_adam_advance<<<1, 1, 0, (cudaStream_t)stream>>>(step, found_inf);
+    INERF_LAUNCH_CHECK();
+    return INERF_OK;
+}

@@ -66,10 +66,15 @@ class MaskTrainStep:
         # cuda_graph: the whole step (march -> field -> composite -> loss -> backward -> Adam) replays as ONE CUDA graph; at
         # 4096 rays the eager step is bound by ~60 launches of host work, not by the GPU
         self.cuda_graph = bool(cuda_graph and dev.type == "cuda" and not data_parallel and fused_adam and fused_loss)
-        kw = dict(fused=True) if (fused_adam and dev.type == "cuda") else {}
-        if self.cuda_graph:
-            kw["capturable"] = True
-        self.optimizer = torch.optim.Adam(params, betas=(0.9, 0.99), eps=1e-15, **kw)   # main_nerf_mask.py:182
+        params = [{"params": g["params"], "lr": float(g["lr"])} for g in params]
+        if fused_adam and dev.type == "cuda" and not data_parallel:
+            # main_nerf_mask.py:182's Adam as ONE pass per tensor that also unscales and clears the gradient (nerf/optim.py)
+            from .optim import FusedAdam
+            self.optimizer = FusedAdam(params, betas=(0.9, 0.99), eps=1e-15)
+        else:
+            kw = dict(fused=True) if (fused_adam and dev.type == "cuda") else {}
+            self.optimizer = torch.optim.Adam(params, betas=(0.9, 0.99), eps=1e-15, **kw)   # main_nerf_mask.py:182
+        self._own_zero = getattr(self.optimizer, "grads_cleared_by_step", False)
         self.scaler = torch.amp.GradScaler("cuda", enabled=fp16 and dev.type == "cuda")
         self.bucket = GradBucket([p for g in params for p in g["params"]]) if data_parallel else None
         self.global_step = 0
@@ -123,7 +128,8 @@ class MaskTrainStep:
     def _step_eager(self, data, guard=None):
         self.model.train()
         self.global_step += 1
-        self.optimizer.zero_grad(set_to_none=False)
+        if not self._own_zero:   # FusedAdam leaves every gradient at zero
+            self.optimizer.zero_grad(set_to_none=False)
         with torch.autocast("cuda", dtype=torch.float16, enabled=self.fp16):
             _, _, loss = self.train_step(data)
         if guard is not None:

@@ -80,10 +80,13 @@ def test_train_step_runs_fused_and_learns(cuda):
         _, _, l_mod = tr.train_step(data)
         m.use_fused = True
     assert abs(float(l_fused) - float(l_mod)) < 2e-2 * max(1.0, abs(float(l_mod)))
+    table0 = m.encoder_mask.embeddings.detach().clone()
     losses = [float(tr.step(data)) for _ in range(40)]
     assert np.isfinite(losses).all()
     assert np.mean(losses[-5:]) < 0.6 * np.mean(losses[:3]), losses
-    assert m.encoder_mask.embeddings.grad is not None and float(m.encoder_mask.embeddings.grad.abs().sum()) > 0
+    # FusedAdam (nerf/optim.py) clears every gradient inside its update pass; the table itself must have moved
+    assert m.encoder_mask.embeddings.grad is not None and float(m.encoder_mask.embeddings.grad.abs().sum()) == 0.0
+    assert float((m.encoder_mask.embeddings.detach() - table0).abs().max()) > 1e-3
 
 
 @pytest.mark.parametrize("K,reg", [(32, 0.1), (7, 0.0), (16, 1.0)])
@@ -167,3 +170,39 @@ def test_graphed_train_step_matches_eager(cuda):
     l2, le2 = float(tr_g.step(data)), float(tr_e.step(data))   # re-captured with a sufficient budget
     assert tr_g.graph_captures == caps + 2 and tr_g._graph is not None
     assert abs(l2 - le2) < 2e-3 * max(1.0, abs(le2))
+
+
+def test_fused_adam_matches_torch_adam(cuda):
+    """nerf/optim.py FusedAdam (one pass: unscale + Adam + clear gradient) against torch.optim.Adam with the reference's
+    hyper-parameters (main_nerf_mask.py:182), including GradScaler's grad_scale / found_inf protocol."""
+    from instance_nerf_b200.nerf.optim import FusedAdam
+    g = torch.Generator().manual_seed(0)
+    shapes = [(100003, 2), (64, 47), (7,)]
+    p0 = [torch.randn(s, generator=g).to(cuda) for s in shapes]
+    pa = [torch.nn.Parameter(t.clone()) for t in p0]
+    pb = [torch.nn.Parameter(t.clone()) for t in p0]
+    oa = FusedAdam([{"params": pa[:1], "lr": 1e-2}, {"params": pa[1:], "lr": 1e-3}], betas=(0.9, 0.99), eps=1e-15)
+    ob = torch.optim.Adam([{"params": pb[:1], "lr": 1e-2}, {"params": pb[1:], "lr": 1e-3}], betas=(0.9, 0.99), eps=1e-15)
+    scale = torch.tensor(1024.0, device=cuda)
+    for it in range(6):
+        grads = [torch.randn(s, generator=g).to(cuda) * (10.0 ** (it - 3)) for s in shapes]
+        grads[0][::7] = 0.0                                         # untouched hash entries: zero gradient, momentum still moves them
+        inf_step = it == 3
+        for a, b, gr in zip(pa, pb, grads):
+            a.grad = (gr * scale).clone()
+            b.grad = gr.clone()
+        oa.grad_scale, oa.found_inf = scale, torch.tensor(1.0 if inf_step else 0.0, device=cuda)
+        oa.step()
+        if not inf_step:
+            ob.step()
+        for a, b in zip(pa, pb):
+            assert float(a.grad.abs().sum()) == 0.0                 # cleared by the step (also on a skipped step)
+            torch.testing.assert_close(a.detach(), b.detach(), rtol=2e-6, atol=1e-7)
+    for a, b in zip(pa, pb):
+        # the gradients of successive steps span five orders of magnitude: compare the moments to fp32 rounding of their LARGEST
+        # entries (entries that cancel to ~0 carry the absolute rounding error of the big terms in both implementations)
+        ma, mb = oa.state[a]["exp_avg"], ob.state[b]["exp_avg"]
+        va, vb = oa.state[a]["exp_avg_sq"], ob.state[b]["exp_avg_sq"]
+        torch.testing.assert_close(ma, mb, rtol=1e-5, atol=2e-7 * float(mb.abs().max()))
+        torch.testing.assert_close(va, vb, rtol=1e-5, atol=2e-7 * float(vb.abs().max()))
+        assert float(oa.state[a]["step"]) == 5.0
