@@ -60,6 +60,10 @@ constexpr uint32_t DA = 2;    // gathered operand stages
 #ifndef INERF_FIRST_HIT
 #define INERF_FIRST_HIT 1      // 1: leading empty space of every ray is walked by a full-occupancy pre-pass (k_first_hit)
 #endif
+#ifndef INERF_TILE_MIN
+#define INERF_TILE_MIN 0      // > 0: a tile with fewer ready rows waits (at most INERF_TILE_RETRY polls) for more
+#define INERF_TILE_RETRY 0
+#endif
 #ifndef INERF_RAY_PATCH
 #define INERF_RAY_PATCH 1     // 1: marcher warps take 32 consecutive rays at a time (coherent gathers); 0: one ray per free lane
 #endif
@@ -129,6 +133,16 @@ __device__ __forceinline__ bool gather_any(bool pred) {
         "selp.b32 %0, 1, 0, p;\n\t}\n"
         : "=r"(r) : "r"((uint32_t)pred), "n"(kGatherT) : "memory");
     return r != 0;
+}
+
+// number of gather-group threads whose predicate is true (named barrier 2)
+__device__ __forceinline__ uint32_t gather_count(bool pred) {
+    uint32_t r;
+    asm volatile(
+        "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t"
+        "barrier.cta.red.popc.u32 %0, 2, %2, q;\n\t}\n"
+        : "=r"(r) : "r"((uint32_t)pred), "n"(kGatherT) : "memory");
+    return r;
 }
 
 // ------------------------------------------------------------------------------------------------ march --
@@ -256,6 +270,8 @@ __device__ __forceinline__ void gather_role(const inerf_field_desc& desc, const 
     for (uint32_t tile = 0;; tile++) {
         const uint32_t st = tile % DT, sa = tile % DA;
         bool stop = false;
+        uint32_t tries = 0;
+        (void)tries;
         while (true) {   // assemble a tile: one queued sample from every slot that has one
             int32_t sel = -1;
             bool not_finished = false;
@@ -267,7 +283,14 @@ __device__ __forceinline__ void gather_role(const inerf_field_desc& desc, const 
                 ctl->tsel[st][row] = sel;
             }
             if (!gather_any(not_finished)) { stop = true; break; }   // all marchers done and every ring drained
+#if INERF_TILE_MIN > 0
+            // a tile with few rows costs a full chain pass: give lagging marcher lanes a moment (bounded) before emitting it
+            const uint32_t ready = gather_count(sel >= 0);
+            if (ready > 0 && ready < INERF_TILE_MIN && tries < INERF_TILE_RETRY) { tries++; __nanosleep(64); continue; }
+            if (ready > 0) {
+#else
             if (gather_any(sel >= 0)) {
+#endif
 #ifdef INERF_DBG_BUBBLES
                 if (quarter == 0 && sel < 0) atomicAdd(&ctl->bub[ld_vol(&ctl->mstate[row])], 1ull);
                 if (gt == 0) atomicAdd(&ctl->bub[6], 1ull);
