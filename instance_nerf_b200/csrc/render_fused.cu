@@ -40,7 +40,10 @@ constexpr uint32_t kChainT = 256, kGatherT = 512, kMarchT = 128;
 #define INERF_REGS_GATHER 64
 #endif
 constexpr uint32_t kRegsChain = INERF_REGS_CHAIN, kRegsGather = INERF_REGS_GATHER, kRegsMarch = 56;
-static_assert(kChainT * kRegsChain + kGatherT * kRegsGather + kMarchT * kRegsMarch <= 65536, "register budget of the three roles");
+// setmaxnreg moves registers inside the CTA's OWN allocation (threads x the launch register count, 896 x 72 here), not inside
+// the SM's 64 K file: a role budget that sums to more than that never gets its registers and the kernel hangs in setmaxnreg.inc
+static_assert(kChainT * kRegsChain + kGatherT * kRegsGather + kMarchT * kRegsMarch <= (kChainT + kGatherT + kMarchT) * 72,
+              "register budget of the three roles");
 constexpr uint32_t kThreadsR = kChainT + kGatherT + kMarchT;
 #ifndef INERF_RING
 #define INERF_RING 14   // 14 x 3 KB of rings keeps the CTA inside the 196 KB shared-memory carve-out at K <= 32 (60 KB of L1 left)

@@ -114,3 +114,42 @@ def test_reference_packages_import_with_backend_shims():
                 sys.modules.pop(k, None)
             else:
                 sys.modules[k] = v
+
+
+def test_new_entry_points_reject_bad_arguments_without_a_gpu(L):
+    """Argument validation of the entry points added for the single-walk marcher and the fused optimizer step."""
+    assert L.inerf_march_scratch_floats(4096, 1024) == 4096 * 1024 and L.inerf_march_scratch_floats(0, 1024) == 0
+    # C = 0 / non power-of-two H are rejected before any launch
+    assert L.inerf_march_rays_train_count_t(None, None, None, 8.0, 0.0, 1024, 16, 0, 128, None, None, None, None, None, None, None) < 0
+    assert L.inerf_march_rays_train_expand(None, None, 8.0, 0.0, 1024, 16, 4, 100, 64, None, None, None, None, None, None, None, None) < 0
+    # NULL tensors with n > 0
+    assert L.inerf_adam_step(None, None, None, None, 8, 1e-2, 0.9, 0.99, 1e-15, None, None, None, None) == -1
+    assert L.inerf_adam_advance(None, None, None) == -1
+    # n == 0 is a no-op
+    assert L.inerf_adam_step(None, None, None, None, 0, 1e-2, 0.9, 0.99, 1e-15, None, None, None, None) == 0
+
+
+def test_field_desc_struct_matches_header():
+    """ctypes mirror of struct inerf_field_desc: field order / types as declared in include/inerf_b200.h."""
+    hdr = open(os.path.join(ROOT, "include", "inerf_b200.h")).read()
+    body = re.search(r"typedef struct inerf_field_desc \{(.*?)\} inerf_field_desc;", hdr, flags=re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    names = re.findall(r"\b([A-Za-z_][A-Za-z0-9_]*)\s*;", body)
+    assert names == [f[0] for f in _lib.FieldDesc._fields_]
+    assert ctypes.sizeof(_lib.FieldDesc) == 3 * 8 + 6 * 4 + 8   # 3 pointers, 6 x 32-bit, 1 pointer (no padding)
+
+
+def test_bench_reference_arm_prints_exactly_one_json_line():
+    """bench.py's contract: ONE JSON line on stdout (library banners are redirected to stderr); the CPU reference arm runs
+    without a GPU, on a bounded sample."""
+    import json
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, r.stdout
+    j = json.loads(lines[0])
+    assert j["impl"] == "reference" and j["unit"] == "Mrays/s" and j["value"] > 0 and j["gpu_launches"] == 0
+    assert j["cpu_baseline"]["kind"] == "port" and j["e2e"]["h2d_bytes_per_step"] == 0

@@ -181,3 +181,25 @@ def test_update_grid_ema_restatement():
     assert np.array_equal(g[~valid], grid[~valid])
     assert np.all(g[valid] >= tmp[valid]) and np.all(g[valid] >= grid[valid] * np.float32(0.95))
     assert np.array_equal(bits, ro.packbits(g, min(mean, 10.0)))
+
+
+def test_extra_state_sweep_points_restatement():
+    """oracle/field_oracle.extra_state_sweep_points (mask_renderer.py:470-494) against the literal construction: build the
+    whole meshgrid block as the reference does, index it through the C oracle's Morton codes, pick the same cells."""
+    G, bound = 32, 8.0
+    ii = np.arange(G, dtype=np.int32)
+    X, Y, Z = np.meshgrid(ii, ii, ii, indexing="ij")                        # custom_meshgrid(xs, ys, zs)
+    coords = np.stack([X.reshape(-1), Y.reshape(-1), Z.reshape(-1)], -1)     # [G^3, 3], row = (x * G + y) * G + z
+    indices = ro.morton3D(coords).astype(np.int64)                           # raymarching.morton3D(coords)
+    assert np.array_equal(ro.morton3D_invert(indices.astype(np.int32)), coords)
+    noise = np.random.RandomState(3).rand(G ** 3, 3).astype(np.float32)
+    xyzs = (2 * coords.astype(np.float32) / (G - 1) - 1).astype(np.float32)
+    for cas in (0, 2, 3):
+        b = min(2 ** cas, bound)
+        hgs = b / G
+        cas_xyzs = xyzs * np.float32(b - hgs) + (noise * 2 - 1) * np.float32(hgs)     # :485-489
+        by_cell = np.empty_like(cas_xyzs)
+        by_cell[indices] = cas_xyzs                                          # what tmp_grid[cas, indices] = sigma(cas_xyzs) pairs up
+        cells = np.random.RandomState(cas).randint(0, G ** 3, size=500)
+        got = fo.extra_state_sweep_points(cells, cas, G, bound, noise)
+        np.testing.assert_allclose(got, by_cell[cells], rtol=0, atol=1e-6)
