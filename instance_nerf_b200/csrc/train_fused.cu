@@ -40,7 +40,18 @@ struct BSmem {
     static constexpr uint32_t MISC = DF + 2 * kTile * 32 * 4; // LevelGeom[16] | mbarrier | tmem slot | df_full[2] | df_empty[2]
     static constexpr uint32_t bytes = MISC + 16 * sizeof(LevelGeom) + 64;
 };
-constexpr uint32_t kBwdChainT = 256, kBwdScatterT = 256, kBwdThreads = kBwdChainT + kBwdScatterT;
+// INERF_BWD_SCATTER_WARPS = 16 (NOT validated on hardware yet, next round's A/B): thread = (row, 4 levels) with setmaxnreg
+// 104 / 64 -- inside the CTA's own 768 x 80 register allocation, which is all setmaxnreg can redistribute (a 112 / 72 split
+// exceeded it and hung).  Default 8: thread = (row, 8 levels), 127 registers for every thread.
+#ifndef INERF_BWD_SCATTER_WARPS
+#define INERF_BWD_SCATTER_WARPS 8
+#endif
+constexpr uint32_t kBwdChainT = 256, kBwdScatterT = 32 * INERF_BWD_SCATTER_WARPS, kBwdThreads = kBwdChainT + kBwdScatterT;
+constexpr uint32_t kScatLevels = 16 / (kBwdScatterT / kTile);   // levels per scatter thread (8 or 4)
+#if INERF_BWD_SCATTER_WARPS == 16
+constexpr uint32_t kBwdRegsChain = 104, kBwdRegsScatter = 64;
+static_assert(kBwdChainT * kBwdRegsChain + kBwdScatterT * kBwdRegsScatter <= kBwdThreads * 80, "setmaxnreg budget exceeds the CTA's allocation");
+#endif
 constexpr uint32_t kSbo128 = sbo_of(128), kSbo64 = sbo_of(64), kSbo48 = sbo_of(48);
 // TMEM columns (512 allocated: one CTA per SM)
 constexpr uint32_t T_a = 0, T_b = 64, T_x = 128, T_w1 = 160, T_w0 = 288, kBwdTmemCols = 512;
@@ -159,6 +170,9 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_field_backward_mask(inerf_fi
     };
 
     if (chain_role) {
+#if INERF_BWD_SCATTER_WARPS == 16
+    umma::reg_alloc<kBwdRegsChain>();
+#endif
     for (uint32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, tiles_done++) {
         const uint32_t s = tile * kTile + row;
         const bool live = s < B_eff;
@@ -275,17 +289,20 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_field_backward_mask(inerf_fi
     }
     } else {
     // ------------------------------------------------------------------------------------------------ scatter role --
+#if INERF_BWD_SCATTER_WARPS == 16
+    umma::reg_dealloc<kBwdRegsScatter>();
+#endif
     uint32_t it = 0;
     for (uint32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, it++) {
         const uint32_t s = tile * kTile + row;
         const bool live = s < B_eff;
         const uint32_t db = it & 1u;
         umma::mbar_wait(&df_full[db], (it >> 1) & 1u);
-        uint32_t v[16];
+        uint32_t v[2 * kScatLevels];
         {
-            const float* src = reinterpret_cast<const float*>(smem + BSmem::DF) + db * (kTile * 32) + (half * 16) * kTile + row;
+            const float* src = reinterpret_cast<const float*>(smem + BSmem::DF) + db * (kTile * 32) + (half * 2 * kScatLevels) * kTile + row;
 #pragma unroll
-            for (int i = 0; i < 16; i++) v[i] = __float_as_uint(src[i * kTile]);
+            for (uint32_t i = 0; i < 2 * kScatLevels; i++) v[i] = __float_as_uint(src[i * kTile]);
         }
         umma::mbar_arrive(&df_empty[db]);   // the values are in registers: the chain may refill this buffer
         {
@@ -300,15 +317,15 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_field_backward_mask(inerf_fi
             }
             const bool ok = live && !(x01[0] < 0.f || x01[0] > 1.f || x01[1] < 0.f || x01[1] > 1.f || x01[2] < 0.f || x01[2] > 1.f);
 #pragma unroll
-            for (uint32_t li = 0; li < 8; li++) {
+            for (uint32_t li = 0; li < kScatLevels; li++) {
                 float g0 = ok ? __uint_as_float(v[2 * li]) : 0.f, g1 = ok ? __uint_as_float(v[2 * li + 1]) : 0.f;
-                const LevelGeom g = lg[half * 8 + li];
+                const LevelGeom g = lg[half * kScatLevels + li];
                 uint32_t idx[8];
                 float w[8];
                 float xs[3] = {ok ? x01[0] : 0.f, ok ? x01[1] : 0.f, ok ? x01[2] : 0.f};
                 level_corners(xs, g, idx, w);
                 float2* base = p.grad_table + g.offset;
-                if (half == 0) {
+                if (half * kScatLevels < 8) {   // levels 0..7 (warp-uniform)
                     // run heads: first lane, or a lane whose cell differs from the previous lane's (corner 0 and corner 7
                     // together identify the cell; a hash collision only splits or merges runs of identical addresses)
                     const uint32_t p0 = __shfl_up_sync(0xffffffffu, idx[0], 1), p7 = __shfl_up_sync(0xffffffffu, idx[7], 1);
