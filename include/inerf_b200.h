@@ -78,24 +78,13 @@ int inerf_packbits(const float *grid, uint32_t N, float density_thresh, uint8_t 
  * counts, i.e. exactly the canonical form of the reference's stream.
  *
  * Two-phase use (lets the host size xyzs/dirs/deltas exactly instead of
- * zero-filling N*max_steps rows as raymarching.py:205-207 does):
- *   inerf_march_rays_train_count  writes rays[N,3] and adds (total, N) to counter[2];
- *   inerf_march_rays_train_write  writes the samples of every ray with offset+count <= M.
- * inerf_march_rays_train does both with the reference's argument list.
- */
-int inerf_march_rays_train_count(const float *rays_o, const float *rays_d, const uint8_t *grid, float bound,
-                                 float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H,
-                                 const float *nears, const float *fars, int32_t *rays, int32_t *counter,
-                                 const float *noises, void *stream);
-int inerf_march_rays_train_write(const float *rays_o, const float *rays_d, const uint8_t *grid, float bound,
-                                 float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M,
-                                 const float *nears, const float *fars, float *xyzs, float *dirs, float *deltas,
-                                 const int32_t *rays, const float *noises, void *stream);
-/*
- * Single-walk variant: the caller passes a float scratch of inerf_march_scratch_floats(N, max_steps) elements
- * ([N, max_steps], uninitialised) to
- * inerf_march_rays_train_count_t, which also records the parameter t of every sample, and replaces the _write call by
- * inerf_march_rays_train_expand (one warp per ray, no second walk, coalesced stores).  Same stream, bit for bit.
+ * zero-filling N*max_steps rows as raymarching.py:205-207 does), every ray walked ONCE:
+ *   inerf_march_rays_train_count_t  walks, writes rays[N,3], adds (total, N) to counter[2] and records the
+ *                                   parameter t of every sample in t_scratch;
+ *   inerf_march_rays_train_expand   rebuilds the samples of every ray with offset+count <= M from t alone (one warp
+ *                                   per ray, coalesced stores) -- the reference walks every ray a second time (:403-479).
+ * inerf_march_rays_train does both with the reference's argument list plus the workspace.
+ * t_scratch: caller-owned float[inerf_march_scratch_floats(N, max_steps)] = [N, max_steps], uninitialised.
  */
 size_t inerf_march_scratch_floats(uint32_t N, uint32_t max_steps);
 int inerf_march_rays_train_count_t(const float *rays_o, const float *rays_d, const uint8_t *grid, float bound,
@@ -109,7 +98,7 @@ int inerf_march_rays_train_expand(const float *rays_o, const float *rays_d, floa
 int inerf_march_rays_train(const float *rays_o, const float *rays_d, const uint8_t *grid, float bound, float dt_gamma,
                            uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M, const float *nears,
                            const float *fars, float *xyzs, float *dirs, float *deltas, int32_t *rays,
-                           int32_t *counter, const float *noises, void *stream);
+                           int32_t *counter, const float *noises, float *t_scratch, void *stream);
 
 /* --------------------------------------------------- training compositing -- */
 

@@ -70,9 +70,7 @@ _PROTOS = {
     "inerf_morton3D": [_P, _U, _P, _P],
     "inerf_morton3D_invert": [_P, _U, _P, _P],
     "inerf_packbits": [_P, _U, _F, _P, _P],
-    "inerf_march_rays_train_count": [_P, _P, _P, _F, _F, _U, _U, _U, _U, _P, _P, _P, _P, _P, _P],
-    "inerf_march_rays_train_write": [_P, _P, _P, _F, _F, _U, _U, _U, _U, _U, _P, _P, _P, _P, _P, _P, _P, _P],
-    "inerf_march_rays_train": [_P, _P, _P, _F, _F, _U, _U, _U, _U, _U, _P, _P, _P, _P, _P, _P, _P, _P, _P],
+    "inerf_march_rays_train": [_P, _P, _P, _F, _F, _U, _U, _U, _U, _U, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "inerf_march_rays_train_count_t": [_P, _P, _P, _F, _F, _U, _U, _U, _U, _P, _P, _P, _P, _P, _P, _P],
     "inerf_march_rays_train_expand": [_P, _P, _F, _F, _U, _U, _U, _U, _U, _P, _P, _P, _P, _P, _P, _P, _P],
     "inerf_composite_rays_train_forward": [_P, _P, _P, _P, _U, _U, _F, _P, _P, _P, _P],

@@ -19,7 +19,7 @@ from types import SimpleNamespace
 
 import torch
 
-from ._lib import call, ptr, stream_ptr
+from ._lib import call, lib, ptr, stream_ptr
 
 _DT = {torch.float32: 0, torch.float16: 1}
 
@@ -50,8 +50,10 @@ def _packbits(grid, N, density_thresh, bitfield):
 
 
 def _march_rays_train(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, M, nears, fars, xyzs, dirs, deltas, rays, counter, noises):
+    # the reference's argument list + the caller-owned workspace the single-walk marcher needs (include/inerf_b200.h)
+    scratch = torch.empty(max(1, int(lib().inerf_march_scratch_floats(int(N), int(max_steps)))), dtype=torch.float32, device=rays_o.device)
     call("inerf_march_rays_train", ptr(rays_o), ptr(rays_d), ptr(grid), float(bound), float(dt_gamma), int(max_steps), int(N), int(C), int(H),
-         int(M), ptr(nears), ptr(fars), ptr(xyzs), ptr(dirs), ptr(deltas), ptr(rays), ptr(counter), ptr(noises), _st(rays_o))
+         int(M), ptr(nears), ptr(fars), ptr(xyzs), ptr(dirs), ptr(deltas), ptr(rays), ptr(counter), ptr(noises), ptr(scratch), _st(rays_o))
 
 
 def _composite_rays_train_forward(sigmas, rgbs, deltas, rays, M, N, T_thresh, weights_sum, depth, image):

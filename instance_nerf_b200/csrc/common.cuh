@@ -14,5 +14,11 @@ static inline unsigned int div_up(unsigned long long a, unsigned int b) { return
 
 // B200: 148 SMs.  Grid-stride kernels are sized to a multiple of this.
 constexpr int kNumSMs = 148;
+// SM count of the CURRENT device (persistent kernels launch one CTA per SM); falls back to the B200 figure on error
+static inline int device_sm_count() {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return kNumSMs;
+    return n;
+}
 
 __device__ __forceinline__ float clampf(float x, float lo, float hi) { return fminf(hi, fmaxf(lo, x)); }

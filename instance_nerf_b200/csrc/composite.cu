@@ -6,18 +6,14 @@
 // Mapping: ONE WARP PER RAY instead of the reference's one thread per ray.
 //   * the sample stream (sigma, deltas, rgb) is read 32 samples at a time with
 //     coalesced loads, alpha is evaluated for 32 samples in parallel;
-//   * lane k owns instance class k (+32, +64, ...): logits[s, :] is one coalesced
-//     128-byte load per sample and the K running sums live in registers, where
-//     the reference read-modify-writes mask_out / grad_masks_acc in global memory
-//     2K times per sample (raymarching.cu:766-768, 894-896);
-//   * the transmittance recurrence T *= (1 - alpha) is evaluated in the
-//     reference's order (every lane redundantly), so the early-stop decision
-//     `T < T_thresh` is warp-uniform and matches the reference sample for sample.
+//   * the K running sums live in registers, where the reference read-modify-writes
+//     mask_out / grad_masks_acc in global memory 2K times per sample
+//     (raymarching.cu:766-768, 894-896);
+//   * training kernels: the transmittance recurrence, the depth prefix and the
+//     "still to come" terms of grad_sigma are warp scans over 32-sample chunks
+//     (see the block comment below); the early-stop decision `T < T_thresh` is one
+//     ballot and matches the reference sample for sample.
 #include "common.cuh"
-
-#ifndef INERF_COMPOSITE_SCAN
-#define INERF_COMPOSITE_SCAN 1   // 1: scan formulation of the training kernels (default); 0: per-sample replay in every lane
-#endif
 
 namespace {
 
@@ -34,94 +30,11 @@ __device__ __forceinline__ float warp_sum(float v) {
 // kRowsInFlight independent 128-byte row loads back to back (64 warps/SM x 8 x 128 B = 64 KB in flight per SM).
 constexpr int kRowsInFlight = 8;
 
-// ---- training forward (K == 0: plain, raymarching.cu:500-577; K > 0: :705-799) ----
-// Per 32-sample chunk: phase A = the T recurrence / colour / depth sums in the reference's order (every lane redundantly,
-// shuffles only), leaving w_j in lane j and the number m of samples that contribute (early stop included);
-// phase B = macc[k] += w_j * logits[j, k] for j < m in the same order, as a pure stream.
-template <int KPL>
-__global__ void __launch_bounds__(256) k_composite_train_fwd(
-    const float* __restrict__ sigmas, const float* __restrict__ rgbs, const float* __restrict__ masks,
-    const float* __restrict__ deltas, const int32_t* __restrict__ rays, uint32_t M, uint32_t N, uint32_t K,
-    float T_thresh, float* __restrict__ weights_sum, float* __restrict__ depth, float* __restrict__ image,
-    float* __restrict__ mask_out) {
-    const uint32_t lane = threadIdx.x & 31;
-    const uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (n >= N) return;
-    const uint32_t index = (uint32_t)rays[n * 3], offset = (uint32_t)rays[n * 3 + 1], num_steps = (uint32_t)rays[n * 3 + 2];
-
-    float macc[KPL > 0 ? KPL : 1];
-#pragma unroll
-    for (int i = 0; i < (KPL > 0 ? KPL : 1); i++) macc[i] = 0.f;
-    float T = 1.0f, r = 0, g = 0, b = 0, ws = 0, t = 0, d = 0;
-
-    if (num_steps != 0 && offset + num_steps <= M) {
-        bool done = false;
-        for (uint32_t base = 0; base < num_steps && !done; base += 32) {
-            const uint32_t s = offset + base + lane;
-            const bool valid = base + lane < num_steps;
-            float alpha = 0.f, d1 = 0.f, cr = 0.f, cg = 0.f, cb = 0.f;
-            if (valid) {
-                const float2 dl = __ldg(reinterpret_cast<const float2*>(deltas) + s);
-                alpha = 1.0f - __expf(-__ldg(sigmas + s) * dl.x);
-                d1 = dl.y;
-                cr = __ldg(rgbs + (size_t)s * 3); cg = __ldg(rgbs + (size_t)s * 3 + 1); cb = __ldg(rgbs + (size_t)s * 3 + 2);
-            }
-            const uint32_t cnt = min(32u, num_steps - base);
-            uint32_t m = cnt;
-            float my_w = 0.f;
-            for (uint32_t j = 0; j < cnt; j++) {
-                const float a = __shfl_sync(kFull, alpha, j);
-                const float weight = a * T;
-                r = fmaf(weight, __shfl_sync(kFull, cr, j), r);
-                g = fmaf(weight, __shfl_sync(kFull, cg, j), g);
-                b = fmaf(weight, __shfl_sync(kFull, cb, j), b);
-                t += __shfl_sync(kFull, d1, j);
-                d = fmaf(weight, t, d);
-                ws += weight;
-                T *= 1.0f - a;
-                if (lane == j) my_w = weight;
-                if (T < T_thresh) { done = true; m = j + 1; break; }
-            }
-            if (KPL > 0) {
-                const float* mbase = masks + (size_t)(offset + base) * K;
-                for (uint32_t j0 = 0; j0 < m; j0 += kRowsInFlight) {
-                    float v[kRowsInFlight][KPL > 0 ? KPL : 1];
-#pragma unroll
-                    for (int u = 0; u < kRowsInFlight; u++)
-#pragma unroll
-                        for (int i = 0; i < KPL; i++) {
-                            const uint32_t k = lane + 32u * i;
-                            v[u][i] = (j0 + u < m && k < K) ? __ldg(mbase + (size_t)(j0 + u) * K + k) : 0.f;
-                        }
-#pragma unroll
-                    for (int u = 0; u < kRowsInFlight; u++) {
-                        if (j0 + u < m) {   // warp-uniform
-                            const float weight = __shfl_sync(kFull, my_w, j0 + u);
-#pragma unroll
-                            for (int i = 0; i < KPL; i++) macc[i] = fmaf(weight, v[u][i], macc[i]);
-                        }
-                    }
-                }
-            }
-        }
-    }
-    if (lane == 0) {
-        weights_sum[index] = ws;
-        depth[index] = d;
-        image[(size_t)index * 3] = r; image[(size_t)index * 3 + 1] = g; image[(size_t)index * 3 + 2] = b;
-    }
-    if (KPL > 0) {
-#pragma unroll
-        for (int i = 0; i < KPL; i++) {
-            const uint32_t k = lane + 32u * i;
-            if (k < K) mask_out[(size_t)index * K + k] = macc[i];
-        }
-    }
-}
-
-// ---- training backward (K == 0: raymarching.cu:601-682; K > 0: :828-940) ----
-// Same two phases.  Phase A leaves in lane j: w_j, T_j (after sample j) and the colour / weights_sum part of grad_sigma_j.
-// Phase B streams the logit rows: macc, grad_masks = g_m * w_j, and the K-term sum of grad_sigma_j (warp reduce per row).
+// ---- training backward for K > 64 (K == 0: raymarching.cu:601-682; K > 0: :828-940) ----
+// Many-class path only (the scan kernel below keeps a ray's K logit gradients in registers, which stops at K = 64): lane k
+// owns class k (+32, ...).  Phase A replays the recurrence in the reference's order (every lane redundantly) and leaves in
+// lane j: w_j, T_j (after sample j) and the colour / weights_sum part of grad_sigma_j.  Phase B streams the logit rows:
+// macc, grad_masks = g_m * w_j, and the K-term sum of grad_sigma_j (one warp reduction per row).
 template <int KPL>
 __global__ void __launch_bounds__(256) k_composite_train_bwd(
     const float* __restrict__ grad_weights_sum, const float* __restrict__ grad_image, const float* __restrict__ grad_mask_out,
@@ -215,10 +128,10 @@ __global__ void __launch_bounds__(256) k_composite_train_bwd(
     }
 }
 
-// ---- training forward / backward, scan formulation (default) -------------------------------------------------------------
-// The kernels above replay the reference's per-sample recurrence in every lane and broadcast each sample with shuffles:
-// 5-11 SHFL per sample, and the shuffle unit retires one warp instruction per clock per SM -- that, not HBM, bounds them
-// (forward 0.45, backward 0.38 of HBM peak at K = 32).  Here lane j of a 32-sample chunk owns sample j:
+// ---- training forward / backward, scan formulation -------------------------------------------------------------------------
+// Replaying the reference's per-sample recurrence in every lane and broadcasting each sample costs 5-11 SHFL per sample, and
+// the shuffle unit retires one warp instruction per clock per SM -- that, not HBM, bounded the first version of these kernels
+// (forward 0.45, backward 0.38 of HBM peak at K = 32; DESIGN.md 4.3).  Here lane j of a 32-sample chunk owns sample j:
 //   T_j      = T_carry * prod_{i<=j}(1 - alpha_i)          one inclusive product scan (5 SHFL per CHUNK)
 //   stop     = first j with T_j < T_thresh                  one ballot; samples after it get weight 0 (raymarching.cu:573)
 //   w_j      = alpha_j * T_{j-1},  t_j = t_carry + sum_{i<=j} delta1_i   (one add scan)
@@ -495,13 +408,7 @@ int composite_train_fwd(const float* sigmas, const float* rgbs, const float* mas
     if (K) { INERF_REQUIRE(mask_out); if (M) INERF_REQUIRE(masks); }
     if ((uintptr_t)deltas & 7u) return INERF_ERR_ALIGN;
     return dispatch_kpl(K, [&](auto kpl) {
-#if INERF_COMPOSITE_SCAN
         k_composite_train_fwd_scan<decltype(kpl)::value><<<div_up((unsigned long long)N * 32, 256), 256, 0, (cudaStream_t)stream>>>(
-            sigmas, rgbs, masks, deltas, rays, M, N, K, T_thresh, weights_sum, depth, image, mask_out);
-        INERF_LAUNCH_CHECK();
-        return (int)INERF_OK;
-#endif
-        k_composite_train_fwd<decltype(kpl)::value><<<div_up((unsigned long long)N * 32, 256), 256, 0, (cudaStream_t)stream>>>(
             sigmas, rgbs, masks, deltas, rays, M, N, K, T_thresh, weights_sum, depth, image, mask_out);
         INERF_LAUNCH_CHECK();
         return (int)INERF_OK;
@@ -517,18 +424,15 @@ int composite_train_bwd(const float* grad_weights_sum, const float* grad_image, 
     INERF_REQUIRE(rays); INERF_REQUIRE(weights_sum); INERF_REQUIRE(image); INERF_REQUIRE(grad_sigmas); INERF_REQUIRE(grad_rgbs);
     if (K) { INERF_REQUIRE(grad_mask_out); INERF_REQUIRE(masks); INERF_REQUIRE(mask_out); INERF_REQUIRE(grad_masks); }
     return dispatch_kpl(K, [&](auto kpl) {
-#if INERF_COMPOSITE_SCAN
         if constexpr (decltype(kpl)::value <= 2) {   // K <= 64: the ray's logit gradients fit in registers
             k_composite_train_bwd_scan<decltype(kpl)::value><<<div_up((unsigned long long)N * 32, 256), 256, 0, (cudaStream_t)stream>>>(
                 grad_weights_sum, grad_image, grad_mask_out, sigmas, rgbs, masks, deltas, rays, weights_sum, image, mask_out, M, N, K,
                 T_thresh, grad_sigmas, grad_rgbs, grad_masks);
-            INERF_LAUNCH_CHECK();
-            return (int)INERF_OK;
+        } else {
+            k_composite_train_bwd<decltype(kpl)::value><<<div_up((unsigned long long)N * 32, 256), 256, 0, (cudaStream_t)stream>>>(
+                grad_weights_sum, grad_image, grad_mask_out, sigmas, rgbs, masks, deltas, rays, weights_sum, image, mask_out, M, N, K,
+                T_thresh, grad_sigmas, grad_rgbs, grad_masks);
         }
-#endif
-        k_composite_train_bwd<decltype(kpl)::value><<<div_up((unsigned long long)N * 32, 256), 256, 0, (cudaStream_t)stream>>>(
-            grad_weights_sum, grad_image, grad_mask_out, sigmas, rgbs, masks, deltas, rays, weights_sum, image, mask_out, M, N, K,
-            T_thresh, grad_sigmas, grad_rgbs, grad_masks);
         INERF_LAUNCH_CHECK();
         return (int)INERF_OK;
     });

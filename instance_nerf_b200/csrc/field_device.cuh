@@ -14,10 +14,6 @@
 #include "common.cuh"
 #include "umma.cuh"
 
-#ifndef INERF_FMUL2
-#define INERF_FMUL2 1   // packed fp32 multiplies (FMUL2) in the trilinear blend: identical products, -0.2 ms/frame at c2
-#endif
-
 namespace field {
 
 constexpr int kTile = 128;        // samples per tile = TMEM lanes = UMMA M
@@ -157,50 +153,23 @@ __device__ __forceinline__ void encode_level(const float x01[3], const LevelGeom
     level_corners(x01, g, idx, w);
     const uint2* base = table + g.offset;
     uint2 v[8];
-#ifdef INERF_DBG_NO_GATHER_LOADS   // dev experiment (scripts/gpu_ab.sh): index math kept alive, no table traffic
-#pragma unroll
-    for (uint32_t c = 0; c < 8; c++) v[c] = make_uint2(idx[c] * 0x9E3779B1u, idx[c]);
-    (void)base;
-#else
     // One 8-byte gather per corner.  (Tried and rejected on B200: fetching the x-neighbour with one aligned 16-byte gather when
     // it is entry a^1 -- 23 % fewer L1 sectors but LDG.128 scatters cost as many data-pipe wavefronts, +6 % time)
 #pragma unroll
     for (uint32_t c = 0; c < 8; c++) v[c] = __ldg(base + idx[c]);
-#endif
     __half2 as = __float2half2_rn(0.f), am = as;
 #pragma unroll
     for (uint32_t c = 0; c < 8; c++) {
         const float2 fs = __half22float2(bits_h2(v[c].x));
         const float2 fm = __half22float2(bits_h2(v[c].y));
-#if INERF_FMUL2   // packed fp32 multiply (FMUL2, sm_100): same round-to-nearest products, half the multiply issue slots
+        // packed fp32 multiply (FMUL2, sm_100): same round-to-nearest products, half the multiply issue slots (-0.2 ms / c2 frame)
         const float2 ww = make_float2(w[c], w[c]);
         const float2 ps = __fmul2_rn(ww, fs), pm = __fmul2_rn(ww, fm);
         as = __hadd2(as, __floats2half2_rn(ps.x, ps.y));
         am = __hadd2(am, __floats2half2_rn(pm.x, pm.y));
-#else
-        as = __hadd2(as, __floats2half2_rn(__fmul_rn(w[c], fs.x), __fmul_rn(w[c], fs.y)));
-        am = __hadd2(am, __floats2half2_rn(__fmul_rn(w[c], fm.x), __fmul_rn(w[c], fm.y)));
-#endif
     }
     out_s = h2_bits(as);
     out_m = h2_bits(am);
-}
-
-// Encode 8 consecutive levels [l0, l0+8) of one point and store the 16+16 fp16 features as 2+2 16-byte core-matrix rows.
-__device__ __forceinline__ void encode8(const float x01[3], bool oob, uint32_t l0, const LevelGeom* __restrict__ lg,
-                                        const uint2* __restrict__ table, uint8_t* smem, uint32_t a_es, uint32_t a_mi, uint32_t row) {
-    uint32_t fs[8], fm[8];
-#pragma unroll
-    for (uint32_t li = 0; li < 8; li++) {
-        encode_level(x01, lg[l0 + li], table, fs[li], fm[li]);
-        if (oob) { fs[li] = 0u; fm[li] = 0u; }
-    }
-    // features k = 2*level + ch: levels l0..l0+3 -> one 16-byte chunk, l0+4..l0+7 -> the next
-    const uint32_t k0 = l0 * 2;
-    *reinterpret_cast<uint4*>(smem + a_es + umma::tile_off(row, k0, kLBO, sbo_of(32))) = make_uint4(fs[0], fs[1], fs[2], fs[3]);
-    *reinterpret_cast<uint4*>(smem + a_es + umma::tile_off(row, k0 + 8, kLBO, sbo_of(32))) = make_uint4(fs[4], fs[5], fs[6], fs[7]);
-    *reinterpret_cast<uint4*>(smem + a_mi + umma::tile_off(row, k0, kLBO, sbo_of(48))) = make_uint4(fm[0], fm[1], fm[2], fm[3]);
-    *reinterpret_cast<uint4*>(smem + a_mi + umma::tile_off(row, k0 + 8, kLBO, sbo_of(48))) = make_uint4(fm[4], fm[5], fm[6], fm[7]);
 }
 
 // Encode 4 consecutive levels [l0, l0+4) of one point: one 16-byte core-matrix row chunk per table.
@@ -210,53 +179,6 @@ __device__ __forceinline__ void encode4(const float x01[3], bool oob, uint32_t l
 #pragma unroll
     for (uint32_t li = 0; li < 4; li++) {
         encode_level(x01, lg[l0 + li], table, fs[li], fm[li]);
-        if (oob) { fs[li] = 0u; fm[li] = 0u; }
-    }
-    const uint32_t k0 = l0 * 2;
-    *reinterpret_cast<uint4*>(smem + a_es + umma::tile_off(row, k0, kLBO, sbo_of(32))) = make_uint4(fs[0], fs[1], fs[2], fs[3]);
-    *reinterpret_cast<uint4*>(smem + a_mi + umma::tile_off(row, k0, kLBO, sbo_of(48))) = make_uint4(fm[0], fm[1], fm[2], fm[3]);
-}
-
-// Software-pipelined encode4: the 8 gathers of level l + 1 are issued BEFORE level l's values are blended, so a thread keeps 16
-// table loads in flight instead of 8 (the straightforward loop above compiles to load-8 / wait / blend per level, and the
-// gather warps spend most of their time on the long-scoreboard of those loads).  Same arithmetic.
-__device__ __forceinline__ void blend_level(const uint2 (&v)[8], const float (&w)[8], uint32_t& out_s, uint32_t& out_m) {
-    __half2 as = __float2half2_rn(0.f), am = as;
-#pragma unroll
-    for (uint32_t c = 0; c < 8; c++) {
-        const float2 fs = __half22float2(bits_h2(v[c].x));
-        const float2 fm = __half22float2(bits_h2(v[c].y));
-        const float2 ww = make_float2(w[c], w[c]);
-        const float2 ps = __fmul2_rn(ww, fs), pm = __fmul2_rn(ww, fm);
-        as = __hadd2(as, __floats2half2_rn(ps.x, ps.y));
-        am = __hadd2(am, __floats2half2_rn(pm.x, pm.y));
-    }
-    out_s = h2_bits(as);
-    out_m = h2_bits(am);
-}
-__device__ __forceinline__ void encode4_pipelined(const float x01[3], bool oob, uint32_t l0, const LevelGeom* __restrict__ lg,
-                                                  const uint2* __restrict__ table, uint8_t* smem, uint32_t a_es, uint32_t a_mi, uint32_t row) {
-    uint32_t fs[4], fm[4];
-    uint2 v[2][8];
-    float w[2][8];
-    {
-        uint32_t idx[8];
-        const LevelGeom g = lg[l0];
-        level_corners(x01, g, idx, w[0]);
-#pragma unroll
-        for (uint32_t c = 0; c < 8; c++) v[0][c] = __ldg(table + g.offset + idx[c]);
-    }
-#pragma unroll
-    for (uint32_t li = 0; li < 4; li++) {
-        const uint32_t cur = li & 1u, nxt = cur ^ 1u;
-        if (li + 1 < 4) {
-            uint32_t idx[8];
-            const LevelGeom g = lg[l0 + li + 1];
-            level_corners(x01, g, idx, w[nxt]);
-#pragma unroll
-            for (uint32_t c = 0; c < 8; c++) v[nxt][c] = __ldg(table + g.offset + idx[c]);
-        }
-        blend_level(v[cur], w[cur], fs[li], fm[li]);
         if (oob) { fs[li] = 0u; fm[li] = 0u; }
     }
     const uint32_t k0 = l0 * 2;
@@ -316,7 +238,7 @@ __device__ __forceinline__ void issue_gemm2(uint32_t smem_base, uint32_t a_off, 
 }
 // D[128 x N] (+)= A^T * B, the reduction running over the 128 ROWS (samples) of two K-major tiles: A is [128 x 128 cols]
 // (row-group stride sbo_a), B is [128 x N cols] (sbo_b).  The tiles are read as MN-major operands: same bytes, descriptor
-// LBO = row-group stride, SBO = 128 (validated by csrc/probe/umma_probe_t.cu).
+// LBO = row-group stride, SBO = 128 (validated by scripts/probe/umma_probe_t.cu).
 __device__ __forceinline__ void issue_gemm_tn(uint32_t smem_base, uint32_t a_off, uint32_t sbo_a, uint32_t b_off, uint32_t sbo_b, uint32_t N,
                                               uint32_t tmem_d, bool accumulate) {
     const uint32_t idesc = umma::make_idesc_f16(128, N) | (1u << 15) | (1u << 16);   // a_major = b_major = MN
@@ -399,13 +321,6 @@ __device__ __forceinline__ float mlp_chain(uint8_t* smem, const ChainBufs& b, ui
     const uint32_t sbase = umma::smem_u32(smem);
     const WeightLayout wl = weight_layout(K);
     const bool issuer = tid == 0;
-#ifdef INERF_DBG_NO_MLP   // dev experiment: the chain only releases the operand stage and composites a constant density
-    if (issuer && release_bar) { umma::fence_after_sync(); umma::commit(release_bar); }
-    __syncwarp();
-    on_sigma(0.05f);
-    sync();
-    return 0.05f;
-#endif
     // sigma layer 0
     if (issuer) {
         umma::fence_after_sync();

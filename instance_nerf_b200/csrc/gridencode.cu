@@ -350,9 +350,6 @@ __global__ void __launch_bounds__(256) k_grid_bwd3x2(const T* __restrict__ grad,
 
 template <typename T>
 bool fast_path_ok(uint32_t D, uint32_t C, uint32_t L, uint32_t gridtype, bool ac, uint32_t interp, int layout, const void* table, const void* act) {
-#ifdef INERF_NO_GRID_FAST
-    return false;
-#endif
     return D == 3 && C == 2 && L % 4 == 0 && L <= 64 && gridtype == 0 && !ac && interp == 0 && layout == 1 &&
            ((uintptr_t)table & (2 * sizeof(T) - 1)) == 0 && ((uintptr_t)act & 15u) == 0 && ((L / 4) * 2 * sizeof(T)) % 16 == 0;
 }

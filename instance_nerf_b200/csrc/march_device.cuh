@@ -148,39 +148,6 @@ struct Walk {
         tt = __fadd_rn(t, fmaxf(0.0f, fminf(tx, fminf(ty, tz))));
         return false;
     }
-
-    // Advance from `t` to the next occupied sample.  On success returns true with the sample position in
-    // (x, y, z), its step in dt, and t advanced past it; on exhaustion (t >= far) returns false.
-    template <bool CACHED = false>
-    __device__ __forceinline__ bool next_sample(float& t, float& x, float& y, float& z, float& dt) {
-        while (t < far) {
-            x = clampf(__fmaf_rn(t, dx, ox), -bound, bound);
-            y = clampf(__fmaf_rn(t, dy, oy), -bound, bound);
-            z = clampf(__fmaf_rn(t, dz, oz), -bound, bound);
-            dt = step_size(t);
-            const float mx = fmaxf(fabsf(x), fmaxf(fabsf(y), fabsf(z)));
-            const float md = __fmul_rn(__fmul_rn(dt, Hf), 0.5f);
-            const int level = max(clamped_exponent(mx, C), clamped_exponent(md, C));
-            const float mip_bound = fminf(__uint_as_float((uint32_t)(127 + level) << 23), bound);
-            const float mip_rbound = __fdiv_rn(1.0f, mip_bound);
-            const float hH = __fmul_rn(0.5f, Hf);
-            const int nx = (int)clampf(__fmul_rn(__fmaf_rn(x, mip_rbound, 1.0f), hH), 0.0f, Hm1);
-            const int ny = (int)clampf(__fmul_rn(__fmaf_rn(y, mip_rbound, 1.0f), hH), 0.0f, Hm1);
-            const int nz = (int)clampf(__fmul_rn(__fmaf_rn(z, mip_rbound, 1.0f), hH), 0.0f, Hm1);
-            const uint32_t index = (uint32_t)__fmaf_rn((float)level, H3, (float)morton3D_enc(nx, ny, nz));
-            const bool occ = CACHED ? occupied_cached(index) : (grid[index >> 3] & (1u << (index & 7u))) != 0;
-            if (occ) {
-                t = __fadd_rn(t, dt);
-                return true;
-            }
-            const float tx = __fmul_rn(__fmaf_rn(__fmaf_rn(__fmul_rn(__fadd_rn(__fadd_rn((float)nx, 0.5f), sx), rH), 2.0f, -1.0f), mip_bound, -x), rdx);
-            const float ty = __fmul_rn(__fmaf_rn(__fmaf_rn(__fmul_rn(__fadd_rn(__fadd_rn((float)ny, 0.5f), sy), rH), 2.0f, -1.0f), mip_bound, -y), rdy);
-            const float tz = __fmul_rn(__fmaf_rn(__fmaf_rn(__fmul_rn(__fadd_rn(__fadd_rn((float)nz, 0.5f), sz), rH), 2.0f, -1.0f), mip_bound, -z), rdz);
-            const float tt = __fadd_rn(t, fmaxf(0.0f, fminf(tx, fminf(ty, tz))));
-            do { t = __fadd_rn(t, step_size(t)); } while (t < tt);
-        }
-        return false;
-    }
 };
 
 

@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(128) k_march_count(const float* __restrict__ r
     w.init(rays_o + (size_t)n * 3, rays_d + (size_t)n * 3, grid, bound, dt_gamma, max_steps, C, H, fars[n]);
     float t0 = nears[n];
     t0 = __fmaf_rn(w.step_size(t0), noises[n], t0);  // :351
-    rays[n * 3 + 2] = (int32_t)w.run<false>(t0, max_steps, nullptr, nullptr, nullptr, t_scratch ? t_scratch + (size_t)n * max_steps : nullptr);
+    rays[n * 3 + 2] = (int32_t)w.run<false>(t0, max_steps, nullptr, nullptr, nullptr, t_scratch + (size_t)n * max_steps);
 }
 
 // Second phase when the count pass recorded every sample's t (t_scratch [N, max_steps]): no second walk.  One warp per ray,
@@ -240,23 +240,6 @@ __global__ void __launch_bounds__(1024) k_march_scan(int32_t* __restrict__ rays,
     if (threadIdx.x == 0) { counter[0] = (int32_t)carry_s; counter[1] += (int32_t)N; }
 }
 
-__global__ void __launch_bounds__(128) k_march_write(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
-                                                     const uint8_t* __restrict__ grid, float bound, float dt_gamma,
-                                                     uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M,
-                                                     const float* __restrict__ nears, const float* __restrict__ fars,
-                                                     const float* __restrict__ noises, const int32_t* __restrict__ rays,
-                                                     float* __restrict__ xyzs, float* __restrict__ dirs, float* __restrict__ deltas) {
-    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= N) return;
-    const uint32_t offset = (uint32_t)rays[n * 3 + 1], num_steps = (uint32_t)rays[n * 3 + 2];
-    if (num_steps == 0 || offset + num_steps > M) return;  // :415-416
-    Walk w;
-    w.init(rays_o + (size_t)n * 3, rays_d + (size_t)n * 3, grid, bound, dt_gamma, max_steps, C, H, fars[n]);
-    float t0 = nears[n];
-    t0 = __fmaf_rn(w.step_size(t0), noises[n], t0);
-    w.run<true>(t0, num_steps, xyzs + (size_t)offset * 3, dirs + (size_t)offset * 3, deltas + (size_t)offset * 2);
-}
-
 // ---- training marching, one WARP per ray (small batches) -------------------------------------------------------------
 // With a few thousand rays the thread-per-ray kernels above run one serial chain of ~4*10^4 dependent instructions per
 // ray on a fraction of a warp slot per SM (c3: 4096 rays = 128 warps on 148 SMs, 120-150 us per pass).  Here the 32
@@ -266,27 +249,19 @@ __global__ void __launch_bounds__(128) k_march_write(const float* __restrict__ r
 // evaluation point to the first t_m >= its exit parameter.  So every lane takes one candidate t_{n+lane}, evaluates its
 // cell (occupancy, exit parameter) in parallel, and the warp then replays the reference's pointer chase over the 32
 // results with ballots.  Same samples bit for bit (tests/test_ops_vs_ref_gpu.py); writes are coalesced.
-template <bool WRITE>
 __global__ void __launch_bounds__(256) k_march_train_warp(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
                                                           const uint8_t* __restrict__ grid, float bound, float dt_gamma, uint32_t max_steps,
-                                                          uint32_t N, uint32_t C, uint32_t H, uint32_t M, const float* __restrict__ nears,
+                                                          uint32_t N, uint32_t C, uint32_t H, const float* __restrict__ nears,
                                                           const float* __restrict__ fars, const float* __restrict__ noises,
-                                                          int32_t* __restrict__ rays, float* __restrict__ xyzs, float* __restrict__ dirs,
-                                                          float* __restrict__ deltas, float* __restrict__ t_scratch) {
+                                                          int32_t* __restrict__ rays, float* __restrict__ t_scratch) {
     const uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
     if (n >= N) return;
-    float* ts = (!WRITE && t_scratch) ? t_scratch + (size_t)n * max_steps : nullptr;   // count pass: record t per sample
-    uint32_t limit = max_steps, offset = 0;
-    if (WRITE) {
-        offset = (uint32_t)rays[n * 3 + 1];
-        limit = (uint32_t)rays[n * 3 + 2];
-        if (limit == 0 || offset + limit > M) return;  // :415-416
-    }
+    float* ts = t_scratch + (size_t)n * max_steps;   // the parameter t of every sample, for k_march_expand
+    const uint32_t limit = max_steps;
     Walk w;
     w.init(rays_o + (size_t)n * 3, rays_d + (size_t)n * 3, grid, bound, dt_gamma, max_steps, C, H, fars[n]);
     float t = nears[n];
     t = __fmaf_rn(w.step_size(t), noises[n], t);  // :351
-    float last_t = t;                               // t after the previous sample (warp-uniform)
     for (uint32_t j = 0; j < lane; j++) t = __fadd_rn(t, w.step_size(t));   // lane j holds candidate t_{n0 + j}
     uint32_t count = 0;
     float pending = -1.0f;                          // exit parameter of an empty cell whose target lies in a later batch
@@ -320,29 +295,13 @@ __global__ void __launch_bounds__(256) k_march_train_warp(const float* __restric
                 else { pending = ttc; have_pending = true; cur = 32u; }
             }
         }
-        // ---- emit ----
-        if (WRITE && emit) {
-            // deltas[1] = (t after this sample) - (t after the previous one); the previous one is the next lower emitting lane
-            const uint32_t below = emit & lt_mask;
-            const int src = below ? 31 - __clz(below) : 0;
-            const float prev_next = __shfl_sync(0xffffffffu, tn, src);
-            if ((emit >> lane) & 1u) {
-                const float lt = below ? prev_next : last_t;
-                const size_t s = (size_t)offset + (count - __popc(emit)) + __popc(below);
-                xyzs[s * 3] = x; xyzs[s * 3 + 1] = y; xyzs[s * 3 + 2] = z;
-                dirs[s * 3] = w.dx; dirs[s * 3 + 1] = w.dy; dirs[s * 3 + 2] = w.dz;
-                deltas[s * 2] = dt;
-                deltas[s * 2 + 1] = __fsub_rn(tn, lt);
-            }
-        }
-        if (ts && ((emit >> lane) & 1u)) ts[(count - __popc(emit)) + __popc(emit & lt_mask)] = t;
-        if (emit) last_t = __shfl_sync(0xffffffffu, tn, 31 - __clz(emit));
+        if ((emit >> lane) & 1u) ts[(count - __popc(emit)) + __popc(emit & lt_mask)] = t;
         if (done || !(in_b >> 31)) break;   // the walk ended, or candidates past this batch are all beyond `far`
         // ---- next batch: every lane advances 32 steps ----
 #pragma unroll 4
         for (int j = 0; j < 32; j++) t = __fadd_rn(t, w.step_size(t));
     }
-    if (!WRITE && lane == 0) rays[n * 3 + 2] = (int32_t)count;
+    if (lane == 0) rays[n * 3 + 2] = (int32_t)count;
 }
 
 // ---- inference marching (raymarching.cu:958-1063) -------------------------------
@@ -464,13 +423,11 @@ extern "C" int inerf_packbits(const float* grid, uint32_t N, float density_thres
 }
 
 // One warp per ray pays off while thread-per-ray cannot fill the machine (a serial walk per thread); it evaluates every
-// step of the empty stretches instead of one per cell, so the thread-per-ray kernels win once there are enough rays.
+// step of the empty stretches instead of one per cell, so the thread-per-ray kernel wins once there are enough rays.
 // The warp kernel reads the bitfield as 8-byte words (Walk::occupied_cached).
-#ifndef INERF_WARP_MARCH_MAX_RAYS
-#define INERF_WARP_MARCH_MAX_RAYS 24576u
-#endif
+constexpr uint32_t kWarpMarchMaxRays = 24576u;   // crossover measured on B200
 static bool use_warp_march(uint32_t N, const uint8_t* grid, uint32_t C, uint32_t H) {
-    return N <= INERF_WARP_MARCH_MAX_RAYS && ((uintptr_t)grid & 7u) == 0 && ((uint64_t)C * H * H * H) % 64u == 0;
+    return N <= kWarpMarchMaxRays && ((uintptr_t)grid & 7u) == 0 && ((uint64_t)C * H * H * H) % 64u == 0;
 }
 
 static int check_march_args(uint32_t C, uint32_t H, uint32_t max_steps) {
@@ -479,28 +436,27 @@ static int check_march_args(uint32_t C, uint32_t H, uint32_t max_steps) {
     return INERF_OK;
 }
 
-extern "C" size_t inerf_march_scratch_floats(uint32_t N, uint32_t max_steps) {
-    // both count kernels (one warp per ray for small batches, one thread per ray for large ones) can record t per sample
-    return (size_t)N * max_steps;
-}
-
-static int march_count_impl(const float* rays_o, const float* rays_d, const uint8_t* grid, float bound,
-                            float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H,
-                            const float* nears, const float* fars, int32_t* rays, int32_t* counter,
-                            const float* noises, float* t_scratch, void* stream);
-
-extern "C" int inerf_march_rays_train_count(const float* rays_o, const float* rays_d, const uint8_t* grid, float bound,
-                                            float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H,
-                                            const float* nears, const float* fars, int32_t* rays, int32_t* counter,
-                                            const float* noises, void* stream) {
-    return march_count_impl(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, nears, fars, rays, counter, noises, nullptr, stream);
-}
+extern "C" size_t inerf_march_scratch_floats(uint32_t N, uint32_t max_steps) { return (size_t)N * max_steps; }
 
 extern "C" int inerf_march_rays_train_count_t(const float* rays_o, const float* rays_d, const uint8_t* grid, float bound,
                                               float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H,
                                               const float* nears, const float* fars, int32_t* rays, int32_t* counter,
                                               const float* noises, float* t_scratch, void* stream) {
-    return march_count_impl(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, nears, fars, rays, counter, noises, t_scratch, stream);
+    if (int e = check_march_args(C, H, max_steps)) return e;
+    INERF_REQUIRE(counter);
+    if (N == 0) return INERF_OK;
+    INERF_REQUIRE(rays_o); INERF_REQUIRE(rays_d); INERF_REQUIRE(grid); INERF_REQUIRE(nears); INERF_REQUIRE(fars);
+    INERF_REQUIRE(rays); INERF_REQUIRE(noises); INERF_REQUIRE(t_scratch);
+    if (use_warp_march(N, grid, C, H))
+        k_march_train_warp<<<div_up(N, 8), 256, 0, (cudaStream_t)stream>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, nears, fars,
+                                                                         noises, rays, t_scratch);
+    else
+        k_march_count<<<div_up(N, 128), 128, 0, (cudaStream_t)stream>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H,
+                                                                      nears, fars, noises, rays, t_scratch);
+    INERF_LAUNCH_CHECK();
+    k_march_scan<<<1, 1024, 0, (cudaStream_t)stream>>>(rays, N, counter);
+    INERF_LAUNCH_CHECK();
+    return INERF_OK;
 }
 
 extern "C" int inerf_march_rays_train_expand(const float* rays_o, const float* rays_d, float bound, float dt_gamma, uint32_t max_steps,
@@ -518,53 +474,14 @@ extern "C" int inerf_march_rays_train_expand(const float* rays_o, const float* r
     return INERF_OK;
 }
 
-static int march_count_impl(const float* rays_o, const float* rays_d, const uint8_t* grid, float bound,
-                            float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H,
-                            const float* nears, const float* fars, int32_t* rays, int32_t* counter,
-                            const float* noises, float* t_scratch, void* stream) {
-    if (int e = check_march_args(C, H, max_steps)) return e;
-    INERF_REQUIRE(counter);
-    if (N == 0) return INERF_OK;
-    INERF_REQUIRE(rays_o); INERF_REQUIRE(rays_d); INERF_REQUIRE(grid); INERF_REQUIRE(nears); INERF_REQUIRE(fars);
-    INERF_REQUIRE(rays); INERF_REQUIRE(noises);
-    if (use_warp_march(N, grid, C, H))
-        k_march_train_warp<false><<<div_up(N, 8), 256, 0, (cudaStream_t)stream>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, 0,
-                                                                                nears, fars, noises, rays, nullptr, nullptr, nullptr, t_scratch);
-    else
-        k_march_count<<<div_up(N, 128), 128, 0, (cudaStream_t)stream>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H,
-                                                                      nears, fars, noises, rays, t_scratch);
-    INERF_LAUNCH_CHECK();
-    k_march_scan<<<1, 1024, 0, (cudaStream_t)stream>>>(rays, N, counter);
-    INERF_LAUNCH_CHECK();
-    return INERF_OK;
-}
-
-extern "C" int inerf_march_rays_train_write(const float* rays_o, const float* rays_d, const uint8_t* grid, float bound,
-                                            float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M,
-                                            const float* nears, const float* fars, float* xyzs, float* dirs, float* deltas,
-                                            const int32_t* rays, const float* noises, void* stream) {
-    if (int e = check_march_args(C, H, max_steps)) return e;
-    if (N == 0 || M == 0) return INERF_OK;
-    INERF_REQUIRE(rays_o); INERF_REQUIRE(rays_d); INERF_REQUIRE(grid); INERF_REQUIRE(nears); INERF_REQUIRE(fars);
-    INERF_REQUIRE(rays); INERF_REQUIRE(noises); INERF_REQUIRE(xyzs); INERF_REQUIRE(dirs); INERF_REQUIRE(deltas);
-    if (use_warp_march(N, grid, C, H))
-        k_march_train_warp<true><<<div_up(N, 8), 256, 0, (cudaStream_t)stream>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, M,
-                                                                               nears, fars, noises, const_cast<int32_t*>(rays), xyzs, dirs, deltas, nullptr);
-    else
-        k_march_write<<<div_up(N, 128), 128, 0, (cudaStream_t)stream>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, M,
-                                                                      nears, fars, noises, rays, xyzs, dirs, deltas);
-    INERF_LAUNCH_CHECK();
-    return INERF_OK;
-}
-
 extern "C" int inerf_march_rays_train(const float* rays_o, const float* rays_d, const uint8_t* grid, float bound, float dt_gamma,
                                       uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M, const float* nears,
                                       const float* fars, float* xyzs, float* dirs, float* deltas, int32_t* rays,
-                                      int32_t* counter, const float* noises, void* stream) {
-    if (int e = inerf_march_rays_train_count(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, nears, fars, rays,
-                                             counter, noises, stream)) return e;
-    return inerf_march_rays_train_write(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, M, nears, fars, xyzs, dirs,
-                                        deltas, rays, noises, stream);
+                                      int32_t* counter, const float* noises, float* t_scratch, void* stream) {
+    if (int e = inerf_march_rays_train_count_t(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, nears, fars, rays,
+                                               counter, noises, t_scratch, stream)) return e;
+    return inerf_march_rays_train_expand(rays_o, rays_d, bound, dt_gamma, max_steps, N, C, H, M, nears, xyzs, dirs, deltas, rays, noises,
+                                         t_scratch, stream);
 }
 
 extern "C" int inerf_march_rays(uint32_t n_alive, uint32_t n_step, const int32_t* rays_alive, const float* rays_t,

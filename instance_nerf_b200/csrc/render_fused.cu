@@ -4,15 +4,15 @@
 // reference launches march_rays, two full-table fp16 casts, two grid encodes, 8 GEMMs + elementwise kernels,
 // composite_rays_with_masks and a boolean-index compaction, with two device->host syncs.
 //
-// One CTA per SM, 640 threads in three roles that run concurrently and hand 128-sample tiles to each other
+// One CTA per SM, 896 threads in three roles that run concurrently and hand 128-sample tiles to each other
 // through mbarrier-guarded rings in shared memory (nothing per-sample ever touches HBM):
 //
-//   march  (4 warps, thread = ray slot)   occupancy-grid DDA (raymarching.cu:1008-1062 semantics), one sample per
-//                                          slot per tile into a 4-deep FIFO; runs AHEAD of compositing
-//                                          (speculatively: a ray killed by T < T_thresh drops its queued samples);
-//                                          finished slots pull the next ray id from a global counter.
-//   gather (8 warps, thread = slot x half  16 levels x 8 corners, one 8-byte gather per corner from the interleaved
-//           of the levels)                 fp16 table (both encoders at once), fp16 trilinear blend, SH degree 4 ->
+//   march  (4 warps, thread = ray slot)   occupancy-grid DDA (raymarching.cu:1008-1062 semantics) into a 14-deep
+//                                          per-slot sample ring; runs AHEAD of compositing (speculatively: a ray
+//                                          killed by T < T_thresh drops its queued samples); a warp whose 32 slots
+//                                          are all free pulls the next 32 consecutive rays from a global counter.
+//   gather (16 warps, thread = slot x 4    16 levels x 8 corners, one 8-byte gather per corner from the interleaved
+//           of the 16 levels)              fp16 table (both encoders at once), fp16 trilinear blend, SH degree 4 ->
 //                                          UMMA operand tiles, double buffered.
 //   chain  (8 warps, thread = TMEM lane x  sigma / colour / mask MLPs as tcgen05.mma chains (fp32 accumulators in
 //           column half)                   TMEM), ReLU / exp / sigmoid epilogues, then the per-ray alpha compositing
@@ -22,7 +22,6 @@
 // Per-ray sample positions equal the reference's for a continuous march from `near`; the reference re-derives t
 // from the composited depth deltas between its n_step-sized chunks, which can differ in the last ulp after long
 // empty-space skips (maps agree to the 1e-3 tolerance of the north star).
-#include <cstdio>
 #include "field_device.cuh"
 #include "march_device.cuh"
 
@@ -32,44 +31,19 @@ using namespace field;
 
 constexpr uint32_t kChainT = 256, kGatherT = 512, kMarchT = 128;
 // register budget per role (setmaxnreg): 896 threads start at 72; 256*96 + 512*64 + 128*56 = 896*72
-#ifndef INERF_GATHER_PIPE
-#define INERF_GATHER_PIPE 0
-#endif
-#ifndef INERF_REGS_CHAIN
-#define INERF_REGS_CHAIN 96
-#define INERF_REGS_GATHER 64
-#endif
-constexpr uint32_t kRegsChain = INERF_REGS_CHAIN, kRegsGather = INERF_REGS_GATHER, kRegsMarch = 56;
+constexpr uint32_t kRegsChain = 96, kRegsGather = 64, kRegsMarch = 56;
 // setmaxnreg moves registers inside the CTA's OWN allocation (threads x the launch register count, 896 x 72 here), not inside
 // the SM's 64 K file: a role budget that sums to more than that never gets its registers and the kernel hangs in setmaxnreg.inc
 static_assert(kChainT * kRegsChain + kGatherT * kRegsGather + kMarchT * kRegsMarch <= (kChainT + kGatherT + kMarchT) * 72,
               "register budget of the three roles");
 constexpr uint32_t kThreadsR = kChainT + kGatherT + kMarchT;
-#ifndef INERF_RING
-#define INERF_RING 14   // 14 x 3 KB of rings keeps the CTA inside the 196 KB shared-memory carve-out at K <= 32 (60 KB of L1 left)
-#endif
-constexpr uint32_t RING = INERF_RING;  // samples queued per ray slot
+// samples queued per ray slot: 14 x 3 KB of rings keeps the CTA inside the 196 KB shared-memory carve-out at K <= 32 (60 KB of L1 left)
+constexpr uint32_t RING = 14;
 constexpr uint32_t DT = 4;    // tile descriptors in flight (gather may run DA tiles ahead of the chain)
 constexpr uint32_t DA = 2;    // gathered operand stages
-#ifndef INERF_SKIP_STEPS
-#define INERF_SKIP_STEPS 6    // empty-space steps a marcher lane advances per warp iteration
-#endif
-#ifndef INERF_MARCH_CELLS
-#define INERF_MARCH_CELLS 8   // occupancy cells a marcher lane may evaluate per warp iteration (1 = one cell, skip steps as their own state)
-#endif
-#ifndef INERF_MARCH_MULTI
-#define INERF_MARCH_MULTI 1   // 1: a lane may queue several samples per warp iteration (as many as its ring has room for)
-#endif
-#ifndef INERF_FIRST_HIT
-#define INERF_FIRST_HIT 1      // 1: leading empty space of every ray is walked by a full-occupancy pre-pass (k_first_hit)
-#endif
-#ifndef INERF_TILE_MIN
-#define INERF_TILE_MIN 0      // > 0: a tile with fewer ready rows waits (at most INERF_TILE_RETRY polls) for more
-#define INERF_TILE_RETRY 0
-#endif
-#ifndef INERF_RAY_PATCH
-#define INERF_RAY_PATCH 1     // 1: marcher warps take 32 consecutive rays at a time (coherent gathers); 0: one ray per free lane
-#endif
+constexpr int kMarchCells = 8;   // occupancy cells a marcher lane may evaluate per warp iteration
+// (the alternatives measured on B200 and rejected -- ring depth, cells / skip steps per iteration, tile hold-back, one ray per
+// free lane instead of 32-ray patches, a software-pipelined gather -- are recorded with their numbers in DESIGN.md 4.1)
 
 struct RenderParams {
     const float* rays_o;
@@ -105,10 +79,6 @@ struct Ctrl {
     float w_s[kTile];
     int32_t fin_s[kTile];
     LevelGeom lg[16];
-#ifdef INERF_DBG_BUBBLES
-    int32_t mstate[kTile];        // marcher state per slot (0 idle, 1 eval, 2 skip, 3 done, 4 eval blocked on ring room)
-    unsigned long long bub[8];    // bubble rows by marcher state at tile assembly, [5] = polls that found nothing, [6] = tiles
-#endif
 };
 
 struct RSmem {
@@ -138,26 +108,13 @@ __device__ __forceinline__ bool gather_any(bool pred) {
     return r != 0;
 }
 
-// number of gather-group threads whose predicate is true (named barrier 2)
-__device__ __forceinline__ uint32_t gather_count(bool pred) {
-    uint32_t r;
-    asm volatile(
-        "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t"
-        "barrier.cta.red.popc.u32 %0, 2, %2, q;\n\t}\n"
-        : "=r"(r) : "r"((uint32_t)pred), "n"(kGatherT) : "memory");
-    return r;
-}
-
 // ------------------------------------------------------------------------------------------------ march --
-// Per-lane state machine; every warp iteration each lane does ONE bounded unit of work (fetch a ray / evaluate one
-// occupancy cell / advance up to kSkipSteps steps through empty space), so a lane crossing a long empty stretch never
-// holds back the other 31.  The sample sequence per ray is the reference's (raymarching.cu:1008-1062).
+// Per-lane state machine; every warp iteration each lane does ONE bounded unit of work (fetch a ray / evaluate up to
+// kMarchCells occupancy cells), so a lane crossing a long empty stretch never holds back the other 31.  The sample
+// sequence per ray is the reference's (raymarching.cu:1008-1062).
 __device__ __forceinline__ void march_role(const inerf_field_desc& desc, const RenderParams& p, Ctrl* ctl, Rings* rg, const uint32_t* coarse,
                                            uint32_t r) {
-    enum : int { NEED_RAY = 0, EVAL = 1, SKIP = 2, DONE = 3 };
-    constexpr int kSkipSteps = INERF_SKIP_STEPS;
-    constexpr int kCells = INERF_MARCH_CELLS;
-    constexpr bool kMulti = INERF_MARCH_MULTI != 0;
+    enum : int { NEED_RAY = 0, EVAL = 1, DONE = 3 };
     march::Walk wk;
     wk.coarse = coarse;
     int state = NEED_RAY;
@@ -169,13 +126,9 @@ __device__ __forceinline__ void march_role(const inerf_field_desc& desc, const R
         const uint32_t chead_seen = ld_vol(&ctl->chead[r]);
         const bool room = tail - chead_seen < RING;
         bool worked = false;
-#ifdef INERF_DBG_BUBBLES
-        st_vol(&ctl->mstate[r], (state == EVAL && !room) ? 4 : state);
-#endif
-#if INERF_RAY_PATCH
         // Rays are taken 32 at a time: a warp's lanes always march 32 CONSECUTIVE rays (neighbouring pixels), sample for
         // sample in step, so the gather warp that consumes these 32 slots reads neighbouring cells -- one L1 sector serves
-        // several lanes at the coarse and middle levels (measured 87 -> ~30 sectors per sample).  A lane
+        // several lanes at the coarse and middle levels (measured 87 -> ~41 sectors per sample).  A lane
         // whose ray ends early idles until its 31 neighbours have finished marching (not compositing): ~5 % bubble rows.
         const bool acquire = __all_sync(0xffffffffu, state == NEED_RAY || state == DONE) && state == NEED_RAY;
         if (state == NEED_RAY && acquire) {
@@ -186,77 +139,56 @@ __device__ __forceinline__ void march_role(const inerf_field_desc& desc, const R
             base = __shfl_sync(takers, base, leader);
             const uint32_t idx = base + (r & 31u);
             if (idx >= p.N) {
-#else
-        if (state == NEED_RAY) {
-            const uint32_t idx = (uint32_t)atomicAdd(p.work_counter, 1);
-            if (idx >= p.N) {
-#endif
                 state = DONE;
                 atomicAdd(&ctl->n_done, 1);
             } else {
                 wk.init(p.rays_o + (size_t)idx * 3, p.rays_d + (size_t)idx * 3, p.bitfield, desc.bound, p.dt_gamma, p.max_steps, p.C, p.H,
                         __ldg(p.fars + idx));
-#if INERF_FIRST_HIT
                 // k_first_hit already walked this ray's leading empty space (same DDA, same t sequence): resume at the first
                 // occupied cell.  The value travels in depth[idx], which goes back to 0 (the output of a ray with no sample).
                 t = *reinterpret_cast<const volatile float*>(p.depth + idx);
                 p.depth[idx] = 0.f;
-#else
-                t = __ldg(p.nears + idx);
-#endif
                 last_t = __ldg(p.nears + idx);
                 nsteps = 0;
                 ray = (int32_t)idx;
                 state = EVAL;
             }
             worked = true;
-        } else if (state == EVAL) {
-            if (room) {
-                worked = true;
-                // up to kCells occupancy cells per warp iteration (the loop's vote / ring bookkeeping is paid once), emitting a
-                // sample for every occupied one while the ring has room: every lane with a ray does the same amount of work per
-                // iteration whether it is crossing empty space or a solid
-                uint32_t free_entries = kMulti ? RING - (tail - chead_seen) : 1u;
+        } else if (state == EVAL && room) {
+            worked = true;
+            // up to kMarchCells occupancy cells per warp iteration (the loop's vote / ring bookkeeping is paid once), emitting a
+            // sample for every occupied one while the ring has room: every lane with a ray does the same amount of work per
+            // iteration whether it is crossing empty space or a solid
+            uint32_t free_entries = RING - (tail - chead_seen);
 #pragma unroll 1
-                for (int c = 0; c < kCells && free_entries; c++) {
-                    const uint32_t e = tail % RING;
-                    if (!(t < wk.far) || nsteps >= p.max_steps) {
-                        if (nsteps > 0) {   // END marker; a ray without samples is never seen by the compositor (outputs pre-zeroed)
-                            rg->dt[e][r] = 0.f;
-                            rg->ray[e][r] = ray;
-                            __threadfence_block();
-                            st_vol(&ctl->tail[r], ++tail);
-                        }
-                        ray = -1;
-                        state = NEED_RAY;
-                        break;
-                    }
-                    float x, y, z, dt;
-                    if (wk.eval_cell(t, x, y, z, dt, tt)) {
-                        rg->x[e][r] = x; rg->y[e][r] = y; rg->z[e][r] = z;
-                        rg->dt[e][r] = dt;
-                        rg->d1[e][r] = __fsub_rn(t, last_t);
+            for (int c = 0; c < kMarchCells && free_entries; c++) {
+                const uint32_t e = tail % RING;
+                if (!(t < wk.far) || nsteps >= p.max_steps) {
+                    if (nsteps > 0) {   // END marker; a ray without samples is never seen by the compositor (outputs pre-zeroed)
+                        rg->dt[e][r] = 0.f;
                         rg->ray[e][r] = ray;
-                        last_t = t;
-                        nsteps++;
                         __threadfence_block();
                         st_vol(&ctl->tail[r], ++tail);
-                        free_entries--;
-                        continue;
                     }
-                    t = __fadd_rn(t, wk.step_size(t));   // do { t += dt } while (t < tt): the first step is unconditional
-                    if (kCells == 1) {
-                        state = (t < tt) ? SKIP : EVAL;
-                    } else {
-                        while (t < tt) t = __fadd_rn(t, wk.step_size(t));
-                    }
+                    ray = -1;
+                    state = NEED_RAY;
+                    break;
                 }
+                float x, y, z, dt;
+                if (wk.eval_cell(t, x, y, z, dt, tt)) {
+                    rg->x[e][r] = x; rg->y[e][r] = y; rg->z[e][r] = z;
+                    rg->dt[e][r] = dt;
+                    rg->d1[e][r] = __fsub_rn(t, last_t);
+                    rg->ray[e][r] = ray;
+                    last_t = t;
+                    nsteps++;
+                    __threadfence_block();
+                    st_vol(&ctl->tail[r], ++tail);
+                    free_entries--;
+                    continue;
+                }
+                do { t = __fadd_rn(t, wk.step_size(t)); } while (t < tt);
             }
-        } else if (state == SKIP) {
-            worked = true;
-#pragma unroll 1
-            for (int i = 0; i < kSkipSteps && t < tt; i++) t = __fadd_rn(t, wk.step_size(t));
-            if (!(t < tt)) state = EVAL;
         }
         if (__all_sync(0xffffffffu, state == DONE)) break;
         if (!__any_sync(0xffffffffu, worked)) __nanosleep(256);
@@ -273,8 +205,6 @@ __device__ __forceinline__ void gather_role(const inerf_field_desc& desc, const 
     for (uint32_t tile = 0;; tile++) {
         const uint32_t st = tile % DT, sa = tile % DA;
         bool stop = false;
-        uint32_t tries = 0;
-        (void)tries;
         while (true) {   // assemble a tile: one queued sample from every slot that has one
             int32_t sel = -1;
             bool not_finished = false;
@@ -286,24 +216,10 @@ __device__ __forceinline__ void gather_role(const inerf_field_desc& desc, const 
                 ctl->tsel[st][row] = sel;
             }
             if (!gather_any(not_finished)) { stop = true; break; }   // all marchers done and every ring drained
-#if INERF_TILE_MIN > 0
-            // a tile with few rows costs a full chain pass: give lagging marcher lanes a moment (bounded) before emitting it
-            const uint32_t ready = gather_count(sel >= 0);
-            if (ready > 0 && ready < INERF_TILE_MIN && tries < INERF_TILE_RETRY) { tries++; __nanosleep(64); continue; }
-            if (ready > 0) {
-#else
             if (gather_any(sel >= 0)) {
-#endif
-#ifdef INERF_DBG_BUBBLES
-                if (quarter == 0 && sel < 0) atomicAdd(&ctl->bub[ld_vol(&ctl->mstate[row])], 1ull);
-                if (gt == 0) atomicAdd(&ctl->bub[6], 1ull);
-#endif
                 if (sel >= 0) ghead++;
                 break;
             }
-#ifdef INERF_DBG_BUBBLES
-            if (gt == 0) atomicAdd(&ctl->bub[5], 1ull);
-#endif
             __nanosleep(128);
         }
         if (tile >= DA) umma::mbar_wait(&ctl->a_empty[sa], ((tile / DA) - 1u) & 1u);
@@ -324,11 +240,7 @@ __device__ __forceinline__ void gather_role(const inerf_field_desc& desc, const 
                     const float* d = p.rays_d + (size_t)ray * 3;
                     sh16_to_smem(__ldg(d), __ldg(d + 1), __ldg(d + 2), smem, a_ci, row);
                 }
-#if INERF_GATHER_PIPE
-                encode4_pipelined(x01, oob, quarter * 4, ctl->lg, table, smem, a_es, a_mi, row);
-#else
                 encode4(x01, oob, quarter * 4, ctl->lg, table, smem, a_es, a_mi, row);
-#endif
             }
         }
         umma::fence_async_smem();
@@ -509,10 +421,6 @@ __global__ void __launch_bounds__(kThreadsR, 1) k_render_fused(inerf_field_desc 
         umma::mbar_fence_init();
     }
     if (tid < kTile) { ctl->kill[tid] = -1; ctl->tail[tid] = 0; ctl->chead[tid] = 0; }
-#ifdef INERF_DBG_BUBBLES
-    if (tid < kTile) ctl->mstate[tid] = 0;
-    if (tid < 8) ctl->bub[tid] = 0ull;
-#endif
     // coarse occupancy: bit b = (8-byte word b of the bitfield != 0), i.e. any of the 64 cells of that 4x4x4 block occupied
     uint32_t* coarse = p.coarse_bytes ? reinterpret_cast<uint32_t*>(smem + RSmem::coarse(K)) : nullptr;
     if (coarse) {
@@ -543,11 +451,6 @@ __global__ void __launch_bounds__(kThreadsR, 1) k_render_fused(inerf_field_desc 
 
     umma::fence_before_sync();
     __syncthreads();
-#ifdef INERF_DBG_BUBBLES
-    if (tid == 0 && (blockIdx.x == 0 || blockIdx.x == 77))
-        printf("[bubbles cta %u] tiles %llu empty-polls %llu | bubble rows: idle %llu eval %llu skip %llu done %llu eval-noroom %llu\n", blockIdx.x,
-               ctl->bub[6], ctl->bub[5], ctl->bub[0], ctl->bub[1], ctl->bub[2], ctl->bub[3], ctl->bub[4]);
-#endif
     if (tid < 32) umma::tmem_dealloc<kTmemCols>(tmem_base);
 }
 
@@ -569,33 +472,24 @@ extern "C" int inerf_render_fused(const inerf_field_desc* desc, const float* ray
     if (ce != cudaSuccess) return (int)ce;
     // rays without a single sample are never touched by the kernel: their outputs are these zeros
     if ((ce = cudaMemsetAsync(weights_sum, 0, (size_t)N * 4, st)) != cudaSuccess) return (int)ce;
-#if !INERF_FIRST_HIT
-    if ((ce = cudaMemsetAsync(depth, 0, (size_t)N * 4, st)) != cudaSuccess) return (int)ce;
-#endif
     if ((ce = cudaMemsetAsync(image, 0, (size_t)N * 12, st)) != cudaSuccess) return (int)ce;
     if (mask_out && (ce = cudaMemsetAsync(mask_out, 0, (size_t)N * desc->K * 4, st)) != cudaSuccess) return (int)ce;
     // coarse bitmap: one bit per 64 cells; needs C*H^3 to be a multiple of 2048 and to fit the spare shared memory
     const uint64_t cells = (uint64_t)C * H * H * H;
     uint32_t coarse_bytes = 0;
-#ifndef INERF_NO_COARSE
     if (cells % 2048 == 0 && cells / 512 <= 48 * 1024) coarse_bytes = (uint32_t)(cells / 512);
-#endif
     RenderParams p{rays_o, rays_d, nears, fars, bitfield, N, C, H, max_steps, dt_gamma, T_thresh, weights_sum, depth, image, mask_out, work_counter, coarse_bytes};
     const uint32_t smem_bytes = RSmem::bytes(desc->K, coarse_bytes);
-    static bool attr_set = false;
-    if (!attr_set) {
-        ce = cudaFuncSetAttribute(k_render_fused<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (ce != cudaSuccess) return (int)ce;
-        ce = cudaFuncSetAttribute(k_render_fused<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (ce != cudaSuccess) return (int)ce;
-        attr_set = true;
-    }
-#if INERF_FIRST_HIT
+    // the attribute is per device and cheap to set: no process-global "already done" flag (a second GPU in the same process
+    // would otherwise launch without the opt-in)
+    if (desc->K <= 32) ce = cudaFuncSetAttribute(k_render_fused<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    else ce = cudaFuncSetAttribute(k_render_fused<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (ce != cudaSuccess) return (int)ce;
     k_first_hit<<<(N + 255u) / 256u, 256, 0, st>>>(p, desc->bound, depth);   // depth[] carries t_first into the render kernel
     INERF_LAUNCH_CHECK();
-#endif
     const uint32_t want = (N + field::kTile - 1) / field::kTile;
-    const uint32_t grid = want < (uint32_t)kNumSMs ? want : (uint32_t)kNumSMs;
+    const uint32_t sms = (uint32_t)device_sm_count();
+    const uint32_t grid = want < sms ? want : sms;
     if (desc->K <= 32) k_render_fused<1><<<grid, kThreadsR, smem_bytes, st>>>(*desc, p);
     else k_render_fused<2><<<grid, kThreadsR, smem_bytes, st>>>(*desc, p);
     INERF_LAUNCH_CHECK();

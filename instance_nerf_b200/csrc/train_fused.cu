@@ -474,15 +474,13 @@ extern "C" int inerf_field_backward_mask(const inerf_field_desc* desc, const voi
     INERF_REQUIRE(weights_bwd); INERF_REQUIRE(xyzs); INERF_REQUIRE(x0); INERF_REQUIRE(grad_logits);
     INERF_REQUIRE(grad_table); INERF_REQUIRE(grad_w0); INERF_REQUIRE(grad_w1); INERF_REQUIRE(grad_w2);
     if (((uintptr_t)weights_bwd & 15u) || ((uintptr_t)x0 & 15u) || ((uintptr_t)grad_table & 7u)) return INERF_ERR_ALIGN;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(k_field_backward_mask, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BSmem::bytes);
-        if (e != cudaSuccess) return (int)e;
-        attr_set = true;
-    }
+    // per-device attribute, cheap to set: no process-global "already done" flag
+    cudaError_t e = cudaFuncSetAttribute(k_field_backward_mask, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BSmem::bytes);
+    if (e != cudaSuccess) return (int)e;
     BwdParams p{xyzs, (const uint4*)x0, grad_logits, B, (float2*)grad_table, grad_w0, grad_w1, grad_w2, weights_bwd};
     const uint32_t num_tiles = (B + kTile - 1) / kTile;
-    const uint32_t grid = num_tiles < (uint32_t)kNumSMs ? num_tiles : (uint32_t)kNumSMs;
+    const uint32_t sms = (uint32_t)device_sm_count();
+    const uint32_t grid = num_tiles < sms ? num_tiles : sms;
     k_field_backward_mask<<<grid, kBwdThreads, BSmem::bytes, (cudaStream_t)stream>>>(*desc, p);
     INERF_LAUNCH_CHECK();
     return INERF_OK;

@@ -116,14 +116,9 @@ def march_rays_train(rays_o, rays_d, bound, density_bitfield, C, H, nears, fars,
 
     # the count pass records t per sample ([N, max_steps] scratch, never zero-filled) and the write pass becomes a parallel
     # expansion (one warp per ray, coalesced stores) instead of a second walk
-    n_scratch = int(lib().inerf_march_scratch_floats(N, int(max_steps))) if N else 0
-    t_scratch = torch.empty(n_scratch, dtype=torch.float32, device=dev) if n_scratch else None
-    if t_scratch is not None:
-        call("inerf_march_rays_train_count_t", ptr(rays_o), ptr(rays_d), ptr(density_bitfield), float(bound), float(dt_gamma),
-             int(max_steps), N, int(C), int(H), ptr(nears), ptr(fars), ptr(rays), ptr(step_counter), ptr(noises), ptr(t_scratch), st)
-    else:
-        call("inerf_march_rays_train_count", ptr(rays_o), ptr(rays_d), ptr(density_bitfield), float(bound), float(dt_gamma),
-             int(max_steps), N, int(C), int(H), ptr(nears), ptr(fars), ptr(rays), ptr(step_counter), ptr(noises), st)
+    t_scratch = torch.empty(max(1, int(lib().inerf_march_scratch_floats(N, int(max_steps)))), dtype=torch.float32, device=dev)
+    call("inerf_march_rays_train_count_t", ptr(rays_o), ptr(rays_d), ptr(density_bitfield), float(bound), float(dt_gamma),
+         int(max_steps), N, int(C), int(H), ptr(nears), ptr(fars), ptr(rays), ptr(step_counter), ptr(noises), ptr(t_scratch), st)
 
     if not force_all_rays and mean_count > 0:
         # budgeted mode: M fixed from the running mean, no host sync; rays past the budget are dropped
@@ -138,13 +133,8 @@ def march_rays_train(rays_o, rays_d, bound, density_bitfield, C, H, nears, fars,
     xyzs = torch.zeros(M, 3, dtype=torch.float32, device=dev)
     dirs = torch.zeros(M, 3, dtype=torch.float32, device=dev)
     deltas = torch.zeros(M, 2, dtype=torch.float32, device=dev)
-    if t_scratch is not None:
-        call("inerf_march_rays_train_expand", ptr(rays_o), ptr(rays_d), float(bound), float(dt_gamma), int(max_steps), N, int(C), int(H),
-             M, ptr(nears), ptr(xyzs), ptr(dirs), ptr(deltas), ptr(rays), ptr(noises), ptr(t_scratch), st)
-    else:
-        call("inerf_march_rays_train_write", ptr(rays_o), ptr(rays_d), ptr(density_bitfield), float(bound), float(dt_gamma),
-             int(max_steps), N, int(C), int(H), M, ptr(nears), ptr(fars), ptr(xyzs), ptr(dirs), ptr(deltas), ptr(rays),
-             ptr(noises), st)
+    call("inerf_march_rays_train_expand", ptr(rays_o), ptr(rays_d), float(bound), float(dt_gamma), int(max_steps), N, int(C), int(H),
+         M, ptr(nears), ptr(xyzs), ptr(dirs), ptr(deltas), ptr(rays), ptr(noises), ptr(t_scratch), st)
     return xyzs, dirs, deltas, rays
 
 

@@ -3,7 +3,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
-#include "../umma.cuh"
+#include "../../instance_nerf_b200/csrc/umma.cuh"
 
 __global__ void __launch_bounds__(128) probe(const __half* A, const __half* B, float* D, int M, int N, int K, uint32_t idesc) {
     extern __shared__ __align__(1024) uint8_t smem[];

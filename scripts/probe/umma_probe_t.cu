@@ -5,7 +5,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
-#include "../umma.cuh"
+#include "../../instance_nerf_b200/csrc/umma.cuh"
 
 __host__ __device__ constexpr uint32_t idesc_t(uint32_t M, uint32_t N, uint32_t amaj, uint32_t bmaj) {
     return (1u << 4) | (amaj << 15) | (bmaj << 16) | ((N >> 3) << 17) | ((M >> 4) << 24);

@@ -90,21 +90,14 @@ def main():
     rays_w = torch.empty_like(rays)
 
     from instance_nerf_b200._lib import lib
-    n_scr = int(lib().inerf_march_scratch_floats(N, bench.MAX_STEPS))
-    t_scr = torch.empty(n_scr, dtype=torch.float32, device=dev) if n_scr else None
+    t_scr = torch.empty(int(lib().inerf_march_scratch_floats(N, bench.MAX_STEPS)), dtype=torch.float32, device=dev)
 
-    def ours_march():   # what raymarching.march_rays_train issues for this batch size (large batch: count + record t, scan, expand)
+    def ours_march():   # what raymarching.march_rays_train issues: count + record t, scan, expand
         counter.zero_()
-        if t_scr is not None:
-            call("inerf_march_rays_train_count_t", ptr(o), ptr(d), ptr(bits), bound, bench.DT_GAMMA, bench.MAX_STEPS, N, C, H, ptr(nears),
-                 ptr(fars), ptr(rays_w), ptr(counter), ptr(noises), ptr(t_scr), st)
-            call("inerf_march_rays_train_expand", ptr(o), ptr(d), bound, bench.DT_GAMMA, bench.MAX_STEPS, N, C, H, M, ptr(nears), ptr(xyzs),
-                 ptr(dirs), ptr(deltas), ptr(rays_w), ptr(noises), ptr(t_scr), st)
-        else:
-            call("inerf_march_rays_train_count", ptr(o), ptr(d), ptr(bits), bound, bench.DT_GAMMA, bench.MAX_STEPS, N, C, H, ptr(nears), ptr(fars),
-                 ptr(rays_w), ptr(counter), ptr(noises), st)
-            call("inerf_march_rays_train_write", ptr(o), ptr(d), ptr(bits), bound, bench.DT_GAMMA, bench.MAX_STEPS, N, C, H, M, ptr(nears), ptr(fars),
-                 ptr(xyzs), ptr(dirs), ptr(deltas), ptr(rays_w), ptr(noises), st)
+        call("inerf_march_rays_train_count_t", ptr(o), ptr(d), ptr(bits), bound, bench.DT_GAMMA, bench.MAX_STEPS, N, C, H, ptr(nears),
+             ptr(fars), ptr(rays_w), ptr(counter), ptr(noises), ptr(t_scr), st)
+        call("inerf_march_rays_train_expand", ptr(o), ptr(d), bound, bench.DT_GAMMA, bench.MAX_STEPS, N, C, H, M, ptr(nears), ptr(xyzs),
+             ptr(dirs), ptr(deltas), ptr(rays_w), ptr(noises), ptr(t_scr), st)
 
     rx = torch.empty(M, 3, device=dev); rd = torch.empty(M, 3, device=dev); rl = torch.empty(M, 2, device=dev)
     rrays = torch.empty(N, 3, dtype=torch.int32, device=dev); rcounter = torch.zeros(2, dtype=torch.int32, device=dev)
