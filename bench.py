@@ -1,28 +1,37 @@
 #!/usr/bin/env python
-"""bench.py -- instance-field render throughput (BASELINE.json metric: Mrays/s) on N B200s.
+"""bench.py -- instance-field render throughput (BASELINE.json metric: Mrays/s; train-step ms @ 4096 rays) on N B200s.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--no-cpu-baseline]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload render|c4|train] [--rays R]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
 
-Workload (BASELINE.json configs[1], SURVEY.md section 8d "c2"): 640x480 frames (307 200 rays each) of the synthetic
-3D-FRONT-shaped room, bound 8 -> 4-cascade 128^3 occupancy grid, two 16-level 2^19-entry hash tables, 32 instance classes,
-dt_gamma 1/128, max_steps 1024, T_thresh 1e-4; seeded random weights / tables (no network, no dataset).
+Workload of the headline line (BASELINE.json configs[1], SURVEY.md section 8d "c2"): 640x480 frames (307 200 rays each) of the
+synthetic 3D-FRONT-shaped room, bound 8 -> 4-cascade 128^3 occupancy grid, two 16-level 2^19-entry hash tables, 32 instance
+classes, dt_gamma 1/128, max_steps 1024, T_thresh 1e-4; seeded random weights / tables (no network, no dataset).
 
-A "step" = one frame rendered through NeRFNetwork.render (the call MaskTrainer.test_step makes, nerf/utils.py:1421): near/far
-+ ONE fused launch (march + hash gathers x2 + tcgen05 MLP + composite) + the bg / depth tail.  Every step renders a different
-camera pose, and L2 (126 MB) is flushed between timed steps by writing a 512 MB buffer (outside the event pair).
-At N > 1 every rank renders its own frame each step (weak scaling, rays sharded by frame) and the finished tiles are
-gathered with ONE NCCL all_gather per step, issued asynchronously so it overlaps the next frame's render (the last
-step waits for its gather inside the timed region).
+A "step" = `world` frames rendered through NeRFNetwork.render (the call MaskTrainer.test_step makes, nerf/utils.py:1421): near/far
++ ONE fused launch (march + hash gathers x2 + tcgen05 MLP + composite) + the bg / depth tail.  Every step renders different
+camera poses; L2 (126 MB) is flushed between timed steps by writing a 512 MB buffer (outside the per-step event pair).
+At N > 1 rank r renders the interleaved row blocks r, r + N, ... of every frame of the step (cost follows marched samples, which
+vary by +-25 % between poses) and the finished tiles are collected on rank 0 with ONE asynchronous NCCL gather per step that
+overlaps the next step's render (the last step waits for its gather inside the timed region).
 
-Keys: value = device-timed Mrays/s with rays resident in HBM; e2e = same through the public API from pinned HOST rays to
-pinned HOST results: every step copies that frame's rays host->device and every rank reads ITS OWN finished frame
-(image | depth | K logits) back to pinned host memory on a side stream, double buffered, so the copy of frame i overlaps the
-render of frame i + 1; ONE event pair brackets the whole e2e region, L2 flushes and the final copy join included; roofline = the fused kernel's algorithmic bytes / its own
-CUDA-event time vs the measured HBM peak; cpu_baseline = the CPU oracle port of the reference's PyTorch (non-cuda_ray)
-renderer on a bounded sample of the same frame, timed on this box's host cores.
+Keys of the JSON line:
+  value        device-timed Mrays/s, rays resident in HBM (generated once by inerf_get_rays)
+  e2e          the same through the public API from HOST inputs to HOST results: per step the camera poses (64 B each) go
+               host->device, inerf_get_rays builds the rays on the device (as a reference user's get_rays does), the frame is
+               rendered and every rank reads ITS OWN rows (image | depth | K logits) back to pinned host memory on a side
+               stream (double buffered); ONE event pair brackets the whole region, L2 flushes and the last copy included
+  roofline     the fused kernel's algorithmic gather bytes / its own CUDA-event time against the L2-RESIDENT read bandwidth
+               measured in this run (instance_nerf_b200/probe.py): the 53 MB interleaved table lives in L2, HBM is not the
+               binding roof (ncu: dram throughput 0.1 %).  `frac_of_hbm` keeps the round-1 figure, `gather_peak` the measured
+               random 8-byte gather rate
+  train_step   config c3 (4096 rays x max_steps 1024, one optimisation step as a CUDA graph), N = 1
+  train_dp     config c5 (65 536 rays per GPU, data parallel, NCCL all-reduce of the gradient buffer inside the graph), every N
+  cpu_baseline the reference's PyTorch (non-cuda_ray) renderer, restated in oracle/field_oracle.py and pinned against the
+               reference's own outputs, on config c1 (160x120, K=16, 128 samples/ray: BASELINE.md B1), best of 3, host cores
+  ref_cuda_path the reference's own CUDA kernels (oracle/_ref) on c2 and c3, timed in a subprocess
 
---impl reference runs ONLY that CPU path (the reference arm): no CUDA code of this repo is touched.
+--impl reference runs ONLY the CPU path (the reference arm): no CUDA code of this repo is touched.
 """
 from __future__ import annotations
 
@@ -44,28 +53,47 @@ W_IMG, H_IMG, K_INST, BOUND = 640, 480, 32, 8.0
 DT_GAMMA, MAX_STEPS, T_THRESH = 1.0 / 128, 1024, 1e-4
 N_POSES = 16
 WORKLOAD = "c2: 640x480 instance-field render, 4x128^3 occupancy grid, 2x(16-level 2^19 hash grid), K=32, synthetic room"
+WORKLOAD_C1 = "c1: 160x120 instance-field render, 128 uniform samples/ray, K=16, reference PyTorch (non-cuda_ray) path on CPU, synthetic room"
+C1 = dict(H=120, W=160, K=16, T=128)
+C4 = dict(H=1080, W=1920, frames=200)
 
 
-def build_scene_and_model(device=None):
+def intrinsics(H=H_IMG, W=W_IMG):
+    from instance_nerf_b200 import synthetic
+    return synthetic.intrinsics(H, W)
+
+
+def build_scene_and_model(device=None, K=K_INST, n_poses=N_POSES):
     import torch
     from instance_nerf_b200 import synthetic
     from instance_nerf_b200.nerf.network_mask import NeRFNetwork
 
     torch.manual_seed(0)
-    model = NeRFNetwork(bound=BOUND, cuda_ray=True, num_instances=K_INST, density_scale=1, density_thresh=10)
+    model = NeRFNetwork(bound=BOUND, cuda_ray=True, num_instances=K, density_scale=1, density_thresh=10)
     synthetic.randomize_tables(model, 0)
-    scene = synthetic.RoomScene(K_INST, BOUND, 0)
+    scene = synthetic.RoomScene(K, BOUND, 0)
     synthetic.install_scene(model, scene)
-    poses = torch.from_numpy(synthetic.camera_poses(scene, N_POSES, 1))
+    poses = torch.from_numpy(synthetic.camera_poses(scene, n_poses, 1))
     if device is not None:
         model = model.to(device)
     return model.eval(), scene, poses
 
 
-def frame_rays(poses, i):
-    from instance_nerf_b200 import synthetic
-    r = synthetic.get_rays(poses[i:i + 1], synthetic.intrinsics(H_IMG, W_IMG), H_IMG, W_IMG)
-    return r["rays_o"].reshape(-1, 3).contiguous(), r["rays_d"].reshape(-1, 3).contiguous()
+def train_batches(dev, scene, poses, n_rays, rank, world, n=8):
+    """`n` training batches of `n_rays` rays as 8x8 patches (nerf/utils.py:83-100) with analytic first-hit labels; rays from the
+    product's get_rays (one launch of inerf_get_rays per batch)."""
+    import numpy as np
+    import torch
+    from instance_nerf_b200.nerf.utils import get_rays
+
+    out = []
+    for i in range(n):
+        g = torch.Generator(device=dev).manual_seed(100 + i * world + rank)
+        r = get_rays(poses[(i * world + rank) % poses.shape[0]][None].to(dev), intrinsics(), H_IMG, W_IMG, N=n_rays, patch_size=8, generator=g)
+        o, d = r["rays_o"].reshape(-1, 3).contiguous(), r["rays_d"].reshape(-1, 3).contiguous()
+        labels = torch.from_numpy(scene.first_hit_labels(o.cpu().numpy().astype(np.float64), d.cpu().numpy().astype(np.float64)))
+        out.append({"rays_o": o[None], "rays_d": d[None], "masks": labels[None].to(dev)})
+    return out
 
 
 # ------------------------------------------------------------------------------------------------ clocks --
@@ -108,58 +136,86 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------- CPU reference arm --
-def make_cpu_reference(n_rays: int, poses=None, model=None):
+def make_cpu_reference(config: str = "c1", n_rays: int = 0):
     """The reference's PyTorch (non-cuda_ray) renderer -- NeRFMaskRenderer.run / staged render, mask_renderer.py:89-231,
-    565-584 -- as restated in oracle/field_oracle.py (pinned against the reference's own outputs, tests/golden/ref_run.npz),
-    set up on `n_rays` rays strided over frame 0 of the workload.  -> (render thunk, n_rays, cores)"""
+    565-584 -- as restated in oracle/field_oracle.py (pinned against the reference's own outputs, tests/golden/ref_run.npz).
+    config "c1": the whole 160x120 frame of the K=16 room; "c2-sample": `n_rays` rays strided over frame 0 of
+    the c2 scene (K=32).  -> (render thunk, n_rays, samples_per_ray, cores)"""
     import torch
     from oracle import field_oracle as fo
+    from oracle import host_oracle
 
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    if model is None:
-        model, _, poses = build_scene_and_model(None)
+    if config == "c1":
+        H, W, K, T = C1["H"], C1["W"], C1["K"], C1["T"]
+    else:
+        H, W, K, T = H_IMG, W_IMG, K_INST, 128
+    model, _, poses = build_scene_and_model(None, K=K)
     sd = {k: v.detach().float().cpu() for k, v in model.state_dict().items()}
-    field = fo.OracleField(sd, BOUND, K_INST, density_scale=1.0)
-    o, d = frame_rays(poses.cpu(), 0)
-    stride = max(1, o.shape[0] // n_rays)
-    o, d = o[::stride][:n_rays].contiguous(), d[::stride][:n_rays].contiguous()
+    field = fo.OracleField(sd, BOUND, K, density_scale=1.0)
+    r = host_oracle.get_rays(poses[0:1], intrinsics(H, W), H, W)
+    o, d = r["rays_o"].reshape(-1, 3).contiguous(), r["rays_d"].reshape(-1, 3).contiguous()
+    if config != "c1":
+        stride = max(1, o.shape[0] // n_rays)
+        o, d = o[::stride][:n_rays].contiguous(), d[::stride][:n_rays].contiguous()
 
     def render():
-        return field.render(o[None], d[None], max_ray_batch=4096, render_mask=True, num_steps=128, bg_color=1)
+        return field.render(o[None], d[None], max_ray_batch=4096, render_mask=True, num_steps=T, bg_color=1)
 
-    return render, o.shape[0], cores
+    return render, o.shape[0], T, cores
+
+
+def time_cpu_reference(config, n_rays=0, warmup=1, repeats=3):
+    render, n, T, cores = make_cpu_reference(config, n_rays)
+    for _ in range(warmup):
+        render()
+    best = float("inf")
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        render()
+        best = min(best, time.perf_counter() - t0)
+    return {"value": n / best / 1e6, "unit": UNIT, "cores": cores, "kind": "port", "rays": n, "samples_per_ray": T, "seconds_best": best,
+            "repeats": repeats}
 
 
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    render, n_rays, cores = make_cpu_reference(8192)
-    for _ in range(args.warmup):
+    render, n_rays, T, cores = make_cpu_reference("c1")
+    for _ in range(max(1, args.warmup)):
         render()
-    t0 = time.perf_counter()
+    times = []
     for _ in range(args.steps):
+        t0 = time.perf_counter()
         render()
-    total = time.perf_counter() - t0
+        times.append(time.perf_counter() - t0)
+    total = sum(times)
     value = n_rays * args.steps / total / 1e6
-    sample = f"{n_rays} rays strided over frame 0 per step, 128 uniform samples/ray (the reference's non-cuda_ray sampler), K=32"
+    sample = (f"c1 = BASELINE.md B1: the whole 160x120 frame ({n_rays} rays) x {T} uniform samples/ray, K={C1['K']}, staged render in chunks of 4096 "
+              f"rays, fp32, {cores} threads; mean of {args.steps} steps (best step {n_rays / min(times) / 1e6:.5f} Mrays/s)")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": total / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic", "config": {"workload": WORKLOAD, "rays_per_step": n_rays, "samples_per_ray": 128},
+        "data": "synthetic", "config": {"workload": WORKLOAD_C1, "rays_per_step": n_rays, "samples_per_ray": T,
+                                        "note": "the reference's only CPU-runnable renderer is the non-cuda_ray path, whose config is c1 (BASELINE.json "
+                                                "configs[0]); the GPU arm's headline config is c2"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    if not args.no_c2_sample:
+        c2 = time_cpu_reference("c2-sample", 8192, warmup=0, repeats=1)
+        line["c2_scene_sample"] = {"value": c2["value"], "unit": UNIT, "sample": f"{c2['rays']} rays strided over frame 0 of the c2 scene (K=32), 128 uniform "
+                                   f"samples/ray, {c2['seconds_best']:.1f} s", "cores": cores}
     emit(line)
 
 
 # --------------------------------------------------------------------------------------------- GPU arm --
-def run_gpu_arm(args):
+def _init_dist():
     import torch
     import torch.distributed as dist
-
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -171,35 +227,41 @@ def run_gpu_arm(args):
         dist.init_process_group("nccl", device_id=dev)
     from instance_nerf_b200 import _lib
     _lib.lib()  # fail loudly if libinerf_b200.so is missing
+    return rank, world, local_rank, dev
 
+
+def run_gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+    from instance_nerf_b200 import parallel
+    from instance_nerf_b200.nerf.utils import get_rays
+
+    rank, world, local_rank, dev = _init_dist()
     model, scene, poses = build_scene_and_model(dev)
     N = H_IMG * W_IMG
     K = K_INST
+    intr = intrinsics()
     # Work units of one step = `world` whole frames.  Rank r renders the row blocks r, r + world, ... of EVERY frame of the step
     # (H / world rows of each), not one frame of its own: cost is proportional to marched samples, which vary by +-25 % from
     # pose to pose, and the per-step tile gather is a synchronisation point -- interleaved rows give every rank the same mix
     # (SURVEY.md section 8e).  Rows stay whole, so the marcher's 32-ray patches remain runs of neighbouring pixels.
-    from instance_nerf_b200 import parallel
     block_rows = 4
     if H_IMG % (world * block_rows):
         raise SystemExit(f"bench.py: {H_IMG} rows do not split into {block_rows}-row blocks over {world} ranks")
-    mine = parallel.shard_rows(H_IMG, W_IMG, rank, world, block_rows=block_rows)    # this rank's pixel ids inside a frame
+    mine = parallel.shard_rows(H_IMG, W_IMG, rank, world, block_rows=block_rows).to(dev)    # this rank's pixel ids inside a frame
     n_groups = max(1, N_POSES // world)
-    host_rays = []
-    for g in range(n_groups):
-        os_, ds_ = [], []
-        for j in range(world):
-            o, d = frame_rays(poses, (g * world + j) % N_POSES)
-            os_.append(o[mine])
-            ds_.append(d[mine])
-        host_rays.append((torch.cat(os_).contiguous().pin_memory(), torch.cat(ds_).contiguous().pin_memory()))
-    dev_rays = [(o.to(dev), d.to(dev)) for o, d in host_rays]
+    host_poses = [torch.stack([poses[(g * world + j) % N_POSES] for j in range(world)]).float().contiguous().pin_memory() for g in range(n_groups)]
+
+    def rays_of(pose_group_dev):   # [world, 4, 4] on the device -> this rank's N rays of the step (ONE launch of inerf_get_rays)
+        r = get_rays(pose_group_dev, intr, H_IMG, W_IMG, inds=mine if world > 1 else None)
+        return r["rays_o"].view(-1, 3), r["rays_d"].view(-1, 3)
+
+    dev_rays = [rays_of(p.to(dev)) for p in host_poses]
     kw = dict(staged=True, render_mask=True, perturb=False, dt_gamma=DT_GAMMA, max_steps=MAX_STEPS, T_thresh=T_THRESH, bg_color=1)
     flush_buf = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device=dev)
-    # image 3 | depth 1 | logits K; double buffered so the NCCL gather of frame i overlaps the render of frame i + 1
+    # image 3 | depth 1 | logits K; double buffered so the NCCL gather of step i overlaps the render of step i + 1
     tiles = [torch.empty(N, 4 + K, dtype=torch.float32, device=dev) for _ in range(2)]
-    gathered = [torch.empty(world * N, 4 + K, dtype=torch.float32, device=dev) for _ in range(2)] if world > 1 else None
-    handles = [None, None]
+    gather = parallel.TileGather(N, 4 + K, dev, dst=0, depth=2)
     copy_done = [None, None]
     copy_stream = torch.cuda.Stream(device=dev)
 
@@ -223,15 +285,12 @@ def run_gpu_arm(args):
     def step(i, e2e=False, out_host=None):
         p = i % n_groups
         if e2e:
-            o = host_rays[p][0].to(dev, non_blocking=True)
-            d = host_rays[p][1].to(dev, non_blocking=True)
+            o, d = rays_of(host_poses[p].to(dev, non_blocking=True))
+            launches["n"] += 1      # k_get_rays
         else:
             o, d = dev_rays[p]
-        b = i & 1
-        if handles[b] is not None:        # the gather that last used this buffer pair must have finished (stream-side wait)
-            handles[b].wait()
-            handles[b] = None
-        if copy_done[b] is not None:      # ... and so must the device->host copy of the frame rendered two steps ago
+        b = gather.slot_ready() if not e2e else (i & 1)      # the gather that last used this buffer pair has finished (stream-side wait)
+        if copy_done[b] is not None:      # ... and so has the device->host copy of the frame rendered two steps ago
             torch.cuda.current_stream().wait_event(copy_done[b])
             copy_done[b] = None
         tile = tiles[b]
@@ -240,11 +299,10 @@ def run_gpu_arm(args):
         tile[:, 0:3] = r["image"][0]
         tile[:, 3] = r["depth"][0]
         tile[:, 4:] = r["instance_mask_logits"][0]
-        if world > 1:
-            handles[b] = dist.all_gather_into_tensor(gathered[b], tile, async_op=True)
         if e2e:
-            # every rank reads ITS OWN frame back over its own PCIe link, on a side stream, so the copy of frame i overlaps the
-            # render of frame i + 1 (double-buffered device tiles and pinned host buffers); the NCCL gather still runs
+            # every rank reads ITS OWN rows back over its own PCIe link, on a side stream, so the copy of step i overlaps the
+            # render of step i + 1 (double-buffered device tiles and pinned host buffers); no collective is needed for a result
+            # that is wanted on the host
             ready = torch.cuda.Event()
             ready.record()
             copy_stream.wait_event(ready)
@@ -252,12 +310,12 @@ def run_gpu_arm(args):
                 out_host[b].copy_(tile, non_blocking=True)
                 copy_done[b] = torch.cuda.Event()
                 copy_done[b].record()
+        else:
+            gather.submit(tile)
 
     def drain():
+        gather.drain()
         for b in range(2):
-            if handles[b] is not None:
-                handles[b].wait()
-                handles[b] = None
             if copy_done[b] is not None:
                 torch.cuda.current_stream().wait_event(copy_done[b])
                 copy_done[b] = None
@@ -298,7 +356,7 @@ def run_gpu_arm(args):
     n_tiles = [int(s[1].item()) for s in samples_seen]
     gpu_launches = launches["n"]
 
-    # ---- end-to-end region: pinned host rays -> render -> pinned host results ----------------------------------------
+    # ---- end-to-end region: pinned host poses -> rays -> render -> pinned host results ----------------------------------
     out_host = [torch.empty(N, 4 + K, dtype=torch.float32).pin_memory() for _ in range(2)]
     for i in range(min(2, args.warmup)):
         step(i, True, out_host)
@@ -315,12 +373,14 @@ def run_gpu_arm(args):
     barrier()
     e2e_ms = e2e0.elapsed_time(e2e1)
     clk = clocks.stop() if rank == 0 else None
+    model._render_fused = fused
 
     if world > 1:
         t = torch.tensor([total_ms, e2e_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms, e2e_ms = float(t[0]), float(t[1])
 
+    line = None
     if rank == 0:
         peaks = {}
         ppath = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -336,7 +396,33 @@ def run_gpu_arm(args):
         mlp_flops = avg_samples * (6144 + 12544 + 14208 + 128 * K)
         ms_per_step = total_ms / args.steps
         value = world * N / (ms_per_step * 1e-3) / 1e6
-        h2d = 2 * N * 3 * 4
+        try:
+            from instance_nerf_b200 import probe
+            l2 = probe.measure_l2_peaks(dev)
+        except Exception as e:   # the probe library is a measurement helper: report its absence, do not lose the line
+            l2 = {"error": f"{type(e).__name__}: {e}"}
+        l2_peak = l2.get("l2_stream_gbs")
+        roof = {"kernel": "k_render_fused", "bound": "l2", "achieved": achieved, "unit": "GB/s", "traffic": None,
+                "peak": l2_peak if l2_peak else hbm_peak, "frac": achieved / (l2_peak if l2_peak else hbm_peak),
+                "peak_source": ("measured in this run: coalesced 16-byte loads over an L2-resident 53 MB buffer (instance_nerf_b200/probe.py); the "
+                                "interleaved fp16 table is L2-resident (ncu: lts hit rate 99.4 %, dram throughput 0.1 %)") if l2_peak else
+                               "L2 probe unavailable: HBM peak used",
+                "kernel_ms": avg_kern_ms, "algorithmic_bytes_per_launch": alg_bytes,
+                "gathers_per_s": avg_samples * 128 / (avg_kern_ms * 1e-3),
+                "gather_peak": {"gathers_per_s": l2.get("gather_gps"), "gbs_at_8B": l2.get("gather_gbs"),
+                                "frac": (avg_samples * 128 / (avg_kern_ms * 1e-3)) / l2["gather_gps"] if l2.get("gather_gps") else None,
+                                "what": "random 8-byte ld.global.nc gathers from a 53 MB table at full occupancy (one sector per lane, no reuse): the "
+                                        "access shape of the six finest hashed levels; the coarse levels coalesce, so the kernel can exceed it"},
+                "frac_of_hbm": achieved / hbm_peak, "hbm_peak": hbm_peak,
+                "hbm_peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650 GB/s",
+                "probe": l2, "mlp_tflops": mlp_flops / (avg_kern_ms * 1e-3) / 1e12}
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            try:
+                roof["traffic"] = json.load(open(tpath)).get("k_render_fused_dram_bytes_per_launch")
+            except Exception:
+                pass
+        h2d = world * 64
         d2h = out_host[0].numel() * 4
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -345,24 +431,21 @@ def run_gpu_arm(args):
             "config": {"workload": WORKLOAD, "rays_per_step_per_gpu": N, "samples_per_ray": avg_samples / N,
                        "tile_fill": (sum(n_samples) / max(1, 128 * sum(n_tiles))), "l2": "flushed between timed steps (512 MB write)",
                        "parallelism": (f"{world} frames per step, every frame's rows interleaved over {world} ranks (balanced by samples), async NCCL "
-                                       f"all_gather of the finished row blocks overlapped with the next step") if world > 1 else "single GPU",
+                                       f"gather of the finished row blocks to rank 0 overlapped with the next step "
+                                       f"({N * (4 + K) * 4} B sent per rank per step over NVLink)") if world > 1 else "single GPU",
                        "wall_s_timed_region_incl_flush": wall_s},
-            "e2e": {"value": world * N / (e2e_ms / args.steps * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "e2e": {"value": world * N / (e2e_ms / args.steps * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "what": "poses (64 B each) host->device, rays built on the device by inerf_get_rays, render, own rows device->pinned host"},
             "gpu_launches": gpu_launches,
-            "roofline": {"kernel": "k_render_fused", "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                         "traffic": None, "peak_source": "MEASURED_PEAKS.json (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
-                         "kernel_ms": avg_kern_ms, "algorithmic_bytes_per_launch": alg_bytes,
-                         "mlp_tflops": mlp_flops / (avg_kern_ms * 1e-3) / 1e12},
+            "roofline": roof,
             "clocks": clk,
         }
-        tpath = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tpath):
-            try:
-                line["roofline"]["traffic"] = json.load(open(tpath)).get("k_render_fused_dram_bytes_per_launch")
-            except Exception:
-                pass
-        if world == 1 and not args.no_train:
-            # second half of BASELINE.json's metric ("train-step ms @ 4096 rays"), measured in the same run (config c3)
+    del flush_buf, tiles
+    torch.cuda.empty_cache()
+
+    # ---- training figures in the same run: c3 at N = 1, c5 (data parallel) at every N --------------------------------------
+    if not args.no_train:
+        if world == 1:
             try:
                 tr = measure_train(dev, 0, 1, 20, 5, 4096, model, scene, poses)
             except Exception as e:   # the headline line must survive a failed graph capture: redo the figure eagerly and say so
@@ -370,18 +453,122 @@ def run_gpu_arm(args):
                 torch.cuda.synchronize()
                 os.environ["INERF_NO_GRAPH"] = "1"
                 tr = measure_train(dev, 0, 1, 20, 5, 4096, model, scene, poses)
-            line["train_step"] = {"ms": tr["ms"], "ms_median": tr["ms_median"], "unit": "ms", "rays": 4096, "samples": tr["samples"],
-                                  "workload": "c3: 4096 rays (8x8 patches) x max_steps 1024, K=32, fp16 autocast, CE + label smoothness, backward, Adam",
-                                  "cuda_graph": tr["cuda_graph"], "graph_replays": tr["graph_replays"], "graph_captures": tr["graph_captures"]}
+            if rank == 0:
+                line["train_step"] = {"ms": tr["ms"], "ms_median": tr["ms_median"], "unit": "ms", "rays": 4096, "samples": tr["samples"],
+                                      "workload": "c3: 4096 rays (8x8 patches) x max_steps 1024, K=32, fp16 autocast, CE + label smoothness, backward, Adam",
+                                      "cuda_graph": tr["cuda_graph"], "graph_replays": tr["graph_replays"], "graph_captures": tr["graph_captures"]}
+        try:
+            dp = measure_train(dev, rank, world, 12, 4, 65536, None, None, None)
+            if rank == 0:
+                line["train_dp"] = {"ms": dp["ms"], "ms_median": dp["ms_median"], "unit": "ms", "rays_per_gpu": 65536, "samples_per_gpu": dp["samples"],
+                                    "rays_per_s": world * 65536 / (dp["ms"] * 1e-3), "n_gpus": world, "cuda_graph": dp["cuda_graph"],
+                                    "graph_replays": dp["graph_replays"], "allreduce_bytes": dp["allreduce_bytes"], "allreduce_ms_alone": dp["allreduce_ms"],
+                                    "workload": "c5: data-parallel instance-field training, 65536 rays/GPU (8x8 patches) x max_steps 1024, K=32, one NCCL "
+                                                "all_reduce(SUM) of the flat gradient buffer inside the step, 1/N folded into the Adam pass"}
+        except Exception as e:
+            print(f"[bench] c5 data-parallel training figure failed ({type(e).__name__}: {e})", file=sys.stderr)
+            if rank == 0:
+                line["train_dp"] = {"error": f"{type(e).__name__}: {e}"}
+
+    if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
-            render, n_cpu, cores = make_cpu_reference(32768)
-            t0 = time.perf_counter()
-            render()
-            secs = time.perf_counter() - t0
-            v = n_cpu / secs / 1e6
-            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": f"{n_cpu} rays strided over frame 0, 128 uniform samples/ray (reference non-cuda_ray sampler), {secs:.1f} s"}
+            c1 = time_cpu_reference("c1", warmup=1, repeats=3)
+            line["cpu_baseline"] = {"value": c1["value"], "unit": UNIT, "cores": c1["cores"], "kind": "port",
+                                    "sample": f"c1 = BASELINE.md B1: whole 160x120 frame ({c1['rays']} rays) x 128 uniform samples/ray, K=16, reference "
+                                              f"non-cuda_ray renderer (oracle port), 1 warm-up + best of 3: {c1['seconds_best']:.2f} s"}
+        if world == 1 and not args.no_ref_cuda:
+            line["ref_cuda_path"] = run_ref_cuda_subprocess()
         emit(line)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_ref_cuda_subprocess():
+    """the reference's own CUDA kernels (oracle/_ref) on c2 / c3, in a separate process so that none of the
+    checker's libraries are ever loaded next to the product's timed regions."""
+    if not os.path.isdir(os.path.join(ROOT, "oracle", "_ref")) or not any(f.endswith(".so") for f in os.listdir(os.path.join(ROOT, "oracle", "_ref"))):
+        return {"skipped": "oracle/_ref is not built (oracle/build_ref.sh needs /root/reference)"}
+    try:
+        r = subprocess.run([sys.executable, "-m", "oracle.ref_cuda_path", "--json", "--frames", "3", "--train-steps", "10"], cwd=ROOT,
+                           capture_output=True, text=True, timeout=600)
+        if r.returncode != 0:
+            return {"skipped": f"oracle.ref_cuda_path exited {r.returncode}: {r.stderr[-300:]}"}
+        return json.loads(r.stdout.strip().splitlines()[-1])
+    except Exception as e:
+        return {"skipped": f"{type(e).__name__}: {e}"}
+
+
+# ---------------------------------------------------------------------------------------------- c4 arm --
+def run_c4_arm(args):
+    """BASELINE.json configs[3]: 1920x1080 multi-view render of 200 camera poses (the 3D-mask projection workload shape,
+    scripts/project_3d_masks.py:135-266), whole frames round-robin over the ranks (parallel.shard_frames), one asynchronous NCCL
+    gather of the finished frames to rank 0 per round.  A "step" = one round of `world` frames; rays are built on the device
+    from the 64-byte pose of each frame."""
+    import torch
+    import torch.distributed as dist
+    from instance_nerf_b200 import parallel, synthetic
+    from instance_nerf_b200.nerf.utils import get_rays
+
+    rank, world, local_rank, dev = _init_dist()
+    H, W, n_frames = C4["H"], C4["W"], args.frames or C4["frames"]
+    model, scene, _ = build_scene_and_model(dev)
+    poses = torch.from_numpy(synthetic.camera_poses(scene, n_frames, 1)).to(dev)
+    intr = intrinsics(H, W)
+    N, K = H * W, K_INST
+    kw = dict(staged=True, render_mask=True, perturb=False, dt_gamma=DT_GAMMA, max_steps=MAX_STEPS, T_thresh=T_THRESH, bg_color=1)
+    tiles = [torch.empty(N, 4 + K, dtype=torch.float32, device=dev) for _ in range(2)]
+    gather = parallel.TileGather(N, 4 + K, dev, dst=0, depth=2)
+    my_frames = parallel.shard_frames(n_frames, rank, world)
+    rounds = (n_frames + world - 1) // world
+
+    def render_round(k):
+        f = my_frames[k] if k < len(my_frames) else my_frames[-1]   # ranks past the end re-render their last frame (uniform collective)
+        r = get_rays(poses[f:f + 1], intr, H, W)
+        b = gather.slot_ready()
+        with torch.no_grad():
+            out = model.render(r["rays_o"], r["rays_d"], **kw)
+        tile = tiles[b]
+        tile[:, 0:3] = out["image"][0]
+        tile[:, 3] = out["depth"][0]
+        tile[:, 4:] = out["instance_mask_logits"][0]
+        gather.submit(tile)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for k in range(min(3, rounds)):
+        render_round(k)
+    gather.drain()
+    barrier()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for k in range(rounds):
+        render_round(k)
+    gather.drain()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    samples = int(model._work_counter[2:4].view(torch.int64).item())
+    clk = clocks.stop() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t[0])
+    if rank == 0:
+        value = n_frames * N / (ms * 1e-3) / 1e6
+        emit({"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": rounds, "warmup": min(3, rounds), "ms_per_step": ms / rounds,
+              "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f16 operands / f32 accumulate", "data": "synthetic",
+              "config": {"workload": f"c4: {n_frames} camera poses x {W}x{H} instance-field render, K=32, whole frames round-robin over {world} GPU(s)",
+                         "frames": n_frames, "rays_per_frame": N, "samples_per_ray_last_frame_rank0": samples / N,
+                         "l2": "inputs larger than L2: every frame reads 2.07 M fresh rays and writes a 299 MB tile; tables stay L2-resident by design",
+                         "parallelism": f"frames sharded round-robin, async NCCL gather of {N * (4 + K) * 4} B per frame to rank 0" if world > 1 else "single GPU"},
+              "total_s": ms * 1e-3, "gpu_launches": 4 * rounds, "clocks": clk})
     if world > 1:
         dist.destroy_process_group()
 
@@ -389,25 +576,17 @@ def run_gpu_arm(args):
 # ------------------------------------------------------------------------------------------- train arm --
 def measure_train(dev, rank, world, steps, warmup, n_rays, model=None, scene=None, poses=None):
     """Times `steps` full optimisation steps (MaskTrainStep.step: render -> loss -> backward -> [all_reduce] -> Adam) with CUDA
-    events, L2 flushed between steps.  -> dict(ms, samples, loss, clocks)"""
-    import numpy as np
+    events, L2 flushed between steps.  -> dict(ms, samples, loss, clocks, ...)"""
     import torch
     import torch.distributed as dist
-    from instance_nerf_b200 import synthetic
     from instance_nerf_b200.nerf.trainer import MaskTrainStep
 
     if model is None:
         model, scene, poses = build_scene_and_model(dev)
+    use_graph = not os.environ.get("INERF_NO_GRAPH")
     trainer = MaskTrainStep(model, lr=1e-2, fp16=True, patch_size=8, label_regularization_weight=0.1, dt_gamma=DT_GAMMA, max_steps=MAX_STEPS,
-                            T_thresh=T_THRESH, data_parallel=world > 1, cuda_graph=(world == 1 and not os.environ.get("INERF_NO_GRAPH")))
-    intr = synthetic.intrinsics(H_IMG, W_IMG)
-    batches = []
-    for i in range(8):
-        g = torch.Generator().manual_seed(100 + i * world + rank)
-        r = synthetic.get_rays(poses[(i * world + rank) % N_POSES][None], intr, H_IMG, W_IMG, N=n_rays, patch_size=8, generator=g)
-        o, d = r["rays_o"].reshape(-1, 3).contiguous(), r["rays_d"].reshape(-1, 3).contiguous()
-        labels = torch.from_numpy(scene.first_hit_labels(o.numpy().astype(np.float64), d.numpy().astype(np.float64)))
-        batches.append({"rays_o": o[None].to(dev), "rays_d": d[None].to(dev), "masks": labels[None].to(dev)})
+                            T_thresh=T_THRESH, data_parallel=world > 1, cuda_graph=use_graph)
+    batches = train_batches(dev, scene, poses, n_rays, rank, world, n=8)
     flush_buf = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device=dev)
 
     def barrier():
@@ -441,44 +620,52 @@ def measure_train(dev, rank, world, steps, warmup, n_rays, model=None, scene=Non
     n_samples = float(model.step_counter[: min(16, steps), 0].float().mean().item())
     if trainer.cuda_graph and trainer.graph_replays:
         n_samples = float(sum(totals)) / max(1, len(totals))
+    ar_ms, ar_bytes = None, 0
     if world > 1:
         t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms = float(t[0])
+        # the exchange on its own (same buffer, same collective), for the record: 10 back-to-back all-reduces
+        ar_bytes = trainer.bucket.numel * 4
+        barrier()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(10):
+            trainer.bucket.all_reduce()
+        a1.record()
+        barrier()
+        ar_ms = a0.elapsed_time(a1) / 10
+        trainer.bucket.flat.zero_()
     model.eval()
     for p in model.parameters():
         p.requires_grad_(True)
+    del flush_buf
     return {"ms": total_ms / steps, "ms_median": times[len(times) // 2], "samples": n_samples, "loss": float(loss.item()), "clocks": clk,
-            "cuda_graph": bool(trainer.cuda_graph), "graph_captures": trainer.graph_captures, "graph_replays": trainer.graph_replays}
+            "cuda_graph": bool(trainer.cuda_graph), "graph_captures": trainer.graph_captures, "graph_replays": trainer.graph_replays,
+            "allreduce_ms": ar_ms, "allreduce_bytes": ar_bytes}
 
 
 def run_train_arm(args):
     """BASELINE.json configs[2] / [4]: instance-field training step (MaskTrainer.train_step + backward + Adam, nerf/utils.py:
     929-936, 1287-1373), `--rays` rays per GPU per step as 8x8 patches, max_steps 1024, fp16 autocast (the `-O` preset).
-    At N > 1: data-parallel, one all_reduce of the mask-table + mask-net gradients per step."""
-    import torch
+    At N > 1: data-parallel, one all_reduce of the flat mask-table + mask-net gradient buffer per step."""
     import torch.distributed as dist
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+    rank, world, local_rank, dev = _init_dist()
     n_rays = args.rays
     r = measure_train(dev, rank, world, args.steps, args.warmup, n_rays)
     if rank == 0:
         ms = r["ms"]
+        cfg = "c3" if n_rays == 4096 and world == 1 else ("c5" if n_rays == 65536 else "train")
         line = {"metric": "instance_field_train_step_ms", "value": ms, "unit": "ms", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms, "higher_is_better": False, "scaling": "weak", "vs_baseline": None, "dtype": "f16 autocast / f32 params",
                 "data": "synthetic",
-                "config": {"workload": f"c3: instance-field training step, {n_rays} rays/GPU (8x8 patches) x max_steps 1024, K=32, hash+MLP backward, Adam",
+                "config": {"workload": f"{cfg}: instance-field training step, {n_rays} rays/GPU (8x8 patches) x max_steps 1024, K=32, hash+MLP backward, Adam",
                            "rays_per_gpu": n_rays, "samples_per_step_per_gpu": r["samples"], "l2": "flushed between timed steps (512 MB write)",
-                           "parallelism": f"dp{world}, flat-bucket all_reduce" if world > 1 else "single GPU"},
-                "ms_per_step_median": r["ms_median"], "rays_per_s": world * n_rays / (ms * 1e-3), "loss": r["loss"], "clocks": r["clocks"]}
+                           "parallelism": f"dp{world}, one in-place all_reduce(SUM) of the flat gradient buffer, 1/N folded into Adam" if world > 1 else "single GPU",
+                           "cuda_graph": r["cuda_graph"], "graph_replays": r["graph_replays"]},
+                "ms_per_step_median": r["ms_median"], "rays_per_s": world * n_rays / (ms * 1e-3), "loss": r["loss"], "clocks": r["clocks"],
+                "allreduce": {"bytes": r["allreduce_bytes"], "ms_alone": r["allreduce_ms"]}}
         emit(line)
     if world > 1:
         dist.destroy_process_group()
@@ -506,19 +693,27 @@ def main():
     _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-train", action="store_true", help="skip the train-step figure appended to the render line at N = 1")
-    ap.add_argument("--workload", default="render", choices=["render", "train"], help="render = the headline metric (default); train = train-step ms")
+    ap.add_argument("--no-ref-cuda", action="store_true", help="skip the reference-CUDA-kernel figure (oracle/_ref subprocess) at N = 1")
+    ap.add_argument("--no-c2-sample", action="store_true", help="reference arm: skip the extra c2-scene sample")
+    ap.add_argument("--no-train", action="store_true", help="skip the train-step figures appended to the render line")
+    ap.add_argument("--workload", default="render", choices=["render", "c4", "train"],
+                    help="render = the headline metric on c2 (default); c4 = 200 poses x 1920x1080; train = train-step ms")
     ap.add_argument("--rays", type=int, default=4096, help="train workload: rays per GPU per step (4096 = config c3, 65536 = c5)")
+    ap.add_argument("--frames", type=int, default=0, help="c4 workload: number of camera poses (default 200)")
     args = ap.parse_args()
+    if args.steps is None:
+        args.steps = 5 if args.impl == "reference" else 50
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
         run_reference_arm(args)
     elif args.workload == "train":
         run_train_arm(args)
+    elif args.workload == "c4":
+        run_c4_arm(args)
     else:
         run_gpu_arm(args)
 

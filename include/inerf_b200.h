@@ -297,6 +297,44 @@ int inerf_occupancy_ema(float *density_grid, const float *tmp_grid, uint32_t n_c
 int inerf_occupancy_pack(const float *density_grid, uint32_t n_cells, const double *sum_in, float density_thresh,
                          uint8_t *bitfield, float *mean_out, void *stream);
 
+/* ------------------------------------------- occupancy grid: sampling front -- */
+
+/*
+ * nerf/mask_renderer.py:466-527 (update_extra_state, the part before the EMA) and :389-452 (mark_untrained_grid) as
+ * device code: no meshgrid / randint / nonzero / index_put, no host read.
+ *
+ * A "sweep" is C * per_cascade samples; sample s belongs to cascade c = s / per_cascade and to the cell with Morton
+ * index cells[s] (cells == NULL: cell s % G^3, the full sweep of the first 16 updates, per_cascade = G^3).  Its point is
+ * the cell centre `(2 * coord / (G - 1) - 1) * (bound_c - bound_c / G)` plus `(u * 2 - 1) * bound_c / G` per axis
+ * (:480-487), u = noise[s, :] when noise != NULL (parity tests inject the reference's rand_like draws) else a
+ * counter-based generator keyed by `seed`.
+ *
+ *   inerf_occupancy_sample_cells  partial update (:498-513): per cascade N uniform cells + N cells drawn with
+ *                                 replacement from the occupied ones (density_grid[c] > 0), compacted in torch.nonzero
+ *                                 order on the device -> cells [C, 2N].  uniform_cells [C, N] / occ_picks [C, N]
+ *                                 (positions in the occupied list) inject the draws; NULL = generator.  scratch:
+ *                                 int32[inerf_occupancy_sample_scratch_ints(C, G)], caller-owned.
+ *   inerf_occupancy_points        the sweep's points xyzs [C * per_cascade, 3] and flat cell indices c * G^3 + cell
+ *                                 (for networks the fused sweep does not cover, and for tests).
+ *   inerf_occupancy_density       fused: point -> hash encode -> sigma-net (tcgen05) -> tmp_grid[c, cell] =
+ *                                 sigma * desc->density_scale, one launch.  tmp_grid [C, G^3] is only written at the
+ *                                 sampled cells (pre-fill with -1 for a partial sweep: inerf_fill_f32).
+ *   inerf_mark_untrained_grid     density_grid[c, cell] = -1 for every cell whose centre no camera sees (c2w poses
+ *                                 [B, 4, 4] row-major, pinhole fx fy cx cy, margin 2 * bound_c / G); *n_marked
+ *                                 (optional, pre-zeroed) counts them.
+ */
+size_t inerf_occupancy_sample_scratch_ints(uint32_t C, uint32_t G);
+int inerf_occupancy_sample_cells(const float *density_grid, uint32_t C, uint32_t G, uint32_t N,
+                                 const int32_t *uniform_cells, const int32_t *occ_picks, uint64_t seed, int32_t *cells,
+                                 int32_t *scratch, void *stream);
+int inerf_occupancy_points(uint32_t C, uint32_t G, float bound, const int32_t *cells, uint32_t per_cascade,
+                           const float *noise, uint64_t seed, float *xyzs, int32_t *flat_index, void *stream);
+int inerf_occupancy_density(const inerf_field_desc *desc, uint32_t C, uint32_t G, const int32_t *cells,
+                            uint32_t per_cascade, const float *noise, uint64_t seed, float *tmp_grid, void *stream);
+int inerf_mark_untrained_grid(const float *poses, uint32_t B, float fx, float fy, float cx, float cy, uint32_t C,
+                              uint32_t G, float bound, float *density_grid, uint32_t *n_marked, void *stream);
+int inerf_fill_f32(float *p, uint32_t n, float value, void *stream);
+
 /* ------------------------------------------------------------- optimizer -- */
 
 /*
@@ -305,11 +343,13 @@ int inerf_occupancy_pack(const float *density_grid, uint32_t n_cells, const doub
  * clearing the gradient: one pass over param / grad / exp_avg / exp_avg_sq (fp32 [n], 16-byte aligned) instead of
  * zero_grad + unscale + Adam.  `step` is a device float holding the number of steps taken so far; grad_scale and
  * found_inf are GradScaler's device scalars (NULL = 1 / 0).  found_inf != 0 leaves parameters and moments unchanged
- * (the gradient is cleared either way).  Call inerf_adam_advance(step, found_inf) once after all tensors of a step.
+ * (the gradient is cleared either way).  grad_div (> 0) divides the gradient once more: data-parallel training passes the
+ * world size, so the SUM all-reduce needs no separate averaging pass (1 = single GPU, bit-identical to no division).
+ * Call inerf_adam_advance(step, found_inf) once after all tensors of a step.
  */
 int inerf_adam_step(float *param, float *grad, float *exp_avg, float *exp_avg_sq, uint64_t n, float lr, float beta1,
                     float beta2, float eps, const float *step, const float *grad_scale, const float *found_inf,
-                    void *stream);
+                    float grad_div, void *stream);
 int inerf_adam_advance(float *step, const float *found_inf, void *stream);
 
 #ifdef __cplusplus

@@ -90,6 +90,11 @@ _PROTOS = {
     "inerf_mask_loss_backward": [_P, _P, _P, _U, _U, _U, _F, _P, _P, _P, _P],
     "inerf_occupancy_ema": [_P, _P, _U, _F, _P, _P],
     "inerf_occupancy_pack": [_P, _U, _P, _F, _P, _P, _P],
+    "inerf_occupancy_sample_cells": [_P, _U, _U, _U, _P, _P, ctypes.c_uint64, _P, _P, _P],
+    "inerf_occupancy_points": [_U, _U, _F, _P, _U, _P, ctypes.c_uint64, _P, _P, _P],
+    "inerf_occupancy_density": [POINTER(FieldDesc), _U, _U, _P, _U, _P, ctypes.c_uint64, _P, _P],
+    "inerf_mark_untrained_grid": [_P, _U, _F, _F, _F, _F, _U, _U, _F, _P, _P, _P],
+    "inerf_fill_f32": [_P, _U, _F, _P],
     "inerf_field_pack_weights": [_P] * 8 + [_U, _P],
     "inerf_field_pack_tables": [_P, _P, _I, ctypes.c_uint64, _P, _P],
     "inerf_field_forward": [POINTER(FieldDesc), _P, _P, _U, _P, _P, _P, _P],
@@ -97,7 +102,7 @@ _PROTOS = {
     "inerf_field_pack_weights_bwd": [_P, _P, _P, _U, _P],
     "inerf_field_pack_weights_device": [_P] * 8 + [_U, _P, _P, _P],
     "inerf_field_backward_mask": [POINTER(FieldDesc), _P, _P, _P, _P, _U, _P, _P, _P, _P, _P],
-    "inerf_adam_step": [_P, _P, _P, _P, ctypes.c_uint64, _F, _F, _F, _F, _P, _P, _P, _P],
+    "inerf_adam_step": [_P, _P, _P, _P, ctypes.c_uint64, _F, _F, _F, _F, _P, _P, _P, _F, _P],
     "inerf_adam_advance": [_P, _P, _P],
     "inerf_render_fused": [POINTER(FieldDesc), _P, _P, _P, _P, _P, _U, _U, _U, _F, _U, _F, _P, _P, _P, _P, _P, _P],
 }
@@ -107,6 +112,7 @@ _SPECIAL = {
     "inerf_field_weights_bytes": ([_U], c_size_t),
     "inerf_field_bwd_weights_bytes": ([], c_size_t),
     "inerf_march_scratch_floats": ([_U, _U], c_size_t),
+    "inerf_occupancy_sample_scratch_ints": ([_U, _U], c_size_t),
 }
 
 # Every symbol include/inerf_b200.h declares; tests check the .so exports all of them.

@@ -388,6 +388,46 @@ __device__ __forceinline__ float mlp_chain(uint8_t* smem, const ChainBufs& b, ui
     return sigma;
 }
 
+// Density only (NeRFNetwork.density, nerf/network_mask.py:160-178, as the occupancy-grid update calls it): the sigma-net
+// half of the chain above -- 32 -> 64 ReLU -> 16, sigma = exp(fp16(h0)) in fp32, unscaled.  Returns sigma for warps 0..3.
+// The gathered stage is released (commit to `release_bar`) as soon as the layer-0 MMAs have been issued.
+template <typename Sync>
+__device__ __forceinline__ float sigma_chain(uint8_t* smem, const ChainBufs& b, uint32_t tmem_base, uint64_t* bar, uint32_t& phase, uint32_t K,
+                                             uint32_t tid, uint64_t* release_bar, Sync&& sync) {
+    const uint32_t sbase = umma::smem_u32(smem);
+    const WeightLayout wl = weight_layout(K);
+    const bool issuer = tid == 0;
+    if (issuer) {
+        umma::fence_after_sync();
+        issue_gemm(sbase, b.a_es, b.w + wl.s0, 32, 64, tmem_base + D_a);
+        umma::commit(bar);
+        if (release_bar) umma::commit(release_bar);
+    }
+    __syncwarp();
+    umma::mbar_wait(bar, phase); phase ^= 1u;
+    umma::fence_after_sync();
+    epilogue_hidden(tmem_base + D_a, smem, b.a_h1, tid);
+    umma::fence_async_smem(); umma::fence_before_sync();
+    sync();
+    if (issuer) {
+        umma::fence_after_sync();
+        issue_gemm(sbase, b.a_h1, b.w + wl.s1, 64, 16, tmem_base + D_c);
+        umma::commit(bar);
+    }
+    __syncwarp();
+    umma::mbar_wait(bar, phase); phase ^= 1u;
+    umma::fence_after_sync();
+    float sigma = 0.f;
+    const uint32_t warp = tid >> 5;
+    if (warp < 4) {
+        uint32_t v[16];
+        umma::tmem_ld16(tmem_base + D_c + ((warp * 32u) << 16), v);
+        umma::tmem_ld_wait();
+        sigma = expf(__half2float(__float2half_rn(__uint_as_float(v[0]))));
+    }
+    return sigma;
+}
+
 // weights -> smem (all threads of the CTA)
 __device__ __forceinline__ void load_weights(uint8_t* smem, uint32_t w_off, const void* weights, uint32_t K) {
     const WeightLayout wl = weight_layout(K);

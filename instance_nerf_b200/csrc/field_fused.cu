@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "field_device.cuh"
+#include "occupancy_device.cuh"
 
 namespace {
 
@@ -149,6 +150,83 @@ __global__ void __launch_bounds__(kWsThreads, 1) k_field_forward_ws(inerf_field_
     if (tid < 32) umma::tmem_dealloc<kTmemCols>(tmem_base);
 }
 
+// ---- occupancy-grid density sweep (update_extra_state, nerf/mask_renderer.py:466-527) ------------------------------------
+// tmp_grid[c, cell] = density(jittered point of the cell) * density_scale for every sample of the sweep, in ONE launch with
+// the role structure above: the gather warps make each point from its cell id (Morton decode, cascade scale, jitter --
+// occupancy_device.cuh) instead of reading a sample stream, the chain warps run the sigma-net only and scatter the result to
+// the cell.  The reference goes through meshgrid / morton3D / rand_like / two table casts / encode / 2 GEMMs / index_put per
+// (block, cascade) from 5 nested Python loops.
+__global__ void __launch_bounds__(kWsThreads, 1) k_occupancy_density(inerf_field_desc desc, occ::OccPoints pts, uint32_t n, float* __restrict__ tmp_grid) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const uint32_t K = desc.K;
+    WsCtrl* ctl = reinterpret_cast<WsCtrl*>(smem + WsSmem::ctrl(K));
+    const uint32_t tid = threadIdx.x;
+    load_weights(smem, WsSmem::W, desc.weights, K);
+    init_levels(ctl->lg, desc.offsets, desc.L, desc.S, desc.H, tid);
+    if (tid == 0) {
+        for (uint32_t i = 0; i < kWsStages; i++) { umma::mbar_init(&ctl->a_full[i], kWsGatherT); umma::mbar_init(&ctl->a_empty[i], 1); }
+        umma::mbar_init(&ctl->mma_bar, 1);
+        umma::mbar_fence_init();
+    }
+    if (tid < 32) umma::tmem_alloc<kTmemCols>(&ctl->tmem_slot);
+    umma::fence_async_smem();
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tmem_base = ctl->tmem_slot;
+    const uint32_t num_tiles = (n + kTile - 1) / kTile;
+
+    if (tid < kWsChainT) {
+        umma::reg_alloc<96>();
+        uint32_t phase = 0, it = 0;
+        auto chain_sync = [] { umma::named_sync<1, kWsChainT>(); };
+        for (uint32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, it++) {
+            const uint32_t sa = it % kWsStages;
+            umma::mbar_wait(&ctl->a_full[sa], (it / kWsStages) & 1u);
+            const uint32_t a_es = WsSmem::A + sa * kStageBytes;
+            const ChainBufs bufs{a_es, a_es + kBytesEs, a_es + kBytesEs + kBytesCi, WsSmem::H1, WsSmem::H2, WsSmem::W};
+            const float sigma = sigma_chain(smem, bufs, tmem_base, &ctl->mma_bar, phase, K, tid, &ctl->a_empty[sa], chain_sync);
+            const uint32_t s = tile * kTile + tid;
+            if (tid < kTile && s < n) {
+                const uint32_t c = s / pts.per_cascade;
+                const uint32_t m = pts.cells ? (uint32_t)__ldg(pts.cells + s) : s - c * pts.per_cascade;
+                tmp_grid[(size_t)c * pts.G * pts.G * pts.G + m] = __fmul_rn(sigma, desc.density_scale);   // `sigmas *= self.density_scale`
+            }
+            umma::fence_before_sync();
+            chain_sync();   // TMEM and the hidden tile are reused by the next tile
+        }
+    } else {
+        umma::reg_dealloc<64>();
+        const uint32_t gt = tid - kWsChainT, row = gt & (kTile - 1), quarter = gt >> 7;
+        const float inv2b = __fdiv_rn(1.0f, __fmul_rn(2.0f, desc.bound));
+        const uint2* table = reinterpret_cast<const uint2*>(desc.table_packed);
+        uint32_t it = 0;
+        for (uint32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, it++) {
+            const uint32_t sa = it % kWsStages;
+            if (it >= kWsStages) umma::mbar_wait(&ctl->a_empty[sa], ((it / kWsStages) - 1u) & 1u);
+            const uint32_t s = tile * kTile + row;
+            if (s < n) {
+                const uint32_t a_es = WsSmem::A + sa * kStageBytes, a_mi = a_es + kBytesEs + kBytesCi;
+                float xyz[3], x01[3];
+                uint32_t flat;
+                occ::occ_point(pts, s, xyz, flat);
+                bool oob = false;
+#pragma unroll
+                for (int d = 0; d < 3; d++) {
+                    x01[d] = __fmul_rn(__fadd_rn(xyz[d], desc.bound), inv2b);  // grid.py:149
+                    oob |= (x01[d] < 0.f || x01[d] > 1.f);
+                }
+                encode4(x01, oob, quarter * 4, ctl->lg, table, smem, a_es, a_mi, row);
+            }
+            umma::fence_async_smem();
+            umma::mbar_arrive(&ctl->a_full[sa]);
+        }
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    if (tid < 32) umma::tmem_dealloc<kTmemCols>(tmem_base);
+}
+
 // fp32 / fp16 embeddings of both encoders -> interleaved fp16 (sigma.c0, sigma.c1, mask.c0, mask.c1), one pass
 template <typename T>
 __global__ void k_pack_tables(const T* __restrict__ es, const T* __restrict__ em, uint64_t n, uint2* __restrict__ out) {
@@ -245,6 +323,21 @@ static int field_forward_impl(const inerf_field_desc* desc, const float* xyzs, c
     const uint32_t grid_ws = num_tiles < sms ? num_tiles : sms;
     k_field_forward_ws<<<grid_ws, kWsThreads, WsSmem::bytes(desc->K), (cudaStream_t)stream>>>(*desc, xyzs, dirs, B, sigmas, rgbs, masks,
                                                                                              (uint4*)x0_save);
+    INERF_LAUNCH_CHECK();
+    return INERF_OK;
+}
+
+extern "C" int inerf_occupancy_density(const inerf_field_desc* desc, uint32_t C, uint32_t G, const int32_t* cells, uint32_t per_cascade,
+                                       const float* noise, uint64_t seed, float* tmp_grid, void* stream) {
+    if (int e = validate_desc(desc)) return e;
+    occ::OccPoints pts;
+    if (int e = occ::make_points(&pts, C, G, desc->bound, cells, per_cascade, noise, seed)) return e;
+    INERF_REQUIRE(tmp_grid);
+    const uint32_t n = C * per_cascade, num_tiles = (n + field::kTile - 1) / field::kTile;
+    cudaError_t ce = cudaFuncSetAttribute(k_occupancy_density, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    if (ce != cudaSuccess) return (int)ce;
+    const uint32_t sms = (uint32_t)device_sm_count();
+    k_occupancy_density<<<num_tiles < sms ? num_tiles : sms, kWsThreads, WsSmem::bytes(desc->K), (cudaStream_t)stream>>>(*desc, pts, n, tmp_grid);
     INERF_LAUNCH_CHECK();
     return INERF_OK;
 }

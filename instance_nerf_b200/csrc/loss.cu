@@ -165,12 +165,12 @@ extern "C" int inerf_mask_loss_backward(const float* logits, const float* depth,
 namespace {
 __global__ void __launch_bounds__(256) k_adam_step(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                                                    uint64_t n, float lr, float b1, float b2, float eps, const float* __restrict__ step,
-                                                   const float* __restrict__ grad_scale, const float* __restrict__ found_inf) {
+                                                   const float* __restrict__ grad_scale, const float* __restrict__ found_inf, float grad_div) {
     const bool skip = found_inf != nullptr && *found_inf != 0.f;
     const float t = *step + 1.0f;
     const float bc1 = 1.0f - (float)pow((double)b1, (double)t), bc2 = 1.0f - (float)pow((double)b2, (double)t);
     const float step_size = lr / bc1, bc2_sqrt = sqrtf(bc2);
-    const float scale = grad_scale ? *grad_scale : 1.0f;
+    const float scale = (grad_scale ? *grad_scale : 1.0f) * grad_div;   // grad_div = 1 leaves the scale bit-identical
     const uint64_t n4 = n >> 2, stride = (uint64_t)gridDim.x * blockDim.x;
     auto upd = [&](float& pp, float gg, float& mm, float& vv) {
         gg = gg / scale;
@@ -200,13 +200,14 @@ __global__ void k_adam_advance(float* __restrict__ step, const float* __restrict
 }  // namespace
 
 extern "C" int inerf_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, uint64_t n, float lr, float beta1, float beta2,
-                               float eps, const float* step, const float* grad_scale, const float* found_inf, void* stream) {
+                               float eps, const float* step, const float* grad_scale, const float* found_inf, float grad_div, void* stream) {
     if (n == 0) return INERF_OK;
+    if (!(grad_div > 0.f)) return INERF_ERR_SIZE;
     INERF_REQUIRE(param); INERF_REQUIRE(grad); INERF_REQUIRE(exp_avg); INERF_REQUIRE(exp_avg_sq); INERF_REQUIRE(step);
     if ((((uintptr_t)param | (uintptr_t)grad | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq) & 15u) != 0) return INERF_ERR_ALIGN;
     const uint64_t want = ((n >> 2) + 255) / 256;
     const unsigned int blocks = (unsigned int)(want < 1 ? 1 : (want > (uint64_t)kNumSMs * 16 ? (uint64_t)kNumSMs * 16 : want));
-    k_adam_step<<<blocks, 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, step, grad_scale, found_inf);
+    k_adam_step<<<blocks, 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, step, grad_scale, found_inf, grad_div);
     INERF_LAUNCH_CHECK();
     return INERF_OK;
 }

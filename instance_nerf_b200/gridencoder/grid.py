@@ -16,7 +16,7 @@ import torch
 import torch.nn as nn
 from torch.autograd import Function
 
-from .._lib import PARAM_EPOCH, call, ptr, stream_ptr
+from .._lib import PARAM_EPOCH, call, invalidate_param_caches, ptr, stream_ptr
 
 _gridtype_to_id = {"hash": 0, "tiled": 1}
 _interp_to_id = {"linear": 0, "smoothstep": 1}
@@ -104,6 +104,7 @@ class GridEncoder(nn.Module):
     def reset_parameters(self):
         std = 1e-4
         self.embeddings.data.uniform_(-std, std)
+        invalidate_param_caches()   # written through `.data`: the version counter the fp16 caches key on did not move
 
     def __repr__(self):
         return (f"GridEncoder(B200): input_dim={self.input_dim} num_levels={self.num_levels} level_dim={self.level_dim} "

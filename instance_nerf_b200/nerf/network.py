@@ -80,6 +80,8 @@ class NeRFNetwork(NeRFRenderer):
                 and getattr(self.encoder_dir, "degree", 0) == 4 and hasattr(lib(), "inerf_field_forward"))
 
     def fused_available(self) -> bool:
+        if getattr(self, "fused_requires_autocast", False) and not torch.is_autocast_enabled():
+            return False
         return bool(self.use_fused and self._standard_arch() and self.encoder.embeddings.is_cuda)
 
     def fused_render_available(self, render_mask: bool) -> bool:
@@ -90,6 +92,7 @@ class NeRFNetwork(NeRFRenderer):
     _field_desc = _InstanceNetwork._field_desc
     forward_fused = _InstanceNetwork.forward_fused
     _render_fused = _InstanceNetwork._render_fused
+    _occupancy_density_fused = _InstanceNetwork._occupancy_density_fused
 
     # ---- reference operator sequence (network.py:96-127) --------------------------------------------------------------
     @staticmethod

@@ -108,6 +108,11 @@ class NeRFNetwork(NeRFMaskRenderer):
             self.bg_net = None
 
         self.use_fused = True     # set False to force the modular operator sequence
+        # The fused kernels compute with fp16 tables / weights / activations and fp32 accumulation = the reference under
+        # autocast (its `-O` / --fp16 preset, which wraps train, eval and update_extra_state in autocast).  By default every
+        # no-grad CUDA call takes them; set True to take them only inside torch.autocast, so that an fp32 run (the
+        # reference without --fp16) evaluates with the same fp32 numerics it trains with.
+        self.fused_requires_autocast = False
         self._packed = None       # (key, forward fp16 weight blob, backward blob | None) on device
         self._tables = None       # (key, interleaved fp16 hash tables on device)
         self._work_counter = None
@@ -123,6 +128,8 @@ class NeRFNetwork(NeRFMaskRenderer):
                 and 1 <= self.num_instances <= 64 and hasattr(lib(), "inerf_field_forward"))
 
     def fused_available(self) -> bool:
+        if getattr(self, "fused_requires_autocast", False) and not torch.is_autocast_enabled():
+            return False
         return bool(self.use_fused and self._standard_arch() and self.encoder.embeddings.is_cuda)
 
     def fused_render_available(self, render_mask: bool) -> bool:
@@ -158,7 +165,11 @@ class NeRFNetwork(NeRFMaskRenderer):
             self._tables = (key, out)
         return self._tables[1]
 
-    def _field_desc(self) -> FieldDesc:
+    def _field_desc(self, density_scale: float = 1.0) -> FieldDesc:
+        """`density_scale` multiplies sigma inside the kernel.  The per-sample field calls (`forward`) return the UNSCALED
+        sigma, as network_mask.py:119-158 does -- `run_cuda` applies `self.density_scale` itself (mask_renderer.py:273) --
+        so they keep the default 1; the one-launch renderer and the occupancy sweep, which consume sigma inside the kernel,
+        pass `self.density_scale`."""
         e = self.encoder
         d = FieldDesc()
         self._keepalive = (self._packed_tables(), self._packed_weights())
@@ -170,7 +181,7 @@ class NeRFNetwork(NeRFMaskRenderer):
         d.S = float(np.log2(e.per_level_scale))
         d.bound = float(self.bound)
         d.K = self.num_instances
-        d.density_scale = float(self.density_scale)
+        d.density_scale = float(density_scale)
         return d
 
     @torch.no_grad()
@@ -213,11 +224,22 @@ class NeRFNetwork(NeRFMaskRenderer):
         mask_out = torch.empty(N, K, dtype=torch.float32, device=dev) if render_mask else None
         if self._work_counter is None or self._work_counter.device != dev:
             self._work_counter = torch.zeros(4, dtype=torch.int32, device=dev)
-        desc = self._field_desc()
+        desc = self._field_desc(self.density_scale)
         call("inerf_render_fused", ctypes.byref(desc), ptr(rays_o), ptr(rays_d), ptr(nears), ptr(fars), ptr(self.density_bitfield),
              N, self.cascade, self.grid_size, float(dt_gamma), int(max_steps), float(T_thresh), ptr(weights_sum), ptr(depth),
              ptr(image), ptr(mask_out), ptr(self._work_counter), stream_ptr(dev))
         return weights_sum, depth, image, mask_out
+
+    def _occupancy_density_fused(self, cells, per_cascade, noises, seed, tmp_grid) -> bool:
+        """update_extra_state's density sweep as ONE launch (inerf_occupancy_density): cell -> jittered point -> hash encode ->
+        sigma-net on tcgen05 -> tmp_grid[c, cell] = sigma * density_scale.  fp16 operands, i.e. what `self.density` computes
+        under the reference's autocast (nerf/utils.py wraps update_extra_state in autocast(enabled=fp16))."""
+        if not self.fused_available():
+            return False
+        desc = self._field_desc(self.density_scale)
+        call("inerf_occupancy_density", ctypes.byref(desc), self.cascade, self.grid_size, ptr(cells), int(per_cascade), ptr(noises), int(seed),
+             ptr(tmp_grid), stream_ptr(tmp_grid.device))
+        return True
 
     # ---- reference operator sequence ----------------------------------------------------
     def _mlp(self, net, h):

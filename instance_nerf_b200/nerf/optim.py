@@ -21,6 +21,9 @@ class FusedAdam(torch.optim.Optimizer):
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8):
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps))
         self.grads_cleared_by_step = True
+        # data-parallel training: gradients arrive as the SUM over ranks; the division by the world size is folded into this
+        # pass (parallel.FlatGradBucket sets it) instead of a separate scaling pass over the 53 MB bucket
+        self.grad_div = 1.0
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -42,6 +45,6 @@ class FusedAdam(torch.optim.Optimizer):
                     st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
                 s = stream_ptr(p.device)
                 call("inerf_adam_step", ptr(p), ptr(p.grad), ptr(st["exp_avg"]), ptr(st["exp_avg_sq"]), p.numel(), lr, float(b1), float(b2), eps,
-                     ptr(st["step"]), ptr(grad_scale), ptr(found_inf), s)
+                     ptr(st["step"]), ptr(grad_scale), ptr(found_inf), float(self.grad_div), s)
                 call("inerf_adam_advance", ptr(st["step"]), ptr(found_inf), s)
         return None

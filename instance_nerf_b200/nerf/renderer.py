@@ -25,11 +25,13 @@ import torch
 import torch.nn as nn
 
 from .. import raymarching
-from .._lib import call, ptr, stream_ptr
+from .._lib import call, lib, ptr, stream_ptr
 
 
-def custom_meshgrid(*args):
-    return torch.meshgrid(*args, indexing="ij")
+def _host_seed() -> int:
+    """63-bit seed for the counter-based device generators, drawn from torch's default CPU generator (so
+    `torch.manual_seed` makes the occupancy sampling reproducible) without touching the GPU."""
+    return int(torch.empty((), dtype=torch.int64).random_().item())
 
 
 def sample_pdf(bins, weights, n_samples, det=False):
@@ -84,7 +86,7 @@ class NeRFRenderer(nn.Module):
             self._mean_density = 0
             self.iter_density = 0
             self.register_buffer("step_counter", torch.zeros(16, 2, dtype=torch.int32))
-            self.mean_count = 0
+            self._mean_count = 0
             self.local_step = 0
 
     # mean_density is produced on the device by the fused EMA kernel; it is read back only when somebody asks.
@@ -246,7 +248,8 @@ class NeRFRenderer(nn.Module):
             else:
                 xyzs, dirs, deltas, rays = raymarching.march_rays_train(
                     rays_o, rays_d, self.bound, self.density_bitfield, self.cascade, self.grid_size, nears, fars, counter,
-                    self.mean_count, perturb, 128, force_all_rays, dt_gamma, max_steps, noises=kwargs.get("noises"))
+                    -1 if force_all_rays else self.mean_count, perturb, 128, force_all_rays, dt_gamma, max_steps,
+                    noises=kwargs.get("noises"))
                 self._n_valid_ptr = None
             sigmas, rgbs, masks = self._field(xyzs, dirs, render_mask)
             sigmas = self.density_scale * sigmas
@@ -317,107 +320,100 @@ class NeRFRenderer(nn.Module):
     # -- occupancy grid lifecycle ------------------------------------------------------
     @torch.no_grad()
     def mark_untrained_grid(self, poses, intrinsic, S=64):
-        """mask_renderer.py:389-452: cells no training camera sees get density -1 (never occupied)."""
+        """mask_renderer.py:389-452: cells whose centre no training camera sees get density -1 and can never become
+        occupied.  One kernel, one thread per (cascade, cell) looping over the cameras (the reference: five nested Python
+        loops of meshgrid / batched matmul / index_put).  `S` (the reference's batching knob) is accepted and ignored.
+        The number of marked cells stays on the device in `self.n_untrained` (the reference prints it)."""
         if not self.cuda_ray:
             return
         if isinstance(poses, np.ndarray):
             poses = torch.from_numpy(poses)
-        B = poses.shape[0]
-        fx, fy, cx, cy = intrinsic
-        dev = self.density_bitfield.device
-        G = self.grid_size
-        X = torch.arange(G, dtype=torch.int32, device=dev).split(S)
-        count = torch.zeros_like(self.density_grid)
-        poses = poses.to(dev).float()
-        for xs in X:
-            for ys in X:
-                for zs in X:
-                    xx, yy, zz = custom_meshgrid(xs, ys, zs)
-                    coords = torch.cat([xx.reshape(-1, 1), yy.reshape(-1, 1), zz.reshape(-1, 1)], dim=-1)
-                    indices = raymarching.morton3D(coords).long()
-                    world_xyzs = (2 * coords.float() / (G - 1) - 1).unsqueeze(0)
-                    for cas in range(self.cascade):
-                        bound = min(2 ** cas, self.bound)
-                        half_grid_size = bound / G
-                        cas_world_xyzs = world_xyzs * (bound - half_grid_size)
-                        head = 0
-                        while head < B:
-                            tail = min(head + S, B)
-                            cam_xyzs = cas_world_xyzs - poses[head:tail, :3, 3].unsqueeze(1)
-                            cam_xyzs = cam_xyzs @ poses[head:tail, :3, :3]
-                            mask_z = cam_xyzs[:, :, 2] > 0
-                            mask_x = torch.abs(cam_xyzs[:, :, 0]) < cx / fx * cam_xyzs[:, :, 2] + half_grid_size * 2
-                            mask_y = torch.abs(cam_xyzs[:, :, 1]) < cy / fy * cam_xyzs[:, :, 2] + half_grid_size * 2
-                            count[cas, indices] += (mask_z & mask_x & mask_y).sum(0).reshape(-1)
-                            head += S
-        self.density_grid[count == 0] = -1
+        fx, fy, cx, cy = (float(v) for v in intrinsic)
+        grid = self.density_grid
+        dev = grid.device
+        poses = poses.to(dev).float().contiguous().view(-1, 4, 4)
+        self.n_untrained = torch.zeros(1, dtype=torch.int32, device=dev)
+        call("inerf_mark_untrained_grid", ptr(poses), poses.shape[0], fx, fy, cx, cy, self.cascade, self.grid_size, float(self.bound),
+             ptr(grid), ptr(self.n_untrained), stream_ptr(dev))
+
+    # mean_count (samples per batch, averaged over the last <= 16 steps) is only consumed as a host int by the budgeted
+    # marcher (`force_all_rays=False`, raymarching.py:200-203): it is kept on the device and read back when asked for.
+    @property
+    def mean_count(self):
+        if isinstance(self._mean_count, torch.Tensor):
+            self._mean_count = int(self._mean_count.item())
+        return self._mean_count
+
+    @mean_count.setter
+    def mean_count(self, v):
+        self._mean_count = v
+
+    def _occupancy_density_fused(self, cells, per_cascade, noises, seed, tmp_grid) -> bool:
+        """Hook: networks with a fused density sweep fill `tmp_grid` and return True (NeRFNetwork)."""
+        return False
 
     @torch.no_grad()
-    def update_extra_state(self, decay=0.95, S=128, noises=None):
-        """mask_renderer.py:454-548.  Sampling follows the reference (same RNG consumption order: one
-        `rand_like` per (block, cascade)); `noises` optionally injects those tensors for parity tests.
-        The EMA / mean / threshold / packbits tail is two kernel launches with no host sync."""
+    def sweep_cells(self, uniform_cells=None, occ_picks=None):
+        """Cells re-sampled by a partial update (mask_renderer.py:498-513) -> int32 [C, 2N] Morton indices, N = G^3 / 4:
+        N uniform cells, then N occupied cells (density_grid > 0) drawn with replacement.  `uniform_cells` / `occ_picks`
+        [C, N] inject the two randint draws of the reference (parity tests); otherwise they come from a counter-based
+        generator seeded from torch's default generator.  Everything, including the occupied-cell count, stays on the device."""
+        dev = self.density_grid.device
+        C, G = self.cascade, self.grid_size
+        N = G ** 3 // 4
+        cells = torch.empty(C, 2 * N, dtype=torch.int32, device=dev)
+        n_scr = int(lib().inerf_occupancy_sample_scratch_ints(C, G))
+        scr = getattr(self, "_occ_scratch", None)
+        if scr is None or scr.numel() < n_scr or scr.device != dev:
+            scr = self._occ_scratch = torch.empty(n_scr, dtype=torch.int32, device=dev)
+        as_i32 = lambda t: None if t is None else t.to(device=dev, dtype=torch.int32).contiguous()
+        call("inerf_occupancy_sample_cells", ptr(self.density_grid), C, G, N, ptr(as_i32(uniform_cells)), ptr(as_i32(occ_picks)),
+             _host_seed(), ptr(cells), ptr(scr), stream_ptr(dev))
+        return cells
+
+    @torch.no_grad()
+    def update_extra_state(self, decay=0.95, S=128, noises=None, cells=None):
+        """mask_renderer.py:454-548 with no Python loop and no host read: the first 16 calls sweep every cell of every
+        cascade, later calls re-sample G^3/4 random + G^3/4 occupied cells per cascade (`sweep_cells`); each sample's
+        jittered point, its density and the scatter into `tmp_grid` are ONE launch when the network has a fused density
+        sweep, else point kernel -> `self.density` -> index_put; then EMA / mean / threshold / packbits (`ema_update_`).
+
+        Extra, optional: `noises` [C * per_cascade, 3] in [0, 1) replaces the jitter draws and `cells` [C, 2N] the
+        partial update's cell choice (parity tests); sample s = (cascade s // per_cascade, cell cells[s] or s % G^3).
+        `S` (the reference's block size) is accepted and ignored."""
         if not self.cuda_ray:
             return
-        dev = self.density_bitfield.device
-        G = self.grid_size
-        tmp_grid = -torch.ones_like(self.density_grid)
-        noise_iter = iter(noises) if noises is not None else None
-
-        def jitter(like):
-            return next(noise_iter) if noise_iter is not None else torch.rand_like(like)
-
+        grid = self.density_grid
+        dev = grid.device
+        C, G = self.cascade, self.grid_size
+        st = stream_ptr(dev)
+        tmp_grid = torch.empty_like(grid)
         if self.iter_density < 16:
-            X = torch.arange(G, dtype=torch.int32, device=dev).split(S)
-            for xs in X:
-                for ys in X:
-                    for zs in X:
-                        # block geometry is a constant of (G, S): built once per device instead of on every update
-                        ck = (str(dev), G, S, int(xs[0]), int(ys[0]), int(zs[0])) if len(X) == 1 else None
-                        cache = getattr(self, "_sweep_cache", None)
-                        if ck is not None and cache is not None and cache[0] == ck:
-                            indices, xyzs = cache[1], cache[2]
-                        else:
-                            xx, yy, zz = custom_meshgrid(xs, ys, zs)
-                            coords = torch.cat([xx.reshape(-1, 1), yy.reshape(-1, 1), zz.reshape(-1, 1)], dim=-1)
-                            indices = raymarching.morton3D(coords).long()
-                            xyzs = 2 * coords.float() / (G - 1) - 1
-                            if ck is not None:
-                                self._sweep_cache = (ck, indices, xyzs)
-                        for cas in range(self.cascade):
-                            bound = min(2 ** cas, self.bound)
-                            half_grid_size = bound / G
-                            cas_xyzs = xyzs * (bound - half_grid_size)
-                            cas_xyzs += (jitter(cas_xyzs) * 2 - 1) * half_grid_size
-                            sigmas = self.density(cas_xyzs)["sigma"].reshape(-1).detach().float()
-                            sigmas *= self.density_scale
-                            tmp_grid[cas, indices] = sigmas
+            cells, per_cascade = None, G ** 3          # every cell is written: no -1 fill needed
         else:
-            N = G ** 3 // 4
-            for cas in range(self.cascade):
-                coords = torch.randint(0, G, (N, 3), device=dev)
-                indices = raymarching.morton3D(coords).long()
-                occ_indices = torch.nonzero(self.density_grid[cas] > 0).squeeze(-1)
-                rand_mask = torch.randint(0, occ_indices.shape[0], [N], dtype=torch.long, device=dev)
-                occ_indices = occ_indices[rand_mask]
-                occ_coords = raymarching.morton3D_invert(occ_indices)
-                indices = torch.cat([indices, occ_indices], dim=0)
-                coords = torch.cat([coords, occ_coords], dim=0)
-                xyzs = 2 * coords.float() / (G - 1) - 1
-                bound = min(2 ** cas, self.bound)
-                half_grid_size = bound / G
-                cas_xyzs = xyzs * (bound - half_grid_size)
-                cas_xyzs += (jitter(cas_xyzs) * 2 - 1) * half_grid_size
-                sigmas = self.density(cas_xyzs)["sigma"].reshape(-1).detach().float()
-                sigmas *= self.density_scale
-                tmp_grid[cas, indices] = sigmas
-
+            if cells is None:
+                cells = self.sweep_cells()
+            cells = cells.to(device=dev, dtype=torch.int32).contiguous()
+            per_cascade = cells.numel() // C
+            call("inerf_fill_f32", ptr(tmp_grid), tmp_grid.numel(), -1.0, st)
+        if noises is not None:
+            noises = noises.to(device=dev, dtype=torch.float32).contiguous().view(-1, 3)
+            if noises.shape[0] != C * per_cascade:
+                raise ValueError(f"noises must have {C * per_cascade} rows, got {noises.shape[0]}")
+        seed = _host_seed()
+        if not self._occupancy_density_fused(cells, per_cascade, noises, seed, tmp_grid):
+            n = C * per_cascade
+            xyzs = torch.empty(n, 3, dtype=torch.float32, device=dev)
+            flat = torch.empty(n, dtype=torch.int32, device=dev)
+            call("inerf_occupancy_points", C, G, float(self.bound), ptr(cells), per_cascade, ptr(noises), seed, ptr(xyzs), ptr(flat), st)
+            sigmas = self.density(xyzs)["sigma"].reshape(-1).detach().float() * self.density_scale
+            tmp_grid.view(-1)[flat.long()] = sigmas
         self.ema_update_(tmp_grid, decay)
         self.iter_density += 1
 
         total_step = min(16, self.local_step)
-        if total_step > 0:
-            self.mean_count = int(self.step_counter[:total_step, 0].sum().item() / total_step)
+        if total_step > 0:   # floor of the mean, as int(sum / total_step); read back only if somebody asks (mean_count property)
+            self._mean_count = torch.div(self.step_counter[:total_step, 0].sum(), total_step, rounding_mode="floor")
         self.local_step = 0
 
     @torch.no_grad()

@@ -1,7 +1,7 @@
 """Instance-stage training step (mirrors MaskTrainer of the reference: nerf/utils.py:1231-1373 train_step /
-label_regularization, and the step loop nerf/utils.py:919-939), reduced to what touches the hot path: freeze the RGB-sigma
-nets, render a ray batch with `render_mask=True`, cross-entropy on labelled pixels + depth-aware label smoothness on the
-8x8 patches, AMP backward, (optional data-parallel gradient all-reduce,) Adam.
+label_regularization / mask3d_loss, and the step loop nerf/utils.py:919-939), reduced to what touches the hot path: freeze the
+RGB-sigma nets, render a ray batch with `render_mask=True`, cross-entropy on labelled pixels + depth-aware label smoothness on
+the 8x8 patches + optional 3D-mask cross-entropy, AMP backward, (optional data-parallel gradient all-reduce,) Adam.
 
 Data providers, logging, checkpoints and evaluation of the reference's Trainer are out of scope.
 """
@@ -12,8 +12,10 @@ from types import SimpleNamespace
 import torch
 import torch.nn as nn
 
+import torch.distributed as dist
+
 from .._lib import call, ptr, stream_ptr
-from ..parallel import GradBucket
+from ..parallel import FlatGradBucket
 
 
 class _MaskLoss(torch.autograd.Function):
@@ -47,9 +49,10 @@ class _MaskLoss(torch.autograd.Function):
 
 class MaskTrainStep:
     def __init__(self, model, lr=1e-2, fp16=True, patch_size=8, label_regularization_weight=0.0, dt_gamma=1 / 128, max_steps=1024,
-                 T_thresh=1e-4, data_parallel=False, fused_adam=True, fused_loss=True, cuda_graph=False):
+                 T_thresh=1e-4, data_parallel=False, fused_adam=True, fused_loss=True, cuda_graph=False, mask3d_loss_weight=0.0):
         self.model = model
-        self.opt = SimpleNamespace(patch_size=patch_size, label_regularization_weight=label_regularization_weight)
+        self.opt = SimpleNamespace(patch_size=patch_size, label_regularization_weight=label_regularization_weight,
+                                   mask3d_loss_weight=mask3d_loss_weight)
         self.render_kw = dict(dt_gamma=dt_gamma, max_steps=max_steps, T_thresh=T_thresh)
         self.fp16 = fp16
         self.fused_loss = fused_loss
@@ -65,9 +68,12 @@ class MaskTrainStep:
         dev = next(model.parameters()).device
         # cuda_graph: the whole step (march -> field -> composite -> loss -> backward -> Adam) replays as ONE CUDA graph; at
         # 4096 rays the eager step is bound by ~60 launches of host work, not by the GPU
-        self.cuda_graph = bool(cuda_graph and dev.type == "cuda" and not data_parallel and fused_adam and fused_loss)
+        # (fp16 is required: the budget-overflow guard below turns the gradients non-finite and relies on an ENABLED
+        # GradScaler to skip that optimizer step; without a scaler the replay would write inf into the parameters)
+        self.cuda_graph = bool(cuda_graph and fp16 and dev.type == "cuda" and fused_adam and fused_loss)
+        self.world = dist.get_world_size() if (data_parallel and dist.is_available() and dist.is_initialized()) else 1
         params = [{"params": g["params"], "lr": float(g["lr"])} for g in params]
-        if fused_adam and dev.type == "cuda" and not data_parallel:
+        if fused_adam and dev.type == "cuda":
             # main_nerf_mask.py:182's Adam as ONE pass per tensor that also unscales and clears the gradient (nerf/optim.py)
             from .optim import FusedAdam
             self.optimizer = FusedAdam(params, betas=(0.9, 0.99), eps=1e-15)
@@ -76,7 +82,13 @@ class MaskTrainStep:
             self.optimizer = torch.optim.Adam(params, betas=(0.9, 0.99), eps=1e-15, **kw)   # main_nerf_mask.py:182
         self._own_zero = getattr(self.optimizer, "grads_cleared_by_step", False)
         self.scaler = torch.amp.GradScaler("cuda", enabled=fp16 and dev.type == "cuda")
-        self.bucket = GradBucket([p for g in params for p in g["params"]]) if data_parallel else None
+        # Data parallel: every gradient is a view of ONE flat buffer; the step all-reduces that buffer in place (SUM) and the
+        # optimizer divides by the world size in its own pass.  One extra slot carries the "a rank overflowed its sample
+        # budget" flag of the graph-captured step through the same collective.
+        self.bucket = FlatGradBucket([p for g in params for p in g["params"]], extra=1).attach() if data_parallel else None
+        if self.bucket is not None and hasattr(self.optimizer, "grad_div"):
+            self.optimizer.grad_div = float(self.world)
+        self._fold_average = self.bucket is not None and hasattr(self.optimizer, "grad_div")
         self.global_step = 0
         self._graph = None          # (torch.cuda.CUDAGraph, static inputs, static loss, budget, counter view)
         self._graph_key = None
@@ -110,14 +122,34 @@ class MaskTrainStep:
         p = self.opt.patch_size
         if self.fused_loss and flat.is_cuda and flat.shape[0] % (p * p) == 0:
             loss = _MaskLoss.apply(flat, outputs["depth"], gt, p, self.opt.label_regularization_weight)
-            return pred.argmax(dim=-1), gt_masks, loss
-        labeled = gt != -1
-        # same value as the reference's boolean-index form, without the host sync of `labeled.sum() > 0`
-        ce = self.criterion(flat.float(), torch.where(labeled, gt, torch.zeros_like(gt)))
-        loss = (ce * labeled).sum() / labeled.sum().clamp(min=1)
-        if self.opt.label_regularization_weight > 0:
-            loss = loss + self.label_regularization(outputs["depth"], pred) * self.opt.label_regularization_weight
+        else:
+            labeled = gt != -1
+            # same value as the reference's boolean-index form, without the host sync of `labeled.sum() > 0`
+            ce = self.criterion(flat.float(), torch.where(labeled, gt, torch.zeros_like(gt)))
+            loss = (ce * labeled).sum() / labeled.sum().clamp(min=1)
+            if self.opt.label_regularization_weight > 0:
+                loss = loss + self.label_regularization(outputs["depth"], pred) * self.opt.label_regularization_weight
+        if self.opt.mask3d_loss_weight > 0:                     # 3d mask constraints (nerf/utils.py:1367-1369)
+            loss = loss + self.mask3d_loss(data).mean() * self.opt.mask3d_loss_weight
         return pred.argmax(dim=-1), gt_masks, loss
+
+    def mask3d_loss(self, data):
+        """nerf/utils.py:1250-1260: cross-entropy of the instance head queried at labelled 3D points (`mask3d_coords` [N,3],
+        `mask3d_labels` [N]) -> [N].  On the fused path the query is the same one-launch field forward / backward the ray
+        samples take (the direction input only feeds the colour net, whose output is not used)."""
+        coords, labels = data["mask3d_coords"].view(-1, 3), data["mask3d_labels"].view(-1).long()
+        model = self.model
+        dirs = torch.zeros_like(coords)
+        dirs[:, 2] = 1.0
+        if hasattr(model, "fused_train_available") and torch.is_grad_enabled() and model.fused_train_available(coords, dirs):
+            saved, model._n_valid_ptr = model._n_valid_ptr, None     # every row of this batch is live (no marcher total applies)
+            try:
+                _, _, logits = model.forward_fused_train(coords, dirs)
+            finally:
+                model._n_valid_ptr = saved
+        else:
+            logits = model.mask(coords, geo_feat=model.density(coords)["geo_feat"])
+        return self.criterion(logits.float(), labels)
 
     def step(self, data):
         """One optimisation step (nerf/utils.py:929-936); returns the loss tensor (no host sync in the eager path)."""
@@ -125,7 +157,7 @@ class MaskTrainStep:
             return self._step_graphed(data)
         return self._step_eager(data)
 
-    def _step_eager(self, data, guard=None):
+    def _step_eager(self, data, guard=None, flag=None):
         self.model.train()
         self.global_step += 1
         if not self._own_zero:   # FusedAdam leaves every gradient at zero
@@ -136,7 +168,12 @@ class MaskTrainStep:
             loss = guard(loss)
         self.scaler.scale(loss).backward()
         if self.bucket is not None:
-            self.bucket.sync()
+            if flag is not None:
+                self.bucket.extra.copy_(flag())
+            if self._fold_average:
+                self.bucket.all_reduce()      # in place, on the current stream; 1/world is folded into FusedAdam's pass
+            else:
+                self.bucket.sync()
         self.scaler.step(self.optimizer)
         self.scaler.update()
         return loss.detach()
@@ -171,14 +208,18 @@ class MaskTrainStep:
         def guard(loss):   # x inf, not where(.., inf, loss): the GRADIENTS must turn non-finite for GradScaler to skip the step
             return loss.float() * torch.where(counter[0] > limit, inf, one)
 
+        def flag():        # data parallel: 1.0 on a rank that overflowed; summed over ranks by the gradient all-reduce itself
+            return (counter[0] > limit).float().view(1)
+
         model.sample_budget = budget
         PARAM_EPOCH[0] += 1                       # the packed fp16 tables / weight blobs must be rebuilt INSIDE the graph
         slot = model.local_step
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
         try:
-            with torch.cuda.graph(g):
-                loss = self._step_eager(static, guard)
+            # thread_local: NCCL's watchdog thread may query events while this thread captures (data-parallel step)
+            with torch.cuda.graph(g, capture_error_mode="thread_local" if self.bucket is not None else "global"):
+                loss = self._step_eager(static, guard, flag if self.bucket is not None else None)
         finally:
             model.sample_budget = 0
             model._n_valid_ptr = None
@@ -210,12 +251,22 @@ class MaskTrainStep:
         self.global_step += 1
         self.graph_replays += 1
         PARAM_EPOCH[0] += 1                       # parameters changed without their version counters moving
-        total = int(counter[0].item())
+        # the replay always writes the captured counter slot; keep the model's per-step bookkeeping (step_counter ring +
+        # local_step, which update_extra_state averages into mean_count, mask_renderer.py:543-546) moving as the eager path does
+        model = self.model
+        model.step_counter[model.local_step % 16].copy_(counter)
+        model.local_step += 1
+        if self.bucket is not None:               # one host read: own total + how many ranks overflowed (rode in the all-reduce)
+            total, n_over = (int(v) for v in torch.stack([counter[0].double(), self.bucket.extra[0].double()]).tolist())
+        else:
+            total = int(counter[0].item())
+            n_over = int(total > budget)
         self.last_total = total
         self._samples_seen = max(self._samples_seen, total)
-        if total > budget:                        # the guard skipped this step on the device: redo it exactly, then re-capture
+        if n_over > 0:                            # the guard skipped this step on EVERY rank (inf gradients are summed): redo it exactly, then re-capture
             self._graph = None
             self.global_step -= 1
+            model.local_step -= 1                 # the eager redo records this step again
             return self._step_eager(data)
         return loss
 

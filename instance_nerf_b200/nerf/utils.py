@@ -3,7 +3,7 @@
 Pixel selection (uniform / patch / error-map sampling) is index bookkeeping on a handful of integers and stays in torch;
 the per-ray arithmetic (pixel centre, normalise, rotate by the pose, optional fused near/far slab test) is ONE launch of
 `inerf_get_rays` instead of the reference's full H*W meshgrid + ~10 elementwise / gather / matmul kernels per call.
-CUDA tensors only (no CPU fallback); `synthetic.get_rays` is the torch restatement the tests compare against."""
+CUDA tensors only (no CPU fallback)."""
 from __future__ import annotations
 
 import torch
@@ -37,18 +37,22 @@ def sample_pixels(H: int, W: int, N: int, device, error_map=None, patch_size: in
 
 
 @torch.no_grad()
-def get_rays(poses, intrinsics, H, W, N=-1, error_map=None, patch_size=1, generator=None, aabb=None, min_near=0.2):
+def get_rays(poses, intrinsics, H, W, N=-1, error_map=None, patch_size=1, generator=None, aabb=None, min_near=0.2, inds=None):
     """poses [B,4,4] cam2world (CUDA), intrinsics (fx, fy, cx, cy) -> dict(rays_o [B,N,3], rays_d [B,N,3], inds [B,N] if N > 0
-    [, inds_coarse]).  Extra (optional): `aabb` [6] fuses near_far_from_aabb and adds `nears`, `fars` [B,N]."""
+    [, inds_coarse]).  Extras (optional): `aabb` [6] fuses near_far_from_aabb and adds `nears`, `fars` [B,N]; `inds` (int64 [N]
+    or [B,N]) injects the pixel choice instead of drawing it (parity tests against the reference's draws)."""
     if not poses.is_cuda:
-        raise RuntimeError("get_rays: CUDA tensors only (no CPU fallback); see synthetic.get_rays for the torch restatement")
+        raise RuntimeError("get_rays: CUDA tensors only (no CPU fallback)")
     dev = poses.device
     B = poses.shape[0]
     fx, fy, cx, cy = (float(v) for v in intrinsics)
     poses = poses.to(torch.float32).contiguous()
     results = {}
-    inds = None
-    if N > 0:
+    if inds is not None:
+        inds = inds.to(device=dev, dtype=torch.int64)
+        N = inds.shape[-1]
+        results["inds"] = inds.expand([B, N]) if inds.dim() == 1 else inds
+    elif N > 0:
         inds, extras = sample_pixels(H, W, N, dev, error_map, patch_size, B, generator)
         results.update(extras)
         N = inds.shape[-1]

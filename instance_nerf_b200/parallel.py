@@ -4,8 +4,9 @@
 
 * rendering shards RAYS with no exchange inside the path; finished tiles `[n, 4 + K]` (image 3 | depth 1 | logits K) are
   collected with ONE collective (`all_gather` or `gather`);
-* training shards the RAY BATCH; the only exchange is ONE `all_reduce(SUM)` per step over a flat fp32 bucket holding the
-  trainable hash-table gradient and the MLP gradients (53.4 MB at K = 32), then a division by the world size.
+* training shards the RAY BATCH; the only exchange is ONE `all_reduce(SUM)` per step over a flat fp32 buffer that the
+  trainable hash-table gradient and the MLP gradients are VIEWS of (53.4 MB at K = 32, no pack / unpack); the division
+  by the world size is folded into the optimizer pass.
 
 Everything here is backend-agnostic host logic; the kernels are reached only through the `render_fn` / model passed in.
 """
@@ -116,44 +117,109 @@ def render_frames_sharded(render_fn: Callable[[int], dict], n_frames: int, dst: 
     return out if (dst is None or rank == dst) else None
 
 
-# --------------------------------------------------------------------------------------- training all-reduce --
-class GradBucket:
-    """Flat fp32 bucket over the gradients of `params` (the instance stage trains `encoder_mask.embeddings` and
-    `mask_net.*.weight`): `sync()` = one all_reduce(SUM) + 1/world, written back into each `.grad` in place."""
+class TileGather:
+    """Asynchronous collection of finished tiles on ONE rank (`dst`), double buffered: `submit(tile)` starts an NCCL gather
+    of this step's `[n, C]` tiles and returns immediately, so the transfer overlaps the next frame's render; a buffer is
+    reused only after the gather that last used it has completed (stream-side wait, no host sync).  Every rank sends
+    n * C * 4 bytes per step over NVLink and `dst` receives (world - 1) of them; nothing lands in the other ranks' HBM
+    (an all_gather writes world * n * C * 4 bytes into EVERY rank)."""
 
-    def __init__(self, params: Iterable[torch.nn.Parameter]):
+    def __init__(self, n_rows: int, n_cols: int, device, dst: int = 0, depth: int = 2):
+        self.rank, self.world = _world()
+        self.dst, self.depth = dst, depth
+        self.recv = None
+        if self.world > 1 and self.rank == dst:
+            self.recv = [[torch.empty(n_rows, n_cols, dtype=torch.float32, device=device) for _ in range(self.world)] for _ in range(depth)]
+        self.handles = [None] * depth
+        self.i = 0
+        self.bytes_sent_per_step = n_rows * n_cols * 4 if (self.world > 1 and self.rank != dst) else 0
+
+    def slot_ready(self) -> int:
+        """Index of the buffer pair the next submit will use, after waiting (on the stream) for its previous gather."""
+        b = self.i % self.depth
+        if self.handles[b] is not None:
+            self.handles[b].wait()
+            self.handles[b] = None
+        return b
+
+    def submit(self, tile: torch.Tensor):
+        b = self.slot_ready()
+        self.i += 1
+        if self.world == 1:
+            return [tile]
+        self.handles[b] = dist.gather(tile, self.recv[b] if self.rank == self.dst else None, dst=self.dst, async_op=True)
+        return self.recv[b] if self.rank == self.dst else None
+
+    def drain(self):
+        for b in range(self.depth):
+            if self.handles[b] is not None:
+                self.handles[b].wait()
+                self.handles[b] = None
+
+
+# --------------------------------------------------------------------------------------- training all-reduce --
+class FlatGradBucket:
+    """Gradients of `params` (the instance stage trains `encoder_mask.embeddings` and `mask_net.*.weight`) as VIEWS of one flat
+    fp32 buffer: the backward kernels accumulate straight into it (`inerf_field_backward_mask` adds into
+    `embeddings.grad`, autograd adds the MLP gradients in place), so the data-parallel exchange is ONE
+    `all_reduce(SUM)` over that buffer with no pack / unpack copies, and the division by the world size is folded into the
+    optimizer pass (`FusedAdam.grad_div`) -- 53.4 MB read + written once by NCCL, nothing else.  The optimizer must clear
+    gradients in place (FusedAdam does; `zero_grad(set_to_none=False)` otherwise) so the views survive.
+
+    `extra` trailing float slots ride along in the same collective (MaskTrainStep uses one as the "some rank overflowed its
+    sample budget" flag of the graph-captured step).  Each parameter's slice starts 16-byte aligned."""
+
+    def __init__(self, params: Iterable[torch.nn.Parameter], extra: int = 0):
         self.params = [p for p in params if p.requires_grad]
-        self.numel = sum(p.numel() for p in self.params)
+        self.offsets, off = [], 0
+        for p in self.params:
+            self.offsets.append(off)
+            off += (p.numel() + 3) // 4 * 4
+        self.extra_offset, self.n_extra = off, extra
+        self.numel = off + (extra + 3) // 4 * 4
         self.flat = None
 
-    def sync(self) -> int:
-        """-> payload bytes that crossed the collective (0 when world == 1)"""
-        rank, world = _world()
-        if world == 1 or not self.params:
-            return 0
+    def attach(self):
+        """(Re)create the flat buffer on the parameters' device and point every `.grad` into it (existing gradients are kept)."""
+        if not self.params:
+            return self
         dev = self.params[0].device
         if self.flat is None or self.flat.device != dev:
             self.flat = torch.zeros(self.numel, dtype=torch.float32, device=dev)
-        off = 0
-        for p in self.params:
-            n = p.numel()
-            if p.grad is None:
-                self.flat[off: off + n].zero_()
-            else:
-                self.flat[off: off + n].copy_(p.grad.reshape(-1))
-            off += n
-        dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
-        self.flat.mul_(1.0 / world)
-        off = 0
-        for p in self.params:
-            n = p.numel()
-            g = self.flat[off: off + n].view_as(p)
-            if p.grad is None:
-                p.grad = g.clone()
-            else:
-                p.grad.copy_(g)
-            off += n
-        return self.numel * 4
+        for p, off in zip(self.params, self.offsets):
+            view = self.flat[off: off + p.numel()].view_as(p)
+            if p.grad is not None and p.grad.data_ptr() != view.data_ptr():
+                view.copy_(p.grad)
+            p.grad = view
+        return self
+
+    def attached(self) -> bool:
+        return self.flat is not None and all(p.grad is not None and p.grad.data_ptr() == self.flat.data_ptr() + 4 * off
+                                             for p, off in zip(self.params, self.offsets))
+
+    @property
+    def extra(self) -> torch.Tensor:
+        return self.flat[self.extra_offset: self.extra_offset + self.n_extra]
+
+    def all_reduce(self, async_op: bool = False):
+        """SUM over ranks, in place, on the current stream (capturable in a CUDA graph).  -> (work handle | None, payload bytes)"""
+        rank, world = _world()
+        if world == 1 or not self.params:
+            return None, 0
+        if not self.attached():
+            self.attach()
+        return dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, async_op=async_op), self.numel * 4
+
+    def sync(self) -> int:
+        """Eager convenience for optimizers that do not fold the averaging: all_reduce(SUM) then one in-place 1/world."""
+        _, world = _world()
+        _, nbytes = self.all_reduce()
+        if nbytes:
+            self.flat.mul_(1.0 / world)
+        return nbytes
+
+
+GradBucket = FlatGradBucket   # round-1 name
 
 
 def broadcast_parameters(module: torch.nn.Module, src: int = 0) -> None:
@@ -163,3 +229,7 @@ def broadcast_parameters(module: torch.nn.Module, src: int = 0) -> None:
         return
     for t in list(module.parameters()) + list(module.buffers()):
         dist.broadcast(t.data, src=src)
+    # parameters were written through `.data`: their version counters did not move, so the derived fp16 tables / weight
+    # blobs cached by the networks (keyed on those counters + this epoch) must be rebuilt
+    from ._lib import invalidate_param_caches
+    invalidate_param_caches()

@@ -3,9 +3,9 @@
 Everything here is host-side numpy / torch-CPU set-up code shared by tests and
 bench.py: a room box with K-1 axis-aligned furniture boxes, its analytic
 occupancy grid in the reference's layout (density_grid [C, 128^3] in Morton
-order, nerf/renderer.py:91-93), pinhole cameras on a seeded walk, and
-`get_rays` with the reference's pixel-centre / patch-order semantics
-(nerf/utils.py:56-140).
+order, nerf/renderer.py:91-93) and pinhole cameras on a seeded walk.  Rays come
+from the product's `nerf.utils.get_rays` (CUDA) or, on the CPU side of a test,
+from the pinned restatement `oracle.host_oracle.get_rays`.
 """
 from __future__ import annotations
 
@@ -149,47 +149,6 @@ def camera_poses(scene: RoomScene, n: int, seed: int = 1) -> np.ndarray:
 def intrinsics(H: int, W: int, fovy_deg: float = 60.0):
     fl = 0.5 * H / math.tan(math.radians(fovy_deg) / 2)
     return (fl, fl, W / 2, H / 2)
-
-
-# ----------------------------------------------------------------------- rays --
-@torch.no_grad()
-def get_rays(poses: torch.Tensor, intr, H: int, W: int, N: int = -1, patch_size: int = 1, generator=None):
-    """nerf/utils.py:56-140 (uniform / patch sampling; the error-map branch is out of scope).
-    poses [B,4,4] cam2world -> dict(rays_o [B,N,3], rays_d [B,N,3], inds [B,N] if N > 0)."""
-    device = poses.device
-    B = poses.shape[0]
-    fx, fy, cx, cy = intr
-    i, j = torch.meshgrid(torch.linspace(0, W - 1, W, device=device), torch.linspace(0, H - 1, H, device=device), indexing="ij")
-    i = i.t().reshape([1, H * W]).expand([B, H * W]) + 0.5
-    j = j.t().reshape([1, H * W]).expand([B, H * W]) + 0.5
-    results = {}
-    if N > 0:
-        N = min(N, H * W)
-        if patch_size > 1:
-            num_patch = N // (patch_size ** 2)
-            inds_x = torch.randint(0, H - patch_size, size=[num_patch], device=device, generator=generator)
-            inds_y = torch.randint(0, W - patch_size, size=[num_patch], device=device, generator=generator)
-            inds = torch.stack([inds_x, inds_y], dim=-1)
-            pi, pj = torch.meshgrid(torch.arange(patch_size, device=device), torch.arange(patch_size, device=device), indexing="ij")
-            offsets = torch.stack([pi.reshape(-1), pj.reshape(-1)], dim=-1)
-            inds = (inds.unsqueeze(1) + offsets.unsqueeze(0)).view(-1, 2)
-            inds = inds[:, 0] * W + inds[:, 1]
-            inds = inds.expand([B, N])
-        else:
-            inds = torch.randint(0, H * W, size=[N], device=device, generator=generator).expand([B, N])
-        i = torch.gather(i, -1, inds)
-        j = torch.gather(j, -1, inds)
-        results["inds"] = inds
-    zs = torch.ones_like(i)
-    xs = (i - cx) / fx * zs
-    ys = (j - cy) / fy * zs
-    directions = torch.stack((xs, ys, zs), dim=-1)
-    directions = directions / torch.norm(directions, dim=-1, keepdim=True)
-    rays_d = directions @ poses[:, :3, :3].transpose(-1, -2)
-    rays_o = poses[..., :3, 3][..., None, :].expand_as(rays_d)
-    results["rays_o"] = rays_o
-    results["rays_d"] = rays_d
-    return results
 
 
 # ---------------------------------------------------------------------- model --

@@ -3,6 +3,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))));
 import numpy as np, torch
 from test_field_gpu import build_model
 from instance_nerf_b200 import synthetic
+from oracle import host_oracle
 from instance_nerf_b200.nerf.trainer import MaskTrainStep
 cuda = torch.device("cuda:0")
 p = torch.nn.Parameter(torch.zeros(10, device=cuda)); p.grad = torch.ones_like(p)
@@ -11,7 +12,7 @@ K = 16
 m, sc = build_model(cuda, K, density_scale=10.0)
 H, W = 96, 128
 poses = torch.from_numpy(synthetic.camera_poses(sc, 1, 1))
-r = synthetic.get_rays(poses, synthetic.intrinsics(H, W), H, W, N=1024, patch_size=8, generator=torch.Generator().manual_seed(0))
+r = host_oracle.get_rays(poses, synthetic.intrinsics(H, W), H, W, N=1024, patch_size=8, generator=torch.Generator().manual_seed(0))
 o, d = r["rays_o"].reshape(-1, 3).contiguous(), r["rays_d"].reshape(-1, 3).contiguous()
 labels = torch.from_numpy(sc.first_hit_labels(o.numpy().astype(np.float64), d.numpy().astype(np.float64)))
 print("labels:", np.unique(labels.numpy(), return_counts=True))

@@ -4,12 +4,13 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import bench
 from instance_nerf_b200 import synthetic
+from oracle import host_oracle
 from instance_nerf_b200.nerf.trainer import MaskTrainStep
 dev = torch.device("cuda:0")
 model, scene, poses = bench.build_scene_and_model(dev)
 tr = MaskTrainStep(model, label_regularization_weight=0.1)
 g = torch.Generator().manual_seed(100)
-r = synthetic.get_rays(poses[0][None], synthetic.intrinsics(480, 640), 480, 640, N=4096, patch_size=8, generator=g)
+r = host_oracle.get_rays(poses[0][None], synthetic.intrinsics(480, 640), 480, 640, N=4096, patch_size=8, generator=g)
 o, d = r["rays_o"].reshape(-1, 3).contiguous(), r["rays_d"].reshape(-1, 3).contiguous()
 labels = torch.from_numpy(scene.first_hit_labels(o.numpy().astype(np.float64), d.numpy().astype(np.float64)))
 data = {"rays_o": o[None].to(dev), "rays_d": d[None].to(dev), "masks": labels[None].to(dev)}

@@ -5,6 +5,7 @@ import numpy as np
 import torch
 
 from instance_nerf_b200 import synthetic
+from oracle import host_oracle
 
 
 @functools.lru_cache(maxsize=4)
@@ -18,7 +19,7 @@ def scene_arrays(K=16, bound=8.0, seed=0):
 
 def make_rays(sc, H, W, n_poses=1, seed=1, pose_index=0):
     poses = synthetic.camera_poses(sc, max(n_poses, pose_index + 1), seed)[pose_index:pose_index + n_poses]
-    r = synthetic.get_rays(torch.from_numpy(poses), synthetic.intrinsics(H, W), H, W)
+    r = host_oracle.get_rays(torch.from_numpy(poses), synthetic.intrinsics(H, W), H, W)
     return r["rays_o"].reshape(-1, 3).contiguous(), r["rays_d"].reshape(-1, 3).contiguous()
 
 

@@ -123,10 +123,10 @@ def test_new_entry_points_reject_bad_arguments_without_a_gpu(L):
     assert L.inerf_march_rays_train_count_t(None, None, None, 8.0, 0.0, 1024, 16, 0, 128, None, None, None, None, None, None, None) < 0
     assert L.inerf_march_rays_train_expand(None, None, 8.0, 0.0, 1024, 16, 4, 100, 64, None, None, None, None, None, None, None, None) < 0
     # NULL tensors with n > 0
-    assert L.inerf_adam_step(None, None, None, None, 8, 1e-2, 0.9, 0.99, 1e-15, None, None, None, None) == -1
+    assert L.inerf_adam_step(None, None, None, None, 8, 1e-2, 0.9, 0.99, 1e-15, None, None, None, 1.0, None) == -1
     assert L.inerf_adam_advance(None, None, None) == -1
     # n == 0 is a no-op
-    assert L.inerf_adam_step(None, None, None, None, 0, 1e-2, 0.9, 0.99, 1e-15, None, None, None, None) == 0
+    assert L.inerf_adam_step(None, None, None, None, 0, 1e-2, 0.9, 0.99, 1e-15, None, None, None, 1.0, None) == 0
 
 
 def test_field_desc_struct_matches_header():

@@ -9,6 +9,7 @@ import torch
 
 from helpers import bits_equal, scene_arrays
 from instance_nerf_b200 import synthetic
+from oracle import host_oracle
 
 pytestmark = pytest.mark.gpu
 
@@ -23,7 +24,7 @@ def test_full_frame(cuda, H, W, B):
     from instance_nerf_b200.nerf.utils import get_rays
     poses = _poses(B)
     intr = synthetic.intrinsics(H, W)
-    want = synthetic.get_rays(poses, intr, H, W)
+    want = host_oracle.get_rays(poses, intr, H, W)
     got = get_rays(poses.to(cuda), intr, H, W)
     assert got["rays_o"].shape == (B, H * W, 3) and "inds" not in got
     assert bits_equal(got["rays_o"], want["rays_o"].contiguous())
@@ -49,7 +50,7 @@ def test_sampled_pixels_and_fused_near_far(cuda, patch):
         assert torch.equal(i0[:, :, 1:] - i0[:, :, :-1], torch.ones_like(i0[:, :, 1:]))
         assert torch.equal(i0[:, 1:, :] - i0[:, :-1, :], torch.full_like(i0[:, 1:, :], W))
         assert int((i0[:, 0, 0] // W).max()) < H - patch and int((i0[:, 0, 0] % W).max()) < W - patch
-    full = synthetic.get_rays(poses, intr, H, W)
+    full = host_oracle.get_rays(poses, intr, H, W)
     want_d = torch.gather(full["rays_d"], 1, inds.cpu()[..., None].expand(B, N, 3))
     torch.testing.assert_close(got["rays_d"].cpu(), want_d, rtol=0, atol=2e-6)
     n1, f1 = rm.near_far_from_aabb(got["rays_o"].view(-1, 3), got["rays_d"].view(-1, 3), aabb, 0.2)

@@ -53,12 +53,31 @@ def _worker(rank, world, port, H, W, n_frames, ret):
         w = torch.nn.Parameter(torch.zeros(7, 3))
         frozen = torch.nn.Parameter(torch.zeros(4), requires_grad=False)
         table.grad = torch.full_like(table, float(rank + 1))
+        bucket = parallel.FlatGradBucket([table, w, frozen], extra=1).attach()
+        # gradients are VIEWS of the flat buffer: what was there is kept, a parameter without a gradient reads as zeros,
+        # in-place accumulation (what autograd and the backward kernel do) lands in the buffer
+        assert bucket.attached() and table.grad.data_ptr() == bucket.flat.data_ptr()
+        assert w.grad.data_ptr() == bucket.flat.data_ptr() + 4 * 2000 and float(w.grad.abs().sum()) == 0.0
         if rank == 0:
-            w.grad = torch.ones_like(w) * 4
-        bucket = parallel.GradBucket([table, w, frozen])
-        nbytes = bucket.sync()
-        assert nbytes == (2000 + 21) * 4
-        assert torch.allclose(table.grad, torch.full_like(table, 1.5)) and torch.allclose(w.grad, torch.full_like(w, 2.0))
+            w.grad += 4
+        bucket.extra[0] = float(rank == 1)            # a flag riding in the same collective
+        _, nbytes = bucket.all_reduce()
+        assert nbytes == (2000 + 24 + 4) * 4          # slices padded to 16 bytes
+        assert torch.allclose(table.grad, torch.full_like(table, 3.0)) and torch.allclose(w.grad, torch.full_like(w, 4.0))
+        assert float(bucket.extra[0]) == 1.0
+        table.grad.zero_(); w.grad.zero_()
+        table.grad += float(rank + 1)
+        assert bucket.sync() == nbytes and torch.allclose(table.grad, torch.full_like(table, 1.5))
+        # async tile gather to one rank, double buffered
+        tg = parallel.TileGather(6, 3, torch.device("cpu"), dst=0)
+        for step in range(3):
+            got = tg.submit(torch.full((6, 3), float(10 * step + rank)))
+            tg.drain()
+            if rank == 0:
+                assert [float(t[0, 0]) for t in got] == [10.0 * step, 10.0 * step + 1]
+            else:
+                assert got is None
+        assert tg.bytes_sent_per_step == (0 if rank == 0 else 6 * 3 * 4)
         # parameter broadcast
         m = torch.nn.Linear(3, 2)
         with torch.no_grad():

@@ -59,12 +59,13 @@ def test_fused_backward_matches_autograd(cuda, K, B):
 
 def test_train_step_runs_fused_and_learns(cuda):
     from instance_nerf_b200 import synthetic
+    from oracle import host_oracle
     from instance_nerf_b200.nerf.trainer import MaskTrainStep
     K = 16
     m, sc = build_model(cuda, K, density_scale=10.0)
     H, W = 96, 128
     poses = torch.from_numpy(synthetic.camera_poses(sc, 1, 1))
-    r = synthetic.get_rays(poses, synthetic.intrinsics(H, W), H, W, N=1024, patch_size=8, generator=torch.Generator().manual_seed(0))
+    r = host_oracle.get_rays(poses, synthetic.intrinsics(H, W), H, W, N=1024, patch_size=8, generator=torch.Generator().manual_seed(0))
     o, d = r["rays_o"].reshape(-1, 3).contiguous(), r["rays_d"].reshape(-1, 3).contiguous()
     labels = torch.from_numpy(sc.first_hit_labels(o.numpy().astype(np.float64), d.numpy().astype(np.float64)))
     data = {"rays_o": o[None].to(cuda), "rays_d": d[None].to(cuda), "masks": labels[None].to(cuda),
@@ -114,10 +115,11 @@ def test_fused_loss_tail_matches_torch(cuda, K, reg):
 
 def _train_setup(cuda, K=16, n_rays=1024, seed=0):
     from instance_nerf_b200 import synthetic
+    from oracle import host_oracle
     m, sc = build_model(cuda, K, density_scale=10.0)
     H, W = 96, 128
     poses = torch.from_numpy(synthetic.camera_poses(sc, 1, 1))
-    r = synthetic.get_rays(poses, synthetic.intrinsics(H, W), H, W, N=n_rays, patch_size=8, generator=torch.Generator().manual_seed(seed))
+    r = host_oracle.get_rays(poses, synthetic.intrinsics(H, W), H, W, N=n_rays, patch_size=8, generator=torch.Generator().manual_seed(seed))
     o, d = r["rays_o"].reshape(-1, 3).contiguous(), r["rays_d"].reshape(-1, 3).contiguous()
     labels = torch.from_numpy(sc.first_hit_labels(o.numpy().astype(np.float64), d.numpy().astype(np.float64)))
     data = {"rays_o": o[None].to(cuda), "rays_d": d[None].to(cuda), "masks": labels[None].to(cuda),
