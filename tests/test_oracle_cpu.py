@@ -203,3 +203,106 @@ def test_extra_state_sweep_points_restatement():
         cells = np.random.RandomState(cas).randint(0, G ** 3, size=500)
         got = fo.extra_state_sweep_points(cells, cas, G, bound, noise)
         np.testing.assert_allclose(got, by_cell[cells], rtol=0, atol=1e-6)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# oracle/host_oracle.py against tests/golden/ref_host.npz = the reference's own host-side functions run on the CPU
+# (tests/golden/make_golden_host.py): get_rays, MaskTrainer.train_step's loss, mark_untrained_grid, update_extra_state.
+def _host_gold():
+    return np.load(os.path.join(GOLD, "ref_host.npz"))
+
+
+def _gold_model_sd(g):
+    """State dict of the golden's reference network: small tensors stored, both hash tables regenerated from the seed."""
+    K, bound, seed = g["model_cfg"]
+    sd = {k[3:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("sd_")}
+    gen = torch.Generator().manual_seed(int(seed))
+    n_rows = int(sd["encoder.offsets"][-1])
+    for name in ("encoder.embeddings", "encoder_mask.embeddings"):
+        sd[name] = (torch.rand(n_rows, 2, generator=gen) * 2 - 1) * 0.5
+    return sd, int(K), float(bound)
+
+
+@pytest.mark.parametrize("case", ["full", "uniform", "patch", "emap"])
+def test_host_oracle_get_rays_matches_reference(case):
+    from instance_nerf_b200 import synthetic
+    from oracle import host_oracle as ho
+    g = _host_gold()
+    B, H, W, N, patch, seed, emap = (int(v) for v in g[f"rays_{case}_cfg"])
+    poses = torch.from_numpy(g["poses"])[:B]
+    error_map = ((torch.arange(B * 128 * 128) % 97).float() + 1).view(B, -1) / 97.0 if emap else None
+    r = ho.get_rays(poses, synthetic.intrinsics(H, W), H, W, N, error_map=error_map, patch_size=patch, generator=torch.Generator().manual_seed(seed))
+    for k in ("rays_o", "rays_d", "inds", "inds_coarse"):
+        if f"rays_{case}_{k}" in g.files:
+            assert np.array_equal(r[k].contiguous().numpy(), g[f"rays_{case}_{k}"]), (case, k)
+        else:
+            assert k not in r
+
+
+def test_host_oracle_mask_loss_matches_reference_train_step():
+    from oracle import host_oracle as ho
+    g = _host_gold()
+    K, patch = int(g["model_cfg"][0]), int(g["loss_patch"])
+    depth, labels = torch.from_numpy(g["loss_depth"]), torch.from_numpy(g["loss_labels"])
+    m3_logits, m3_labels = torch.from_numpy(g["m3_logits"]), torch.from_numpy(g["m3_labels"])
+    for tag in ("ce", "reg", "all"):
+        want, reg_w, m3_w = g[f"loss_{tag}"]
+        logits = torch.from_numpy(g["loss_logits"]).clone().requires_grad_(True)
+        loss = ho.mask_train_loss(logits, depth, labels, patch, K, float(reg_w), m3_logits, m3_labels, float(m3_w))
+        (grad,) = torch.autograd.grad(loss, logits)
+        assert abs(float(loss) - float(want)) < 1e-6 * max(1.0, abs(float(want))), tag
+        np.testing.assert_allclose(grad.numpy(), g[f"loss_{tag}_grad"], rtol=1e-5, atol=1e-8)
+    assert abs(float(ho.mask_train_loss(torch.from_numpy(g["loss_logits"]), depth, torch.full_like(labels, -1), patch, K, 0.0)) - float(g["loss_unlabelled"])) == 0.0
+    np.testing.assert_allclose(float(torch.nn.functional.cross_entropy(m3_logits, m3_labels)), float(g["m3_loss"]), rtol=1e-6)
+
+
+def test_host_oracle_mask3d_logits_match_reference_network():
+    """The 3D-mask query (nerf/utils.py:1250-1260: density -> geo_feat -> mask) through the oracle field vs the reference net."""
+    g = _host_gold()
+    sd, K, bound = _gold_model_sd(g)
+    field = fo.OracleField(sd, bound, K)
+    x = torch.from_numpy(g["m3_coords"])
+    with torch.no_grad():
+        logits = field.mask(x, geo_feat=field.density(x)["geo_feat"])
+    np.testing.assert_allclose(logits.numpy(), g["m3_logits"], rtol=1e-4, atol=1e-5)
+
+
+def test_host_oracle_occupancy_update_matches_reference():
+    """Full sweep and partial update of update_extra_state with the reference's recorded draws: the restated sample points
+    are bit-identical, the EMA / mean / packbits tail (field_oracle.update_grid_ema) reproduces grid, mean and bitfield."""
+    from oracle import host_oracle as ho
+    g = _host_gold()
+    C, G, bound = int(g["occ_cfg"][0]), int(g["occ_cfg"][1]), float(g["occ_cfg"][2])
+    ii = np.arange(G, dtype=np.int32)
+    X, Y, Z = np.meshgrid(ii, ii, ii, indexing="ij")
+    mesh = np.stack([X.ravel(), Y.ravel(), Z.ravel()], -1)
+    for tag in ("full", "partial"):
+        tmp = -np.ones((C, G ** 3), np.float32)
+        for c in range(C):
+            if tag == "full":
+                coords, indices = mesh, ro.morton3D(mesh).astype(np.int64)
+            else:
+                indices, coords = ho.partial_cells(g["occ_partial_grid_in"][c], g["occ_partial_coords"][c], g["occ_partial_picks"][c])
+            pts = ho.sweep_points(coords, c, G, bound, g[f"occ_{tag}_noise"][c])
+            assert np.array_equal(pts.view(np.uint32), g[f"occ_{tag}_points"][c].view(np.uint32)), (tag, c)
+            tmp[c, indices] = g[f"occ_{tag}_sigma"][c]      # density_scale = 1; duplicates: last write wins, as index_put on the CPU
+        grid, mean, bits = fo.update_grid_ema(g[f"occ_{tag}_grid_in"], tmp, 0.95, 0.5)
+        assert np.array_equal(grid.view(np.uint32), g[f"occ_{tag}_grid_out"].view(np.uint32)), tag
+        assert abs(mean - float(g[f"occ_{tag}_mean"])) < 1e-6 * max(1.0, mean)
+        assert np.array_equal(bits, g[f"occ_{tag}_bits"]), tag
+    # the recorded densities are the reference network's: the oracle field reproduces them at the recorded points
+    sd, K, b = _gold_model_sd(g)
+    field = fo.OracleField(sd, b, K)
+    with torch.no_grad():
+        sig = field.density(torch.from_numpy(g["occ_partial_points"][1]))["sigma"]
+    np.testing.assert_allclose(sig.numpy(), g["occ_partial_sigma"][1], rtol=1e-4, atol=1e-6)
+
+
+def test_host_oracle_mark_untrained_grid_matches_reference():
+    from oracle import host_oracle as ho
+    g = _host_gold()
+    C, G, bound = int(g["occ_cfg"][0]), int(g["occ_cfg"][1]), float(g["occ_cfg"][2])
+    got = ho.mark_untrained_grid(np.zeros((C, G ** 3), np.float32), g["mark_poses"], tuple(g["mark_intr"]), bound, G)
+    want = g["mark_grid"]
+    assert 0 < int((want == -1).sum()) < want.size
+    assert np.array_equal(got, want)
