@@ -230,19 +230,30 @@ __global__ void __launch_bounds__(256) k_composite_train_fwd_scan(
     }
 }
 
+// Logit rows [32 samples x K] of a chunk are one CONTIGUOUS block of the [M, K] stream, but the lane that owns sample j needs
+// row j: read straight from global memory, every 16-byte load of the warp touches 32 different 128-byte lines (32 L1
+// wavefronts for 512 useful bytes) and the gradient rows go back the same way -- the L1 wavefront rate, not HBM, bounded the
+// first version of this kernel (0.43 of HBM peak at K = 32).  The block is therefore staged through shared memory: coalesced
+// 512-byte warp loads -> rotated [row][chunk] layout (chunk index rotated by the row, so both the coalesced side and the
+// row-owner side are bank-conflict free for K = 32) -> lane j reads its row, overwrites it with the gradient row -> coalesced
+// warp stores.  Only the rows that contribute (j < m) move.
+template <int KPL> struct BwdCfg { static constexpr int kWarps = KPL == 2 ? 4 : 8; };   // 32 KB of staging per CTA either way
+
 template <int KPL>   // K <= 32 * KPL, KPL <= 2: every lane keeps the ray's K logit gradients in registers
-__global__ void __launch_bounds__(256) k_composite_train_bwd_scan(
+__global__ void __launch_bounds__(32 * BwdCfg<KPL>::kWarps) k_composite_train_bwd_scan(
     const float* __restrict__ grad_weights_sum, const float* __restrict__ grad_image, const float* __restrict__ grad_mask_out,
     const float* __restrict__ sigmas, const float* __restrict__ rgbs, const float* __restrict__ masks,
     const float* __restrict__ deltas, const int32_t* __restrict__ rays, const float* __restrict__ weights_sum,
     const float* __restrict__ image, const float* __restrict__ mask_out, uint32_t M, uint32_t N, uint32_t K, float T_thresh,
     float* __restrict__ grad_sigmas, float* __restrict__ grad_rgbs, float* __restrict__ grad_masks) {
     constexpr int KMAX = KPL > 0 ? 32 * KPL : 1;
+    __shared__ float4 stage_all[KPL > 0 ? BwdCfg<KPL>::kWarps * 32 * (KMAX / 4) : 1];
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (n >= N) return;
+    if (n >= N) return;   // whole warps leave together; only __syncwarp is used below
     const uint32_t index = (uint32_t)rays[n * 3], offset = (uint32_t)rays[n * 3 + 1], num_steps = (uint32_t)rays[n * 3 + 2];
     if (num_steps == 0 || offset + num_steps > M) return;
+    float4* stage = stage_all + (KPL > 0 ? (threadIdx.x >> 5) * 32 * (KMAX / 4) : 0);
 
     const float gr = grad_image[(size_t)index * 3], gg = grad_image[(size_t)index * 3 + 1], gb = grad_image[(size_t)index * 3 + 2];
     const float Qfin = gr * image[(size_t)index * 3] + gg * image[(size_t)index * 3 + 1] + gb * image[(size_t)index * 3 + 2];
@@ -257,6 +268,11 @@ __global__ void __launch_bounds__(256) k_composite_train_bwd_scan(
         }
     }
     const bool vec = KPL > 0 && (K & 3u) == 0 && (((uintptr_t)masks | (uintptr_t)grad_masks) & 15u) == 0;
+    const uint32_t C4 = K >> 2;   // 16-byte chunks per row (vec path)
+    const bool pow2 = (C4 & (C4 - 1u)) == 0u;            // K = 16 / 32 / 64: shifts and masks instead of divisions
+    const uint32_t sh = 31u - (uint32_t)__clz((int)(C4 | 1u));
+    // staging slot of chunk c of row r: the chunk index is rotated by the row
+    auto slot = [&](uint32_t r, uint32_t c) { return r * C4 + (pow2 ? ((c + r) & (C4 - 1u)) : ((c + r) % C4)); };
     float Tc = 1.0f, Qc = 0.f, Pc = 0.f;
 
     for (uint32_t base = 0; base < num_steps; base += 32) {
@@ -281,26 +297,41 @@ __global__ void __launch_bounds__(256) k_composite_train_bwd_scan(
         float gs = T_after * q - (Qfin - Qrun) + ws_term;
         if (KPL > 0) {
             float p = 0.f;
-            if (inc) {
-                const float* mrow = masks + (size_t)s * K;
-                float* grow = grad_masks + (size_t)s * K;
-                if (vec) {
+            if (vec) {
+                const float4* src = reinterpret_cast<const float4*>(masks + (size_t)(offset + base) * K);
+                float4* dst = reinterpret_cast<float4*>(grad_masks + (size_t)(offset + base) * K);
+                const uint32_t n16 = m * C4;   // contiguous 16-byte chunks of the rows that contribute
+                for (uint32_t i = lane; i < n16; i += 32) {
+                    const uint32_t r = pow2 ? i >> sh : i / C4, c = i - r * C4;
+                    stage[slot(r, c)] = __ldg(src + i);
+                }
+                __syncwarp();
+                if (inc) {
 #pragma unroll
                     for (int k4 = 0; k4 < KMAX / 4; k4++) {
-                        if ((uint32_t)k4 * 4u < K) {
-                            const float4 v = __ldg(reinterpret_cast<const float4*>(mrow) + k4);
+                        if ((uint32_t)k4 < C4) {
+                            const uint32_t at = slot(lane, (uint32_t)k4);
+                            const float4 v = stage[at];
                             p = fmaf(gm[4 * k4], v.x, p); p = fmaf(gm[4 * k4 + 1], v.y, p);
                             p = fmaf(gm[4 * k4 + 2], v.z, p); p = fmaf(gm[4 * k4 + 3], v.w, p);
-                            reinterpret_cast<float4*>(grow)[k4] = make_float4(gm[4 * k4] * w, gm[4 * k4 + 1] * w, gm[4 * k4 + 2] * w, gm[4 * k4 + 3] * w);
+                            stage[at] = make_float4(gm[4 * k4] * w, gm[4 * k4 + 1] * w, gm[4 * k4 + 2] * w, gm[4 * k4 + 3] * w);
                         }
                     }
-                } else {
+                }
+                __syncwarp();
+                for (uint32_t i = lane; i < n16; i += 32) {
+                    const uint32_t r = pow2 ? i >> sh : i / C4, c = i - r * C4;
+                    dst[i] = stage[slot(r, c)];
+                }
+                __syncwarp();   // the staging block is reused by the next chunk
+            } else if (inc) {
+                const float* mrow = masks + (size_t)s * K;
+                float* grow = grad_masks + (size_t)s * K;
 #pragma unroll
-                    for (int k = 0; k < KMAX; k++) {
-                        if ((uint32_t)k < K) {
-                            p = fmaf(gm[k], __ldg(mrow + k), p);
-                            grow[k] = gm[k] * w;
-                        }
+                for (int k = 0; k < KMAX; k++) {
+                    if ((uint32_t)k < K) {
+                        p = fmaf(gm[k], __ldg(mrow + k), p);
+                        grow[k] = gm[k] * w;
                     }
                 }
             }
@@ -425,7 +456,8 @@ int composite_train_bwd(const float* grad_weights_sum, const float* grad_image, 
     if (K) { INERF_REQUIRE(grad_mask_out); INERF_REQUIRE(masks); INERF_REQUIRE(mask_out); INERF_REQUIRE(grad_masks); }
     return dispatch_kpl(K, [&](auto kpl) {
         if constexpr (decltype(kpl)::value <= 2) {   // K <= 64: the ray's logit gradients fit in registers
-            k_composite_train_bwd_scan<decltype(kpl)::value><<<div_up((unsigned long long)N * 32, 256), 256, 0, (cudaStream_t)stream>>>(
+            constexpr unsigned threads = 32 * BwdCfg<decltype(kpl)::value>::kWarps;
+            k_composite_train_bwd_scan<decltype(kpl)::value><<<div_up((unsigned long long)N * 32, threads), threads, 0, (cudaStream_t)stream>>>(
                 grad_weights_sum, grad_image, grad_mask_out, sigmas, rgbs, masks, deltas, rays, weights_sum, image, mask_out, M, N, K,
                 T_thresh, grad_sigmas, grad_rgbs, grad_masks);
         } else {

@@ -46,6 +46,9 @@ struct BSmem {
 #ifndef INERF_BWD_SCATTER_WARPS
 #define INERF_BWD_SCATTER_WARPS 8
 #endif
+#ifndef INERF_BWD_RED16
+#define INERF_BWD_RED16 0   // A/B this round: 16-byte RED for x-neighbour corner pairs of the unreduced (fine) levels
+#endif
 constexpr uint32_t kBwdChainT = 256, kBwdScatterT = 32 * INERF_BWD_SCATTER_WARPS, kBwdThreads = kBwdChainT + kBwdScatterT;
 constexpr uint32_t kScatLevels = 16 / (kBwdScatterT / kTile);   // levels per scatter thread (8 or 4)
 #if INERF_BWD_SCATTER_WARPS == 16
@@ -351,8 +354,26 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_field_backward_mask(inerf_fi
                             if (a0[c] != 0.f || a1[c] != 0.f) atomicAdd(base + idx[c], make_float2(a0[c], a1[c]));
                     }
                 } else if (g0 != 0.f || g1 != 0.f) {
+#if INERF_BWD_RED16
+                    // x-neighbour corners (2i, 2i+1) sit in one 16-byte aligned slot whenever the cell's x index is even (prime[0] = 1:
+                    // entry a and a ^ 1): one 16-byte RED instead of two 8-byte ones
+#pragma unroll
+                    for (uint32_t c = 0; c < 8; c += 2) {
+                        const float2 va = make_float2(__fmul_rn(w[c], g0), __fmul_rn(w[c], g1));
+                        const float2 vb = make_float2(__fmul_rn(w[c + 1], g0), __fmul_rn(w[c + 1], g1));
+                        if ((idx[c] ^ idx[c + 1]) == 1u) {
+                            const bool odd = idx[c] & 1u;
+                            atomicAdd(reinterpret_cast<float4*>(base + (idx[c] & ~1u)),
+                                      odd ? make_float4(vb.x, vb.y, va.x, va.y) : make_float4(va.x, va.y, vb.x, vb.y));
+                        } else {
+                            atomicAdd(base + idx[c], va);
+                            atomicAdd(base + idx[c + 1], vb);
+                        }
+                    }
+#else
 #pragma unroll
                     for (uint32_t c = 0; c < 8; c++) atomicAdd(base + idx[c], make_float2(__fmul_rn(w[c], g0), __fmul_rn(w[c], g1)));
+#endif
                 }
             }
         }

@@ -27,7 +27,11 @@ from instance_nerf_b200._lib import call, ptr, stream_ptr  # noqa: E402
 from oracle import ref_loader  # noqa: E402
 
 
-def timeit(fn, iters=10, warm=3):
+ITERS, WARM = [10], [3]     # --iters / --warm (1 / 1 under ncu: two launches per kernel are enough there)
+
+
+def timeit(fn, iters=None, warm=None):
+    iters, warm = iters or ITERS[0], WARM[0] if warm is None else warm
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()
@@ -56,7 +60,10 @@ def hbm_peak():
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--rays", type=int, default=65536)
+    ap.add_argument("--iters", type=int, default=10)
+    ap.add_argument("--warm", type=int, default=3)
     args = ap.parse_args()
+    ITERS[0], WARM[0] = args.iters, args.warm
     ref = ref_loader.load()
     assert ref is not None, "oracle/_ref is not built"
     dev = torch.device("cuda:0")
@@ -153,6 +160,22 @@ def main():
     row("field_forward fused (2x hash encode + SH + 3 MLPs, tcgen05)", "sample", M, 1024 + 24 + (4 + K) * 4, t1, None,
         note="no single reference kernel: the reference runs 2 encodes + SH + 8 cuBLAS GEMMs + elementwise; see ref_gpu_path.json")
     del sig, rgb, msk
+
+    # ---------------------------------------------------------------- fused field backward (instance head) --------
+    import ctypes
+    desc = model._field_desc()
+    _, wb = model._packed_weights(want_bwd=True)
+    x0 = torch.empty(M, 48, dtype=torch.float16, device=dev)
+    sig = torch.empty(M, device=dev); rgb = torch.empty(M, 3, device=dev); msk = torch.empty(M, K, device=dev)
+    call("inerf_field_forward_train", ctypes.byref(desc), ptr(xyzs), ptr(dirs), M, ptr(sig), ptr(rgb), ptr(msk), ptr(x0), st)
+    gl = (torch.randn(M, K, device=dev) * 1e-3).contiguous()
+    gt = torch.zeros_like(model.encoder_mask.embeddings)
+    gw0 = torch.zeros(64, 47, device=dev); gw1 = torch.zeros(64, 64, device=dev); gw2 = torch.zeros(K, 64, device=dev)
+    t1 = timeit(lambda: call("inerf_field_backward_mask", ctypes.byref(desc), ptr(wb), ptr(xyzs), ptr(x0), ptr(gl), M, ptr(gt), ptr(gw0), ptr(gw1),
+                             ptr(gw2), st))
+    row("field_backward_mask fused (mask-net dX/dW on tcgen05 + fp32 table scatter)", "sample", M, 12 + 96 + 4 * K + 2048, t1, None,
+        note="table-gradient atomics counted as read+write of 16 levels x 8 corners x 8 B; the reference runs 6 GEMMs + grid backward through autograd")
+    del x0, sig, rgb, msk, gl, gt
 
     # ---------------------------------------------------------------- composite train fwd / bwd -------------------
     g = torch.Generator().manual_seed(5)

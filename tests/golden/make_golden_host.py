@@ -13,6 +13,7 @@ fixture small; nothing in the code under test depends on the value.
 
     python tests/golden/make_golden_host.py
 """
+import json
 import os
 from types import SimpleNamespace
 
@@ -58,6 +59,8 @@ with torch.no_grad():
 small = {k: v.detach().numpy() for k, v in model.state_dict().items() if "embeddings" not in k and "density" not in k}
 out.update({"sd_" + k: v for k, v in small.items()})
 out["model_cfg"] = np.array([K, bound, 7])
+# the reference network's complete state-dict layout (names, shapes, dtypes): what a reference checkpoint contains
+out["ref_sd_layout"] = np.array(json.dumps([[k, list(v.shape), str(v.dtype)] for k, v in model.state_dict().items()]))
 
 gl = torch.Generator().manual_seed(21)
 N, patch = 256, 8

@@ -306,3 +306,36 @@ def test_host_oracle_mark_untrained_grid_matches_reference():
     want = g["mark_grid"]
     assert 0 < int((want == -1).sum()) < want.size
     assert np.array_equal(got, want)
+
+
+def test_checkpoint_layout_matches_reference_and_round_trips(tmp_path):
+    """nerf/checkpoint.py against the reference's checkpoint contents: the product network's state dict has exactly the
+    names / shapes / dtypes of the REFERENCE network's (recorded from the reference class in tests/golden/ref_host.npz), a
+    checkpoint in the reference trainer's dict layout (nerf/utils.py:1100-1140) loads strictly, and save -> load round-trips."""
+    import json
+    from instance_nerf_b200.nerf import checkpoint
+    from instance_nerf_b200.nerf.network_mask import NeRFNetwork
+    g = _host_gold()
+    layout = json.loads(str(g["ref_sd_layout"]))
+    K, bound, _ = g["model_cfg"]
+    m = NeRFNetwork(bound=float(bound), cuda_ray=True, num_instances=int(K), density_scale=1, density_thresh=0.5)
+    ours = [[k, list(v.shape), str(v.dtype)] for k, v in m.state_dict().items()]
+    assert sorted(ours) == sorted(layout)
+    # a reference-trainer checkpoint: {'epoch', 'global_step', 'stats', 'mean_count', 'mean_density', 'model'}
+    gen = torch.Generator().manual_seed(3)
+    ref_sd = {k: (torch.rand(shape, generator=gen) if "float" in dt else torch.zeros(shape, dtype=getattr(torch, dt.split(".")[1])))
+              for k, shape, dt in layout}
+    path = tmp_path / "ngp_ep0003.pth"
+    torch.save({"epoch": 3, "global_step": 300, "stats": {"loss": [1.0]}, "mean_count": 4242, "mean_density": 0.25, "model": ref_sd}, path)
+    r = checkpoint.load_checkpoint(str(path), m)
+    assert r["missing_keys"] == [] and r["unexpected_keys"] == [] and r["epoch"] == 3 and r["global_step"] == 300
+    assert m.mean_count == 4242 and m.mean_density == 0.25
+    for k, v in m.state_dict().items():
+        assert torch.equal(v, ref_sd[k]), k
+    # "best" checkpoints drop density_grid (utils.py:1150-1152)
+    p2 = tmp_path / "best.pth"
+    checkpoint.save_checkpoint(str(p2), m, epoch=4, global_step=400, best=True)
+    m2 = NeRFNetwork(bound=float(bound), cuda_ray=True, num_instances=int(K))
+    r2 = checkpoint.load_checkpoint(str(p2), m2, model_only=True)
+    assert r2["missing_keys"] == ["density_grid"] and r2["unexpected_keys"] == []
+    assert torch.equal(m2.encoder_mask.embeddings, m.encoder_mask.embeddings) and m2.mean_count == 4242
