@@ -155,6 +155,8 @@ __device__ __forceinline__ void encode_level(const float x01[3], const LevelGeom
     uint2 v[8];
     // One 8-byte gather per corner.  (Tried and rejected on B200: fetching the x-neighbour with one aligned 16-byte gather when
     // it is entry a^1 -- 23 % fewer L1 sectors but LDG.128 scatters cost as many data-pipe wavefronts, +6 % time)
+    // (Also rejected on B200: L1::no_allocate for the finest levels -- 9.5 -> 14.5 ms per c2 frame: the x-neighbour of a corner
+    // is fetched by the next instruction of the same thread and hits the line the first one allocated.)
 #pragma unroll
     for (uint32_t c = 0; c < 8; c++) v[c] = __ldg(base + idx[c]);
     __half2 as = __float2half2_rn(0.f), am = as;

@@ -83,6 +83,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* mbar, uint32_t parity) {
     uint32_t spins = 0;
     long long t0 = 0;
     while (!mbar_try_wait(mbar, parity)) {
+#ifdef INERF_NO_WATCHDOG   // A/B only
+        continue;
+#endif
         if ((++spins & 1023u) == 0u) {
             const long long now = clock64();
             if (spins == 1024u) t0 = now;

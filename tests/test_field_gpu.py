@@ -138,9 +138,13 @@ def test_update_extra_state_full_sweep_vs_oracle(cuda):
     m.reset_extra_state()
     G, C = m.grid_size, m.cascade
     g = torch.Generator().manual_seed(5)
-    noises = [torch.rand(G ** 3, 3, generator=g) for _ in range(C)]
+    noises = [torch.rand(G ** 3, 3, generator=g) for _ in range(C)]          # the reference's draw order: meshgrid rows
+    # the device sweep walks the cells in Morton order: row m of cascade c takes the draw of the cell with Morton index m
+    from oracle import raymarch_oracle as ro
+    cc = ro.morton3D_invert(np.arange(G ** 3, dtype=np.int32)).astype(np.int64)
+    lin = torch.from_numpy((cc[:, 0] * G + cc[:, 1]) * G + cc[:, 2])
     with torch.autocast("cuda", dtype=torch.float16):
-        m.update_extra_state(decay=0.95, noises=[n.to(cuda) for n in noises])
+        m.update_extra_state(decay=0.95, noises=torch.cat([n[lin] for n in noises]).to(cuda))
     torch.cuda.synchronize()
     grid = m.density_grid.detach().cpu().numpy()
     assert m.iter_density == 1 and np.isfinite(grid).all() and (grid >= 0).all()
