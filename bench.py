@@ -402,26 +402,39 @@ def run_gpu_arm(args):
         except Exception as e:   # the probe library is a measurement helper: report its absence, do not lose the line
             l2 = {"error": f"{type(e).__name__}: {e}"}
         l2_peak = l2.get("l2_stream_gbs")
-        roof = {"kernel": "k_render_fused", "bound": "l2", "achieved": achieved, "unit": "GB/s", "traffic": None,
-                "peak": l2_peak if l2_peak else hbm_peak, "frac": achieved / (l2_peak if l2_peak else hbm_peak),
-                "peak_source": ("measured in this run: coalesced 16-byte loads over an L2-resident 53 MB buffer (instance_nerf_b200/probe.py); the "
-                                "interleaved fp16 table is L2-resident (ncu: lts hit rate 99.4 %, dram throughput 0.1 %)") if l2_peak else
-                               "L2 probe unavailable: HBM peak used",
-                "kernel_ms": avg_kern_ms, "algorithmic_bytes_per_launch": alg_bytes,
-                "gathers_per_s": avg_samples * 128 / (avg_kern_ms * 1e-3),
-                "gather_peak": {"gathers_per_s": l2.get("gather_gps"), "gbs_at_8B": l2.get("gather_gbs"),
-                                "frac": (avg_samples * 128 / (avg_kern_ms * 1e-3)) / l2["gather_gps"] if l2.get("gather_gps") else None,
-                                "what": "random 8-byte ld.global.nc gathers from a 53 MB table at full occupancy (one sector per lane, no reuse): the "
-                                        "access shape of the six finest hashed levels; the coarse levels coalesce, so the kernel can exceed it"},
-                "frac_of_hbm": achieved / hbm_peak, "hbm_peak": hbm_peak,
-                "hbm_peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650 GB/s",
-                "probe": l2, "mlp_tflops": mlp_flops / (avg_kern_ms * 1e-3) / 1e12}
+        prof = {}
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):
             try:
-                roof["traffic"] = json.load(open(tpath)).get("k_render_fused_dram_bytes_per_launch")
+                prof = json.load(open(tpath))
             except Exception:
-                pass
+                prof = {}
+        gathers_per_s = avg_samples * 128 / (avg_kern_ms * 1e-3)
+        # What actually binds this kernel is the L1TEX tag stage: a warp's 32 8-byte gathers cost one lookup per distinct 32-byte
+        # sector, and the probe's fully divergent gathers run at exactly 1 sector / clock / SM.  sectors / sample comes from the
+        # committed ncu capture (l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum / composited samples), the peak from this run.
+        spp = prof.get("k_render_fused_l1_sectors_per_sample")
+        l1tex = None
+        if spp and l2.get("gather_gps"):
+            sect_s = avg_samples * spp / (avg_kern_ms * 1e-3)
+            l1tex = {"sectors_per_sample": spp, "sectors_per_sample_source": prof.get("l1_sectors_source"), "achieved_gsectors_s": sect_s / 1e9,
+                     "peak_gsectors_s": l2["gather_gps"] / 1e9, "frac": sect_s / l2["gather_gps"],
+                     "what": "L1TEX sector (tag) lookups per second against the measured rate of fully divergent 8-byte gathers (1 sector / clock / SM)"}
+        roof = {"kernel": "k_render_fused", "bound": "l2", "achieved": achieved, "unit": "GB/s", "traffic": prof.get("k_render_fused_dram_bytes_per_launch"),
+                "peak": l2_peak if l2_peak else hbm_peak, "frac": achieved / (l2_peak if l2_peak else hbm_peak),
+                "peak_source": ("measured in this run: coalesced 16-byte loads over an L2-resident 53 MB buffer (instance_nerf_b200/probe.py); the "
+                                "interleaved fp16 table is L2-resident (ncu: lts hit rate 99.4 %, dram throughput 0.1 %).  8-byte gathers cannot "
+                                "reach this figure: see l1tex (the binding unit) and gather_peak") if l2_peak else "L2 probe unavailable: HBM peak used",
+                "kernel_ms": avg_kern_ms, "algorithmic_bytes_per_launch": alg_bytes, "gathers_per_s": gathers_per_s,
+                "l1tex": l1tex,
+                "gather_peak": {"gathers_per_s": l2.get("gather_gps"), "gbs_at_8B": l2.get("gather_gbs"),
+                                "frac": gathers_per_s / l2["gather_gps"] if l2.get("gather_gps") else None,
+                                "what": "random 8-byte ld.global.nc gathers from a 53 MB table at full occupancy (one sector per lane, no reuse): the "
+                                        "access shape of the finest hashed levels; the coarse levels coalesce (several lanes per sector), so the "
+                                        "kernel's gather rate exceeds it"},
+                "frac_of_hbm": achieved / hbm_peak, "hbm_peak": hbm_peak,
+                "hbm_peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650 GB/s",
+                "probe": l2, "mlp_tflops": mlp_flops / (avg_kern_ms * 1e-3) / 1e12}
         h2d = world * 64
         d2h = out_host[0].numel() * 4
         line = {

@@ -175,6 +175,14 @@ int inerf_grid_encode_backward(const void *grad, const float *inputs, const void
                                void *grad_embeddings, uint32_t B, uint32_t D, uint32_t C, uint32_t L, float S,
                                uint32_t H, const void *dy_dx, void *grad_inputs, uint32_t gridtype,
                                int align_corners, uint32_t interp, int dtype, int grad_layout, void *stream);
+/*
+ * gridencoder.h:15 grad_total_variation (gridencoder.cu:504-642): adds the total-variation gradient of the grid vertices
+ * hit by `inputs` (float [B, D] in [0, 1]; points outside are skipped) into `grad` (same shape / dtype as `embeddings`).
+ * D in {2, 3}, C in {1, 2, 4, 8}.
+ */
+int inerf_grad_total_variation(const float *inputs, const void *embeddings, void *grad, const int32_t *offsets, float weight,
+                               uint32_t B, uint32_t D, uint32_t C, uint32_t L, float S, uint32_t H, uint32_t gridtype,
+                               int align_corners, int dtype, void *stream);
 
 /* -------------------------------------------------------------- SH encoder -- */
 

@@ -84,6 +84,7 @@ _PROTOS = {
     "inerf_get_rays": [_P, _U, _F, _F, _F, _F, _U, _U, _P, _U, _P, _P, _P, _F, _P, _P, _P],
     "inerf_grid_encode_forward": [_P, _P, _P, _P, _U, _U, _U, _U, _F, _U, _P, _U, _I, _U, _I, _I, _P],
     "inerf_grid_encode_backward": [_P, _P, _P, _P, _P, _U, _U, _U, _U, _F, _U, _P, _P, _U, _I, _U, _I, _I, _P],
+    "inerf_grad_total_variation": [_P, _P, _P, _P, _F, _U, _U, _U, _U, _F, _U, _U, _I, _I, _P],
     "inerf_sh_encode_forward": [_P, _P, _U, _U, _U, _P, _P],
     "inerf_sh_encode_backward": [_P, _P, _U, _U, _U, _P, _P, _P],
     "inerf_mask_loss": [_P, _P, _P, _U, _U, _U, _F, _P, _P, _P],

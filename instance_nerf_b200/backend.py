@@ -119,8 +119,9 @@ def _grid_encode_backward(grad, inputs, embeddings, offsets, grad_embeddings, B,
          _st(inputs))
 
 
-def _grad_total_variation(*args, **kwargs):
-    raise NotImplementedError("grad_total_variation (gridencoder.cu:504-642) is never called on the instance-field path (SURVEY.md section 8f)")
+def _grad_total_variation(inputs, embeddings, grad, offsets, weight, B, D, C, L, S, H, gridtype, align_corners):
+    call("inerf_grad_total_variation", ptr(inputs.float().contiguous()), ptr(embeddings), ptr(grad), ptr(offsets), float(weight), int(B), int(D), int(C),
+         int(L), float(S), int(H), int(gridtype), int(bool(align_corners)), _DT[embeddings.dtype], _st(inputs))
 
 
 gridencoder = SimpleNamespace(grid_encode_forward=_grid_encode_forward, grid_encode_backward=_grid_encode_backward,

@@ -400,6 +400,81 @@ int launch_bwd_c(const T* grad, const float* inputs, const int32_t* offsets, T* 
     return INERF_OK;
 }
 
+// gridencoder.cu:504-603: total-variation gradient on the grid vertices hit by `inputs`, added into `grad` (the embeddings'
+// gradient, after loss.backward()).  Thread = (point, level), levels on consecutive threads as in the encode kernels.
+// Per channel: r = sum over the 2D face neighbours n of (v - v_n), s = sum of (v - v_n)^2, grad[v] += weight / (2D) * r * rsqrt(s + 1e-9).
+template <typename T, uint32_t D, uint32_t C>
+__global__ void __launch_bounds__(256) k_grad_tv(const float* __restrict__ inputs, const T* __restrict__ grid, T* __restrict__ grad,
+                                                 const int32_t* __restrict__ offsets, float weight, uint32_t B, uint32_t L, float S, uint32_t H,
+                                                 uint32_t gridtype, bool align_corners) {
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (uint64_t)B * L) return;
+    const uint32_t b = (uint32_t)(t / L), level = (uint32_t)(t - (uint64_t)b * L);
+    const float* x = inputs + (size_t)b * D;
+#pragma unroll
+    for (uint32_t d = 0; d < D; d++)
+        if (x[d] < 0.f || x[d] > 1.f) return;
+    const LevelGeom g = level_geom(offsets, level, S, H);
+    grid += (size_t)offsets[level] * C;
+    grad += (size_t)offsets[level] * C;
+    uint32_t pos_grid[D];
+#pragma unroll
+    for (uint32_t d = 0; d < D; d++) pos_grid[d] = (uint32_t)floorf(__fmaf_rn(x[d], g.scale, align_corners ? 0.0f : 0.5f));
+    const uint32_t index = grid_index<D, C>(gridtype, align_corners, g.hashmap_size, g.resolution, pos_grid);
+    float results[C], idelta[C], centre[C];
+#pragma unroll
+    for (uint32_t ch = 0; ch < C; ch++) { results[ch] = 0.f; idelta[ch] = 0.f; centre[ch] = (float)grid[index + ch]; }
+    const float w = (float)(T)(weight / (float)(2 * D));   // `scalar_t w = weight / (2 * D)`
+#pragma unroll
+    for (uint32_t d = 0; d < D; d++) {
+        const uint32_t cur = pos_grid[d];
+#pragma unroll
+        for (int side = 0; side < 2; side++) {
+            if (side == 0 ? cur < g.resolution : cur > 0) {
+                pos_grid[d] = side == 0 ? cur + 1 : cur - 1;
+                const uint32_t nb = grid_index<D, C>(gridtype, align_corners, g.hashmap_size, g.resolution, pos_grid);
+#pragma unroll
+                for (uint32_t ch = 0; ch < C; ch++) {
+                    const float gv = (float)(T)(centre[ch] - (float)grid[nb + ch]);     // the reference keeps every intermediate in scalar_t
+                    results[ch] = (float)(T)(results[ch] + gv);
+                    idelta[ch] = (float)(T)(idelta[ch] + (float)(T)(gv * gv));
+                }
+            }
+        }
+        pos_grid[d] = cur;
+    }
+#pragma unroll
+    for (uint32_t ch = 0; ch < C; ch++) {
+        const float v = (float)(T)((float)(T)(w * results[ch]) * rsqrtf(idelta[ch] + 1e-9f));
+        if constexpr (std::is_same<T, float>::value) atomicAdd(grad + index + ch, v);
+        else atomicAdd(grad + index + ch, __float2half_rn(v));
+    }
+}
+
+template <typename T, uint32_t D>
+int launch_tv_c(const float* inputs, const T* emb, T* grad, const int32_t* offsets, float weight, uint32_t B, uint32_t C, uint32_t L, float S,
+                uint32_t H, uint32_t gridtype, bool ac, cudaStream_t st) {
+    const unsigned blocks = div_up((unsigned long long)B * L, 256);
+    switch (C) {
+        case 1: k_grad_tv<T, D, 1><<<blocks, 256, 0, st>>>(inputs, emb, grad, offsets, weight, B, L, S, H, gridtype, ac); break;
+        case 2: k_grad_tv<T, D, 2><<<blocks, 256, 0, st>>>(inputs, emb, grad, offsets, weight, B, L, S, H, gridtype, ac); break;
+        case 4: k_grad_tv<T, D, 4><<<blocks, 256, 0, st>>>(inputs, emb, grad, offsets, weight, B, L, S, H, gridtype, ac); break;
+        case 8: k_grad_tv<T, D, 8><<<blocks, 256, 0, st>>>(inputs, emb, grad, offsets, weight, B, L, S, H, gridtype, ac); break;
+        default: return INERF_ERR_UNSUPPORTED;
+    }
+    INERF_LAUNCH_CHECK();
+    return INERF_OK;
+}
+template <typename T>
+int tv_t(const float* inputs, const void* emb, void* grad, const int32_t* offsets, float weight, uint32_t B, uint32_t D, uint32_t C, uint32_t L,
+         float S, uint32_t H, uint32_t gridtype, bool ac, cudaStream_t st) {
+    switch (D) {
+        case 2: return launch_tv_c<T, 2>(inputs, (const T*)emb, (T*)grad, offsets, weight, B, C, L, S, H, gridtype, ac, st);
+        case 3: return launch_tv_c<T, 3>(inputs, (const T*)emb, (T*)grad, offsets, weight, B, C, L, S, H, gridtype, ac, st);
+        default: return INERF_ERR_UNSUPPORTED;
+    }
+}
+
 template <typename T>
 int fwd_t(const float* inputs, const void* emb, const int32_t* offsets, void* out, uint32_t B, uint32_t D, uint32_t C, uint32_t L, float S,
           uint32_t H, void* dy_dx, uint32_t gridtype, bool ac, uint32_t interp, int layout, cudaStream_t st) {
@@ -463,5 +538,16 @@ extern "C" int inerf_grid_encode_backward(const void* grad, const float* inputs,
         return bwd_t<float>(grad, inputs, offsets, grad_embeddings, B, D, C, L, S, H, dy_dx, grad_inputs, gridtype, align_corners != 0, interp, grad_layout, (cudaStream_t)stream);
     if (dtype == INERF_F16)
         return bwd_t<__half>(grad, inputs, offsets, grad_embeddings, B, D, C, L, S, H, dy_dx, grad_inputs, gridtype, align_corners != 0, interp, grad_layout, (cudaStream_t)stream);
+    return INERF_ERR_UNSUPPORTED;
+}
+
+extern "C" int inerf_grad_total_variation(const float* inputs, const void* embeddings, void* grad, const int32_t* offsets, float weight,
+                                          uint32_t B, uint32_t D, uint32_t C, uint32_t L, float S, uint32_t H, uint32_t gridtype,
+                                          int align_corners, int dtype, void* stream) {
+    if (L == 0 || L > 64 || gridtype > 1) return INERF_ERR_SIZE;
+    if (B == 0) return INERF_OK;
+    INERF_REQUIRE(inputs); INERF_REQUIRE(embeddings); INERF_REQUIRE(grad); INERF_REQUIRE(offsets);
+    if (dtype == INERF_F32) return tv_t<float>(inputs, embeddings, grad, offsets, weight, B, D, C, L, S, H, gridtype, align_corners != 0, (cudaStream_t)stream);
+    if (dtype == INERF_F16) return tv_t<__half>(inputs, embeddings, grad, offsets, weight, B, D, C, L, S, H, gridtype, align_corners != 0, (cudaStream_t)stream);
     return INERF_ERR_UNSUPPORTED;
 }

@@ -49,6 +49,17 @@ struct BSmem {
 #ifndef INERF_BWD_RED16
 #define INERF_BWD_RED16 0   // A/B this round: 16-byte RED for x-neighbour corner pairs of the unreduced (fine) levels
 #endif
+#ifndef INERF_BWD_STREAM
+#define INERF_BWD_STREAM 0  // A/B this round: the sample streams (x0, dL/dlogits, xyz) are read once -> ld.global.cs (evict first),
+#endif                      // so that they do not push the 107 MB fp32 table gradient out of L2
+#ifndef INERF_BWD_L2PERSIST
+#define INERF_BWD_L2PERSIST 0   // A/B this round: launch with an access-policy window that keeps the table gradient persisting in L2
+#endif
+#if INERF_BWD_STREAM
+#define INERF_LD_STREAM(p) __ldcs(p)
+#else
+#define INERF_LD_STREAM(p) __ldg(p)
+#endif
 constexpr uint32_t kBwdChainT = 256, kBwdScatterT = 32 * INERF_BWD_SCATTER_WARPS, kBwdThreads = kBwdChainT + kBwdScatterT;
 constexpr uint32_t kScatLevels = 16 / (kBwdScatterT / kTile);   // levels per scatter thread (8 or 4)
 #if INERF_BWD_SCATTER_WARPS == 16
@@ -183,7 +194,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_field_backward_mask(inerf_fi
 #pragma unroll
         for (uint32_t c = 0; c < 3; c++) {
             const uint32_t chunk = half * 3 + c;
-            const uint4 v = live ? __ldg(p.x0 + (size_t)s * 6 + chunk) : make_uint4(0u, 0u, 0u, 0u);
+            const uint4 v = live ? INERF_LD_STREAM(p.x0 + (size_t)s * 6 + chunk) : make_uint4(0u, 0u, 0u, 0u);
             *reinterpret_cast<uint4*>(smem + BSmem::TX + umma::tile_off(row, chunk * 8, kLBO, kSbo48)) = v;
         }
         {
@@ -195,8 +206,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_field_backward_mask(inerf_fi
 #pragma unroll
                 for (uint32_t i = 0; i < 4; i++) {
                     const uint32_t ka = k0 + 2 * i;
-                    const float a = (live && ka < K) ? __ldg(g + ka) : 0.f;
-                    const float b = (live && ka + 1 < K) ? __ldg(g + ka + 1) : 0.f;
+                    const float a = (live && ka < K) ? INERF_LD_STREAM(g + ka) : 0.f;
+                    const float b = (live && ka + 1 < K) ? INERF_LD_STREAM(g + ka + 1) : 0.f;
                     q[i] = h2_bits(__floats2half2_rn(a, b));
                 }
                 *reinterpret_cast<uint4*>(smem + BSmem::TG + umma::tile_off(row, k0, kLBO, kSbo128)) = make_uint4(q[0], q[1], q[2], q[3]);
@@ -316,7 +327,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_field_backward_mask(inerf_fi
             float x01[3] = {2.f, 2.f, 2.f};
             if (live) {
 #pragma unroll
-                for (int d = 0; d < 3; d++) x01[d] = __fmul_rn(__fadd_rn(__ldg(p.xyzs + (size_t)s * 3 + d), desc.bound), inv2b);
+                for (int d = 0; d < 3; d++) x01[d] = __fmul_rn(__fadd_rn(INERF_LD_STREAM(p.xyzs + (size_t)s * 3 + d), desc.bound), inv2b);
             }
             const bool ok = live && !(x01[0] < 0.f || x01[0] > 1.f || x01[1] < 0.f || x01[1] > 1.f || x01[2] < 0.f || x01[2] > 1.f);
 #pragma unroll
@@ -487,6 +498,11 @@ extern "C" int inerf_field_pack_weights_bwd(const float* mask0, const float* mas
     return INERF_OK;
 }
 
+#if INERF_BWD_L2PERSIST
+// the level offsets live on the device: bound the table size from above (16 levels x 2^19 entries); the window may cover more
+static size_t desc_table_entries(const inerf_field_desc* d) { return (size_t)d->L << 19; }
+#endif
+
 extern "C" int inerf_field_backward_mask(const inerf_field_desc* desc, const void* weights_bwd, const float* xyzs, const void* x0,
                                          const float* grad_logits, uint32_t B, float* grad_table, float* grad_w0, float* grad_w1,
                                          float* grad_w2, void* stream) {
@@ -502,6 +518,34 @@ extern "C" int inerf_field_backward_mask(const inerf_field_desc* desc, const voi
     const uint32_t num_tiles = (B + kTile - 1) / kTile;
     const uint32_t sms = (uint32_t)device_sm_count();
     const uint32_t grid = num_tiles < sms ? num_tiles : sms;
+#if INERF_BWD_L2PERSIST
+    {
+        // keep the fp32 table gradient (the target of ~60 scattered REDs per sample) persisting in L2 while the kernel streams
+        // 230 B / sample of inputs through it
+        int dev = 0, max_persist = 0, max_window = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
+        cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev);
+        const size_t table_bytes = (size_t)desc_table_entries(desc) * 8;
+        if (max_persist > 0 && max_window > 0) {
+            cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)max_persist);
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
+            attr[0].val.accessPolicyWindow.base_ptr = grad_table;
+            attr[0].val.accessPolicyWindow.num_bytes = table_bytes < (size_t)max_window ? table_bytes : (size_t)max_window;
+            attr[0].val.accessPolicyWindow.hitRatio = table_bytes <= (size_t)max_persist ? 1.0f : (float)max_persist / (float)table_bytes;
+            attr[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            attr[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kBwdThreads); cfg.dynamicSmemBytes = BSmem::bytes; cfg.stream = (cudaStream_t)stream;
+            cfg.attrs = attr; cfg.numAttrs = 1;
+            cudaError_t le = cudaLaunchKernelEx(&cfg, k_field_backward_mask, *desc, p);
+            if (le != cudaSuccess) return (int)le;
+            INERF_LAUNCH_CHECK();
+            return INERF_OK;
+        }
+    }
+#endif
     k_field_backward_mask<<<grid, kBwdThreads, BSmem::bytes, (cudaStream_t)stream>>>(*desc, p);
     INERF_LAUNCH_CHECK();
     return INERF_OK;

@@ -134,5 +134,18 @@ class GridEncoder(nn.Module):
 
     @torch.no_grad()
     def grad_total_variation(self, weight=1e-7, inputs=None, bound=1, B=1000000):
-        # gridencoder.cu:504-642: never called on the instance-field path
-        raise NotImplementedError("grad_total_variation is outside the instance-field hot path")
+        """grid.py:163-185 / gridencoder.cu:504-642: adds the TV gradient of the vertices hit by `inputs` (random points when
+        None) into `self.embeddings.grad`; call after loss.backward() and before optimizer.step().  Always fp32 (the reference
+        disables autocast here)."""
+        if inputs is None:
+            inputs = torch.rand(B, self.input_dim, device=self.embeddings.device)
+        else:
+            inputs = ((inputs + bound) / (2 * bound)).view(-1, self.input_dim)
+            B = inputs.shape[0]
+        if self.embeddings.grad is None:
+            raise ValueError("grad is None, should be called after loss.backward() and before optimizer.step()!")
+        inputs = inputs.float().contiguous()
+        emb, grad = self.embeddings, self.embeddings.grad
+        call("inerf_grad_total_variation", ptr(inputs), ptr(emb.detach()), ptr(grad), ptr(self.offsets), float(weight), B, self.input_dim,
+             emb.shape[1], self.num_levels, float(np.log2(self.per_level_scale)), self.base_resolution, self.gridtype_id, int(self.align_corners),
+             0 if emb.dtype == torch.float32 else 1, stream_ptr(emb.device))
