@@ -85,7 +85,7 @@ class NeRFNetwork(NeRFRenderer):
         return bool(self.use_fused and self._standard_arch() and self.encoder.embeddings.is_cuda)
 
     def fused_render_available(self, render_mask: bool) -> bool:
-        return (not render_mask) and self.fused_available() and self.bg_radius <= 0 and hasattr(lib(), "inerf_render_fused")
+        return (not render_mask) and self.fused_available() and hasattr(lib(), "inerf_render_fused")
 
     _packed_weights = _InstanceNetwork._packed_weights
     _packed_tables = _InstanceNetwork._packed_tables

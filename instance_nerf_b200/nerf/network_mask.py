@@ -133,7 +133,9 @@ class NeRFNetwork(NeRFMaskRenderer):
         return bool(self.use_fused and self._standard_arch() and self.encoder.embeddings.is_cuda)
 
     def fused_render_available(self, render_mask: bool) -> bool:
-        return self.fused_available() and self.bg_radius <= 0 and hasattr(lib(), "inerf_render_fused")
+        # the background model (bg_radius > 0) only enters through the `(1 - weights_sum) * bg_color` tail of run_cuda, which is
+        # outside the kernel: the one-launch renderer serves it as well
+        return self.fused_available() and hasattr(lib(), "inerf_render_fused")
 
     def _packed_weights(self, want_bwd: bool = False):
         """fp16 operand blobs for the tcgen05 kernels, re-packed ON THE DEVICE (one launch, no host round trip) whenever a

@@ -366,9 +366,12 @@ class NeRFRenderer(nn.Module):
         scr = getattr(self, "_occ_scratch", None)
         if scr is None or scr.numel() < n_scr or scr.device != dev:
             scr = self._occ_scratch = torch.empty(n_scr, dtype=torch.int32, device=dev)
-        as_i32 = lambda t: None if t is None else t.to(device=dev, dtype=torch.int32).contiguous()
-        call("inerf_occupancy_sample_cells", ptr(self.density_grid), C, G, N, ptr(as_i32(uniform_cells)), ptr(as_i32(occ_picks)),
-             _host_seed(), ptr(cells), ptr(scr), stream_ptr(dev))
+        # both converted tensors must stay alive until the launch is queued (a temporary freed between the two conversions would
+        # hand its block to the second one)
+        uni = None if uniform_cells is None else uniform_cells.to(device=dev, dtype=torch.int32).contiguous()
+        picks = None if occ_picks is None else occ_picks.to(device=dev, dtype=torch.int32).contiguous()
+        call("inerf_occupancy_sample_cells", ptr(self.density_grid), C, G, N, ptr(uni), ptr(picks), _host_seed(), ptr(cells), ptr(scr),
+             stream_ptr(dev))
         return cells
 
     @torch.no_grad()

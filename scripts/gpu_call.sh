@@ -10,7 +10,7 @@ timeout -k 10 900 python bench.py --steps 20 --warmup 5 > $out/${tag}_bench.json
 timeout -k 10 400 python tests/dev_op_bench.py > $out/${tag}_opbench.log 2>&1
 cp $out/op_bench.json $out/${tag}_op_bench.json 2>/dev/null
 # A/B builds of the backward kernel (csrc/Makefile VARIANT=...): parity tests first, then the op bench
-for v in red16 sw16red16; do
+for v in red16 sw16red16 bstream bpersist; do
   if [ -f instance_nerf_b200/libinerf_b200_$v.so ]; then
     export INERF_B200_LIB=$PWD/instance_nerf_b200/libinerf_b200_$v.so
     timeout -k 10 400 python -m pytest tests/test_train_gpu.py -m gpu -q --timeout=300 -k "backward_matches or graphed or runs_fused" 2>&1 | tail -30 > $out/${tag}_${v}_pytest.log

@@ -193,3 +193,34 @@ def test_run_non_cuda_ray_matches_reference_python_renderer(cuda):
     with torch.no_grad():
         r2 = m.render(o[None], d[None], staged=True, max_ray_batch=100, render_mask=True, num_steps=int(T), upsample_steps=16, perturb=False, bg_color=1)
     assert r2["image"].shape == res["image"].shape and bool(torch.isfinite(r2["image"]).all()) and bool(torch.isfinite(r2["instance_mask_logits"]).all())
+
+
+def test_background_model_fused_vs_loop(cuda):
+    """bg_radius > 0 (network_mask.py:95-114, 268; mask_renderer.py:246-249): the background colour comes from sph_from_ray ->
+    2-D hash grid + SH -> bg_net and is mixed in by run_cuda's `(1 - weights_sum) * bg_color` tail, so the one-launch renderer
+    and the alive-ray loop (modular field) must agree; it must also differ from the constant-background render."""
+    from instance_nerf_b200 import synthetic
+    from instance_nerf_b200.nerf.network_mask import NeRFNetwork
+    torch.manual_seed(0)
+    m = NeRFNetwork(bound=8.0, cuda_ray=True, num_instances=8, density_scale=0.05, density_thresh=10, bg_radius=12.0)
+    synthetic.randomize_tables(m, 0)
+    with torch.no_grad():
+        m.encoder_bg.embeddings.uniform_(-1.0, 1.0)
+    sc, cascade, grid, bits = scene_arrays(16, 8.0, 0)
+    with torch.no_grad():
+        m.density_grid.copy_(torch.from_numpy(grid)); m.density_bitfield.copy_(torch.from_numpy(bits))
+    m = m.to(cuda).eval()
+    o, d = (t.to(cuda) for t in make_rays(sc, 48, 64))
+    kw = dict(staged=True, render_mask=True, perturb=False, dt_gamma=1 / 128, max_steps=1024, T_thresh=1e-4)
+    with torch.no_grad():
+        assert m.fused_render_available(True)
+        a = m.render(o[None], d[None], **kw)
+        m.use_fused = False
+        with torch.autocast("cuda", dtype=torch.float16):
+            b = m.render(o[None], d[None], **kw)
+        m.use_fused = True
+        m.bg_radius = -1
+        c = m.render(o[None], d[None], bg_color=1, **kw)
+    torch.testing.assert_close(a["image"], b["image"].float(), rtol=0, atol=2e-3)
+    torch.testing.assert_close(a["depth"], b["depth"].float(), rtol=0, atol=1e-3)
+    assert float((a["image"] - c["image"]).abs().max()) > 0.05      # thin medium: the background shows through

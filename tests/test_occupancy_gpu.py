@@ -93,7 +93,7 @@ def test_sweep_points_and_cells_bit_exact(cuda):
     off = (a - centre).view(C, -1, 3)
     for c in range(C):
         hgs = min(2 ** c, bound) / G
-        assert float(off[c].abs().max()) <= hgs * (1 + 1e-6) and abs(float(off[c].mean())) < 0.05 * hgs and float(off[c].std()) > 0.5 * hgs
+        assert float(off[c].abs().max()) <= hgs * (1 + 1e-5) and abs(float(off[c].mean())) < 0.05 * hgs and float(off[c].std()) > 0.5 * hgs
     # sampled cells without injection: in range, the occupied half really occupied
     cells = m.sweep_cells()
     assert int(cells.min()) >= 0 and int(cells.max()) < G ** 3
