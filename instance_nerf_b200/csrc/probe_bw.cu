@@ -48,7 +48,26 @@ __global__ void __launch_bounds__(1024) k_gather(const uint2* __restrict__ table
     if (acc == 0x9E3779B9u) sink[0] = acc;
 }
 
+// random float2 (8-byte) or float4 (16-byte) REDs into a table: the scatter rate of the hash-grid backward
+template <int V>
+__global__ void __launch_bounds__(1024) k_red(float* __restrict__ table, uint32_t n_entries, uint32_t per_thread) {
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t s = hash32(tid * 2654435761u + 777u);
+    for (uint32_t i = 0; i < per_thread; i++) {
+        s = s * 1664525u + 1013904223u;
+        const uint32_t idx = (uint32_t)(((uint64_t)hash32(s) * n_entries) >> 32);
+        if (V == 2) atomicAdd(reinterpret_cast<float2*>(table) + idx, make_float2(1e-9f, 1e-9f));
+        else atomicAdd(reinterpret_cast<float4*>(table) + (idx >> 1), make_float4(1e-9f, 1e-9f, 1e-9f, 1e-9f));
+    }
+}
+
 }  // namespace
+
+extern "C" int inerf_probe_red(void* table, uint32_t n_entries, uint32_t per_thread, uint32_t blocks, int vec, void* stream) {
+    if (vec == 4) k_red<4><<<blocks, 1024, 0, (cudaStream_t)stream>>>((float*)table, n_entries, per_thread);
+    else k_red<2><<<blocks, 1024, 0, (cudaStream_t)stream>>>((float*)table, n_entries, per_thread);
+    return (int)cudaGetLastError();
+}
 
 extern "C" int inerf_probe_stream(const void* buf, uint64_t bytes, uint32_t reps, uint32_t blocks, uint32_t* sink, void* stream) {
     k_stream<<<blocks, 1024, 0, (cudaStream_t)stream>>>((const uint4*)buf, bytes / 16, reps, sink);

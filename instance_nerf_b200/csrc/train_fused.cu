@@ -40,32 +40,14 @@ struct BSmem {
     static constexpr uint32_t MISC = DF + 2 * kTile * 32 * 4; // LevelGeom[16] | mbarrier | tmem slot | df_full[2] | df_empty[2]
     static constexpr uint32_t bytes = MISC + 16 * sizeof(LevelGeom) + 64;
 };
-// INERF_BWD_SCATTER_WARPS = 16 (NOT validated on hardware yet, next round's A/B): thread = (row, 4 levels) with setmaxnreg
-// 104 / 64 -- inside the CTA's own 768 x 80 register allocation, which is all setmaxnreg can redistribute (a 112 / 72 split
-// exceeded it and hung).  Default 8: thread = (row, 8 levels), 127 registers for every thread.
-#ifndef INERF_BWD_SCATTER_WARPS
-#define INERF_BWD_SCATTER_WARPS 8
-#endif
-#ifndef INERF_BWD_RED16
-#define INERF_BWD_RED16 0   // A/B this round: 16-byte RED for x-neighbour corner pairs of the unreduced (fine) levels
-#endif
-#ifndef INERF_BWD_STREAM
-#define INERF_BWD_STREAM 0  // A/B this round: the sample streams (x0, dL/dlogits, xyz) are read once -> ld.global.cs (evict first),
-#endif                      // so that they do not push the 107 MB fp32 table gradient out of L2
-#ifndef INERF_BWD_L2PERSIST
-#define INERF_BWD_L2PERSIST 0   // A/B this round: launch with an access-policy window that keeps the table gradient persisting in L2
-#endif
-#if INERF_BWD_STREAM
-#define INERF_LD_STREAM(p) __ldcs(p)
-#else
-#define INERF_LD_STREAM(p) __ldg(p)
-#endif
-constexpr uint32_t kBwdChainT = 256, kBwdScatterT = 32 * INERF_BWD_SCATTER_WARPS, kBwdThreads = kBwdChainT + kBwdScatterT;
-constexpr uint32_t kScatLevels = 16 / (kBwdScatterT / kTile);   // levels per scatter thread (8 or 4)
-#if INERF_BWD_SCATTER_WARPS == 16
+// Scatter role: 16 warps, thread = (row, 4 levels), with setmaxnreg 104 (chain) / 64 (scatter) -- inside the CTA's own
+// 768 x 80 register allocation, which is all setmaxnreg can redistribute (a 112 / 72 split exceeds it and hangs in
+// setmaxnreg.inc).  Measured on B200 for 7.8 M samples: 8 scatter warps x 8 levels at 127 registers
+// 5.02 ms -> 16 warps 4.79 ms -> + 16-byte REDs for x-neighbour pairs 4.24 ms.
+constexpr uint32_t kBwdChainT = 256, kBwdScatterT = 512, kBwdThreads = kBwdChainT + kBwdScatterT;
+constexpr uint32_t kScatLevels = 16 / (kBwdScatterT / kTile);   // levels per scatter thread
 constexpr uint32_t kBwdRegsChain = 104, kBwdRegsScatter = 64;
 static_assert(kBwdChainT * kBwdRegsChain + kBwdScatterT * kBwdRegsScatter <= kBwdThreads * 80, "setmaxnreg budget exceeds the CTA's allocation");
-#endif
 constexpr uint32_t kSbo128 = sbo_of(128), kSbo64 = sbo_of(64), kSbo48 = sbo_of(48);
 // TMEM columns (512 allocated: one CTA per SM)
 constexpr uint32_t T_a = 0, T_b = 64, T_x = 128, T_w1 = 160, T_w0 = 288, kBwdTmemCols = 512;
@@ -184,9 +166,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_field_backward_mask(inerf_fi
     };
 
     if (chain_role) {
-#if INERF_BWD_SCATTER_WARPS == 16
     umma::reg_alloc<kBwdRegsChain>();
-#endif
     for (uint32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, tiles_done++) {
         const uint32_t s = tile * kTile + row;
         const bool live = s < B_eff;
@@ -194,7 +174,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_field_backward_mask(inerf_fi
 #pragma unroll
         for (uint32_t c = 0; c < 3; c++) {
             const uint32_t chunk = half * 3 + c;
-            const uint4 v = live ? INERF_LD_STREAM(p.x0 + (size_t)s * 6 + chunk) : make_uint4(0u, 0u, 0u, 0u);
+            const uint4 v = live ? __ldg(p.x0 + (size_t)s * 6 + chunk) : make_uint4(0u, 0u, 0u, 0u);
             *reinterpret_cast<uint4*>(smem + BSmem::TX + umma::tile_off(row, chunk * 8, kLBO, kSbo48)) = v;
         }
         {
@@ -206,8 +186,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_field_backward_mask(inerf_fi
 #pragma unroll
                 for (uint32_t i = 0; i < 4; i++) {
                     const uint32_t ka = k0 + 2 * i;
-                    const float a = (live && ka < K) ? INERF_LD_STREAM(g + ka) : 0.f;
-                    const float b = (live && ka + 1 < K) ? INERF_LD_STREAM(g + ka + 1) : 0.f;
+                    const float a = (live && ka < K) ? __ldg(g + ka) : 0.f;
+                    const float b = (live && ka + 1 < K) ? __ldg(g + ka + 1) : 0.f;
                     q[i] = h2_bits(__floats2half2_rn(a, b));
                 }
                 *reinterpret_cast<uint4*>(smem + BSmem::TG + umma::tile_off(row, k0, kLBO, kSbo128)) = make_uint4(q[0], q[1], q[2], q[3]);
@@ -303,9 +283,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_field_backward_mask(inerf_fi
     }
     } else {
     // ------------------------------------------------------------------------------------------------ scatter role --
-#if INERF_BWD_SCATTER_WARPS == 16
     umma::reg_dealloc<kBwdRegsScatter>();
-#endif
     uint32_t it = 0;
     for (uint32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, it++) {
         const uint32_t s = tile * kTile + row;
@@ -327,7 +305,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_field_backward_mask(inerf_fi
             float x01[3] = {2.f, 2.f, 2.f};
             if (live) {
 #pragma unroll
-                for (int d = 0; d < 3; d++) x01[d] = __fmul_rn(__fadd_rn(INERF_LD_STREAM(p.xyzs + (size_t)s * 3 + d), desc.bound), inv2b);
+                for (int d = 0; d < 3; d++) x01[d] = __fmul_rn(__fadd_rn(__ldg(p.xyzs + (size_t)s * 3 + d), desc.bound), inv2b);
             }
             const bool ok = live && !(x01[0] < 0.f || x01[0] > 1.f || x01[1] < 0.f || x01[1] > 1.f || x01[2] < 0.f || x01[2] > 1.f);
 #pragma unroll
@@ -365,9 +343,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_field_backward_mask(inerf_fi
                             if (a0[c] != 0.f || a1[c] != 0.f) atomicAdd(base + idx[c], make_float2(a0[c], a1[c]));
                     }
                 } else if (g0 != 0.f || g1 != 0.f) {
-#if INERF_BWD_RED16
                     // x-neighbour corners (2i, 2i+1) sit in one 16-byte aligned slot whenever the cell's x index is even (prime[0] = 1:
-                    // entry a and a ^ 1): one 16-byte RED instead of two 8-byte ones
+                    // entry a and a ^ 1): one 16-byte RED instead of two 8-byte ones (-11 % kernel time on B200)
 #pragma unroll
                     for (uint32_t c = 0; c < 8; c += 2) {
                         const float2 va = make_float2(__fmul_rn(w[c], g0), __fmul_rn(w[c], g1));
@@ -381,10 +358,6 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_field_backward_mask(inerf_fi
                             atomicAdd(base + idx[c + 1], vb);
                         }
                     }
-#else
-#pragma unroll
-                    for (uint32_t c = 0; c < 8; c++) atomicAdd(base + idx[c], make_float2(__fmul_rn(w[c], g0), __fmul_rn(w[c], g1)));
-#endif
                 }
             }
         }
@@ -498,11 +471,6 @@ extern "C" int inerf_field_pack_weights_bwd(const float* mask0, const float* mas
     return INERF_OK;
 }
 
-#if INERF_BWD_L2PERSIST
-// the level offsets live on the device: bound the table size from above (16 levels x 2^19 entries); the window may cover more
-static size_t desc_table_entries(const inerf_field_desc* d) { return (size_t)d->L << 19; }
-#endif
-
 extern "C" int inerf_field_backward_mask(const inerf_field_desc* desc, const void* weights_bwd, const float* xyzs, const void* x0,
                                          const float* grad_logits, uint32_t B, float* grad_table, float* grad_w0, float* grad_w1,
                                          float* grad_w2, void* stream) {
@@ -518,34 +486,6 @@ extern "C" int inerf_field_backward_mask(const inerf_field_desc* desc, const voi
     const uint32_t num_tiles = (B + kTile - 1) / kTile;
     const uint32_t sms = (uint32_t)device_sm_count();
     const uint32_t grid = num_tiles < sms ? num_tiles : sms;
-#if INERF_BWD_L2PERSIST
-    {
-        // keep the fp32 table gradient (the target of ~60 scattered REDs per sample) persisting in L2 while the kernel streams
-        // 230 B / sample of inputs through it
-        int dev = 0, max_persist = 0, max_window = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
-        cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev);
-        const size_t table_bytes = (size_t)desc_table_entries(desc) * 8;
-        if (max_persist > 0 && max_window > 0) {
-            cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)max_persist);
-            cudaLaunchAttribute attr[1];
-            attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
-            attr[0].val.accessPolicyWindow.base_ptr = grad_table;
-            attr[0].val.accessPolicyWindow.num_bytes = table_bytes < (size_t)max_window ? table_bytes : (size_t)max_window;
-            attr[0].val.accessPolicyWindow.hitRatio = table_bytes <= (size_t)max_persist ? 1.0f : (float)max_persist / (float)table_bytes;
-            attr[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-            attr[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-            cudaLaunchConfig_t cfg = {};
-            cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kBwdThreads); cfg.dynamicSmemBytes = BSmem::bytes; cfg.stream = (cudaStream_t)stream;
-            cfg.attrs = attr; cfg.numAttrs = 1;
-            cudaError_t le = cudaLaunchKernelEx(&cfg, k_field_backward_mask, *desc, p);
-            if (le != cudaSuccess) return (int)le;
-            INERF_LAUNCH_CHECK();
-            return INERF_OK;
-        }
-    }
-#endif
     k_field_backward_mask<<<grid, kBwdThreads, BSmem::bytes, (cudaStream_t)stream>>>(*desc, p);
     INERF_LAUNCH_CHECK();
     return INERF_OK;

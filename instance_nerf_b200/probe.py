@@ -30,7 +30,8 @@ def _probe():
         L = ctypes.CDLL(PROBE_PATH)
         L.inerf_probe_stream.argtypes = [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_void_p]
         L.inerf_probe_gather.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_void_p]
-        L.inerf_probe_stream.restype = L.inerf_probe_gather.restype = ctypes.c_int
+        L.inerf_probe_red.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_int, ctypes.c_void_p]
+        L.inerf_probe_stream.restype = L.inerf_probe_gather.restype = L.inerf_probe_red.restype = ctypes.c_int
         _lib = L
     return _lib
 
@@ -81,4 +82,23 @@ def measure_l2_peaks(device=None, table_bytes: int = 6664784 * 8, hbm_bytes: int
         ms = _best_ms(lambda: check(L.inerf_probe_stream(big.data_ptr(), hbm_bytes, 1, 8 * sms, sink.data_ptr(), st)), reps=3)
         out["hbm_stream_gbs"] = hbm_bytes / (ms * 1e-3) / 1e9
         del big
+    return out
+
+
+def measure_red_peak(device=None, n_entries: int = 6664784) -> dict:
+    """Random 8-byte (float2) and 16-byte (float4) REDs into an fp32 [n_entries, 2] table (the hash-table gradient, 53 MB at the
+    instance field's size) at full occupancy -> REDs / s: the scatter rate that bounds the hash-grid backward."""
+    dev = torch.device(device if device is not None else "cuda")
+    L = _probe()
+    st = torch.cuda.current_stream(dev).cuda_stream
+    sms = torch.cuda.get_device_properties(dev).multi_processor_count
+    table = torch.zeros(n_entries, 2, dtype=torch.float32, device=dev)
+    out = {"n_entries": n_entries, "table_bytes": n_entries * 8}
+    per_thread, blocks = 256, 2 * sms
+    for vec, key in ((2, "red8_gps"), (4, "red16_gps")):
+        def run():
+            rc = L.inerf_probe_red(table.data_ptr(), n_entries, per_thread, blocks, vec, st)
+            if rc != 0:
+                raise RuntimeError(f"probe kernel failed: cudaError {rc}")
+        out[key] = blocks * 1024 * per_thread / (_best_ms(run) * 1e-3)
     return out

@@ -1,7 +1,18 @@
-mkdir -p gpurun_out
+#!/bin/bash
+# Multi-GPU session: gpurun --gpus N -- bash scripts/gpu_multi.sh N <tag>
 N=${1:-2}
-TAG=${2:-x}
-nvidia-smi --query-gpu=index,name --format=csv,noheader
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 20 --warmup 3 > gpurun_out/bench_n${N}_$TAG.json 2> gpurun_out/bench_n${N}_$TAG.err; echo "render N=$N rc=$?"; cat gpurun_out/bench_n${N}_$TAG.json; tail -3 gpurun_out/bench_n${N}_$TAG.err
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $N --workload train --rays 65536 --steps 10 --warmup 5 > gpurun_out/train_n${N}_$TAG.json 2> gpurun_out/train_n${N}_$TAG.err; echo "train N=$N rc=$?"; cat gpurun_out/train_n${N}_$TAG.json; tail -3 gpurun_out/train_n${N}_$TAG.err
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus $N --impl reference --steps 2 --warmup 1 | tail -1 | cut -c1-300
+tag=${2:-m}
+out=gpurun_out
+mkdir -p $out
+nvidia-smi -L > $out/${tag}_smi.txt 2>&1
+TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
+if [ "$N" = "2" ]; then
+  timeout -k 10 600 python -m pytest tests/test_dp_gpu.py -m gpu -q --timeout=500 2>&1 | tail -40 > $out/${tag}_dp_pytest.log
+fi
+timeout -k 10 900 $TR --master-port 29511 bench.py --gpus $N --steps 20 --warmup 5 > $out/${tag}_bench_n$N.json 2> $out/${tag}_bench_n$N.err
+timeout -k 10 600 $TR --master-port 29512 bench.py --gpus $N --workload c4 > $out/${tag}_c4_n$N.json 2> $out/${tag}_c4_n$N.err
+timeout -k 10 600 $TR --master-port 29513 bench.py --gpus $N --workload train --rays 65536 --steps 30 --warmup 5 > $out/${tag}_train_c5_n$N.json 2> $out/${tag}_train_c5_n$N.err
+INERF_NO_GRAPH=1 timeout -k 10 600 $TR --master-port 29514 bench.py --gpus $N --workload train --rays 65536 --steps 30 --warmup 5 > $out/${tag}_train_c5_eager_n$N.json 2> $out/${tag}_train_c5_eager_n$N.err
+tail -3 $out/${tag}_dp_pytest.log 2>/dev/null
+head -c 600 $out/${tag}_bench_n$N.json; echo; head -c 400 $out/${tag}_c4_n$N.json; echo; head -c 400 $out/${tag}_train_c5_n$N.json; echo
+tail -3 $out/${tag}_bench_n$N.err

@@ -29,6 +29,8 @@ def main():
         print(json.dumps(r), flush=True)
     out["table"] = probe.measure_l2_peaks(dev)     # the interleaved fp16 table's size (6 664 784 x 8 B) + an HBM-sized stream
     print(json.dumps(out["table"]), flush=True)
+    out["red"] = probe.measure_red_peak(dev)       # scatter rate into the fp32 table gradient (hash-grid backward)
+    print(json.dumps(out["red"]), flush=True)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", "l2_peak.json"), "w") as f:
         json.dump(out, f, indent=1)

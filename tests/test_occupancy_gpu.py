@@ -85,6 +85,7 @@ def test_sweep_points_and_cells_bit_exact(cuda):
     assert bits_equal(xyzs.view(C, 2 * N, 3), g["occ_partial_points"])
     # ---- generator mode: uniform in the cell, deterministic in the seed, different across seeds ----
     a = torch.empty(n, 3, device=cuda); b = torch.empty(n, 3, device=cuda); c2 = torch.empty(n, 3, device=cuda)
+    flat = torch.empty(n, dtype=torch.int32, device=cuda)
     for buf, seed in ((a, 7), (b, 7), (c2, 8)):
         call("inerf_occupancy_points", C, G, bound, None, G ** 3, None, seed, ptr(buf), ptr(flat), st)
     assert torch.equal(a, b) and not torch.equal(a, c2)
