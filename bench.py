@@ -224,7 +224,8 @@ def _init_dist():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        from datetime import timedelta
+        dist.init_process_group("nccl", device_id=dev, timeout=timedelta(seconds=180))
     from instance_nerf_b200 import _lib
     _lib.lib()  # fail loudly if libinerf_b200.so is missing
     return rank, world, local_rank, dev

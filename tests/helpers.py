@@ -66,3 +66,16 @@ def bits_equal(a, b):
     if a.dtype.kind == "f":
         return np.array_equal(a.view(np.uint32 if a.itemsize == 4 else np.uint16), b.view(np.uint32 if b.itemsize == 4 else np.uint16))
     return np.array_equal(a, b)
+
+
+def record_metric(name, **kv):
+    """Append a measured figure of a GPU test to gpurun_out/test_metrics.jsonl (brought back by gpurun; best effort)."""
+    import json
+    import os
+    try:
+        root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        os.makedirs(os.path.join(root, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(root, "gpurun_out", "test_metrics.jsonl"), "a") as f:
+            f.write(json.dumps({"test": name, **kv}) + "\n")
+    except OSError:
+        pass

@@ -22,7 +22,8 @@ def _worker(rank, world, port, ret):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     torch.cuda.set_device(rank)
     dev = torch.device("cuda", rank)
-    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    from datetime import timedelta
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev, timeout=timedelta(seconds=90))
     try:
         import bench
         from instance_nerf_b200 import parallel
@@ -70,6 +71,7 @@ def _worker(rank, world, port, ret):
         dist.destroy_process_group()
 
 
+@pytest.mark.timeout(420)
 def test_dp_training_two_gpus(cuda):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")

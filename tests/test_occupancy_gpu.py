@@ -15,7 +15,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import bits_equal
+from helpers import bits_equal, record_metric
 from test_train_gpu import _gold_model, _host_gold
 
 pytestmark = pytest.mark.gpu
@@ -157,6 +157,8 @@ def test_update_extra_state_matches_reference(cuda, tag):
         flips = int(((gb != wb) & single).sum())
         print(f"[occupancy {tag}] {what}: median rel {np.median(rel):.2e}, max {rel.max():.2e}, threshold bit flips {flips} / {int(single.sum())} "
               f"(cells sampled once), {len(dup_cells)} duplicate cells")
+        record_metric(f"occupancy_{tag}", what=what, median_rel=float(np.median(rel)), max_rel=float(rel.max()), bit_flips=flips,
+                      cells_sampled_once=int(single.sum()), duplicate_cells=len(dup_cells))
         assert flips <= max_flips, (what, flips)
 
     # (2) the whole update on the device (fused fp16 density sweep), same draws
@@ -217,6 +219,8 @@ def test_update_extra_state_full_size_no_host_sync(cuda):
     flips = int((out["fused"][1] != out["modular"][1]).sum())
     print(f"[occupancy] fused vs modular-autocast sweep, 4 x 128^3: density median rel {float(rel.median()):.2e}, p99.9 {float(rel.quantile(0.999)):.2e}; "
           f"occupancy bits flipped {flips} / {out['fused'][1].size} ({flips / out['fused'][1].size:.2e})")
+    record_metric("occupancy_full_size_fused_vs_modular_autocast", density_median_rel=float(rel.median()), density_p999_rel=float(rel.quantile(0.999)),
+                  bits_flipped=flips, bits=int(out["fused"][1].size))
     assert float(rel.median()) < 2e-3 and flips < out["fused"][1].size * 2e-3
     occ = float(np.unpackbits(m.density_bitfield.cpu().numpy()).mean())
     assert 0.0 < occ < 1.0 and m.mean_density > 0
@@ -234,4 +238,5 @@ def test_update_extra_state_full_size_no_host_sync(cuda):
     m.iter_density = 16
     t_part = ms(m.update_extra_state)
     print(f"[occupancy] update_extra_state at C=4, 128^3: full sweep {t_full:.3f} ms, partial update {t_part:.3f} ms")
+    record_metric("update_extra_state_ms", full_sweep_ms=t_full, partial_update_ms=t_part, cascades=4, grid=128)
     del bits0

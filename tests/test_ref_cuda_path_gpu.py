@@ -26,6 +26,9 @@ def test_c2_frame_matches_reference_cuda_path(ref, cuda):
     e_prob = float((torch.softmax(got["instance_mask_logits"][0], -1) - torch.softmax(want["instance_mask_logits"], -1)).abs().max())
     agree = float((got["instance_mask_logits"][0].argmax(-1) == want["instance_mask_logits"].argmax(-1)).float().mean())
     print(f"[c2 frame vs reference CUDA path] max abs diff image {e_img:.2e} depth {e_dep:.2e} instance-prob {e_prob:.2e}, argmax agreement {agree:.6f}")
+    from helpers import record_metric
+    record_metric("c2_frame_vs_reference_cuda_path", image=e_img, depth=e_dep, instance_prob=e_prob, argmax_agreement=agree,
+                  evaluated_samples_reference=int(want["evaluated"]))
     assert e_img <= 1e-3 and e_dep <= 1e-3 and e_prob <= 1e-3
     assert agree == 1.0
 
@@ -48,4 +51,6 @@ def test_reference_train_step_runs_and_matches_product_loss(ref, cuda):
     tr = MaskTrainStep(model, lr=1e-2, fp16=True, patch_size=8, label_regularization_weight=0.1, **kw)
     l_ours = float(tr.step(batch))
     print(f"[train step] first-step loss: reference kernels {l_ref:.6f}, product {l_ours:.6f}")
+    from helpers import record_metric
+    record_metric("train_step_first_loss", reference_kernels=l_ref, product=l_ours)
     assert abs(l_ours - l_ref) <= 2e-3 * max(1.0, abs(l_ref))
