@@ -81,16 +81,28 @@ def build_scene_and_model(device=None, K=K_INST, n_poses=N_POSES):
 
 def train_batches(dev, scene, poses, n_rays, rank, world, n=8):
     """`n` training batches of `n_rays` rays as 8x8 patches (nerf/utils.py:83-100) with analytic first-hit labels; rays from the
-    product's get_rays (one launch of inerf_get_rays per batch)."""
+    product's get_rays (one launch of inerf_get_rays per pose).  c3-sized batches (<= 8192 rays) come from ONE camera pose, as
+    the reference's loader yields them (provider.py:635 batch_size 1); the large data-parallel batches (c5) take an equal share
+    of patches from every pose, so that the marched-sample count -- which varies 2x between poses -- is the same mix on every
+    rank and every step (weak scaling compares equal work per GPU)."""
     import numpy as np
     import torch
     from instance_nerf_b200.nerf.utils import get_rays
 
     out = []
+    n_poses = poses.shape[0]
     for i in range(n):
         g = torch.Generator(device=dev).manual_seed(100 + i * world + rank)
-        r = get_rays(poses[(i * world + rank) % poses.shape[0]][None].to(dev), intrinsics(), H_IMG, W_IMG, N=n_rays, patch_size=8, generator=g)
-        o, d = r["rays_o"].reshape(-1, 3).contiguous(), r["rays_d"].reshape(-1, 3).contiguous()
+        if n_rays <= 8192:
+            sel, per = [(i * world + rank) % n_poses], n_rays
+        else:
+            sel, per = list(range(n_poses)), n_rays // n_poses
+        os_, ds_ = [], []
+        for p in sel:
+            r = get_rays(poses[p][None].to(dev), intrinsics(), H_IMG, W_IMG, N=per, patch_size=8, generator=g)
+            os_.append(r["rays_o"].reshape(-1, 3))
+            ds_.append(r["rays_d"].reshape(-1, 3))
+        o, d = torch.cat(os_).contiguous(), torch.cat(ds_).contiguous()
         labels = torch.from_numpy(scene.first_hit_labels(o.cpu().numpy().astype(np.float64), d.cpu().numpy().astype(np.float64)))
         out.append({"rays_o": o[None], "rays_d": d[None], "masks": labels[None].to(dev)})
     return out

@@ -167,8 +167,11 @@ class MaskTrainStep:
         if guard is not None:
             loss = guard(loss)
         self.scaler.scale(loss).backward()
-        if self.bucket is not None and flag is not None:
-            self.bucket.extra.copy_(flag())
+        if self.bucket is not None:     # the "a rank overflowed its budget" slot rides in the gradient all-reduce; eager steps never overflow
+            if flag is not None:
+                self.bucket.extra.copy_(flag())
+            else:
+                self.bucket.extra.zero_()
         return loss.detach()
 
     def _exchange(self):
@@ -252,7 +255,9 @@ class MaskTrainStep:
             model._n_valid_ptr = None
         model.local_step = slot                   # capture advanced it; replays always use the captured slot
         self.global_step -= 1
-        self._graph = (g, static, loss, budget, counter, g2)
+        # `limit`, `inf`, `one` are read by the captured kernels on every replay: they must outlive this function (a tensor freed
+        # here goes back to the caching allocator and the graph would read whatever lands in its block next)
+        self._graph = (g, static, loss, budget, counter, g2, (limit, inf, one))
         self._graph_key = tuple((k, tuple(v.shape), v.dtype) for k, v in static.items())
         self.graph_captures += 1
 
@@ -271,7 +276,7 @@ class MaskTrainStep:
                 self._graph_key = key
                 return loss
             self._capture(data)
-        g, static, loss, budget, counter, g2 = self._graph
+        g, static, loss, budget, counter, g2, _keep = self._graph
         for k, v in tensors.items():
             static[k].copy_(v, non_blocking=True)
         g.replay()
