@@ -46,6 +46,11 @@ struct BSmem {
 // 5.02 ms -> 16 warps 4.79 ms -> + 16-byte REDs for x-neighbour pairs 4.24 ms.
 constexpr uint32_t kBwdChainT = 256, kBwdScatterT = 512, kBwdThreads = kBwdChainT + kBwdScatterT;
 constexpr uint32_t kScatLevels = 16 / (kBwdScatterT / kTile);   // levels per scatter thread
+#ifdef INERF_SCAT_CONTIG   // A/B only: contiguous level groups per scatter thread (the round-2 first version)
+#define INERF_SCAT_LEVEL(li) (half * kScatLevels + (li))
+#else
+#define INERF_SCAT_LEVEL(li) (half + (li) * (16 / kScatLevels))
+#endif
 constexpr uint32_t kBwdRegsChain = 104, kBwdRegsScatter = 64;
 static_assert(kBwdChainT * kBwdRegsChain + kBwdScatterT * kBwdRegsScatter <= kBwdThreads * 80, "setmaxnreg budget exceeds the CTA's allocation");
 constexpr uint32_t kSbo128 = sbo_of(128), kSbo64 = sbo_of(64), kSbo48 = sbo_of(48);
@@ -167,21 +172,51 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_field_backward_mask(inerf_fi
 
     if (chain_role) {
     umma::reg_alloc<kBwdRegsChain>();
+    // The tile's inputs -- X0 (96 B / row) and dL/dlogits (4K B / row) -- are PREFETCHED into registers one tile ahead (issued
+    // right after the first MMAs of the current tile), so their ~1 us of HBM latency is off the chain's critical path (the chain
+    // alone took 5.7 us per tile).  16-byte loads; thread (row, half) takes the 8-column logit chunks half,
+    // half + 2 (K <= 32 needs no more; further chunks of a wider head are loaded in place).  Columns >= K of the dY tile are
+    // never written: they keep the zeros of the initial clear.
+    const uint32_t nch = (K + 7u) >> 3;                     // 8-column chunks of dY that carry data
+    const bool vec_ok = (K & 3u) == 0 && (((uintptr_t)p.grad_logits) & 15u) == 0;
+    uint4 px[3];
+    float4 pg[4];
+    auto prefetch = [&](uint32_t tile_n) {
+        const uint32_t sn = tile_n * kTile + row;
+        const bool live_n = tile_n < num_tiles && sn < B_eff;
+#pragma unroll
+        for (uint32_t c = 0; c < 3; c++) px[c] = live_n ? __ldg(p.x0 + (size_t)sn * 6 + half * 3 + c) : make_uint4(0u, 0u, 0u, 0u);
+        const float4* g4 = reinterpret_cast<const float4*>(p.grad_logits + (size_t)sn * K);
+#pragma unroll
+        for (uint32_t j = 0; j < 2; j++) {
+            const uint32_t chunk = half + 2 * j;
+            const bool ok0 = vec_ok && live_n && chunk * 8 < K, ok1 = vec_ok && live_n && chunk * 8 + 4 < K;
+            pg[2 * j] = ok0 ? __ldg(g4 + chunk * 2) : make_float4(0.f, 0.f, 0.f, 0.f);
+            pg[2 * j + 1] = ok1 ? __ldg(g4 + chunk * 2 + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    };
+    prefetch(blockIdx.x);
     for (uint32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, tiles_done++) {
         const uint32_t s = tile * kTile + row;
         const bool live = s < B_eff;
         // ---- S0: X0 and dY rows -> operand tiles --------------------------------------------------------------
 #pragma unroll
-        for (uint32_t c = 0; c < 3; c++) {
-            const uint32_t chunk = half * 3 + c;
-            const uint4 v = live ? __ldg(p.x0 + (size_t)s * 6 + chunk) : make_uint4(0u, 0u, 0u, 0u);
-            *reinterpret_cast<uint4*>(smem + BSmem::TX + umma::tile_off(row, chunk * 8, kLBO, kSbo48)) = v;
-        }
-        {
-            const float* g = p.grad_logits + (size_t)s * K;
+        for (uint32_t c = 0; c < 3; c++)
+            *reinterpret_cast<uint4*>(smem + BSmem::TX + umma::tile_off(row, (half * 3 + c) * 8, kLBO, kSbo48)) = px[c];
+        if (vec_ok) {
 #pragma unroll
-            for (uint32_t c = 0; c < 4; c++) {
-                const uint32_t k0 = half * 32 + c * 8;
+            for (uint32_t j = 0; j < 2; j++) {
+                const uint32_t chunk = half + 2 * j;
+                if (chunk < nch)
+                    *reinterpret_cast<uint4*>(smem + BSmem::TG + umma::tile_off(row, chunk * 8, kLBO, kSbo128)) =
+                        make_uint4(h2_bits(__floats2half2_rn(pg[2 * j].x, pg[2 * j].y)), h2_bits(__floats2half2_rn(pg[2 * j].z, pg[2 * j].w)),
+                                   h2_bits(__floats2half2_rn(pg[2 * j + 1].x, pg[2 * j + 1].y)), h2_bits(__floats2half2_rn(pg[2 * j + 1].z, pg[2 * j + 1].w)));
+            }
+        }
+        {   // chunks the prefetch does not cover: K > 32, or a K / alignment the 16-byte loads cannot serve
+            const float* g = p.grad_logits + (size_t)s * K;
+            for (uint32_t chunk = vec_ok ? 4u + half : half; chunk < nch; chunk += 2) {
+                const uint32_t k0 = chunk * 8;
                 uint32_t q[4];
 #pragma unroll
                 for (uint32_t i = 0; i < 4; i++) {
@@ -201,6 +236,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_field_backward_mask(inerf_fi
             issue_gemm2(sbase, BSmem::TG, kSbo128, BSmem::W + BwdWeights::w2t, kSbo64, 64, 64, tmem + T_b);
             umma::commit(bar);
         }
+        prefetch(tile + gridDim.x);   // next tile's inputs: in flight during the four MMA stages of this one
         wait_mma();
         const uint32_t mask1 = epi_relu32(tmem + T_a + lane_base + half * 32, smem, BSmem::TH, row, 64 + half * 32);   // H1 -> TH[:, 64:128]
         publish();
@@ -292,11 +328,21 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_field_backward_mask(inerf_fi
         umma::mbar_wait(&df_full[db], (it >> 1) & 1u);
         uint32_t v[2 * kScatLevels];
         {
-            const float* src = reinterpret_cast<const float*>(smem + BSmem::DF) + db * (kTile * 32) + (half * 2 * kScatLevels) * kTile + row;
+            // scatter thread (row, q) owns levels q, q + 4, q + 8, q + 12 (INERF_SCAT_LEVEL(li)): every warp gets run-reduced coarse
+            // levels AND RED-heavy fine ones.  With contiguous level groups only the 8 warps of the fine levels issued REDs and
+            // that path ran at 46 % of the measured RED rate while the other 8 warps waited (4.24 -> 3.x ms).
+            const float* src = reinterpret_cast<const float*>(smem + BSmem::DF) + db * (kTile * 32) + row;
 #pragma unroll
-            for (uint32_t i = 0; i < 2 * kScatLevels; i++) v[i] = __float_as_uint(src[i * kTile]);
+            for (uint32_t li = 0; li < kScatLevels; li++) {
+                v[2 * li] = __float_as_uint(src[(2 * INERF_SCAT_LEVEL(li)) * kTile]);
+                v[2 * li + 1] = __float_as_uint(src[(2 * INERF_SCAT_LEVEL(li) + 1) * kTile]);
+            }
         }
         umma::mbar_arrive(&df_empty[db]);   // the values are in registers: the chain may refill this buffer
+#ifdef INERF_DBG_NO_SCATTER
+        if (v[0] == 0x7fc12345u) p.grad_table[0].x = 1.f;   // keep v alive
+        continue;
+#endif
         {
             // Consecutive rows of a tile are consecutive samples of the same ray (the stream is sorted by ray and by t), so on the
             // coarse levels whole runs of lanes fall into the SAME cell: left alone, their atomics serialise on a handful of
@@ -311,13 +357,14 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_field_backward_mask(inerf_fi
 #pragma unroll
             for (uint32_t li = 0; li < kScatLevels; li++) {
                 float g0 = ok ? __uint_as_float(v[2 * li]) : 0.f, g1 = ok ? __uint_as_float(v[2 * li + 1]) : 0.f;
-                const LevelGeom g = lg[half * kScatLevels + li];
+                const uint32_t level = INERF_SCAT_LEVEL(li);
+                const LevelGeom g = lg[level];
                 uint32_t idx[8];
                 float w[8];
                 float xs[3] = {ok ? x01[0] : 0.f, ok ? x01[1] : 0.f, ok ? x01[2] : 0.f};
                 level_corners(xs, g, idx, w);
                 float2* base = p.grad_table + g.offset;
-                if (half * kScatLevels < 8) {   // levels 0..7 (warp-uniform)
+                if (level < 8) {   // levels 0..7 (warp-uniform)
                     // run heads: first lane, or a lane whose cell differs from the previous lane's (corner 0 and corner 7
                     // together identify the cell; a hash collision only splits or merges runs of identical addresses)
                     const uint32_t p0 = __shfl_up_sync(0xffffffffu, idx[0], 1), p7 = __shfl_up_sync(0xffffffffu, idx[7], 1);
@@ -345,6 +392,10 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_field_backward_mask(inerf_fi
                 } else if (g0 != 0.f || g1 != 0.f) {
                     // x-neighbour corners (2i, 2i+1) sit in one 16-byte aligned slot whenever the cell's x index is even (prime[0] = 1:
                     // entry a and a ^ 1): one 16-byte RED instead of two 8-byte ones (-11 % kernel time on B200)
+#ifdef INERF_DBG_NO_RED
+                    if (__float_as_uint(w[0] * g0 + w[7] * g1) == 0x7fc12345u && idx[3] == 0x12345u) p.grad_table[idx[0]].x = 1.f;
+                    continue;
+#endif
 #pragma unroll
                     for (uint32_t c = 0; c < 8; c += 2) {
                         const float2 va = make_float2(__fmul_rn(w[c], g0), __fmul_rn(w[c], g1));

@@ -31,6 +31,7 @@ class FusedAdam(torch.optim.Optimizer):
             raise RuntimeError("FusedAdam does not take a closure")
         grad_scale = getattr(self, "grad_scale", None)
         found_inf = getattr(self, "found_inf", None)
+        advanced = []          # distinct step counters touched by this call: ONE advance launch each (normally one in total)
         for group in self.param_groups:
             lr, (b1, b2), eps = float(group["lr"]), group["betas"], float(group["eps"])
             for p in group["params"]:
@@ -40,11 +41,16 @@ class FusedAdam(torch.optim.Optimizer):
                     raise RuntimeError("FusedAdam: fp32 CUDA parameters only (there is no CPU fallback)")
                 st = self.state[p]
                 if not st:
-                    st["step"] = torch.zeros((), dtype=torch.float32, device=p.device)
+                    # every parameter of a device steps together: they share one device-side step counter
+                    shared = next((s_["step"] for s_ in self.state.values() if "step" in s_ and s_["step"].device == p.device), None)
+                    st["step"] = shared if shared is not None else torch.zeros((), dtype=torch.float32, device=p.device)
                     st["exp_avg"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
                     st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
                 s = stream_ptr(p.device)
                 call("inerf_adam_step", ptr(p), ptr(p.grad), ptr(st["exp_avg"]), ptr(st["exp_avg_sq"]), p.numel(), lr, float(b1), float(b2), eps,
                      ptr(st["step"]), ptr(grad_scale), ptr(found_inf), float(self.grad_div), s)
-                call("inerf_adam_advance", ptr(st["step"]), ptr(found_inf), s)
+                if not any(t is st["step"] for t in advanced):
+                    advanced.append(st["step"])
+        for t in advanced:
+            call("inerf_adam_advance", ptr(t), ptr(found_inf), stream_ptr(t.device))
         return None
