@@ -127,6 +127,18 @@ int inerf_composite_rays_with_masks_train_backward(const float *grad_weights_sum
                                                    float *grad_sigmas, float *grad_rgbs, float *grad_masks_acc,
                                                    float *grad_masks, void *stream);
 
+/* Same backward for a DENSE sample stream (every row of the gradient buffers belongs to exactly one ray of `rays`, as the
+ * count -> scan -> expand marcher produces it): the kernel writes the zero gradients of the samples behind a ray's
+ * termination itself, so grad_sigmas / grad_rgbs / grad_masks may be uninitialised memory (no memset of 16 + 4K bytes per
+ * sample), and grad_sigmas / grad_rgbs may be NULL when the caller does not need them (instance stage: the sigma and colour
+ * nets are frozen, nerf/utils.py:1242-1246).  K == 0: composite_rays_train_backward (raymarching.h:16).  K <= 64. */
+int inerf_composite_rays_with_masks_train_backward_dense(const float *grad_weights_sum, const float *grad_image,
+                                                         const float *grad_mask_out, const float *sigmas, const float *rgbs,
+                                                         const float *masks, const float *deltas, const int32_t *rays,
+                                                         const float *weights_sum, const float *image, const float *mask_out,
+                                                         uint32_t M, uint32_t N, uint32_t K, float T_thresh,
+                                                         float *grad_sigmas, float *grad_rgbs, float *grad_masks, void *stream);
+
 /* -------------------------------------------------------------- inference -- */
 
 /* raymarching.h:20 march_rays (raymarching.cu:958-1073); xyzs/dirs/deltas pre-zeroed by the caller */
@@ -260,6 +272,25 @@ int inerf_field_pack_weights_bwd(const float *mask0, const float *mask1, const f
 int inerf_field_backward_mask(const inerf_field_desc *desc, const void *weights_bwd, const float *xyzs, const void *x0,
                               const float *grad_logits, uint32_t B, float *grad_table, float *grad_w0, float *grad_w1,
                               float *grad_w2, void *stream);
+
+/* ---- stage-1 (RGB-sigma) training: Trainer.train_step (nerf/utils.py:536-632) on network.py:96-127 ----------------------
+ * inerf_field_forward_train_rgb = inerf_field_forward with the instance head off, plus `xs_save` fp16 [B, 64]: the inputs of
+ * sigma_net (32 table features) and color_net (SH16 | geo15 | 0) per sample.
+ * inerf_field_backward_rgb replaces, in ONE launch, what autograd runs for that network: 10 GEMMs, the ReLU / sigmoid /
+ * trunc_exp (activation.py:13-17) backward kernels and kernel_grid_backward of `encoder` (gridencoder.cu:245-337).
+ *   sigmas / rgbs          the forward outputs (sigma unscaled), grad_sigmas / grad_rgbs their gradients (float [B], [B,3])
+ *   grad_table             float [offsets[L], 2] (encoder.embeddings.grad)
+ *   grad_ws0 [64,32], grad_ws1 [16,64], grad_wc0 [64,31], grad_wc1 [64,64], grad_wc2 [3,64]   (nn.Linear layout)
+ * All gradient outputs are ACCUMULATED into (atomics): the caller zeroes them or passes .grad buffers. */
+size_t inerf_field_rgb_bwd_weights_bytes(void);
+int inerf_field_pack_weights_rgb_bwd_device(const float *sigma0, const float *sigma1, const float *color0, const float *color1,
+                                            const float *color2, void *packed_bwd, void *stream);
+int inerf_field_forward_train_rgb(const inerf_field_desc *desc, const float *xyzs, const float *dirs, uint32_t B, float *sigmas,
+                                  float *rgbs, void *xs_save, void *stream);
+int inerf_field_backward_rgb(const inerf_field_desc *desc, const void *weights_bwd, const float *xyzs, const void *xs,
+                             const float *sigmas, const float *rgbs, const float *grad_sigmas, const float *grad_rgbs,
+                             uint32_t B, float *grad_table, float *grad_ws0, float *grad_ws1, float *grad_wc0,
+                             float *grad_wc1, float *grad_wc2, void *stream);
 
 /*
  * Whole-frame inference render in ONE persistent launch, replacing the host

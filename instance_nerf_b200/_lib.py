@@ -77,6 +77,7 @@ _PROTOS = {
     "inerf_composite_rays_train_backward": [_P, _P, _P, _P, _P, _P, _P, _P, _U, _U, _F, _P, _P, _P],
     "inerf_composite_rays_with_masks_train_forward": [_P, _P, _P, _P, _P, _U, _U, _U, _F, _P, _P, _P, _P, _P],
     "inerf_composite_rays_with_masks_train_backward": [_P] * 11 + [_U, _U, _U, _F, _P, _P, _P, _P, _P],
+    "inerf_composite_rays_with_masks_train_backward_dense": [_P] * 11 + [_U, _U, _U, _F, _P, _P, _P, _P],
     "inerf_march_rays": [_U, _U, _P, _P, _P, _P, _F, _F, _U, _U, _U, _P, _P, _P, _P, _P, _P, _P, _P],
     "inerf_composite_rays": [_U, _U, _F, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "inerf_composite_rays_with_masks": [_U, _U, _U, _F, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
@@ -103,6 +104,9 @@ _PROTOS = {
     "inerf_field_pack_weights_bwd": [_P, _P, _P, _U, _P],
     "inerf_field_pack_weights_device": [_P] * 8 + [_U, _P, _P, _P],
     "inerf_field_backward_mask": [POINTER(FieldDesc), _P, _P, _P, _P, _U, _P, _P, _P, _P, _P],
+    "inerf_field_forward_train_rgb": [POINTER(FieldDesc), _P, _P, _U, _P, _P, _P, _P],
+    "inerf_field_pack_weights_rgb_bwd_device": [_P, _P, _P, _P, _P, _P, _P],
+    "inerf_field_backward_rgb": [POINTER(FieldDesc), _P, _P, _P, _P, _P, _P, _P, _U, _P, _P, _P, _P, _P, _P, _P],
     "inerf_adam_step": [_P, _P, _P, _P, ctypes.c_uint64, _F, _F, _F, _F, _P, _P, _P, _F, _P],
     "inerf_adam_advance": [_P, _P, _P],
     "inerf_render_fused": [POINTER(FieldDesc), _P, _P, _P, _P, _P, _U, _U, _U, _F, _U, _F, _P, _P, _P, _P, _P, _P],
@@ -112,6 +116,7 @@ _SPECIAL = {
     "inerf_error_string": ([c_int], c_char_p),
     "inerf_field_weights_bytes": ([_U], c_size_t),
     "inerf_field_bwd_weights_bytes": ([], c_size_t),
+    "inerf_field_rgb_bwd_weights_bytes": ([], c_size_t),
     "inerf_march_scratch_floats": ([_U, _U], c_size_t),
     "inerf_occupancy_sample_scratch_ints": ([_U, _U], c_size_t),
 }

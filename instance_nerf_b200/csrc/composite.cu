@@ -245,7 +245,7 @@ __global__ void __launch_bounds__(32 * BwdCfg<KPL>::kWarps) k_composite_train_bw
     const float* __restrict__ sigmas, const float* __restrict__ rgbs, const float* __restrict__ masks,
     const float* __restrict__ deltas, const int32_t* __restrict__ rays, const float* __restrict__ weights_sum,
     const float* __restrict__ image, const float* __restrict__ mask_out, uint32_t M, uint32_t N, uint32_t K, float T_thresh,
-    float* __restrict__ grad_sigmas, float* __restrict__ grad_rgbs, float* __restrict__ grad_masks) {
+    float* __restrict__ grad_sigmas, float* __restrict__ grad_rgbs, float* __restrict__ grad_masks, bool zero_tail) {
     constexpr int KMAX = KPL > 0 ? 32 * KPL : 1;
     __shared__ float4 stage_all[KPL > 0 ? BwdCfg<KPL>::kWarps * 32 * (KMAX / 4) : 1];
     const uint32_t lane = threadIdx.x & 31;
@@ -340,10 +340,36 @@ __global__ void __launch_bounds__(32 * BwdCfg<KPL>::kWarps) k_composite_train_bw
             Pc = __shfl_sync(kFull, Prun, 31);
         }
         if (inc) {
-            grad_sigmas[s] = d0 * gs;
-            grad_rgbs[(size_t)s * 3] = gr * w; grad_rgbs[(size_t)s * 3 + 1] = gg * w; grad_rgbs[(size_t)s * 3 + 2] = gb * w;
+            if (grad_sigmas) grad_sigmas[s] = d0 * gs;
+            if (grad_rgbs) { grad_rgbs[(size_t)s * 3] = gr * w; grad_rgbs[(size_t)s * 3 + 1] = gg * w; grad_rgbs[(size_t)s * 3 + 2] = gb * w; }
         }
-        if (term) break;
+        if (term) {
+            // Samples behind the one that terminated the ray have zero gradients (raymarching.cu:905-907 leaves them as the
+            // caller's zero fill).  With zero_tail the kernel writes those zeros itself, so the caller's buffers need no
+            // memset (148 B / sample of fills at K = 32 for the three gradient streams).
+            if (zero_tail) {
+                for (uint32_t r0 = base + m; r0 < num_steps; r0 += 32) {
+                    const uint32_t r = r0 + lane;
+                    if (r < num_steps) {
+                        const size_t z = (size_t)offset + r;
+                        if (grad_sigmas) grad_sigmas[z] = 0.f;
+                        if (grad_rgbs) { grad_rgbs[z * 3] = 0.f; grad_rgbs[z * 3 + 1] = 0.f; grad_rgbs[z * 3 + 2] = 0.f; }
+                    }
+                }
+                if (KPL > 0) {
+                    if (vec) {
+                        float4* dst = reinterpret_cast<float4*>(grad_masks + (size_t)(offset + base + m) * K);
+                        const uint32_t n16 = (num_steps - base - m) * C4;
+                        for (uint32_t i = lane; i < n16; i += 32) dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    } else {
+                        float* dst = grad_masks + (size_t)(offset + base + m) * K;
+                        const uint32_t nf = (num_steps - base - m) * K;
+                        for (uint32_t i = lane; i < nf; i += 32) dst[i] = 0.f;
+                    }
+                }
+            }
+            break;
+        }
         Tc = __shfl_sync(kFull, T_after, 31);
         Qc = __shfl_sync(kFull, Qrun, 31);
     }
@@ -449,18 +475,20 @@ int composite_train_fwd(const float* sigmas, const float* rgbs, const float* mas
 int composite_train_bwd(const float* grad_weights_sum, const float* grad_image, const float* grad_mask_out, const float* sigmas,
                         const float* rgbs, const float* masks, const float* deltas, const int32_t* rays, const float* weights_sum,
                         const float* image, const float* mask_out, uint32_t M, uint32_t N, uint32_t K, float T_thresh,
-                        float* grad_sigmas, float* grad_rgbs, float* grad_masks, void* stream) {
+                        float* grad_sigmas, float* grad_rgbs, float* grad_masks, void* stream, bool dense = false) {
     if (N == 0 || M == 0) return INERF_OK;
     INERF_REQUIRE(grad_weights_sum); INERF_REQUIRE(grad_image); INERF_REQUIRE(sigmas); INERF_REQUIRE(rgbs); INERF_REQUIRE(deltas);
-    INERF_REQUIRE(rays); INERF_REQUIRE(weights_sum); INERF_REQUIRE(image); INERF_REQUIRE(grad_sigmas); INERF_REQUIRE(grad_rgbs);
+    INERF_REQUIRE(rays); INERF_REQUIRE(weights_sum); INERF_REQUIRE(image);
+    if (!dense) { INERF_REQUIRE(grad_sigmas); INERF_REQUIRE(grad_rgbs); }
     if (K) { INERF_REQUIRE(grad_mask_out); INERF_REQUIRE(masks); INERF_REQUIRE(mask_out); INERF_REQUIRE(grad_masks); }
     return dispatch_kpl(K, [&](auto kpl) {
         if constexpr (decltype(kpl)::value <= 2) {   // K <= 64: the ray's logit gradients fit in registers
             constexpr unsigned threads = 32 * BwdCfg<decltype(kpl)::value>::kWarps;
             k_composite_train_bwd_scan<decltype(kpl)::value><<<div_up((unsigned long long)N * 32, threads), threads, 0, (cudaStream_t)stream>>>(
                 grad_weights_sum, grad_image, grad_mask_out, sigmas, rgbs, masks, deltas, rays, weights_sum, image, mask_out, M, N, K,
-                T_thresh, grad_sigmas, grad_rgbs, grad_masks);
+                T_thresh, grad_sigmas, grad_rgbs, grad_masks, dense);
         } else {
+            if (dense) return (int)INERF_ERR_UNSUPPORTED;   // K > 64: the thread-per-ray kernel keeps the reference's contract
             k_composite_train_bwd<decltype(kpl)::value><<<div_up((unsigned long long)N * 32, 256), 256, 0, (cudaStream_t)stream>>>(
                 grad_weights_sum, grad_image, grad_mask_out, sigmas, rgbs, masks, deltas, rays, weights_sum, image, mask_out, M, N, K,
                 T_thresh, grad_sigmas, grad_rgbs, grad_masks);
@@ -517,6 +545,17 @@ extern "C" int inerf_composite_rays_with_masks_train_backward(const float* grad_
     if (K == 0) return INERF_ERR_SIZE;
     return composite_train_bwd(grad_weights_sum, grad_image, grad_mask_out, sigmas, rgbs, masks, deltas, rays, weights_sum, image,
                                mask_out, M, N, K, T_thresh, grad_sigmas, grad_rgbs, grad_masks, stream);
+}
+extern "C" int inerf_composite_rays_with_masks_train_backward_dense(const float* grad_weights_sum, const float* grad_image,
+                                                                    const float* grad_mask_out, const float* sigmas, const float* rgbs,
+                                                                    const float* masks, const float* deltas, const int32_t* rays,
+                                                                    const float* weights_sum, const float* image, const float* mask_out,
+                                                                    uint32_t M, uint32_t N, uint32_t K, float T_thresh, float* grad_sigmas,
+                                                                    float* grad_rgbs, float* grad_masks, void* stream) {
+    if (K > 64) return INERF_ERR_UNSUPPORTED;
+    return composite_train_bwd(grad_weights_sum, grad_image, K ? grad_mask_out : nullptr, sigmas, rgbs, K ? masks : nullptr, deltas, rays,
+                               weights_sum, image, K ? mask_out : nullptr, M, N, K, T_thresh, grad_sigmas, grad_rgbs, K ? grad_masks : nullptr,
+                               stream, true);
 }
 extern "C" int inerf_composite_rays(uint32_t n_alive, uint32_t n_step, float T_thresh, int32_t* rays_alive, float* rays_t,
                                     const float* sigmas, const float* rgbs, const float* deltas, float* weights_sum, float* depth,

@@ -39,7 +39,8 @@ struct WsSmem {
 __global__ void __launch_bounds__(kWsThreads, 1) k_field_forward_ws(inerf_field_desc desc, const float* __restrict__ xyzs,
                                                                     const float* __restrict__ dirs, uint32_t B_rows,
                                                                     float* __restrict__ sigmas, float* __restrict__ rgbs,
-                                                                    float* __restrict__ masks, uint4* __restrict__ x0_save) {
+                                                                    float* __restrict__ masks, uint4* __restrict__ x0_save,
+                                                                    uint4* __restrict__ xs_save) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t K = desc.K, Kp = weight_layout(K).Kp;
     WsCtrl* ctl = reinterpret_cast<WsCtrl*>(smem + WsSmem::ctrl(K));
@@ -82,6 +83,14 @@ __global__ void __launch_bounds__(kWsThreads, 1) k_field_forward_ws(inerf_field_
                     for (uint32_t c = 0; c < 6; c++)
                         x0_save[(size_t)orow * 6 + c] =
                             *reinterpret_cast<const uint4*>(smem + bufs.a_mi + umma::tile_off(tid, c * 8, kLBO, sbo_of(48)));
+                }
+                // stage-1 training: keep the inputs of BOTH nets -- 32 sigma-table features | SH16, geo15, 0 (fp16 [.,64])
+                if (xs_save != nullptr && warp < 4 && orow < B) {
+#pragma unroll
+                    for (uint32_t c = 0; c < 4; c++) {
+                        xs_save[(size_t)orow * 8 + c] = *reinterpret_cast<const uint4*>(smem + bufs.a_es + umma::tile_off(tid, c * 8, kLBO, sbo_of(32)));
+                        xs_save[(size_t)orow * 8 + 4 + c] = *reinterpret_cast<const uint4*>(smem + bufs.a_ci + umma::tile_off(tid, c * 8, kLBO, sbo_of(32)));
+                    }
                 }
             });
             if (warp < 4) {
@@ -310,11 +319,12 @@ extern "C" int inerf_field_pack_weights(const float* sigma0, const float* sigma1
 }
 
 static int field_forward_impl(const inerf_field_desc* desc, const float* xyzs, const float* dirs, uint32_t B, float* sigmas, float* rgbs,
-                              float* masks, void* x0_save, void* stream) {
+                              float* masks, void* x0_save, void* stream, void* xs_save = nullptr) {
     if (int e = validate_desc(desc)) return e;
     if (B == 0) return INERF_OK;
     INERF_REQUIRE(xyzs); INERF_REQUIRE(dirs); INERF_REQUIRE(sigmas); INERF_REQUIRE(rgbs);
     if (x0_save && (((uintptr_t)x0_save & 15u) || masks == nullptr)) return INERF_ERR_ALIGN;
+    if (xs_save && ((uintptr_t)xs_save & 15u)) return INERF_ERR_ALIGN;
     const uint32_t num_tiles = (B + field::kTile - 1) / field::kTile;
     // per-device attribute, cheap to set: no process-global "already done" flag
     cudaError_t e = cudaFuncSetAttribute(k_field_forward_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
@@ -322,7 +332,7 @@ static int field_forward_impl(const inerf_field_desc* desc, const float* xyzs, c
     const uint32_t sms = (uint32_t)device_sm_count();
     const uint32_t grid_ws = num_tiles < sms ? num_tiles : sms;
     k_field_forward_ws<<<grid_ws, kWsThreads, WsSmem::bytes(desc->K), (cudaStream_t)stream>>>(*desc, xyzs, dirs, B, sigmas, rgbs, masks,
-                                                                                             (uint4*)x0_save);
+                                                                                             (uint4*)x0_save, (uint4*)xs_save);
     INERF_LAUNCH_CHECK();
     return INERF_OK;
 }
@@ -351,4 +361,12 @@ extern "C" int inerf_field_forward_train(const inerf_field_desc* desc, const flo
                                          float* rgbs, float* masks, void* x0_save, void* stream) {
     INERF_REQUIRE(x0_save);
     return field_forward_impl(desc, xyzs, dirs, B, sigmas, rgbs, masks, x0_save, stream);
+}
+
+// Stage-1 (RGB-sigma) training forward: sigma / rgb as inerf_field_forward with the instance head off, plus the saved inputs of
+// the sigma and colour nets for inerf_field_backward_rgb.
+extern "C" int inerf_field_forward_train_rgb(const inerf_field_desc* desc, const float* xyzs, const float* dirs, uint32_t B, float* sigmas,
+                                             float* rgbs, void* xs_save, void* stream) {
+    INERF_REQUIRE(xs_save);
+    return field_forward_impl(desc, xyzs, dirs, B, sigmas, rgbs, nullptr, nullptr, stream, xs_save);
 }

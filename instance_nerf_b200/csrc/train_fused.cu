@@ -89,6 +89,29 @@ __device__ __forceinline__ uint32_t epi_relu32(uint32_t taddr, uint8_t* smem, ui
     return mask;
 }
 
+// same, into a tile whose 8-row groups are `sbo` bytes apart
+__device__ __forceinline__ uint32_t epi_relu_to(uint32_t taddr, uint8_t* smem, uint32_t tile_off0, uint32_t sbo, uint32_t row, uint32_t col0) {
+    uint32_t v[2][16];
+    umma::tmem_ld16(taddr, v[0]);
+    umma::tmem_ld16(taddr + 16, v[1]);
+    umma::tmem_ld_wait();
+    uint32_t mask = 0;
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        uint32_t p[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            p[i] = cvt_relu_f16x2(__uint_as_float(v[h][2 * i]), __uint_as_float(v[h][2 * i + 1]));
+            mask |= ((p[i] & 0xffffu) ? 1u : 0u) << (h * 16 + 2 * i);
+            mask |= ((p[i] >> 16) ? 1u : 0u) << (h * 16 + 2 * i + 1);
+        }
+        const uint32_t k = col0 + h * 16;
+        *reinterpret_cast<uint4*>(smem + tile_off0 + umma::tile_off(row, k, kLBO, sbo)) = make_uint4(p[0], p[1], p[2], p[3]);
+        *reinterpret_cast<uint4*>(smem + tile_off0 + umma::tile_off(row, k + 8, kLBO, sbo)) = make_uint4(p[4], p[5], p[6], p[7]);
+    }
+    return mask;
+}
+
 // 32 TMEM columns . mask -> fp16 -> 4 chunks of a 128-column tile
 __device__ __forceinline__ void epi_masked32(uint32_t taddr, uint32_t mask, uint8_t* smem, uint32_t tile_off0, uint32_t row, uint32_t col0) {
     uint32_t v[2][16];
@@ -107,6 +130,101 @@ __device__ __forceinline__ void epi_masked32(uint32_t taddr, uint32_t mask, uint
         const uint32_t k = col0 + h * 16;
         *reinterpret_cast<uint4*>(smem + tile_off0 + umma::tile_off(row, k, kLBO, kSbo128)) = make_uint4(p[0], p[1], p[2], p[3]);
         *reinterpret_cast<uint4*>(smem + tile_off0 + umma::tile_off(row, k + 8, kLBO, kSbo128)) = make_uint4(p[4], p[5], p[6], p[7]);
+    }
+}
+
+// ---- scatter role (shared by the instance-stage and the stage-1 backward kernels) ------------------------------------------------
+// 16 warps, thread = (row, 4 interleaved levels): takes the 32 feature gradients of a sample from the double-buffered fp32 tile
+// the chain warps fill and adds w * g to the 8 corners of each of its levels in the fp32 table gradient.
+__device__ __forceinline__ void scatter_role(const inerf_field_desc& desc, const float* __restrict__ xyzs, float2* __restrict__ grad_table,
+                                             const LevelGeom* lg, const uint8_t* df_tiles, uint64_t* df_full, uint64_t* df_empty,
+                                             uint32_t num_tiles, uint32_t B_eff, uint32_t rt) {
+    const uint32_t lane = rt & 31, row = rt & (kTile - 1), half = rt >> 7;
+    const float inv2b = __fdiv_rn(1.0f, __fmul_rn(2.0f, desc.bound));
+    uint32_t it = 0;
+    for (uint32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, it++) {
+        const uint32_t s = tile * kTile + row;
+        const bool live = s < B_eff;
+        const uint32_t db = it & 1u;
+        umma::mbar_wait(&df_full[db], (it >> 1) & 1u);
+        uint32_t v[2 * kScatLevels];
+        {
+            // levels interleaved over the scatter threads (scat_level): every warp gets run-reduced coarse levels AND RED-heavy fine
+            // ones.  With contiguous level groups only the 8 warps of the fine levels issued REDs, at 46 % of the measured RED
+            // rate, while the other 8 warps waited: 3.74 -> 3.66 ms; without any scatter the kernel takes 1.28 ms (DESIGN.md 4.4).
+            const float* src = reinterpret_cast<const float*>(df_tiles) + db * (kTile * 32) + row;
+#pragma unroll
+            for (uint32_t li = 0; li < kScatLevels; li++) {
+                v[2 * li] = __float_as_uint(src[(2 * scat_level(half, li)) * kTile]);
+                v[2 * li + 1] = __float_as_uint(src[(2 * scat_level(half, li) + 1) * kTile]);
+            }
+        }
+        umma::mbar_arrive(&df_empty[db]);   // the values are in registers: the chain may refill this buffer
+        {
+            // Consecutive rows of a tile are consecutive samples of the same ray (the stream is sorted by ray and by t), so on the
+            // coarse levels whole runs of lanes fall into the SAME cell: left alone, their atomics serialise on a handful of
+            // addresses in L2.  Levels 0..7 (threads of half 0) therefore reduce each run inside the warp first -- segmented
+            // reduction towards the run's first lane, bounded by the next run head -- and only run heads issue atomics.
+            float x01[3] = {2.f, 2.f, 2.f};
+            if (live) {
+#pragma unroll
+                for (int d = 0; d < 3; d++) x01[d] = __fmul_rn(__fadd_rn(__ldg(xyzs + (size_t)s * 3 + d), desc.bound), inv2b);
+            }
+            const bool ok = live && !(x01[0] < 0.f || x01[0] > 1.f || x01[1] < 0.f || x01[1] > 1.f || x01[2] < 0.f || x01[2] > 1.f);
+#pragma unroll
+            for (uint32_t li = 0; li < kScatLevels; li++) {
+                float g0 = ok ? __uint_as_float(v[2 * li]) : 0.f, g1 = ok ? __uint_as_float(v[2 * li + 1]) : 0.f;
+                const uint32_t level = scat_level(half, li);
+                const LevelGeom g = lg[level];
+                uint32_t idx[8];
+                float w[8];
+                float xs[3] = {ok ? x01[0] : 0.f, ok ? x01[1] : 0.f, ok ? x01[2] : 0.f};
+                level_corners(xs, g, idx, w);
+                float2* base = grad_table + g.offset;
+                if (level < 8) {   // levels 0..7 (warp-uniform)
+                    // run heads: first lane, or a lane whose cell differs from the previous lane's (corner 0 and corner 7
+                    // together identify the cell; a hash collision only splits or merges runs of identical addresses)
+                    const uint32_t p0 = __shfl_up_sync(0xffffffffu, idx[0], 1), p7 = __shfl_up_sync(0xffffffffu, idx[7], 1);
+                    const bool head = lane == 0 || p0 != idx[0] || p7 != idx[7];
+                    const uint32_t heads = __ballot_sync(0xffffffffu, head);
+                    const uint32_t after = lane == 31 ? 0u : (heads >> (lane + 1));
+                    const uint32_t next_head = after ? (lane + 1 + (uint32_t)__ffs(after) - 1u) : 32u;
+                    float a0[8], a1[8];
+#pragma unroll
+                    for (uint32_t c = 0; c < 8; c++) { a0[c] = __fmul_rn(w[c], g0); a1[c] = __fmul_rn(w[c], g1); }
+#pragma unroll
+                    for (uint32_t off = 1; off < 32; off <<= 1) {
+                        const bool take = lane + off < next_head;
+#pragma unroll
+                        for (uint32_t c = 0; c < 8; c++) {
+                            const float o0 = __shfl_down_sync(0xffffffffu, a0[c], off), o1 = __shfl_down_sync(0xffffffffu, a1[c], off);
+                            if (take) { a0[c] += o0; a1[c] += o1; }
+                        }
+                    }
+                    if (head) {
+#pragma unroll
+                        for (uint32_t c = 0; c < 8; c++)
+                            if (a0[c] != 0.f || a1[c] != 0.f) atomicAdd(base + idx[c], make_float2(a0[c], a1[c]));
+                    }
+                } else if (g0 != 0.f || g1 != 0.f) {
+                    // x-neighbour corners (2i, 2i+1) sit in one 16-byte aligned slot whenever the cell's x index is even (prime[0] = 1:
+                    // entry a and a ^ 1): one 16-byte RED instead of two 8-byte ones (-11 % kernel time on B200)
+#pragma unroll
+                    for (uint32_t c = 0; c < 8; c += 2) {
+                        const float2 va = make_float2(__fmul_rn(w[c], g0), __fmul_rn(w[c], g1));
+                        const float2 vb = make_float2(__fmul_rn(w[c + 1], g0), __fmul_rn(w[c + 1], g1));
+                        if ((idx[c] ^ idx[c + 1]) == 1u) {
+                            const bool odd = idx[c] & 1u;
+                            atomicAdd(reinterpret_cast<float4*>(base + (idx[c] & ~1u)),
+                                      odd ? make_float4(vb.x, vb.y, va.x, va.y) : make_float4(va.x, va.y, vb.x, vb.y));
+                        } else {
+                            atomicAdd(base + idx[c], va);
+                            atomicAdd(base + idx[c + 1], vb);
+                        }
+                    }
+                }
+            }
+        }
     }
 }
 
@@ -315,93 +433,282 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_field_backward_mask(inerf_fi
         }
     }
     } else {
-    // ------------------------------------------------------------------------------------------------ scatter role --
     umma::reg_dealloc<kBwdRegsScatter>();
-    uint32_t it = 0;
-    for (uint32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, it++) {
-        const uint32_t s = tile * kTile + row;
-        const bool live = s < B_eff;
-        const uint32_t db = it & 1u;
-        umma::mbar_wait(&df_full[db], (it >> 1) & 1u);
-        uint32_t v[2 * kScatLevels];
-        {
-            // levels interleaved over the scatter threads (scat_level): every warp gets run-reduced coarse levels AND RED-heavy fine
-            // ones.  With contiguous level groups only the 8 warps of the fine levels issued REDs, at 46 % of the measured RED
-            // rate, while the other 8 warps waited: 3.74 -> 3.66 ms; without any scatter the kernel takes 1.28 ms (DESIGN.md 4.4).
-            const float* src = reinterpret_cast<const float*>(smem + BSmem::DF) + db * (kTile * 32) + row;
+    scatter_role(desc, p.xyzs, p.grad_table, lg, smem + BSmem::DF, df_full, df_empty, num_tiles, B_eff, rt);
+    }
+
+    umma::fence_before_sync();
+    __syncthreads();
+    if (tid < 32) umma::tmem_dealloc<kBwdTmemCols>(tmem);
+}
+
+// =================================================================================================================================
+// inerf_field_backward_rgb: backward of the stage-1 (RGB-sigma) field -- sigma_net (32->64->16) and color_net (32->64->64->3) with
+// the sigma hash table (Trainer.train_step, nerf/utils.py:536-632; network.py:96-127 through autograd: 10 cuBLAS GEMMs, 3
+// ReLU-backward kernels, sigmoid / trunc_exp backward, cat / slice backward, kernel_grid_backward, whole-table zero + cast).
+// Per 128-sample tile, all on tcgen05 (fp16 operands as autocast rounds them, fp32 accumulators in TMEM):
+//
+//   recompute  Hs = relu(E Ws0^T), Hc1 = relu(Ci Wc0^T), Hc2 = relu(Hc1 Wc1^T)        (E, Ci = saved net inputs, fp16 [.,64])
+//   colour     dP = fp16(g_rgb) . rgb (1 - rgb);  dHc2 = (dP Wc2) . [Hc2>0];  dHc1 = (dHc2 Wc1) . [Hc1>0];  dCi = dHc1 Wc0
+//   sigma      dO = [fp16(g_sigma * clamp(sigma, e^-15, e^15)) | dCi[:, 16:31]];  dHs = (dO Ws1) . [Hs>0];  dE = dHs Ws0
+//   dW         [dHc2|dHc1]^T [Hc1|Ci] -> dWc1, dWc0 ;  [dHs|dP|dO]^T [E|Hc2|Hs] -> dWs0, dWc2, dWs1   (diagonal blocks of two
+//              M = 128 products whose operands are the tiles above read MN-major; accumulated ACROSS tiles in TMEM)
+//   scatter    dE (32 feature gradients / sample) -> the fp32 sigma-table gradient (scatter_role).
+struct RgbBwdWeights {   // byte offsets inside the packed blob (B operands, K-major)
+    static constexpr uint32_t ws0 = 0;                    // [64 x 32]  Ws0[o][j]
+    static constexpr uint32_t wc0 = ws0 + 64 * 32 * 2;    // [64 x 32]  Wc0[o][j], j = 31 zero
+    static constexpr uint32_t wc1 = wc0 + 64 * 32 * 2;    // [64 x 64]  Wc1[o][j]
+    static constexpr uint32_t wc2t = wc1 + 64 * 64 * 2;   // [64 x 16]  (n=j, k=o) = Wc2[o][j], o >= 3 zero
+    static constexpr uint32_t wc1t = wc2t + 64 * 16 * 2;  // [64 x 64]  (n=j, k=o) = Wc1[o][j]
+    static constexpr uint32_t wc0t = wc1t + 64 * 64 * 2;  // [32 x 64]  (n=j, k=o) = Wc0[o][j], j = 31 zero
+    static constexpr uint32_t ws1t = wc0t + 32 * 64 * 2;  // [64 x 16]  (n=j, k=o) = Ws1[o][j]
+    static constexpr uint32_t ws0t = ws1t + 64 * 16 * 2;  // [32 x 64]  (n=j, k=o) = Ws0[o][j]
+    static constexpr uint32_t total = ws0t + 32 * 64 * 2;
+};
+struct RSm {   // operand tiles: column ranges of four wide K-major tiles, so that the dW products read them whole
+    static constexpr uint32_t GA = 0;                        // [128 x 128]  dHc2 (64) | dHc1 (64)
+    static constexpr uint32_t HA = GA + kTile * 128 * 2;     // [128 x 96]   Hc1 (64) | Ci (32)
+    static constexpr uint32_t GB = HA + kTile * 96 * 2;      // [128 x 128]  dHs (64) | dP (16) | 0 (16) | dO (16) | 0 (16)
+    static constexpr uint32_t HB = GB + kTile * 128 * 2;     // [128 x 160]  E (32) | Hc2 (64) | Hs (64)
+    static constexpr uint32_t W = HB + kTile * 160 * 2;
+    static constexpr uint32_t DF = W + RgbBwdWeights::total;
+    static constexpr uint32_t MISC = DF + 2 * kTile * 32 * 4;
+    static constexpr uint32_t bytes = MISC + 16 * sizeof(LevelGeom) + 64;
+};
+constexpr uint32_t kSbo96 = sbo_of(96), kSbo160 = sbo_of(160), kSbo32 = sbo_of(32), kSbo16 = sbo_of(16);
+// TMEM columns: three 64-wide working accumulators, one 32-wide, and the two weight-gradient products
+constexpr uint32_t R_a = 0, R_b = 64, R_c = 128, R_x = 192, R_w1 = 224, R_w2 = 320;   // R_w1: 96 columns, R_w2: 160 columns
+static_assert(R_w2 + 160 <= kBwdTmemCols, "TMEM plan");
+static_assert(RSm::bytes <= 227 * 1024, "shared memory plan");
+
+struct RgbBwdParams {
+    const float* xyzs;          // [B, 3]
+    const uint4* xs;            // fp16 [B, 64] = E (32) | Ci (32), 8 x 16 B per row
+    const float* sigmas;        // [B]   forward output (unscaled)
+    const float* rgbs;          // [B, 3] forward output
+    const float* grad_sigmas;   // [B]
+    const float* grad_rgbs;     // [B, 3]
+    uint32_t B;
+    float2* grad_table;         // fp32 [T, 2] (encoder.embeddings.grad), accumulated
+    float* grad_ws0;            // [64, 32]
+    float* grad_ws1;            // [16, 64]
+    float* grad_wc0;            // [64, 31]
+    float* grad_wc1;            // [64, 64]
+    float* grad_wc2;            // [3, 64]
+    const void* weights;        // packed blob (RgbBwdWeights)
+};
+
+__global__ void __launch_bounds__(kBwdThreads, 1) k_field_backward_rgb(inerf_field_desc desc, RgbBwdParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const uint32_t tid = threadIdx.x;
+    LevelGeom* lg = reinterpret_cast<LevelGeom*>(smem + RSm::MISC);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + RSm::MISC + 16 * sizeof(LevelGeom));
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + RSm::MISC + 16 * sizeof(LevelGeom) + 8);
+    uint64_t* df_full = reinterpret_cast<uint64_t*>(smem + RSm::MISC + 16 * sizeof(LevelGeom) + 16);    // [2]
+    uint64_t* df_empty = df_full + 2;                                                                     // [2]
+
+    // zero the operand tiles once: the padding columns of GB (and dP's columns 3..15) stay zero for the whole launch
+    for (uint32_t i = tid; i < RSm::W / 16; i += kBwdThreads) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
+    {
+        const uint4* wsrc = reinterpret_cast<const uint4*>(p.weights);
+        uint4* wdst = reinterpret_cast<uint4*>(smem + RSm::W);
+        for (uint32_t i = tid; i < RgbBwdWeights::total / 16; i += kBwdThreads) wdst[i] = __ldg(wsrc + i);
+    }
+    init_levels(lg, desc.offsets, desc.L, desc.S, desc.H, tid);
+    if (tid == 0) {
+        umma::mbar_init(bar, 1);
+        for (int i = 0; i < 2; i++) { umma::mbar_init(&df_full[i], kBwdChainT); umma::mbar_init(&df_empty[i], kBwdScatterT); }
+        umma::mbar_fence_init();
+    }
+    if (tid < 32) umma::tmem_alloc<kBwdTmemCols>(tmem_slot);
+    umma::fence_async_smem();
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t sbase = umma::smem_u32(smem);
+
+    const bool chain_role = tid < kBwdChainT;
+    const uint32_t rt = chain_role ? tid : tid - kBwdChainT;
+    const uint32_t warp = rt >> 5, lane = rt & 31;
+    const uint32_t row = rt & (kTile - 1), half = rt >> 7;
+    const uint32_t lane_base = ((warp & 3u) * 32u) << 16;
+    const uint32_t B_eff = desc.n_valid ? min(p.B, (uint32_t)max(0, __ldg(desc.n_valid))) : p.B;
+    const uint32_t num_tiles = (B_eff + kTile - 1) / kTile;
+    uint32_t phase = 0, tiles_done = 0;
+    const bool issuer = tid == 0;
+    constexpr uint32_t Wb = RSm::W;
+
+    auto wait_mma = [&] {
+        __syncwarp();
+        umma::mbar_wait(bar, phase);
+        phase ^= 1u;
+        umma::fence_after_sync();
+    };
+    auto publish = [&] {
+        umma::fence_async_smem();
+        umma::fence_before_sync();
+        umma::named_sync<1, kBwdChainT>();
+    };
+
+    if (chain_role) {
+    umma::reg_alloc<kBwdRegsChain>();
+    // inputs of the next tile prefetched into registers (as in k_field_backward_mask): thread (row, 0) takes E and the colour
+    // head's (g_rgb, rgb), thread (row, 1) takes Ci and the density head's (g_sigma, sigma)
+    uint4 px[4];
+    float pf[6];
+    auto prefetch = [&](uint32_t tile_n) {
+        const uint32_t sn = tile_n * kTile + row;
+        const bool live_n = tile_n < num_tiles && sn < B_eff;
 #pragma unroll
-            for (uint32_t li = 0; li < kScatLevels; li++) {
-                v[2 * li] = __float_as_uint(src[(2 * scat_level(half, li)) * kTile]);
-                v[2 * li + 1] = __float_as_uint(src[(2 * scat_level(half, li) + 1) * kTile]);
+        for (uint32_t c = 0; c < 4; c++) px[c] = live_n ? __ldg(p.xs + (size_t)sn * 8 + half * 4 + c) : make_uint4(0u, 0u, 0u, 0u);
+        if (half == 0) {
+#pragma unroll
+            for (uint32_t c = 0; c < 3; c++) {
+                pf[c] = live_n ? __ldg(p.grad_rgbs + (size_t)sn * 3 + c) : 0.f;
+                pf[3 + c] = live_n ? __ldg(p.rgbs + (size_t)sn * 3 + c) : 0.f;
             }
+        } else {
+            pf[0] = live_n ? __ldg(p.grad_sigmas + sn) : 0.f;
+            pf[1] = live_n ? __ldg(p.sigmas + sn) : 0.f;
         }
-        umma::mbar_arrive(&df_empty[db]);   // the values are in registers: the chain may refill this buffer
+    };
+    prefetch(blockIdx.x);
+    for (uint32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, tiles_done++) {
+        // ---- S0: saved inputs and the head gradients -> operand tiles ---------------------------------------------------
+        uint32_t dh0_bits = 0;   // fp16 gradient of the sigma-net's output 0 (thread (row, 1))
+        if (half == 0) {
+#pragma unroll
+            for (uint32_t c = 0; c < 4; c++)
+                *reinterpret_cast<uint4*>(smem + RSm::HB + umma::tile_off(row, c * 8, kLBO, kSbo160)) = px[c];          // E -> HB[:, 0:32]
+            // sigmoid backward as autocast runs it: the incoming gradient is cast to fp16, g * (1 - y) * y in fp32, ONE rounding
+            float dp[3];
+#pragma unroll
+            for (uint32_t c = 0; c < 3; c++) {
+                const float g16 = __half2float(__float2half_rn(pf[c])), y = pf[3 + c];
+                dp[c] = __fmul_rn(__fmul_rn(g16, __fsub_rn(1.0f, y)), y);
+            }
+            *reinterpret_cast<uint4*>(smem + RSm::GB + umma::tile_off(row, 64, kLBO, kSbo128)) =
+                make_uint4(h2_bits(__floats2half2_rn(dp[0], dp[1])), h2_bits(__floats2half2_rn(dp[2], 0.f)), 0u, 0u);    // dP -> GB[:, 64:72]
+        } else {
+#pragma unroll
+            for (uint32_t c = 0; c < 4; c++)
+                *reinterpret_cast<uint4*>(smem + RSm::HA + umma::tile_off(row, 64 + c * 8, kLBO, kSbo96)) = px[c];      // Ci -> HA[:, 64:96]
+            // trunc_exp backward (activation.py:13-17): g * exp(clamp(x, -15, 15)) in fp32, then the cast back to the fp16 activation
+            const float e = fminf(fmaxf(pf[1], 3.0590232e-07f), 3269017.4f);
+            dh0_bits = (uint32_t)__half_as_ushort(__float2half_rn(__fmul_rn(pf[0], e)));
+        }
+        publish();
+        // ---- S1: Hs, Hc1 pre-activations; dP Wc2 ---------------------------------------------------------------------------
+        if (issuer) {
+            umma::fence_after_sync();
+            issue_gemm2(sbase, RSm::HB, kSbo160, Wb + RgbBwdWeights::ws0, kSbo32, 32, 64, tmem + R_a);
+            issue_gemm2(sbase, RSm::HA + 8 * kLBO, kSbo96, Wb + RgbBwdWeights::wc0, kSbo32, 32, 64, tmem + R_b);
+            issue_gemm2(sbase, RSm::GB + 8 * kLBO, kSbo128, Wb + RgbBwdWeights::wc2t, kSbo16, 16, 64, tmem + R_c);
+            umma::commit(bar);
+        }
+        prefetch(tile + gridDim.x);
+        wait_mma();
+        const uint32_t mask_s = epi_relu_to(tmem + R_a + lane_base + half * 32, smem, RSm::HB, kSbo160, row, 96 + half * 32);    // Hs  -> HB[:, 96:160]
+        const uint32_t mask_c1 = epi_relu_to(tmem + R_b + lane_base + half * 32, smem, RSm::HA, kSbo96, row, half * 32);        // Hc1 -> HA[:, 0:64]
+        publish();
+        // ---- S2: Hc2 pre-activation; dHc2 = (dP Wc2) . [Hc2 > 0] --------------------------------------------------------------
+        if (issuer) {
+            umma::fence_after_sync();
+            issue_gemm2(sbase, RSm::HA, kSbo96, Wb + RgbBwdWeights::wc1, kSbo64, 64, 64, tmem + R_a);
+            umma::commit(bar);
+        }
+        wait_mma();
+        const uint32_t mask_c2 = epi_relu_to(tmem + R_a + lane_base + half * 32, smem, RSm::HB, kSbo160, row, 32 + half * 32);   // Hc2 -> HB[:, 32:96]
+        epi_masked32(tmem + R_c + lane_base + half * 32, mask_c2, smem, RSm::GA, row, half * 32);                               // dHc2 -> GA[:, 0:64]
+        publish();
+        // ---- S3: dHc1 = (dHc2 Wc1) . [Hc1 > 0] ----------------------------------------------------------------------------------
+        if (issuer) {
+            umma::fence_after_sync();
+            issue_gemm2(sbase, RSm::GA, kSbo128, Wb + RgbBwdWeights::wc1t, kSbo64, 64, 64, tmem + R_b);
+            umma::commit(bar);
+        }
+        wait_mma();
+        epi_masked32(tmem + R_b + lane_base + half * 32, mask_c1, smem, RSm::GA, row, 64 + half * 32);                          // dHc1 -> GA[:, 64:128]
+        publish();
+        // ---- S4: dCi = dHc1 Wc0; the density head's output gradient dO = [dh0 | dgeo15] ----------------------------------------
+        if (issuer) {
+            umma::fence_after_sync();
+            issue_gemm2(sbase, RSm::GA + 8 * kLBO, kSbo128, Wb + RgbBwdWeights::wc0t, kSbo64, 64, 32, tmem + R_x);
+            umma::commit(bar);
+        }
+        wait_mma();
+        if (half == 1) {   // columns 16..31 of dCi: geo15 (column 31 is the zero padding of Ci)
+            uint32_t v[16];
+            umma::tmem_ld16(tmem + R_x + lane_base + 16, v);
+            umma::tmem_ld_wait();
+            uint32_t q[8];
+            q[0] = dh0_bits | ((uint32_t)__half_as_ushort(__float2half_rn(__uint_as_float(v[0]))) << 16);
+#pragma unroll
+            for (int i = 1; i < 8; i++) q[i] = h2_bits(__floats2half2_rn(__uint_as_float(v[2 * i - 1]), __uint_as_float(v[2 * i])));
+            *reinterpret_cast<uint4*>(smem + RSm::GB + umma::tile_off(row, 96, kLBO, kSbo128)) = make_uint4(q[0], q[1], q[2], q[3]);
+            *reinterpret_cast<uint4*>(smem + RSm::GB + umma::tile_off(row, 104, kLBO, kSbo128)) = make_uint4(q[4], q[5], q[6], q[7]);
+        }
+        publish();
+        // ---- S5: dHs = (dO Ws1) . [Hs > 0] ---------------------------------------------------------------------------------------
+        if (issuer) {
+            umma::fence_after_sync();
+            issue_gemm2(sbase, RSm::GB + 12 * kLBO, kSbo128, Wb + RgbBwdWeights::ws1t, kSbo16, 16, 64, tmem + R_a);
+            umma::commit(bar);
+        }
+        wait_mma();
+        epi_masked32(tmem + R_a + lane_base + half * 32, mask_s, smem, RSm::GB, row, half * 32);                                // dHs -> GB[:, 0:64]
+        publish();
+        // ---- S6: dE = dHs Ws0; weight gradients accumulate across tiles ----------------------------------------------------------
+        if (issuer) {
+            umma::fence_after_sync();
+            issue_gemm2(sbase, RSm::GB, kSbo128, Wb + RgbBwdWeights::ws0t, kSbo64, 64, 32, tmem + R_x);
+            issue_gemm_tn(sbase, RSm::GA, kSbo128, RSm::HA, kSbo96, 96, tmem + R_w1, tiles_done > 0);
+            issue_gemm_tn(sbase, RSm::GB, kSbo128, RSm::HB, kSbo160, 160, tmem + R_w2, tiles_done > 0);
+            umma::commit(bar);
+        }
+        wait_mma();
         {
-            // Consecutive rows of a tile are consecutive samples of the same ray (the stream is sorted by ray and by t), so on the
-            // coarse levels whole runs of lanes fall into the SAME cell: left alone, their atomics serialise on a handful of
-            // addresses in L2.  Levels 0..7 (threads of half 0) therefore reduce each run inside the warp first -- segmented
-            // reduction towards the run's first lane, bounded by the next run head -- and only run heads issue atomics.
-            float x01[3] = {2.f, 2.f, 2.f};
-            if (live) {
+            const uint32_t db = tiles_done & 1u;
+            if (tiles_done >= 2) umma::mbar_wait(&df_empty[db], ((tiles_done >> 1) - 1u) & 1u);
+            uint32_t v[16];
+            umma::tmem_ld16(tmem + R_x + lane_base + half * 16, v);
+            umma::tmem_ld_wait();
+            float* dst = reinterpret_cast<float*>(smem + RSm::DF) + db * (kTile * 32) + (half * 16) * kTile + row;
 #pragma unroll
-                for (int d = 0; d < 3; d++) x01[d] = __fmul_rn(__fadd_rn(__ldg(p.xyzs + (size_t)s * 3 + d), desc.bound), inv2b);
+            for (int i = 0; i < 16; i++) dst[i * kTile] = __uint_as_float(v[i]);
+            umma::mbar_arrive(&df_full[db]);
+        }
+        umma::fence_before_sync();
+        umma::named_sync<1, kBwdChainT>();
+    }
+
+    // ---- weight gradients of this CTA: TMEM -> global (fp32 atomics).  Lane m of R_w1 / R_w2 = column m of GA / GB. ------------
+    if (tiles_done > 0) {
+        const uint32_t q = warp & 3u, m = q * 32u + lane;
+        auto flush = [&](uint32_t tcol, uint32_t ncols, float* dst, uint32_t ld, uint32_t r, uint32_t c_lim, bool row_ok) {
+            for (uint32_t c = 0; c < ncols; c += 16) {
+                uint32_t v[16];
+                umma::tmem_ld16(tmem + tcol + lane_base + c, v);
+                umma::tmem_ld_wait();
+                if (row_ok)
+#pragma unroll
+                    for (int j = 0; j < 16; j++)
+                        if (c + j < c_lim) atomicAdd(dst + (size_t)r * ld + c + j, __uint_as_float(v[j]));
             }
-            const bool ok = live && !(x01[0] < 0.f || x01[0] > 1.f || x01[1] < 0.f || x01[1] > 1.f || x01[2] < 0.f || x01[2] > 1.f);
-#pragma unroll
-            for (uint32_t li = 0; li < kScatLevels; li++) {
-                float g0 = ok ? __uint_as_float(v[2 * li]) : 0.f, g1 = ok ? __uint_as_float(v[2 * li + 1]) : 0.f;
-                const uint32_t level = scat_level(half, li);
-                const LevelGeom g = lg[level];
-                uint32_t idx[8];
-                float w[8];
-                float xs[3] = {ok ? x01[0] : 0.f, ok ? x01[1] : 0.f, ok ? x01[2] : 0.f};
-                level_corners(xs, g, idx, w);
-                float2* base = p.grad_table + g.offset;
-                if (level < 8) {   // levels 0..7 (warp-uniform)
-                    // run heads: first lane, or a lane whose cell differs from the previous lane's (corner 0 and corner 7
-                    // together identify the cell; a hash collision only splits or merges runs of identical addresses)
-                    const uint32_t p0 = __shfl_up_sync(0xffffffffu, idx[0], 1), p7 = __shfl_up_sync(0xffffffffu, idx[7], 1);
-                    const bool head = lane == 0 || p0 != idx[0] || p7 != idx[7];
-                    const uint32_t heads = __ballot_sync(0xffffffffu, head);
-                    const uint32_t after = lane == 31 ? 0u : (heads >> (lane + 1));
-                    const uint32_t next_head = after ? (lane + 1 + (uint32_t)__ffs(after) - 1u) : 32u;
-                    float a0[8], a1[8];
-#pragma unroll
-                    for (uint32_t c = 0; c < 8; c++) { a0[c] = __fmul_rn(w[c], g0); a1[c] = __fmul_rn(w[c], g1); }
-#pragma unroll
-                    for (uint32_t off = 1; off < 32; off <<= 1) {
-                        const bool take = lane + off < next_head;
-#pragma unroll
-                        for (uint32_t c = 0; c < 8; c++) {
-                            const float o0 = __shfl_down_sync(0xffffffffu, a0[c], off), o1 = __shfl_down_sync(0xffffffffu, a1[c], off);
-                            if (take) { a0[c] += o0; a1[c] += o1; }
-                        }
-                    }
-                    if (head) {
-#pragma unroll
-                        for (uint32_t c = 0; c < 8; c++)
-                            if (a0[c] != 0.f || a1[c] != 0.f) atomicAdd(base + idx[c], make_float2(a0[c], a1[c]));
-                    }
-                } else if (g0 != 0.f || g1 != 0.f) {
-                    // x-neighbour corners (2i, 2i+1) sit in one 16-byte aligned slot whenever the cell's x index is even (prime[0] = 1:
-                    // entry a and a ^ 1): one 16-byte RED instead of two 8-byte ones (-11 % kernel time on B200)
-#pragma unroll
-                    for (uint32_t c = 0; c < 8; c += 2) {
-                        const float2 va = make_float2(__fmul_rn(w[c], g0), __fmul_rn(w[c], g1));
-                        const float2 vb = make_float2(__fmul_rn(w[c + 1], g0), __fmul_rn(w[c + 1], g1));
-                        if ((idx[c] ^ idx[c + 1]) == 1u) {
-                            const bool odd = idx[c] & 1u;
-                            atomicAdd(reinterpret_cast<float4*>(base + (idx[c] & ~1u)),
-                                      odd ? make_float4(vb.x, vb.y, va.x, va.y) : make_float4(va.x, va.y, vb.x, vb.y));
-                        } else {
-                            atomicAdd(base + idx[c], va);
-                            atomicAdd(base + idx[c + 1], vb);
-                        }
-                    }
-                }
-            }
+        };
+        if (half == 0) {
+            if (q < 2) flush(R_w1, 64, p.grad_wc1, 64, m, 64, true);                       // dWc1[o = m][j]        lanes 0..63,   HA cols 0..63
+            else flush(R_w1 + 64, 32, p.grad_wc0, 31, m - 64, 31, true);                   // dWc0[o = m - 64][j]   lanes 64..127, HA cols 64..94
+        } else {
+            if (q < 2) flush(R_w2, 32, p.grad_ws0, 32, m, 32, true);                       // dWs0[o = m][j]        lanes 0..63,   HB cols 0..31
+            else if (q == 2) flush(R_w2 + 32, 64, p.grad_wc2, 64, m - 64, 64, m - 64 < 3); // dWc2[o = m - 64][j]   lanes 64..66,  HB cols 32..95
+            else flush(R_w2 + 96, 64, p.grad_ws1, 64, m - 96, 64, m - 96 < 16);            // dWs1[o = m - 96][j]   lanes 96..111, HB cols 96..159
         }
     }
+    } else {
+    umma::reg_dealloc<kBwdRegsScatter>();
+    scatter_role(desc, p.xyzs, p.grad_table, lg, smem + RSm::DF, df_full, df_empty, num_tiles, B_eff, rt);
     }
 
     umma::fence_before_sync();
@@ -527,6 +834,55 @@ extern "C" int inerf_field_backward_mask(const inerf_field_desc* desc, const voi
     const uint32_t sms = (uint32_t)device_sm_count();
     const uint32_t grid = num_tiles < sms ? num_tiles : sms;
     k_field_backward_mask<<<grid, kBwdThreads, BSmem::bytes, (cudaStream_t)stream>>>(*desc, p);
+    INERF_LAUNCH_CHECK();
+    return INERF_OK;
+}
+
+// ---- stage-1 (RGB-sigma) backward ------------------------------------------------------------------------------------------
+extern "C" size_t inerf_field_rgb_bwd_weights_bytes(void) { return RgbBwdWeights::total; }
+
+// fp32 nn.Linear matrices (DEVICE) -> the operand blob of inerf_field_backward_rgb (DEVICE), one launch on `stream`
+extern "C" int inerf_field_pack_weights_rgb_bwd_device(const float* sigma0, const float* sigma1, const float* color0, const float* color1,
+                                                       const float* color2, void* packed_bwd, void* stream) {
+    INERF_REQUIRE(sigma0); INERF_REQUIRE(sigma1); INERF_REQUIRE(color0); INERF_REQUIRE(color1); INERF_REQUIRE(color2);
+    INERF_REQUIRE(packed_bwd);
+    if ((uintptr_t)packed_bwd & 15u) return INERF_ERR_ALIGN;
+    PackJobs jobs{};
+    uint32_t n = 0;
+    auto add = [&](const float* W, uint32_t n_out, uint32_t n_in, uint32_t Npad, uint32_t Kpad, uint32_t dst, uint32_t tr, uint32_t n_lim) {
+        jobs.j[n++] = PackJob{W, n_out, n_in, Npad, Kpad, dst, tr, n_lim};
+    };
+    add(sigma0, 64, 32, 64, 32, RgbBwdWeights::ws0, 0, 64);
+    add(color0, 64, 31, 64, 32, RgbBwdWeights::wc0, 0, 64);
+    add(color1, 64, 64, 64, 64, RgbBwdWeights::wc1, 0, 64);
+    add(color2, 3, 64, 64, 16, RgbBwdWeights::wc2t, 1, 64);
+    add(color1, 64, 64, 64, 64, RgbBwdWeights::wc1t, 1, 64);
+    add(color0, 64, 31, 32, 64, RgbBwdWeights::wc0t, 1, 32);
+    add(sigma1, 16, 64, 64, 16, RgbBwdWeights::ws1t, 1, 64);
+    add(sigma0, 64, 32, 32, 64, RgbBwdWeights::ws0t, 1, 32);
+    jobs.n = n;
+    k_pack_weights<<<dim3(4, n), 256, 0, (cudaStream_t)stream>>>(jobs, nullptr, (uint8_t*)packed_bwd, 0);
+    INERF_LAUNCH_CHECK();
+    return INERF_OK;
+}
+
+extern "C" int inerf_field_backward_rgb(const inerf_field_desc* desc, const void* weights_bwd, const float* xyzs, const void* xs,
+                                        const float* sigmas, const float* rgbs, const float* grad_sigmas, const float* grad_rgbs, uint32_t B,
+                                        float* grad_table, float* grad_ws0, float* grad_ws1, float* grad_wc0, float* grad_wc1,
+                                        float* grad_wc2, void* stream) {
+    if (int e = field::validate(desc)) return e;
+    if (B == 0) return INERF_OK;
+    INERF_REQUIRE(weights_bwd); INERF_REQUIRE(xyzs); INERF_REQUIRE(xs); INERF_REQUIRE(sigmas); INERF_REQUIRE(rgbs);
+    INERF_REQUIRE(grad_sigmas); INERF_REQUIRE(grad_rgbs); INERF_REQUIRE(grad_table);
+    INERF_REQUIRE(grad_ws0); INERF_REQUIRE(grad_ws1); INERF_REQUIRE(grad_wc0); INERF_REQUIRE(grad_wc1); INERF_REQUIRE(grad_wc2);
+    if (((uintptr_t)weights_bwd & 15u) || ((uintptr_t)xs & 15u) || ((uintptr_t)grad_table & 15u)) return INERF_ERR_ALIGN;
+    cudaError_t e = cudaFuncSetAttribute(k_field_backward_rgb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RSm::bytes);
+    if (e != cudaSuccess) return (int)e;
+    RgbBwdParams p{xyzs, (const uint4*)xs, sigmas, rgbs, grad_sigmas, grad_rgbs, B, (float2*)grad_table,
+                   grad_ws0, grad_ws1, grad_wc0, grad_wc1, grad_wc2, weights_bwd};
+    const uint32_t num_tiles = (B + kTile - 1) / kTile;
+    const uint32_t sms = (uint32_t)device_sm_count();
+    k_field_backward_rgb<<<num_tiles < sms ? num_tiles : sms, kBwdThreads, RSm::bytes, (cudaStream_t)stream>>>(*desc, p);
     INERF_LAUNCH_CHECK();
     return INERF_OK;
 }

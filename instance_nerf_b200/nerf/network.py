@@ -19,11 +19,57 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from .._lib import lib
+import ctypes
+
+from .._lib import call, lib, ptr, stream_ptr
 from ..activation import trunc_exp
 from ..encoding import get_encoder
 from .network_mask import NeRFNetwork as _InstanceNetwork
 from .renderer import NeRFRenderer
+
+
+class _FusedRGBField(torch.autograd.Function):
+    """Stage-1 field forward (inerf_field_forward_train_rgb) / backward (inerf_field_backward_rgb), one launch each: sigma_net,
+    color_net, SH and the sigma hash table.  The table gradient is accumulated straight into `encoder.embeddings.grad` by the
+    kernel's fp32 atomics, so `None` is returned for that input."""
+
+    @staticmethod
+    def forward(ctx, model, x, d, table, ws0, ws1, wc0, wc1, wc2):
+        B, dev = x.shape[0], x.device
+        sigmas = torch.empty(B, dtype=torch.float32, device=dev)
+        rgbs = torch.empty(B, 3, dtype=torch.float32, device=dev)
+        xs = torch.empty(B, 64, dtype=torch.float16, device=dev)
+        desc = model._field_desc()
+        desc.n_valid = getattr(model, "_n_valid_ptr", None)
+        ctx.n_valid = desc.n_valid
+        call("inerf_field_forward_train_rgb", ctypes.byref(desc), ptr(x), ptr(d), B, ptr(sigmas), ptr(rgbs), ptr(xs), stream_ptr(dev))
+        ctx.model = model
+        ctx.save_for_backward(x, xs, sigmas, rgbs)
+        return sigmas, rgbs
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g_sigmas, g_rgbs):
+        x, xs, sigmas, rgbs = ctx.saved_tensors
+        model = ctx.model
+        B, dev = x.shape[0], x.device
+        table = model.encoder.embeddings
+        if table.grad is None:
+            table.grad = torch.zeros_like(table)
+        gs0 = torch.zeros(64, 32, dtype=torch.float32, device=dev)
+        gs1 = torch.zeros(16, 64, dtype=torch.float32, device=dev)
+        gc0 = torch.zeros(64, 31, dtype=torch.float32, device=dev)
+        gc1 = torch.zeros(64, 64, dtype=torch.float32, device=dev)
+        gc2 = torch.zeros(3, 64, dtype=torch.float32, device=dev)
+        if B > 0:
+            desc = model._field_desc()
+            desc.n_valid = ctx.n_valid
+            wb = model._packed_weights_rgb_bwd()
+            g_sigmas = (torch.zeros_like(sigmas) if g_sigmas is None else g_sigmas.float()).contiguous()
+            g_rgbs = (torch.zeros_like(rgbs) if g_rgbs is None else g_rgbs.float()).contiguous()
+            call("inerf_field_backward_rgb", ctypes.byref(desc), ptr(wb), ptr(x), ptr(xs), ptr(sigmas), ptr(rgbs), ptr(g_sigmas), ptr(g_rgbs), B,
+                 ptr(table.grad), ptr(gs0), ptr(gs1), ptr(gc0), ptr(gc1), ptr(gc2), stream_ptr(dev))
+        return None, None, None, None, gs0, gs1, gc0, gc1, gc2
 
 
 class NeRFNetwork(NeRFRenderer):
@@ -59,6 +105,7 @@ class NeRFNetwork(NeRFRenderer):
         self._tables = None
         self._work_counter = None
         self._zero_head = None
+        self._packed_rgb_bwd = None
 
     # ---- fused inference: the instance-stage kernels with the head switched off ------------------------------------
     @property
@@ -94,6 +141,32 @@ class NeRFNetwork(NeRFRenderer):
     _render_fused = _InstanceNetwork._render_fused
     _occupancy_density_fused = _InstanceNetwork._occupancy_density_fused
 
+    # ---- fused training (fp16 autocast, standard architecture): one launch forward, one launch backward -----------------
+    def fused_train_available(self, x, d) -> bool:
+        if not (self.fused_available() and x.is_cuda and torch.is_autocast_enabled() and not x.requires_grad and not d.requires_grad):
+            return False
+        if not hasattr(lib(), "inerf_field_backward_rgb"):
+            return False
+        ps = [self.encoder.embeddings, *[l.weight for l in self.sigma_net], *[l.weight for l in self.color_net]]
+        return all(p.requires_grad for p in ps)
+
+    def _packed_weights_rgb_bwd(self):
+        ws = [m.weight for m in (*self.sigma_net, *self.color_net)]
+        dev = ws[0].device
+        key = tuple((w.data_ptr(), w._version) for w in ws) + (str(dev),)
+        if self._packed_rgb_bwd is None or self._packed_rgb_bwd[0] != key:
+            blob = self._packed_rgb_bwd[1] if self._packed_rgb_bwd is not None and self._packed_rgb_bwd[1].device == dev else \
+                torch.empty(lib().inerf_field_rgb_bwd_weights_bytes(), dtype=torch.uint8, device=dev)
+            call("inerf_field_pack_weights_rgb_bwd_device", *[ptr(w.detach()) for w in ws], ptr(blob), stream_ptr(dev))
+            self._packed_rgb_bwd = (key, blob)
+        return self._packed_rgb_bwd[1]
+
+    def forward_fused_train(self, x, d):
+        x = x.float().contiguous().view(-1, 3)
+        d = d.float().contiguous().view(-1, 3)
+        return _FusedRGBField.apply(self, x, d, self.encoder.embeddings, *[l.weight for l in self.sigma_net],
+                                    *[l.weight for l in self.color_net])
+
     # ---- reference operator sequence (network.py:96-127) --------------------------------------------------------------
     @staticmethod
     def _mlp(net, h):
@@ -109,6 +182,8 @@ class NeRFNetwork(NeRFRenderer):
         if not torch.is_grad_enabled() and x.is_cuda and self.fused_available():
             sigma, rgb, _ = self.forward_fused(x, d, want_masks=False)
             return sigma, rgb
+        if torch.is_grad_enabled() and self.fused_train_available(x, d):
+            return self.forward_fused_train(x, d)
         h = self._mlp(self.sigma_net, self.encoder(x, bound=self.bound))
         sigma = trunc_exp(h[..., 0])
         geo_feat = h[..., 1:]

@@ -211,6 +211,15 @@ class NeRFNetwork(NeRFMaskRenderer):
             return False
         return self.encoder_mask.embeddings.requires_grad and all(l.weight.requires_grad for l in self.mask_net)
 
+    def bounded_stream(self) -> bool:
+        """The fused training forward / backward stop at the marcher's device-side sample total (inerf_field_desc.n_valid)."""
+        if not (self.fused_available() and torch.is_autocast_enabled() and hasattr(lib(), "inerf_field_backward_mask")):
+            return False
+        frozen = (self.encoder, self.sigma_net, self.encoder_dir, self.color_net)
+        if any(p.requires_grad for m in frozen for p in m.parameters()):
+            return False
+        return self.encoder_mask.embeddings.requires_grad and all(l.weight.requires_grad for l in self.mask_net)
+
     def forward_fused_train(self, x, d):
         x = x.float().contiguous().view(-1, 3)
         d = d.float().contiguous().view(-1, 3)

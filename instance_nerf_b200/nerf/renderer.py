@@ -237,13 +237,16 @@ class NeRFRenderer(nn.Module):
             counter.zero_()
             self.local_step += 1
             budget = int(getattr(self, "sample_budget", 0) or 0)
+            # every consumer of the stream stops at the device-side total (fused field forward / backward, n_valid): rows past it
+            # are never read, so neither the stream nor the compositing gradients need zero fills
+            bounded = budget > 0 and self.bounded_stream()
             if budget > 0:
                 # fixed-size sample stream (CUDA-graph-captured training step, nerf/trainer.py): `budget` rows, no host read of
                 # the marched total; the field kernels stop at the device-side total (counter[0]), rows beyond it are padding.
                 # The caller guarantees budget >= total (and checks counter[0] afterwards), so no ray is dropped.
                 xyzs, dirs, deltas, rays = raymarching.march_rays_train(
                     rays_o, rays_d, self.bound, self.density_bitfield, self.cascade, self.grid_size, nears, fars, counter,
-                    budget, perturb, -1, False, dt_gamma, max_steps, noises=kwargs.get("noises"))
+                    budget, perturb, -1, False, dt_gamma, max_steps, noises=kwargs.get("noises"), zero_fill=not bounded)
                 self._n_valid_ptr = counter.data_ptr()
             else:
                 xyzs, dirs, deltas, rays = raymarching.march_rays_train(
@@ -253,11 +256,15 @@ class NeRFRenderer(nn.Module):
                 self._n_valid_ptr = None
             sigmas, rgbs, masks = self._field(xyzs, dirs, render_mask)
             sigmas = self.density_scale * sigmas
+            # fixed-size stream: every row below the device-side total belongs to a ray and the rows above it are never read, so
+            # the compositing backward needs no zero-filled gradient buffers (the eager stream has zero-padded alignment rows
+            # that ARE fed through the network backward: it keeps the reference's zero fill)
+            dense = bounded
             if not render_mask:
-                weights_sum, depth, image = raymarching.composite_rays_train(sigmas, rgbs, deltas, rays, T_thresh)
+                weights_sum, depth, image = raymarching.composite_rays_train(sigmas, rgbs, deltas, rays, T_thresh, dense=dense)
             else:
                 weights_sum, depth, image, mask_out = raymarching.composite_rays_with_masks_train(
-                    sigmas, rgbs, masks, deltas, rays, T_thresh)
+                    sigmas, rgbs, masks, deltas, rays, T_thresh, dense=dense)
             results["weights_sum"] = weights_sum
         else:
             if not perturb and self.fused_render_available(render_mask):
@@ -273,6 +280,10 @@ class NeRFRenderer(nn.Module):
         results["image"] = image.view(*prefix, 3)
         results["instance_mask_logits"] = mask_out.view(*prefix, self.num_instances) if render_mask else None
         return results
+
+    def bounded_stream(self) -> bool:
+        """True when the network's training forward / backward honour `_n_valid_ptr` (see NeRFNetwork in network_mask.py)."""
+        return False
 
     def _field(self, xyzs, dirs, render_mask):
         out = self(xyzs, dirs)

@@ -91,7 +91,7 @@ def packbits(grid, thresh, bitfield=None):
 
 
 def march_rays_train(rays_o, rays_d, bound, density_bitfield, C, H, nears, fars, step_counter=None, mean_count=-1,
-                     perturb=False, align=-1, force_all_rays=False, dt_gamma=0, max_steps=1024, noises=None):
+                     perturb=False, align=-1, force_all_rays=False, dt_gamma=0, max_steps=1024, noises=None, zero_fill=True):
     """raymarching.py:161-235 -> (xyzs [M,3], dirs [M,3], deltas [M,2], rays int32 [N,3]).
 
     `noises` (extra, optional) injects the per-ray jitter in [0,1) instead of
@@ -129,10 +129,12 @@ def march_rays_train(rays_o, rays_d, bound, density_bitfield, C, H, nears, fars,
         M = int(step_counter[0].item())  # D2H sync, as raymarching.py:224
         if align > 0:
             M += align - M % align       # a full extra `align` rows when already aligned (reference quirk)
-    # rows past the last sample must be zero: they are fed through the network (padding)
-    xyzs = torch.zeros(M, 3, dtype=torch.float32, device=dev)
-    dirs = torch.zeros(M, 3, dtype=torch.float32, device=dev)
-    deltas = torch.zeros(M, 2, dtype=torch.float32, device=dev)
+    # rows past the last sample must be zero: they are fed through the network (padding) -- unless the caller bounds every
+    # consumer by the device-side total (zero_fill=False: the CUDA-graph training step, inerf_field_desc.n_valid)
+    alloc = torch.zeros if zero_fill else torch.empty
+    xyzs = alloc(M, 3, dtype=torch.float32, device=dev)
+    dirs = alloc(M, 3, dtype=torch.float32, device=dev)
+    deltas = alloc(M, 2, dtype=torch.float32, device=dev)
     call("inerf_march_rays_train_expand", ptr(rays_o), ptr(rays_d), float(bound), float(dt_gamma), int(max_steps), N, int(C), int(H),
          M, ptr(nears), ptr(xyzs), ptr(dirs), ptr(deltas), ptr(rays), ptr(noises), ptr(t_scratch), st)
     return xyzs, dirs, deltas, rays
@@ -142,7 +144,8 @@ class _composite_rays_train(Function):
     """raymarching.py:238-291"""
 
     @staticmethod
-    def forward(ctx, sigmas, rgbs, deltas, rays, T_thresh=1e-4):
+    def forward(ctx, sigmas, rgbs, deltas, rays, T_thresh=1e-4, dense=False):
+        ctx.dense = bool(dense)
         sigmas, rgbs, deltas = _f32(sigmas), _f32(rgbs), _f32(deltas)
         rays = rays.contiguous()
         M, N = sigmas.shape[0], rays.shape[0]
@@ -162,23 +165,35 @@ class _composite_rays_train(Function):
         sigmas, rgbs, deltas, rays, weights_sum, image = ctx.saved_tensors
         M, N, T_thresh = ctx.dims
         grad_weights_sum, grad_image = _f32(grad_weights_sum), _f32(grad_image)
+        if ctx.dense:   # every row belongs to a ray: the kernel writes the zeros behind a ray's termination itself
+            grad_sigmas = torch.empty_like(sigmas) if ctx.needs_input_grad[0] else None
+            grad_rgbs = torch.empty_like(rgbs) if ctx.needs_input_grad[1] else None
+            if grad_sigmas is not None or grad_rgbs is not None:
+                call("inerf_composite_rays_with_masks_train_backward_dense", ptr(grad_weights_sum), ptr(grad_image), None, ptr(sigmas),
+                     ptr(rgbs), None, ptr(deltas), ptr(rays), ptr(weights_sum), ptr(image), None, M, N, 0, float(T_thresh),
+                     ptr(grad_sigmas), ptr(grad_rgbs), None, stream_ptr(sigmas.device))
+            return grad_sigmas, grad_rgbs, None, None, None, None
         grad_sigmas = torch.zeros_like(sigmas)
         grad_rgbs = torch.zeros_like(rgbs)
         call("inerf_composite_rays_train_backward", ptr(grad_weights_sum), ptr(grad_image), ptr(sigmas), ptr(rgbs), ptr(deltas),
              ptr(rays), ptr(weights_sum), ptr(image), M, N, float(T_thresh), ptr(grad_sigmas), ptr(grad_rgbs),
              stream_ptr(sigmas.device))
-        return grad_sigmas, grad_rgbs, None, None, None
+        return grad_sigmas, grad_rgbs, None, None, None, None
 
 
-def composite_rays_train(sigmas, rgbs, deltas, rays, T_thresh=1e-4):
-    return _composite_rays_train.apply(sigmas, rgbs, deltas, rays, T_thresh)
+def composite_rays_train(sigmas, rgbs, deltas, rays, T_thresh=1e-4, dense=False):
+    """`dense=True` (not in the reference): the caller guarantees that every row of the sample stream belongs to a ray of `rays`
+    (the count -> scan -> expand marcher's output), so the backward needs no zero-filled gradient buffers and skips the
+    gradients nobody asked for."""
+    return _composite_rays_train.apply(sigmas, rgbs, deltas, rays, T_thresh, dense)
 
 
 class _composite_rays_with_masks_train(Function):
     """raymarching.py:297-364"""
 
     @staticmethod
-    def forward(ctx, sigmas, rgbs, masks, deltas, rays, T_thresh=1e-4):
+    def forward(ctx, sigmas, rgbs, masks, deltas, rays, T_thresh=1e-4, dense=False):
+        ctx.dense = bool(dense) and masks.shape[1] <= 64
         sigmas, rgbs, masks, deltas = _f32(sigmas), _f32(rgbs), _f32(masks), _f32(deltas)
         rays = rays.contiguous()
         M, N, K = sigmas.shape[0], rays.shape[0], masks.shape[1]
@@ -198,17 +213,25 @@ class _composite_rays_with_masks_train(Function):
         sigmas, rgbs, masks, deltas, rays, weights_sum, image, mask_out = ctx.saved_tensors
         M, N, K, T_thresh = ctx.dims
         grad_weights_sum, grad_image, grad_mask_out = _f32(grad_weights_sum), _f32(grad_image), _f32(grad_mask_out)
+        if ctx.dense:
+            grad_sigmas = torch.empty_like(sigmas) if ctx.needs_input_grad[0] else None
+            grad_rgbs = torch.empty_like(rgbs) if ctx.needs_input_grad[1] else None
+            grad_masks = torch.empty_like(masks)
+            call("inerf_composite_rays_with_masks_train_backward_dense", ptr(grad_weights_sum), ptr(grad_image), ptr(grad_mask_out),
+                 ptr(sigmas), ptr(rgbs), ptr(masks), ptr(deltas), ptr(rays), ptr(weights_sum), ptr(image), ptr(mask_out),
+                 M, N, K, float(T_thresh), ptr(grad_sigmas), ptr(grad_rgbs), ptr(grad_masks), stream_ptr(sigmas.device))
+            return grad_sigmas, grad_rgbs, grad_masks, None, None, None, None
         grad_sigmas = torch.zeros_like(sigmas)
         grad_rgbs = torch.zeros_like(rgbs)
         grad_masks = torch.zeros_like(masks)
         call("inerf_composite_rays_with_masks_train_backward", ptr(grad_weights_sum), ptr(grad_image), ptr(grad_mask_out),
              ptr(sigmas), ptr(rgbs), ptr(masks), ptr(deltas), ptr(rays), ptr(weights_sum), ptr(image), ptr(mask_out),
              M, N, K, float(T_thresh), ptr(grad_sigmas), ptr(grad_rgbs), None, ptr(grad_masks), stream_ptr(sigmas.device))
-        return grad_sigmas, grad_rgbs, grad_masks, None, None, None
+        return grad_sigmas, grad_rgbs, grad_masks, None, None, None, None
 
 
-def composite_rays_with_masks_train(sigmas, rgbs, masks, deltas, rays, T_thresh=1e-4):
-    return _composite_rays_with_masks_train.apply(sigmas, rgbs, masks, deltas, rays, T_thresh)
+def composite_rays_with_masks_train(sigmas, rgbs, masks, deltas, rays, T_thresh=1e-4, dense=False):
+    return _composite_rays_with_masks_train.apply(sigmas, rgbs, masks, deltas, rays, T_thresh, dense)
 
 
 def march_rays(n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, bound, density_bitfield, C, H, near, far, align=-1,

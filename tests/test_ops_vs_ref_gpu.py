@@ -200,6 +200,53 @@ def test_composite_train_fwd_bwd(ref, cuda, K):
     torch.testing.assert_close(sigmas.grad, gs0, rtol=1e-3, atol=1e-4)   # K-term sum is re-associated (warp reduce)
 
 
+@pytest.mark.parametrize("K", [0, 32, 40])
+def test_composite_train_bwd_dense_needs_no_zero_fill(ref, cuda, K):
+    """inerf_composite_rays_with_masks_train_backward_dense: NaN-poisoned gradient buffers come back equal, bit for bit, to
+    the zero-filled contract of raymarching.cu:828-951 (checked against the reference kernel above), and the sigma / rgb
+    gradients may be left out."""
+    from instance_nerf_b200._lib import call, ptr, stream_ptr
+    sc, cascade, grid, bits = scene_arrays(16, 8.0, 0)
+    o, d = _dev(*make_rays(sc, 48, 64), device=cuda)
+    bits_t = torch.from_numpy(bits).to(cuda)
+    ours, _, _ = _march_both(ref, cuda, o, d, bits_t, 8.0, cascade, 1 / 128, 1024, 11)
+    xyzs, dirs, deltas, rays, counter = ours
+    M, N = int(counter[0].item()), rays.shape[0]          # the dense part of the stream: no alignment rows
+    deltas = deltas[:M].contiguous()
+    sigmas, rgbs, masks = _fake_field(M, K, cuda, 5)
+    sigmas = sigmas * 4                                    # early termination on most rays: long zero tails
+    T = 1e-4
+    g = torch.Generator().manual_seed(9)
+    gws = torch.randn(N, generator=g).to(cuda); gim = torch.randn(N, 3, generator=g).to(cuda)
+    gmo = torch.randn(N, max(K, 1), generator=g).to(cuda)
+    ws = torch.empty(N, device=cuda); dp = torch.empty(N, device=cuda); im = torch.empty(N, 3, device=cuda); mo = torch.empty(N, max(K, 1), device=cuda)
+    st = stream_ptr(cuda)
+    if K:
+        call("inerf_composite_rays_with_masks_train_forward", ptr(sigmas), ptr(rgbs), ptr(masks), ptr(deltas), ptr(rays), M, N, K, T, ptr(ws), ptr(dp), ptr(im), ptr(mo), st)
+    else:
+        call("inerf_composite_rays_train_forward", ptr(sigmas), ptr(rgbs), ptr(deltas), ptr(rays), M, N, T, ptr(ws), ptr(dp), ptr(im), st)
+    gs0 = torch.zeros(M, device=cuda); gr0 = torch.zeros(M, 3, device=cuda); gm0 = torch.zeros(M, max(K, 1), device=cuda)
+    if K:
+        call("inerf_composite_rays_with_masks_train_backward", ptr(gws), ptr(gim), ptr(gmo), ptr(sigmas), ptr(rgbs), ptr(masks), ptr(deltas),
+             ptr(rays), ptr(ws), ptr(im), ptr(mo), M, N, K, T, ptr(gs0), ptr(gr0), None, ptr(gm0), st)
+    else:
+        call("inerf_composite_rays_train_backward", ptr(gws), ptr(gim), ptr(sigmas), ptr(rgbs), ptr(deltas), ptr(rays), ptr(ws), ptr(im), M, N, T,
+             ptr(gs0), ptr(gr0), st)
+    assert float((gs0 == 0).float().mean()) > 0.2        # the case really has terminated rays
+    nan = float("nan")
+    gs1 = torch.full((M,), nan, device=cuda); gr1 = torch.full((M, 3), nan, device=cuda); gm1 = torch.full((M, max(K, 1)), nan, device=cuda)
+    call("inerf_composite_rays_with_masks_train_backward_dense", ptr(gws), ptr(gim), ptr(gmo) if K else None, ptr(sigmas), ptr(rgbs),
+         ptr(masks) if K else None, ptr(deltas), ptr(rays), ptr(ws), ptr(im), ptr(mo) if K else None, M, N, K, T, ptr(gs1), ptr(gr1),
+         ptr(gm1) if K else None, st)
+    assert bits_equal(gs1, gs0) and bits_equal(gr1, gr0)
+    if K:
+        assert bits_equal(gm1, gm0)
+        gm2 = torch.full((M, K), nan, device=cuda)       # instance stage: sigma / colour frozen, their gradients left out
+        call("inerf_composite_rays_with_masks_train_backward_dense", ptr(gws), ptr(gim), ptr(gmo), ptr(sigmas), ptr(rgbs), ptr(masks),
+             ptr(deltas), ptr(rays), ptr(ws), ptr(im), ptr(mo), M, N, K, T, None, None, ptr(gm2), st)
+        assert bits_equal(gm2, gm0)
+
+
 @pytest.mark.parametrize("K", [0, 32])
 @pytest.mark.parametrize("n_step", [1, 4, 8])
 def test_composite_infer(ref, cuda, K, n_step):
