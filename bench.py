@@ -485,6 +485,14 @@ def run_gpu_arm(args):
                 line["train_step"] = {"ms": tr["ms"], "ms_median": tr["ms_median"], "unit": "ms", "rays": 4096, "samples": tr["samples"],
                                       "workload": "c3: 4096 rays (8x8 patches) x max_steps 1024, K=32, fp16 autocast, CE + label smoothness, backward, Adam",
                                       "cuda_graph": tr["cuda_graph"], "graph_replays": tr["graph_replays"], "graph_captures": tr["graph_captures"]}
+            try:   # stage-1 (RGB-sigma) training step, same rays: fused tcgen05 forward / backward vs the op-level kernels + cuBLAS autograd
+                s1 = measure_train_rgb(dev, 20, 5, 4096, model, scene, poses)
+                if rank == 0:
+                    line["train_step_stage1"] = s1
+            except Exception as e:
+                print(f"[bench] stage-1 training figure failed ({type(e).__name__}: {e})", file=sys.stderr)
+                if rank == 0:
+                    line["train_step_stage1"] = {"error": f"{type(e).__name__}: {e}"}
         try:
             dp = measure_train(dev, rank, world, 12, 4, 65536, None, None, None)
             if rank == 0:
@@ -602,6 +610,58 @@ def run_c4_arm(args):
               "total_s": ms * 1e-3, "gpu_launches": 4 * rounds, "clocks": clk})
     if world > 1:
         dist.destroy_process_group()
+
+
+def measure_train_rgb(dev, steps, warmup, n_rays, model, scene, poses):
+    """Stage-1 (RGB-sigma) optimisation step, Trainer.train_step semantics (nerf/utils.py:536-632): a network with the instance
+    model's sigma / colour tensors learns the colours that model renders for the same rays.  Timed twice: the fused path
+    (inerf_field_forward_train_rgb / inerf_field_backward_rgb, whole step as a CUDA graph) and the reference's operator sequence on
+    the op-level kernels + nn.Linear autograd (eager)."""
+    import torch
+    from instance_nerf_b200.nerf.network import NeRFNetwork
+    from instance_nerf_b200.nerf.trainer import RGBTrainStep
+
+    sd = {k: v for k, v in model.state_dict().items() if not (k.startswith("encoder_mask") or k.startswith("mask_net"))}
+    kw = dict(dt_gamma=DT_GAMMA, max_steps=MAX_STEPS, T_thresh=T_THRESH)
+    batches = train_batches(dev, scene, poses, n_rays, 0, 1, n=8)
+    teacher = NeRFNetwork(bound=model.bound, cuda_ray=True, density_scale=model.density_scale, density_thresh=10)
+    teacher.load_state_dict(sd)
+    teacher = teacher.to(dev).eval()
+    with torch.no_grad():
+        for b in batches:
+            b["images"] = teacher.render(b["rays_o"], b["rays_d"], staged=True, perturb=False, bg_color=1, **kw)["image"].clone()
+            b.pop("masks")
+    flush_buf = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    out = {"unit": "ms", "rays": n_rays,
+           "workload": "stage-1 RGB-sigma step: 4096 rays x max_steps 1024, fp16 autocast, MSE, backward through compositing, both MLPs, SH "
+                       "and the sigma hash table, Adam"}
+    for tag, fused in (("fused", True), ("op_level", False)):
+        student = NeRFNetwork(bound=model.bound, cuda_ray=True, density_scale=model.density_scale, density_thresh=10)
+        student.load_state_dict(sd)
+        student = student.to(dev)
+        with torch.no_grad():
+            student.encoder.embeddings.mul_(0.9)
+        student.use_fused = fused
+        tr = RGBTrainStep(student, lr=1e-3, fp16=True, patch_size=8, cuda_graph=fused and not os.environ.get("INERF_NO_GRAPH"), **kw)
+        for i in range(max(warmup, 2 * len(batches))):
+            tr.step(batches[i % 8])
+        torch.cuda.synchronize()
+        ev = []
+        for i in range(steps):
+            flush_buf.fill_(i & 0xFF)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            loss = tr.step(batches[(warmup + i) % 8])
+            e1.record()
+            ev.append((e0, e1))
+        torch.cuda.synchronize()
+        times = sorted(a.elapsed_time(b) for a, b in ev)
+        out[tag] = {"ms": sum(times) / steps, "ms_median": times[len(times) // 2], "loss": float(loss.item()), "cuda_graph": bool(tr.cuda_graph),
+                    "graph_replays": tr.graph_replays}
+        del student, tr
+    del flush_buf, teacher
+    torch.cuda.empty_cache()
+    return out
 
 
 # ------------------------------------------------------------------------------------------- train arm --

@@ -21,7 +21,7 @@ import torch.nn.functional as F
 
 import ctypes
 
-from .._lib import call, lib, ptr, stream_ptr
+from .._lib import PARAM_EPOCH, call, lib, ptr, stream_ptr
 from ..activation import trunc_exp
 from ..encoding import get_encoder
 from .network_mask import NeRFNetwork as _InstanceNetwork
@@ -150,10 +150,16 @@ class NeRFNetwork(NeRFRenderer):
         ps = [self.encoder.embeddings, *[l.weight for l in self.sigma_net], *[l.weight for l in self.color_net]]
         return all(p.requires_grad for p in ps)
 
+    def bounded_stream(self) -> bool:
+        """The fused training forward / backward stop at the marcher's device-side sample total (inerf_field_desc.n_valid)."""
+        ps = [self.encoder.embeddings, *[l.weight for l in self.sigma_net], *[l.weight for l in self.color_net]]
+        return bool(self.fused_available() and torch.is_autocast_enabled() and hasattr(lib(), "inerf_field_backward_rgb")
+                    and self.bg_radius <= 0 and all(p.requires_grad for p in ps))
+
     def _packed_weights_rgb_bwd(self):
         ws = [m.weight for m in (*self.sigma_net, *self.color_net)]
         dev = ws[0].device
-        key = tuple((w.data_ptr(), w._version) for w in ws) + (str(dev),)
+        key = tuple((w.data_ptr(), w._version) for w in ws) + (str(dev), PARAM_EPOCH[0])
         if self._packed_rgb_bwd is None or self._packed_rgb_bwd[0] != key:
             blob = self._packed_rgb_bwd[1] if self._packed_rgb_bwd is not None and self._packed_rgb_bwd[1].device == dev else \
                 torch.empty(lib().inerf_field_rgb_bwd_weights_bytes(), dtype=torch.uint8, device=dev)

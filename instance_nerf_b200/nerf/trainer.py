@@ -47,30 +47,17 @@ class _MaskLoss(torch.autograd.Function):
         return grad, None, None, None, None
 
 
-class MaskTrainStep:
-    def __init__(self, model, lr=1e-2, fp16=True, patch_size=8, label_regularization_weight=0.0, dt_gamma=1 / 128, max_steps=1024,
-                 T_thresh=1e-4, data_parallel=False, fused_adam=True, fused_loss=True, cuda_graph=False, mask3d_loss_weight=0.0):
-        self.model = model
-        self.opt = SimpleNamespace(patch_size=patch_size, label_regularization_weight=label_regularization_weight,
-                                   mask3d_loss_weight=mask3d_loss_weight)
-        self.render_kw = dict(dt_gamma=dt_gamma, max_steps=max_steps, T_thresh=T_thresh)
-        self.fp16 = fp16
-        self.fused_loss = fused_loss
-        self.num_instances = model.num_instances
-        # freeze rgb and density (nerf/utils.py:1242-1246)
-        model.encoder.requires_grad_(False)
-        model.sigma_net.requires_grad_(False)
-        model.encoder_dir.requires_grad_(False)
-        model.color_net.requires_grad_(False)
-        self.criterion = nn.CrossEntropyLoss(reduction="none")          # main_nerf_mask.py:177
-        params = [{"params": [p for p in g["params"] if p.requires_grad], "lr": g["lr"]} for g in model.get_params(lr)]
-        params = [g for g in params if g["params"]]
+class _TrainStepBase:
+    """What the instance-stage and the stage-1 steps share: AMP (GradScaler), FusedAdam, the optional data-parallel flat
+    gradient bucket, and the CUDA-graph replay of the whole step over a fixed-size sample stream."""
+
+    def _setup(self, model, params, fp16, data_parallel, fused_adam, cuda_graph):
         dev = next(model.parameters()).device
         # cuda_graph: the whole step (march -> field -> composite -> loss -> backward -> Adam) replays as ONE CUDA graph; at
         # 4096 rays the eager step is bound by ~60 launches of host work, not by the GPU (DESIGN.md section 4.4)
         # (fp16 is required: the budget-overflow guard below turns the gradients non-finite and relies on an ENABLED
         # GradScaler to skip that optimizer step; without a scaler the replay would write inf into the parameters)
-        self.cuda_graph = bool(cuda_graph and fp16 and dev.type == "cuda" and fused_adam and fused_loss)
+        self.cuda_graph = bool(cuda_graph and fp16 and dev.type == "cuda" and fused_adam)
         self.world = dist.get_world_size() if (data_parallel and dist.is_available() and dist.is_initialized()) else 1
         params = [{"params": g["params"], "lr": float(g["lr"])} for g in params]
         if fused_adam and dev.type == "cuda":
@@ -97,59 +84,6 @@ class MaskTrainStep:
         self.graph_replays = 0
         self.last_total = 0         # marched samples of the last replayed step
         self.graph_captures = 0
-
-    def label_regularization(self, depth, pred_masks):
-        """nerf/utils.py:1262-1285: squared differences of neighbouring logits inside each patch, weighted by exp(-ddepth^2)."""
-        p = self.opt.patch_size
-        pm = pred_masks.view(-1, p, p, self.num_instances).permute(0, 3, 1, 2).contiguous()
-        diff_x = pm[:, :, :, 1:] - pm[:, :, :, :-1]
-        diff_y = pm[:, :, 1:, :] - pm[:, :, :-1, :]
-        depth = depth.view(-1, p, p)
-        ddx = depth[:, :, 1:] - depth[:, :, :-1]
-        ddy = depth[:, 1:, :] - depth[:, :-1, :]
-        wx = torch.exp(-(ddx * ddx)).unsqueeze(1).expand_as(diff_x)
-        wy = torch.exp(-(ddy * ddy)).unsqueeze(1).expand_as(diff_y)
-        return torch.sum(diff_x * diff_x * wx) / torch.sum(wx) + torch.sum(diff_y * diff_y * wy) / torch.sum(wy)
-
-    def train_step(self, data):
-        """nerf/utils.py:1287-1373 -> (pred_masks [B,N] argmax, gt_masks, loss)"""
-        rays_o, rays_d, gt_masks = data["rays_o"], data["rays_d"], data["masks"]
-        outputs = self.model.render(rays_o, rays_d, render_mask=True, staged=False, bg_color=1, perturb=True,
-                                    force_all_rays=self.opt.patch_size != 1, noises=data.get("noises"), **self.render_kw)
-        pred = outputs["instance_mask_logits"]
-        flat = pred.view(-1, self.num_instances)
-        gt = gt_masks.view(-1)
-        p = self.opt.patch_size
-        if self.fused_loss and flat.is_cuda and flat.shape[0] % (p * p) == 0:
-            loss = _MaskLoss.apply(flat, outputs["depth"], gt, p, self.opt.label_regularization_weight)
-        else:
-            labeled = gt != -1
-            # same value as the reference's boolean-index form, without the host sync of `labeled.sum() > 0`
-            ce = self.criterion(flat.float(), torch.where(labeled, gt, torch.zeros_like(gt)))
-            loss = (ce * labeled).sum() / labeled.sum().clamp(min=1)
-            if self.opt.label_regularization_weight > 0:
-                loss = loss + self.label_regularization(outputs["depth"], pred) * self.opt.label_regularization_weight
-        if self.opt.mask3d_loss_weight > 0:                     # 3d mask constraints (nerf/utils.py:1367-1369)
-            loss = loss + self.mask3d_loss(data).mean() * self.opt.mask3d_loss_weight
-        return pred.argmax(dim=-1), gt_masks, loss
-
-    def mask3d_loss(self, data):
-        """nerf/utils.py:1250-1260: cross-entropy of the instance head queried at labelled 3D points (`mask3d_coords` [N,3],
-        `mask3d_labels` [N]) -> [N].  On the fused path the query is the same one-launch field forward / backward the ray
-        samples take (the direction input only feeds the colour net, whose output is not used)."""
-        coords, labels = data["mask3d_coords"].view(-1, 3), data["mask3d_labels"].view(-1).long()
-        model = self.model
-        dirs = torch.zeros_like(coords)
-        dirs[:, 2] = 1.0
-        if hasattr(model, "fused_train_available") and torch.is_grad_enabled() and model.fused_train_available(coords, dirs):
-            saved, model._n_valid_ptr = model._n_valid_ptr, None     # every row of this batch is live (no marcher total applies)
-            try:
-                _, _, logits = model.forward_fused_train(coords, dirs)
-            finally:
-                model._n_valid_ptr = saved
-        else:
-            logits = model.mask(coords, geo_feat=model.density(coords)["geo_feat"])
-        return self.criterion(logits.float(), labels)
 
     def step(self, data):
         """One optimisation step (nerf/utils.py:929-936); returns the loss tensor (no host sync in the eager path)."""
@@ -306,27 +240,98 @@ class MaskTrainStep:
         return loss
 
 
-class RGBTrainStep:
+class MaskTrainStep(_TrainStepBase):
+    def __init__(self, model, lr=1e-2, fp16=True, patch_size=8, label_regularization_weight=0.0, dt_gamma=1 / 128, max_steps=1024,
+                 T_thresh=1e-4, data_parallel=False, fused_adam=True, fused_loss=True, cuda_graph=False, mask3d_loss_weight=0.0):
+        self.model = model
+        self.opt = SimpleNamespace(patch_size=patch_size, label_regularization_weight=label_regularization_weight,
+                                   mask3d_loss_weight=mask3d_loss_weight)
+        self.render_kw = dict(dt_gamma=dt_gamma, max_steps=max_steps, T_thresh=T_thresh)
+        self.fp16 = fp16
+        self.fused_loss = fused_loss
+        self.num_instances = model.num_instances
+        # freeze rgb and density (nerf/utils.py:1242-1246)
+        model.encoder.requires_grad_(False)
+        model.sigma_net.requires_grad_(False)
+        model.encoder_dir.requires_grad_(False)
+        model.color_net.requires_grad_(False)
+        self.criterion = nn.CrossEntropyLoss(reduction="none")          # main_nerf_mask.py:177
+        params = [{"params": [p for p in g["params"] if p.requires_grad], "lr": g["lr"]} for g in model.get_params(lr)]
+        params = [g for g in params if g["params"]]
+        self._setup(model, params, fp16, data_parallel, fused_adam, cuda_graph and fused_loss)
+
+    def label_regularization(self, depth, pred_masks):
+        """nerf/utils.py:1262-1285: squared differences of neighbouring logits inside each patch, weighted by exp(-ddepth^2)."""
+        p = self.opt.patch_size
+        pm = pred_masks.view(-1, p, p, self.num_instances).permute(0, 3, 1, 2).contiguous()
+        diff_x = pm[:, :, :, 1:] - pm[:, :, :, :-1]
+        diff_y = pm[:, :, 1:, :] - pm[:, :, :-1, :]
+        depth = depth.view(-1, p, p)
+        ddx = depth[:, :, 1:] - depth[:, :, :-1]
+        ddy = depth[:, 1:, :] - depth[:, :-1, :]
+        wx = torch.exp(-(ddx * ddx)).unsqueeze(1).expand_as(diff_x)
+        wy = torch.exp(-(ddy * ddy)).unsqueeze(1).expand_as(diff_y)
+        return torch.sum(diff_x * diff_x * wx) / torch.sum(wx) + torch.sum(diff_y * diff_y * wy) / torch.sum(wy)
+
+    def train_step(self, data):
+        """nerf/utils.py:1287-1373 -> (pred_masks [B,N] argmax, gt_masks, loss)"""
+        rays_o, rays_d, gt_masks = data["rays_o"], data["rays_d"], data["masks"]
+        outputs = self.model.render(rays_o, rays_d, render_mask=True, staged=False, bg_color=1, perturb=True,
+                                    force_all_rays=self.opt.patch_size != 1, noises=data.get("noises"), **self.render_kw)
+        pred = outputs["instance_mask_logits"]
+        flat = pred.view(-1, self.num_instances)
+        gt = gt_masks.view(-1)
+        p = self.opt.patch_size
+        if self.fused_loss and flat.is_cuda and flat.shape[0] % (p * p) == 0:
+            loss = _MaskLoss.apply(flat, outputs["depth"], gt, p, self.opt.label_regularization_weight)
+        else:
+            labeled = gt != -1
+            # same value as the reference's boolean-index form, without the host sync of `labeled.sum() > 0`
+            ce = self.criterion(flat.float(), torch.where(labeled, gt, torch.zeros_like(gt)))
+            loss = (ce * labeled).sum() / labeled.sum().clamp(min=1)
+            if self.opt.label_regularization_weight > 0:
+                loss = loss + self.label_regularization(outputs["depth"], pred) * self.opt.label_regularization_weight
+        if self.opt.mask3d_loss_weight > 0:                     # 3d mask constraints (nerf/utils.py:1367-1369)
+            loss = loss + self.mask3d_loss(data).mean() * self.opt.mask3d_loss_weight
+        return pred.argmax(dim=-1), gt_masks, loss
+
+    def mask3d_loss(self, data):
+        """nerf/utils.py:1250-1260: cross-entropy of the instance head queried at labelled 3D points (`mask3d_coords` [N,3],
+        `mask3d_labels` [N]) -> [N].  On the fused path the query is the same one-launch field forward / backward the ray
+        samples take (the direction input only feeds the colour net, whose output is not used)."""
+        coords, labels = data["mask3d_coords"].view(-1, 3), data["mask3d_labels"].view(-1).long()
+        model = self.model
+        dirs = torch.zeros_like(coords)
+        dirs[:, 2] = 1.0
+        if hasattr(model, "fused_train_available") and torch.is_grad_enabled() and model.fused_train_available(coords, dirs):
+            saved, model._n_valid_ptr = model._n_valid_ptr, None     # every row of this batch is live (no marcher total applies)
+            try:
+                _, _, logits = model.forward_fused_train(coords, dirs)
+            finally:
+                model._n_valid_ptr = saved
+        else:
+            logits = model.mask(coords, geo_feat=model.density(coords)["geo_feat"])
+        return self.criterion(logits.float(), labels)
+
+
+class RGBTrainStep(_TrainStepBase):
     """Stage-1 RGB-sigma training step (mirrors Trainer.train_step, nerf/utils.py:536-632, and the step loop :919-939):
     render a ray batch, MSE against the ground-truth colours (alpha-blended onto a random per-pixel background when the
-    images carry alpha), AMP backward through compositing, both MLPs, SH and the sigma hash table, Adam.  The LPIPS patch
+    images carry alpha), AMP backward through compositing, both MLPs, SH and the sigma hash table, Adam.  With fp16 autocast
+    and the standard architecture the field is one launch forward (inerf_field_forward_train_rgb) and one launch backward
+    (inerf_field_backward_rgb), and `cuda_graph=True` replays the whole step as the instance stage does.  The LPIPS patch
     term, CLIP loss and the error-map resampling of the reference's Trainer are outside the hot path."""
 
     def __init__(self, model, lr=1e-2, fp16=True, patch_size=1, dt_gamma=1 / 128, max_steps=1024, T_thresh=1e-4, data_parallel=False,
-                 fused_adam=True):
+                 fused_adam=True, cuda_graph=False):
         self.model = model
         self.opt = SimpleNamespace(patch_size=patch_size)
         self.render_kw = dict(dt_gamma=dt_gamma, max_steps=max_steps, T_thresh=T_thresh)
         self.fp16 = fp16
         self.criterion = nn.MSELoss(reduction="none")                                   # main_nerf.py:104
-        params = [{"params": list(g["params"]), "lr": g["lr"]} for g in model.get_params(lr)]
+        params = [{"params": list(g["params"]), "lr": g["lr"]} for g in model.get_params(lr)]   # main_nerf.py:120: Adam(betas=(0.9, 0.99), eps=1e-15)
         params = [g for g in params if g["params"]]
-        dev = next(model.parameters()).device
-        kw = dict(fused=True) if (fused_adam and dev.type == "cuda") else {}
-        self.optimizer = torch.optim.Adam(params, betas=(0.9, 0.99), eps=1e-15, **kw)   # main_nerf.py:120
-        self.scaler = torch.amp.GradScaler("cuda", enabled=fp16 and dev.type == "cuda")
-        self.bucket = GradBucket([p for g in params for p in g["params"]]) if data_parallel else None
-        self.global_step = 0
+        self._setup(model, params, fp16, data_parallel, fused_adam, cuda_graph)
 
     def train_step(self, data):
         """-> (pred_rgb [B,N,3], gt_rgb [B,N,3], loss)"""
@@ -343,16 +348,3 @@ class RGBTrainStep:
         pred_rgb = outputs["image"]
         loss = self.criterion(pred_rgb, gt_rgb).mean(-1).mean()
         return pred_rgb, gt_rgb, loss
-
-    def step(self, data):
-        self.model.train()
-        self.global_step += 1
-        self.optimizer.zero_grad(set_to_none=False)
-        with torch.autocast("cuda", dtype=torch.float16, enabled=self.fp16):
-            _, _, loss = self.train_step(data)
-        self.scaler.scale(loss).backward()
-        if self.bucket is not None:
-            self.bucket.sync()
-        self.scaler.step(self.optimizer)
-        self.scaler.update()
-        return loss.detach()

@@ -71,8 +71,10 @@ def test_rgb_train_step_learns(cuda):
     ts = RGBTrainStep(student, lr=5e-3, fp16=True)
     data = dict(rays_o=o, rays_d=d, images=target)
     losses = [float(ts.step(data)) for _ in range(30)]
+    ts._forward_backward(data)                  # gradients of one more batch, before the optimizer pass clears them (FusedAdam)
     for p in (student.encoder.embeddings, *[l.weight for l in (*student.sigma_net, *student.color_net)]):
         assert p.grad is not None and torch.isfinite(p.grad).all() and float(p.grad.abs().sum()) > 0
+    ts._optimizer_step()
     assert losses[-1] < 0.5 * losses[0], losses
     # RGBA target with an explicit per-pixel background (utils.py:563-571)
     rgba = torch.cat([target, torch.full_like(target[..., :1], 0.75)], -1)
