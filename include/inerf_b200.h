@@ -391,6 +391,15 @@ int inerf_adam_step(float *param, float *grad, float *exp_avg, float *exp_avg_sq
                     float grad_div, void *stream);
 int inerf_adam_advance(float *step, const float *found_inf, void *stream);
 
+/* ---- 3D-mask projection (scripts/project_3d_masks.py:135-266) ------------------------------------------------------------
+ * The labelled voxels of the predicted 3D masks (generate_predicted_grid, :108-131: labels int32 [nx, ny, nz], 0 = none) seen
+ * from a camera: every ray (rays_o / rays_d as inerf_get_rays builds them for that pose) walks the grid of cells centred on the
+ * reference's points (grid_pts_coord, :72-83; bbox_host = room_bbox as 6 HOST floats: min xyz, max xyz) with an exact 3D DDA;
+ * out_label[r] = first non-zero label along ray r (0: none), out_t[r] (may be NULL) = ray parameter where that cell is entered.
+ * Replaces the PyTorch3D point rasteriser of the reference (nearest labelled point per pixel). */
+int inerf_project_labels(const float *rays_o, const float *rays_d, uint32_t N, const int32_t *labels, uint32_t nx, uint32_t ny,
+                         uint32_t nz, const float *bbox_host, int32_t *out_label, float *out_t, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -140,3 +140,15 @@ def composite_rays(n_alive, n_step, T_thresh, rays_alive, rays_t, sigmas, rgbs, 
     masks = None if masks is None else _f32(masks)
     lib().oracle_composite_rays(ctypes.c_uint32(n_alive), ctypes.c_uint32(n_step), ctypes.c_uint32(K), ctypes.c_float(T_thresh), _p(rays_alive),
                                 _p(rays_t), _p(sigmas), _p(rgbs), _p(masks), _p(deltas), _p(weights_sum), _p(depth), _p(image), _p(mask_out))
+
+
+def project_labels(rays_o, rays_d, labels, bbox):
+    """oracle_project_labels: labels int32 [nx, ny, nz], bbox [6] (min xyz, max xyz) -> (label int32 [N], t float32 [N])."""
+    o, d = _f32(rays_o).reshape(-1, 3), _f32(rays_d).reshape(-1, 3)
+    lab = np.ascontiguousarray(labels, dtype=np.int32)
+    bb = _f32(bbox).reshape(6)
+    N = o.shape[0]
+    out_l, out_t = np.zeros(N, np.int32), np.zeros(N, np.float32)
+    lib().oracle_project_labels(_p(o), _p(d), ctypes.c_uint32(N), _p(lab), ctypes.c_uint32(lab.shape[0]), ctypes.c_uint32(lab.shape[1]),
+                                ctypes.c_uint32(lab.shape[2]), _p(bb), _p(out_l), _p(out_t))
+    return out_l, out_t
