@@ -220,23 +220,20 @@ __device__ __forceinline__ void sh16_to_smem(float x, float y, float z, uint8_t*
 __device__ __forceinline__ void issue_gemm(uint32_t smem_base, uint32_t a_off, uint32_t b_off, uint32_t Kdim, uint32_t N,
                                            uint32_t tmem_d) {
     const uint32_t idesc = umma::make_idesc_f16(128, N);
-    const uint32_t sbo = sbo_of(Kdim);
-    for (uint32_t k = 0; k < Kdim / 16; k++) {
-        const uint64_t da = umma::make_desc(smem_base + a_off + k * 2 * kLBO, kLBO, sbo);
-        const uint64_t db = umma::make_desc(smem_base + b_off + k * 2 * kLBO, kLBO, sbo);
-        umma::mma_f16(tmem_d, da, db, idesc, k > 0);
-    }
+    const uint32_t hi = umma::desc_hi(sbo_of(Kdim));
+    const uint32_t a_lo = umma::desc_lo(smem_base + a_off, kLBO), b_lo = umma::desc_lo(smem_base + b_off, kLBO);
+#pragma unroll
+    for (uint32_t k = 0; k < Kdim / 16; k++) umma::mma_f16_lohi(tmem_d, a_lo + k * (2 * kLBO >> 4), hi, b_lo + k * (2 * kLBO >> 4), hi, idesc, k > 0);
 }
 
 // general form: separate core-matrix row-group strides for A and B (operands that are column ranges of wider tiles)
 __device__ __forceinline__ void issue_gemm2(uint32_t smem_base, uint32_t a_off, uint32_t sbo_a, uint32_t b_off, uint32_t sbo_b, uint32_t Kdim,
                                             uint32_t N, uint32_t tmem_d) {
     const uint32_t idesc = umma::make_idesc_f16(128, N);
-    for (uint32_t k = 0; k < Kdim / 16; k++) {
-        const uint64_t da = umma::make_desc(smem_base + a_off + k * 2 * kLBO, kLBO, sbo_a);
-        const uint64_t db = umma::make_desc(smem_base + b_off + k * 2 * kLBO, kLBO, sbo_b);
-        umma::mma_f16(tmem_d, da, db, idesc, k > 0);
-    }
+    const uint32_t a_hi = umma::desc_hi(sbo_a), b_hi = umma::desc_hi(sbo_b);
+    const uint32_t a_lo = umma::desc_lo(smem_base + a_off, kLBO), b_lo = umma::desc_lo(smem_base + b_off, kLBO);
+#pragma unroll
+    for (uint32_t k = 0; k < Kdim / 16; k++) umma::mma_f16_lohi(tmem_d, a_lo + k * (2 * kLBO >> 4), a_hi, b_lo + k * (2 * kLBO >> 4), b_hi, idesc, k > 0);
 }
 // D[128 x N] (+)= A^T * B, the reduction running over the 128 ROWS (samples) of two K-major tiles: A is [128 x 128 cols]
 // (row-group stride sbo_a), B is [128 x N cols] (sbo_b).  The tiles are read as MN-major operands: same bytes, descriptor
@@ -244,11 +241,11 @@ __device__ __forceinline__ void issue_gemm2(uint32_t smem_base, uint32_t a_off, 
 __device__ __forceinline__ void issue_gemm_tn(uint32_t smem_base, uint32_t a_off, uint32_t sbo_a, uint32_t b_off, uint32_t sbo_b, uint32_t N,
                                               uint32_t tmem_d, bool accumulate) {
     const uint32_t idesc = umma::make_idesc_f16(128, N) | (1u << 15) | (1u << 16);   // a_major = b_major = MN
-    for (uint32_t k = 0; k < kTile / 16; k++) {
-        const uint64_t da = umma::make_desc(smem_base + a_off + k * 2 * sbo_a, sbo_a, 128);
-        const uint64_t db = umma::make_desc(smem_base + b_off + k * 2 * sbo_b, sbo_b, 128);
-        umma::mma_f16(tmem_d, da, db, idesc, accumulate || k > 0);
-    }
+    const uint32_t hi = umma::desc_hi(128);
+    const uint32_t a_lo = umma::desc_lo(smem_base + a_off, sbo_a), b_lo = umma::desc_lo(smem_base + b_off, sbo_b);
+#pragma unroll
+    for (uint32_t k = 0; k < kTile / 16; k++)
+        umma::mma_f16_lohi(tmem_d, a_lo + k * (2 * sbo_a >> 4), hi, b_lo + k * (2 * sbo_b >> 4), hi, idesc, accumulate || k > 0);
 }
 
 // ---- epilogues (chain group: 8 warps; warp w owns TMEM lanes 32*(w&3).., column half w>>2) ---------
@@ -322,9 +319,9 @@ __device__ __forceinline__ float mlp_chain(uint8_t* smem, const ChainBufs& b, ui
                                            OnSigma&& on_sigma) {
     const uint32_t sbase = umma::smem_u32(smem);
     const WeightLayout wl = weight_layout(K);
-    const bool issuer = tid == 0;
+    const bool issue_warp = tid < 32;   // warp 0 of the chain group; one elected lane issues
     // sigma layer 0
-    if (issuer) {
+    if (issue_warp && umma::elect_one()) {
         umma::fence_after_sync();
         issue_gemm(sbase, b.a_es, b.w + wl.s0, 32, 64, tmem_base + D_a);
         umma::commit(bar);
@@ -336,7 +333,7 @@ __device__ __forceinline__ float mlp_chain(uint8_t* smem, const ChainBufs& b, ui
     umma::fence_async_smem(); umma::fence_before_sync();
     sync();
     // sigma layer 1
-    if (issuer) {
+    if (issue_warp && umma::elect_one()) {
         umma::fence_after_sync();
         issue_gemm(sbase, b.a_h1, b.w + wl.s1, 64, 16, tmem_base + D_c);
         umma::commit(bar);
@@ -349,7 +346,7 @@ __device__ __forceinline__ float mlp_chain(uint8_t* smem, const ChainBufs& b, ui
     umma::fence_async_smem(); umma::fence_before_sync();
     sync();
     // colour layer 0 + mask layer 0
-    if (issuer) {
+    if (issue_warp && umma::elect_one()) {
         umma::fence_after_sync();
         issue_gemm(sbase, b.a_ci, b.w + wl.c0, 32, 64, tmem_base + D_a);
         if (with_masks) issue_gemm(sbase, b.a_mi, b.w + wl.m0, 48, 64, tmem_base + D_b);
@@ -364,7 +361,7 @@ __device__ __forceinline__ float mlp_chain(uint8_t* smem, const ChainBufs& b, ui
     umma::fence_async_smem(); umma::fence_before_sync();
     sync();
     // colour layer 1 + mask layer 1
-    if (issuer) {
+    if (issue_warp && umma::elect_one()) {
         umma::fence_after_sync();
         issue_gemm(sbase, b.a_h1, b.w + wl.c1, 64, 64, tmem_base + D_a);
         if (with_masks) issue_gemm(sbase, b.a_h2, b.w + wl.m1, 64, 64, tmem_base + D_b);
@@ -378,7 +375,7 @@ __device__ __forceinline__ float mlp_chain(uint8_t* smem, const ChainBufs& b, ui
     umma::fence_async_smem(); umma::fence_before_sync();
     sync();
     // colour layer 2 + mask layer 2
-    if (issuer) {
+    if (issue_warp && umma::elect_one()) {
         umma::fence_after_sync();
         issue_gemm(sbase, b.a_h1, b.w + wl.c2, 64, 16, tmem_base + D_c);
         if (with_masks) issue_gemm(sbase, b.a_h2, b.w + wl.m2, 64, wl.Kp, tmem_base + D_d);
@@ -398,8 +395,8 @@ __device__ __forceinline__ float sigma_chain(uint8_t* smem, const ChainBufs& b, 
                                              uint32_t tid, uint64_t* release_bar, Sync&& sync) {
     const uint32_t sbase = umma::smem_u32(smem);
     const WeightLayout wl = weight_layout(K);
-    const bool issuer = tid == 0;
-    if (issuer) {
+    const bool issue_warp = tid < 32;   // warp 0 of the chain group; one elected lane issues
+    if (issue_warp && umma::elect_one()) {
         umma::fence_after_sync();
         issue_gemm(sbase, b.a_es, b.w + wl.s0, 32, 64, tmem_base + D_a);
         umma::commit(bar);
@@ -411,7 +408,7 @@ __device__ __forceinline__ float sigma_chain(uint8_t* smem, const ChainBufs& b, 
     epilogue_hidden(tmem_base + D_a, smem, b.a_h1, tid);
     umma::fence_async_smem(); umma::fence_before_sync();
     sync();
-    if (issuer) {
+    if (issue_warp && umma::elect_one()) {
         umma::fence_after_sync();
         issue_gemm(sbase, b.a_h1, b.w + wl.s1, 64, 16, tmem_base + D_c);
         umma::commit(bar);

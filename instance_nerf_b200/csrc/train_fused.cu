@@ -271,7 +271,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_field_backward_mask(inerf_fi
     const uint32_t B_eff = desc.n_valid ? min(p.B, (uint32_t)max(0, __ldg(desc.n_valid))) : p.B;   // rows past *n_valid are padding
     const uint32_t num_tiles = (B_eff + kTile - 1) / kTile;
     uint32_t phase = 0, tiles_done = 0;
-    const bool issuer = tid == 0;
+    const bool issue_warp = tid < 32;   // one elected lane of warp 0 issues the MMAs (uniform branch for the compiler)
 
     auto wait_mma = [&] {
         __syncwarp();
@@ -345,7 +345,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_field_backward_mask(inerf_fi
         }
         publish();
         // ---- S1: H1 pre-activation and dY W2 -----------------------------------------------------------------------
-        if (issuer) {
+        if (issue_warp && umma::elect_one()) {
             umma::fence_after_sync();
             issue_gemm2(sbase, BSmem::TX, kSbo48, BSmem::W + BwdWeights::w0, kSbo48, 48, 64, tmem + T_a);
             issue_gemm2(sbase, BSmem::TG, kSbo128, BSmem::W + BwdWeights::w2t, kSbo64, 64, 64, tmem + T_b);
@@ -356,7 +356,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_field_backward_mask(inerf_fi
         const uint32_t mask1 = epi_relu32(tmem + T_a + lane_base + half * 32, smem, BSmem::TH, row, 64 + half * 32);   // H1 -> TH[:, 64:128]
         publish();
         // ---- S2: H2 pre-activation; dH2 = (dY W2) . [H2 > 0] ---------------------------------------------------
-        if (issuer) {
+        if (issue_warp && umma::elect_one()) {
             umma::fence_after_sync();
             issue_gemm2(sbase, BSmem::TH + 8 * kLBO, kSbo128, BSmem::W + BwdWeights::w1, kSbo64, 64, 64, tmem + T_a);
             umma::commit(bar);
@@ -366,7 +366,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_field_backward_mask(inerf_fi
         epi_masked32(tmem + T_b + lane_base + half * 32, mask2, smem, BSmem::TG, row, 64 + half * 32);                 // dH2 -> TG[:, 64:128]
         publish();
         // ---- S3: dH1 = (dH2 W1) . [H1 > 0] --------------------------------------------------------------------------
-        if (issuer) {
+        if (issue_warp && umma::elect_one()) {
             umma::fence_after_sync();
             issue_gemm2(sbase, BSmem::TG + 8 * kLBO, kSbo128, BSmem::W + BwdWeights::w1t, kSbo64, 64, 64, tmem + T_b);
             umma::commit(bar);
@@ -375,7 +375,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_field_backward_mask(inerf_fi
         epi_masked32(tmem + T_b + lane_base + half * 32, mask1, smem, BSmem::TG2, row, half * 32);                     // dH1 -> TG2[:, 0:64]
         publish();
         // ---- S4: dF = dH1 W0[:, :32]; weight gradients accumulate across tiles ------------------------------------
-        if (issuer) {
+        if (issue_warp && umma::elect_one()) {
             umma::fence_after_sync();
             issue_gemm2(sbase, BSmem::TG2, kSbo128, BSmem::W + BwdWeights::w0t, kSbo64, 64, 32, tmem + T_x);
             issue_gemm_tn(sbase, BSmem::TG, kSbo128, BSmem::TH, kSbo128, 128, tmem + T_w1, tiles_done > 0);
@@ -536,7 +536,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_field_backward_rgb(inerf_fie
     const uint32_t B_eff = desc.n_valid ? min(p.B, (uint32_t)max(0, __ldg(desc.n_valid))) : p.B;
     const uint32_t num_tiles = (B_eff + kTile - 1) / kTile;
     uint32_t phase = 0, tiles_done = 0;
-    const bool issuer = tid == 0;
+    const bool issue_warp = tid < 32;   // one elected lane of warp 0 issues the MMAs (uniform branch for the compiler)
     constexpr uint32_t Wb = RSm::W;
 
     auto wait_mma = [&] {
@@ -600,7 +600,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_field_backward_rgb(inerf_fie
         }
         publish();
         // ---- S1: Hs, Hc1 pre-activations; dP Wc2 ---------------------------------------------------------------------------
-        if (issuer) {
+        if (issue_warp && umma::elect_one()) {
             umma::fence_after_sync();
             issue_gemm2(sbase, RSm::HB, kSbo160, Wb + RgbBwdWeights::ws0, kSbo32, 32, 64, tmem + R_a);
             issue_gemm2(sbase, RSm::HA + 8 * kLBO, kSbo96, Wb + RgbBwdWeights::wc0, kSbo32, 32, 64, tmem + R_b);
@@ -613,7 +613,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_field_backward_rgb(inerf_fie
         const uint32_t mask_c1 = epi_relu_to(tmem + R_b + lane_base + half * 32, smem, RSm::HA, kSbo96, row, half * 32);        // Hc1 -> HA[:, 0:64]
         publish();
         // ---- S2: Hc2 pre-activation; dHc2 = (dP Wc2) . [Hc2 > 0] --------------------------------------------------------------
-        if (issuer) {
+        if (issue_warp && umma::elect_one()) {
             umma::fence_after_sync();
             issue_gemm2(sbase, RSm::HA, kSbo96, Wb + RgbBwdWeights::wc1, kSbo64, 64, 64, tmem + R_a);
             umma::commit(bar);
@@ -623,7 +623,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_field_backward_rgb(inerf_fie
         epi_masked32(tmem + R_c + lane_base + half * 32, mask_c2, smem, RSm::GA, row, half * 32);                               // dHc2 -> GA[:, 0:64]
         publish();
         // ---- S3: dHc1 = (dHc2 Wc1) . [Hc1 > 0] ----------------------------------------------------------------------------------
-        if (issuer) {
+        if (issue_warp && umma::elect_one()) {
             umma::fence_after_sync();
             issue_gemm2(sbase, RSm::GA, kSbo128, Wb + RgbBwdWeights::wc1t, kSbo64, 64, 64, tmem + R_b);
             umma::commit(bar);
@@ -632,7 +632,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_field_backward_rgb(inerf_fie
         epi_masked32(tmem + R_b + lane_base + half * 32, mask_c1, smem, RSm::GA, row, 64 + half * 32);                          // dHc1 -> GA[:, 64:128]
         publish();
         // ---- S4: dCi = dHc1 Wc0; the density head's output gradient dO = [dh0 | dgeo15] ----------------------------------------
-        if (issuer) {
+        if (issue_warp && umma::elect_one()) {
             umma::fence_after_sync();
             issue_gemm2(sbase, RSm::GA + 8 * kLBO, kSbo128, Wb + RgbBwdWeights::wc0t, kSbo64, 64, 32, tmem + R_x);
             umma::commit(bar);
@@ -651,7 +651,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_field_backward_rgb(inerf_fie
         }
         publish();
         // ---- S5: dHs = (dO Ws1) . [Hs > 0] ---------------------------------------------------------------------------------------
-        if (issuer) {
+        if (issue_warp && umma::elect_one()) {
             umma::fence_after_sync();
             issue_gemm2(sbase, RSm::GB + 12 * kLBO, kSbo128, Wb + RgbBwdWeights::ws1t, kSbo16, 16, 64, tmem + R_a);
             umma::commit(bar);
@@ -660,7 +660,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_field_backward_rgb(inerf_fie
         epi_masked32(tmem + R_a + lane_base + half * 32, mask_s, smem, RSm::GB, row, half * 32);                                // dHs -> GB[:, 0:64]
         publish();
         // ---- S6: dE = dHs Ws0; weight gradients accumulate across tiles ----------------------------------------------------------
-        if (issuer) {
+        if (issue_warp && umma::elect_one()) {
             umma::fence_after_sync();
             issue_gemm2(sbase, RSm::GB, kSbo128, Wb + RgbBwdWeights::ws0t, kSbo64, 64, 32, tmem + R_x);
             issue_gemm_tn(sbase, RSm::GA, kSbo128, RSm::HA, kSbo96, 96, tmem + R_w1, tiles_done > 0);

@@ -6,7 +6,7 @@ from test_field_gpu import build_model
 from helpers import make_rays
 
 cuda = torch.device("cuda:0")
-for ds in (1.0, 10.0, 50.0):
+for ds in (10.0,):
     m, sc = build_model(cuda, 32, density_scale=ds)
     o, d = make_rays(sc, 480, 640)
     o, d = o.to(cuda), d.to(cuda)
