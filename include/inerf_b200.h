@@ -400,6 +400,12 @@ int inerf_adam_advance(float *step, const float *found_inf, void *stream);
 int inerf_project_labels(const float *rays_o, const float *rays_d, uint32_t N, const int32_t *labels, uint32_t nx, uint32_t ny,
                          uint32_t nz, const float *bbox_host, int32_t *out_label, float *out_t, void *stream);
 
+/* ---- frame finalisation (MaskTrainer.test / evaluate_one_epoch, nerf/utils.py:1425-1431, 1461-1485, 1624-1634) ----------------
+ * rgb[N,3] / depth_u8[N] = (x * 255) truncated to uint8 (saturating), label[N] = argmax_k logits[N,K] (= the reference's
+ * softmax + argmax; lowest index on ties; K <= 256).  depth / depth_u8 and logits / label may be NULL in pairs. */
+int inerf_frame_to_u8(const float *image, const float *depth, const float *logits, uint32_t N, uint32_t K, uint8_t *rgb,
+                      uint8_t *depth_u8, uint8_t *label, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

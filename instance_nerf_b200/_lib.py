@@ -82,6 +82,7 @@ _PROTOS = {
     "inerf_composite_rays": [_U, _U, _F, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "inerf_composite_rays_with_masks": [_U, _U, _U, _F, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "inerf_compact_alive": [_P, _U, _P, _P, _P],
+    "inerf_frame_to_u8": [_P, _P, _P, _U, _U, _P, _P, _P, _P],
     "inerf_project_labels": [_P, _P, _U, _P, _U, _U, _U, _P, _P, _P, _P],
     "inerf_get_rays": [_P, _U, _F, _F, _F, _F, _U, _U, _P, _U, _P, _P, _P, _F, _P, _P, _P],
     "inerf_grid_encode_forward": [_P, _P, _P, _P, _U, _U, _U, _U, _F, _U, _P, _U, _I, _U, _I, _I, _P],

@@ -3,7 +3,8 @@ label_regularization / mask3d_loss, and the step loop nerf/utils.py:919-939), re
 RGB-sigma nets, render a ray batch with `render_mask=True`, cross-entropy on labelled pixels + depth-aware label smoothness on
 the 8x8 patches + optional 3D-mask cross-entropy, AMP backward, (optional data-parallel gradient all-reduce,) Adam.
 
-Data providers, logging, checkpoints and evaluation of the reference's Trainer are out of scope.
+Data providers: nerf/provider.py; checkpoints: nerf/checkpoint.py; the test loop and image writers: nerf/evaluate.py.  Logging,
+metrics and the epoch loop of the reference's Trainer are out of scope.
 """
 from __future__ import annotations
 
@@ -294,6 +295,31 @@ class MaskTrainStep(_TrainStepBase):
         if self.opt.mask3d_loss_weight > 0:                     # 3d mask constraints (nerf/utils.py:1367-1369)
             loss = loss + self.mask3d_loss(data).mean() * self.opt.mask3d_loss_weight
         return pred.argmax(dim=-1), gt_masks, loss
+
+    @torch.no_grad()
+    def eval_step(self, data, bg_color=1):
+        """nerf/utils.py:1375-1408 -> (pred_rgb [B,H,W,3], pred_depth [B,H,W], pred_masks [B,H,W] argmax, gt_masks, loss)"""
+        rays_o, rays_d, gt_masks = data["rays_o"], data["rays_d"], data["masks"]
+        B, H, W = gt_masks.shape
+        outputs = self.model.render(rays_o, rays_d, render_mask=True, staged=True, bg_color=bg_color, perturb=False, **self.render_kw)
+        logits = outputs["instance_mask_logits"].reshape(B, H, W, -1)
+        flat, gt = logits.view(-1, self.num_instances).float(), gt_masks.view(-1)
+        labeled = gt != -1
+        loss = (self.criterion(flat, torch.where(labeled, gt, torch.zeros_like(gt))) * labeled).sum() / labeled.sum().clamp(min=1)
+        if self.opt.label_regularization_weight > 0:
+            loss = loss + self.label_regularization(outputs["depth"], logits) * self.opt.label_regularization_weight
+        if self.opt.mask3d_loss_weight > 0:
+            loss = loss + self.mask3d_loss(data).mean() * self.opt.mask3d_loss_weight
+        return outputs["image"].reshape(B, H, W, 3), outputs["depth"].reshape(B, H, W), logits.argmax(dim=-1), gt_masks, loss
+
+    @torch.no_grad()
+    def test_step(self, data, bg_color=None, perturb=False):
+        """nerf/utils.py:1410-1431 -> (pred_rgb [B,H,W,3], pred_depth [B,H,W], pred_masks [B,H,W])"""
+        B, H, W = data["rays_o"].shape[0], data["H"], data["W"]
+        outputs = self.model.render(data["rays_o"], data["rays_d"], render_mask=True, staged=True, bg_color=bg_color, perturb=perturb,
+                                    **self.render_kw)
+        return (outputs["image"].reshape(-1, H, W, 3), outputs["depth"].reshape(-1, H, W),
+                outputs["instance_mask_logits"].reshape(B, H, W, -1).argmax(dim=-1))
 
     def mask3d_loss(self, data):
         """nerf/utils.py:1250-1260: cross-entropy of the instance head queried at labelled 3D points (`mask3d_coords` [N,3],
