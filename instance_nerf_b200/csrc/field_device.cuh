@@ -65,11 +65,15 @@ constexpr uint32_t kStageBytes = kBytesEs + kBytesCi + kBytesMi;   // what the g
 constexpr uint32_t sbo_of(uint32_t kdim) { return (kdim / 8) * 128; }
 
 // TMEM column plan (fp32 accumulators)
-constexpr uint32_t kTmemCols = 256;
+constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t D_a = 0;     // 64: sigma hidden / colour hidden
 constexpr uint32_t D_b = 64;    // 64: mask hidden
 constexpr uint32_t D_c = 128;   // 16: sigma-net output / rgb
 constexpr uint32_t D_d = 144;   // up to 64: logits
+// hidden activations as tcgen05 A operands IN TENSOR MEMORY (fp16 pairs, 32 columns per 64-wide layer): the epilogue of layer
+// i writes them with tcgen05.st and the MMAs of layer i + 1 read them there -- they never touch shared memory
+constexpr uint32_t A_h1 = 208;  // 32: sigma hidden, then colour hidden
+constexpr uint32_t A_h2 = 240;  // 32: mask hidden
 
 __device__ __forceinline__ uint32_t pack_half2(__half a, __half b) {
     return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16);
@@ -226,6 +230,15 @@ __device__ __forceinline__ void issue_gemm(uint32_t smem_base, uint32_t a_off, u
     for (uint32_t k = 0; k < Kdim / 16; k++) umma::mma_f16_lohi(tmem_d, a_lo + k * (2 * kLBO >> 4), hi, b_lo + k * (2 * kLBO >> 4), hi, idesc, k > 0);
 }
 
+// A operand in tensor memory (columns tmem_a .. tmem_a + Kdim / 2), B [N x Kdim] in shared memory
+__device__ __forceinline__ void issue_gemm_ts(uint32_t tmem_a, uint32_t smem_base, uint32_t b_off, uint32_t Kdim, uint32_t N, uint32_t tmem_d) {
+    const uint32_t idesc = umma::make_idesc_f16(128, N);
+    const uint32_t hi = umma::desc_hi(sbo_of(Kdim));
+    const uint32_t b_lo = umma::desc_lo(smem_base + b_off, kLBO);
+#pragma unroll
+    for (uint32_t k = 0; k < Kdim / 16; k++) umma::mma_f16_ts(tmem_d, tmem_a + k * 8, b_lo + k * (2 * kLBO >> 4), hi, idesc, k > 0);
+}
+
 // general form: separate core-matrix row-group strides for A and B (operands that are column ranges of wider tiles)
 __device__ __forceinline__ void issue_gemm2(uint32_t smem_base, uint32_t a_off, uint32_t sbo_a, uint32_t b_off, uint32_t sbo_b, uint32_t Kdim,
                                             uint32_t N, uint32_t tmem_d) {
@@ -268,6 +281,24 @@ __device__ __forceinline__ void epilogue_hidden(uint32_t tmem_d, uint8_t* smem, 
         *reinterpret_cast<uint4*>(smem + a_off + umma::tile_off(row, k, kLBO, sbo_of(64))) = make_uint4(p[0], p[1], p[2], p[3]);
         *reinterpret_cast<uint4*>(smem + a_off + umma::tile_off(row, k + 8, kLBO, sbo_of(64))) = make_uint4(p[4], p[5], p[6], p[7]);
     }
+}
+
+// Same, the result going to TENSOR MEMORY as the next layer's A operand: columns tmem_a + 16 * (warp >> 2) .. + 16 of this
+// thread's lane hold its 32 fp16 values as 16 packed pairs.  The caller waits (tmem_st_wait) before the group barrier.
+__device__ __forceinline__ void epilogue_hidden_tmem(uint32_t tmem_d, uint32_t tmem_a, uint32_t tid) {
+    const uint32_t warp = tid >> 5;
+    const uint32_t lane_base = ((warp & 3u) * 32u) << 16, half = warp >> 2;
+    uint32_t v[2][16];
+    umma::tmem_ld16(tmem_d + lane_base + half * 32u, v[0]);
+    umma::tmem_ld16(tmem_d + lane_base + half * 32u + 16u, v[1]);
+    umma::tmem_ld_wait();
+    uint32_t p[16];
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        p[i] = cvt_relu_f16x2(__uint_as_float(v[0][2 * i]), __uint_as_float(v[0][2 * i + 1]));
+        p[8 + i] = cvt_relu_f16x2(__uint_as_float(v[1][2 * i]), __uint_as_float(v[1][2 * i + 1]));
+    }
+    umma::tmem_st16(tmem_a + lane_base + half * 16u, p);
 }
 
 // sigma-net output (16 columns): h0 -> sigma (returned, valid for warps 0..3), geo15 -> A_ci[:,16:32] and A_mi[:,32:48]
@@ -329,13 +360,13 @@ __device__ __forceinline__ float mlp_chain(uint8_t* smem, const ChainBufs& b, ui
     __syncwarp();
     umma::mbar_wait(bar, phase); phase ^= 1u;
     umma::fence_after_sync();
-    epilogue_hidden(tmem_base + D_a, smem, b.a_h1, tid);
-    umma::fence_async_smem(); umma::fence_before_sync();
+    epilogue_hidden_tmem(tmem_base + D_a, tmem_base + A_h1, tid);
+    umma::tmem_st_wait(); umma::fence_before_sync();
     sync();
     // sigma layer 1
     if (issue_warp && umma::elect_one()) {
         umma::fence_after_sync();
-        issue_gemm(sbase, b.a_h1, b.w + wl.s1, 64, 16, tmem_base + D_c);
+        issue_gemm_ts(tmem_base + A_h1, sbase, b.w + wl.s1, 64, 16, tmem_base + D_c);
         umma::commit(bar);
     }
     __syncwarp();
@@ -356,29 +387,29 @@ __device__ __forceinline__ float mlp_chain(uint8_t* smem, const ChainBufs& b, ui
     __syncwarp();
     umma::mbar_wait(bar, phase); phase ^= 1u;
     umma::fence_after_sync();
-    epilogue_hidden(tmem_base + D_a, smem, b.a_h1, tid);
-    if (with_masks) epilogue_hidden(tmem_base + D_b, smem, b.a_h2, tid);
-    umma::fence_async_smem(); umma::fence_before_sync();
+    epilogue_hidden_tmem(tmem_base + D_a, tmem_base + A_h1, tid);
+    if (with_masks) epilogue_hidden_tmem(tmem_base + D_b, tmem_base + A_h2, tid);
+    umma::tmem_st_wait(); umma::fence_before_sync();
     sync();
     // colour layer 1 + mask layer 1
     if (issue_warp && umma::elect_one()) {
         umma::fence_after_sync();
-        issue_gemm(sbase, b.a_h1, b.w + wl.c1, 64, 64, tmem_base + D_a);
-        if (with_masks) issue_gemm(sbase, b.a_h2, b.w + wl.m1, 64, 64, tmem_base + D_b);
+        issue_gemm_ts(tmem_base + A_h1, sbase, b.w + wl.c1, 64, 64, tmem_base + D_a);
+        if (with_masks) issue_gemm_ts(tmem_base + A_h2, sbase, b.w + wl.m1, 64, 64, tmem_base + D_b);
         umma::commit(bar);
     }
     __syncwarp();
     umma::mbar_wait(bar, phase); phase ^= 1u;
     umma::fence_after_sync();
-    epilogue_hidden(tmem_base + D_a, smem, b.a_h1, tid);
-    if (with_masks) epilogue_hidden(tmem_base + D_b, smem, b.a_h2, tid);
-    umma::fence_async_smem(); umma::fence_before_sync();
+    epilogue_hidden_tmem(tmem_base + D_a, tmem_base + A_h1, tid);
+    if (with_masks) epilogue_hidden_tmem(tmem_base + D_b, tmem_base + A_h2, tid);
+    umma::tmem_st_wait(); umma::fence_before_sync();
     sync();
     // colour layer 2 + mask layer 2
     if (issue_warp && umma::elect_one()) {
         umma::fence_after_sync();
-        issue_gemm(sbase, b.a_h1, b.w + wl.c2, 64, 16, tmem_base + D_c);
-        if (with_masks) issue_gemm(sbase, b.a_h2, b.w + wl.m2, 64, wl.Kp, tmem_base + D_d);
+        issue_gemm_ts(tmem_base + A_h1, sbase, b.w + wl.c2, 64, 16, tmem_base + D_c);
+        if (with_masks) issue_gemm_ts(tmem_base + A_h2, sbase, b.w + wl.m2, 64, wl.Kp, tmem_base + D_d);
         umma::commit(bar);
     }
     __syncwarp();
@@ -405,12 +436,12 @@ __device__ __forceinline__ float sigma_chain(uint8_t* smem, const ChainBufs& b, 
     __syncwarp();
     umma::mbar_wait(bar, phase); phase ^= 1u;
     umma::fence_after_sync();
-    epilogue_hidden(tmem_base + D_a, smem, b.a_h1, tid);
-    umma::fence_async_smem(); umma::fence_before_sync();
+    epilogue_hidden_tmem(tmem_base + D_a, tmem_base + A_h1, tid);
+    umma::tmem_st_wait(); umma::fence_before_sync();
     sync();
     if (issue_warp && umma::elect_one()) {
         umma::fence_after_sync();
-        issue_gemm(sbase, b.a_h1, b.w + wl.s1, 64, 16, tmem_base + D_c);
+        issue_gemm_ts(tmem_base + A_h1, sbase, b.w + wl.s1, 64, 16, tmem_base + D_c);
         umma::commit(bar);
     }
     __syncwarp();
