@@ -51,13 +51,11 @@ struct LevelGeom {
     uint32_t pad;
 };
 
-// Operand-tile byte offsets of one pipeline stage + the chain's private tiles + the weight blob.
+// Operand-tile byte offsets of one pipeline stage + the weight blob (the hidden activations live in tensor memory).
 struct ChainBufs {
     uint32_t a_es;   // [128 x 32] sigma-table features
     uint32_t a_ci;   // [128 x 32] SH16 | geo15 | 0
     uint32_t a_mi;   // [128 x 48] mask-table features 32 | geo15 | 0
-    uint32_t a_h1;   // [128 x 64] hidden (sigma, then colour)
-    uint32_t a_h2;   // [128 x 64] hidden (mask)
     uint32_t w;      // weight blob
 };
 constexpr uint32_t kBytesEs = kTile * 32 * 2, kBytesCi = kTile * 32 * 2, kBytesMi = kTile * 48 * 2, kBytesH = kTile * 64 * 2;
@@ -262,29 +260,9 @@ __device__ __forceinline__ void issue_gemm_tn(uint32_t smem_base, uint32_t a_off
 }
 
 // ---- epilogues (chain group: 8 warps; warp w owns TMEM lanes 32*(w&3).., column half w>>2) ---------
-// 64-wide hidden layer: TMEM -> fp16 round -> ReLU -> next A tile.
-__device__ __forceinline__ void epilogue_hidden(uint32_t tmem_d, uint8_t* smem, uint32_t a_off, uint32_t tid) {
-    const uint32_t warp = tid >> 5, lane = tid & 31;
-    const uint32_t row = (warp & 3u) * 32u + lane, c0 = (warp >> 2) * 32u;
-    const uint32_t taddr = tmem_d + (((warp & 3u) * 32u) << 16) + c0;
-    uint32_t v[2][16];
-    umma::tmem_ld16(taddr, v[0]);
-    umma::tmem_ld16(taddr + 16, v[1]);
-    umma::tmem_ld_wait();
-#pragma unroll
-    for (int h = 0; h < 2; h++) {
-        uint32_t p[8];
-#pragma unroll
-        for (int i = 0; i < 8; i++)
-            p[i] = cvt_relu_f16x2(__uint_as_float(v[h][2 * i]), __uint_as_float(v[h][2 * i + 1]));
-        const uint32_t k = c0 + h * 16;
-        *reinterpret_cast<uint4*>(smem + a_off + umma::tile_off(row, k, kLBO, sbo_of(64))) = make_uint4(p[0], p[1], p[2], p[3]);
-        *reinterpret_cast<uint4*>(smem + a_off + umma::tile_off(row, k + 8, kLBO, sbo_of(64))) = make_uint4(p[4], p[5], p[6], p[7]);
-    }
-}
-
-// Same, the result going to TENSOR MEMORY as the next layer's A operand: columns tmem_a + 16 * (warp >> 2) .. + 16 of this
-// thread's lane hold its 32 fp16 values as 16 packed pairs.  The caller waits (tmem_st_wait) before the group barrier.
+// 64-wide hidden layer: TMEM accumulators -> fp16 round -> ReLU -> the next layer's A operand IN TENSOR MEMORY: columns
+// tmem_a + 16 * (warp >> 2) .. + 16 of this thread's lane hold its 32 fp16 values as 16 packed pairs.  The caller waits
+// (tmem_st_wait) before the group barrier.
 __device__ __forceinline__ void epilogue_hidden_tmem(uint32_t tmem_d, uint32_t tmem_a, uint32_t tid) {
     const uint32_t warp = tid >> 5;
     const uint32_t lane_base = ((warp & 3u) * 32u) << 16, half = warp >> 2;

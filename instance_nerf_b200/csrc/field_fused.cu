@@ -29,9 +29,7 @@ struct WsCtrl {
 };
 struct WsSmem {
     static constexpr uint32_t A = 0;
-    static constexpr uint32_t H1 = A + kWsStages * kStageBytes;
-    static constexpr uint32_t H2 = H1 + kBytesH;
-    static constexpr uint32_t W = H2 + kBytesH;
+    static constexpr uint32_t W = A + kWsStages * kStageBytes;
     static __host__ __device__ uint32_t ctrl(uint32_t K) { return (W + weight_layout(K).total + 15u) & ~15u; }
     static __host__ __device__ uint32_t bytes(uint32_t K) { return ctrl(K) + (uint32_t)sizeof(WsCtrl) + 16u; }
 };
@@ -72,7 +70,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) k_field_forward_ws(inerf_field_
             const uint32_t sa = it % kWsStages;
             umma::mbar_wait(&ctl->a_full[sa], (it / kWsStages) & 1u);
             const uint32_t a_es = WsSmem::A + sa * kStageBytes;
-            const ChainBufs bufs{a_es, a_es + kBytesEs, a_es + kBytesEs + kBytesCi, WsSmem::H1, WsSmem::H2, WsSmem::W};
+            const ChainBufs bufs{a_es, a_es + kBytesEs, a_es + kBytesEs + kBytesCi, WsSmem::W};
             const uint32_t orow = tile * kTile + (warp & 3u) * 32u + lane;
             const float sigma = mlp_chain(smem, bufs, tmem_base, &ctl->mma_bar, phase, K, desc.density_scale, with_masks, tid, &ctl->a_empty[sa],
                                           chain_sync, [&](float) {
@@ -193,7 +191,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) k_occupancy_density(inerf_field
             const uint32_t sa = it % kWsStages;
             umma::mbar_wait(&ctl->a_full[sa], (it / kWsStages) & 1u);
             const uint32_t a_es = WsSmem::A + sa * kStageBytes;
-            const ChainBufs bufs{a_es, a_es + kBytesEs, a_es + kBytesEs + kBytesCi, WsSmem::H1, WsSmem::H2, WsSmem::W};
+            const ChainBufs bufs{a_es, a_es + kBytesEs, a_es + kBytesEs + kBytesCi, WsSmem::W};
             const float sigma = sigma_chain(smem, bufs, tmem_base, &ctl->mma_bar, phase, K, tid, &ctl->a_empty[sa], chain_sync);
             const uint32_t s = tile * kTile + tid;
             if (tid < kTile && s < n) {

@@ -37,8 +37,10 @@ constexpr uint32_t kRegsChain = 96, kRegsGather = 64, kRegsMarch = 56;
 static_assert(kChainT * kRegsChain + kGatherT * kRegsGather + kMarchT * kRegsMarch <= (kChainT + kGatherT + kMarchT) * 72,
               "register budget of the three roles");
 constexpr uint32_t kThreadsR = kChainT + kGatherT + kMarchT;
-// samples queued per ray slot: 14 x 3 KB of rings keeps the CTA inside the 196 KB shared-memory carve-out at K <= 32 (60 KB of L1 left)
-constexpr uint32_t RING = 14;
+// samples queued per ray slot: 24 x 3 KB of rings fill the 196 KB shared-memory carve-out at K <= 32 (60 KB of L1 left) now that the
+// hidden activations live in tensor memory; measured on B200 (c2): 10 / 14 / 20 / 24 deep -> tile fill 0.905 / 0.921 / 0.943 / 0.955,
+// 8.92 / 8.77 / 8.71 / 8.68 ms (14-deep fits the 164 KB carve-out with 92 KB of L1; a third operand stage instead: 8.82 ms)
+constexpr uint32_t RING = 24;
 constexpr uint32_t DT = 4;    // tile descriptors in flight (gather may run DA tiles ahead of the chain)
 constexpr uint32_t DA = 2;    // gathered operand stages
 constexpr int kMarchCells = 8;   // occupancy cells a marcher lane may evaluate per warp iteration
@@ -83,9 +85,7 @@ struct Ctrl {
 
 struct RSmem {
     static constexpr uint32_t A = 0;                                 // DA stages of (es | ci | mi)
-    static constexpr uint32_t H1 = A + DA * kStageBytes;
-    static constexpr uint32_t H2 = H1 + kBytesH;
-    static constexpr uint32_t W = H2 + kBytesH;
+    static constexpr uint32_t W = A + DA * kStageBytes;
     static __host__ __device__ uint32_t ctrl(uint32_t K) { return (W + weight_layout(K).total + 15u) & ~15u; }
     static __host__ __device__ uint32_t rings(uint32_t K) { return (ctrl(K) + (uint32_t)sizeof(Ctrl) + 15u) & ~15u; }
     static __host__ __device__ uint32_t coarse(uint32_t K) { return rings(K) + (uint32_t)sizeof(Rings); }
@@ -279,7 +279,7 @@ __device__ __forceinline__ void chain_role(const inerf_field_desc& desc, const R
         tile_count = tile;
         if (ld_vol(&ctl->a_flag[sa])) break;
         const uint32_t a_es = RSmem::A + sa * kStageBytes;
-        const ChainBufs bufs{a_es, a_es + kBytesEs, a_es + kBytesEs + kBytesCi, RSmem::H1, RSmem::H2, RSmem::W};
+        const ChainBufs bufs{a_es, a_es + kBytesEs, a_es + kBytesEs + kBytesCi, RSmem::W};
         float weight = 0.f;
         mlp_chain(smem, bufs, tmem_base, &ctl->mma_bar, phase, K, desc.density_scale, with_masks, ct, &ctl->a_empty[sa], chain_sync,
                   [&](float sigma) {
