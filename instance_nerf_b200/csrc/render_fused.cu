@@ -7,7 +7,7 @@
 // One CTA per SM, 896 threads in three roles that run concurrently and hand 128-sample tiles to each other
 // through mbarrier-guarded rings in shared memory (nothing per-sample ever touches HBM):
 //
-//   march  (4 warps, thread = ray slot)   occupancy-grid DDA (raymarching.cu:1008-1062 semantics) into a 14-deep
+//   march  (4 warps, thread = ray slot)   occupancy-grid DDA (raymarching.cu:1008-1062 semantics) into a 24-deep
 //                                          per-slot sample ring; runs AHEAD of compositing (speculatively: a ray
 //                                          killed by T < T_thresh drops its queued samples); a warp whose 32 slots
 //                                          are all free pulls the next 32 consecutive rays from a global counter.
