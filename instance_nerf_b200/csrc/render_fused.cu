@@ -215,16 +215,20 @@ __device__ __forceinline__ void gather_role(const inerf_field_desc& desc, const 
                 not_finished = sel >= 0 || nd != (int32_t)kMarchT;
                 ctl->tsel[st][row] = sel;
             }
-            if (!gather_any(not_finished)) { stop = true; break; }   // all marchers done and every ring drained
-            if (gather_any(sel >= 0)) {
+            if (gather_any(sel >= 0)) {   // the common case costs ONE group barrier
                 if (sel >= 0) ghead++;
                 break;
             }
+            if (!gather_any(not_finished)) { stop = true; break; }   // all marchers done and every ring drained
             __nanosleep(128);
         }
         if (tile >= DA) umma::mbar_wait(&ctl->a_empty[sa], ((tile / DA) - 1u) & 1u);
         if (gt == 0) ctl->a_flag[sa] = stop ? 1 : 0;
-        if (stop) { umma::mbar_arrive(&ctl->a_full[sa]); break; }
+        if (stop) {
+            __syncwarp();
+            if ((gt & 31u) == 0) umma::mbar_arrive(&ctl->a_full[sa]);
+            break;
+        }
         const int32_t e = ctl->tsel[st][row];
         if (e >= 0) {
             __threadfence_block();
@@ -243,8 +247,10 @@ __device__ __forceinline__ void gather_role(const inerf_field_desc& desc, const 
                 encode4(x01, oob, quarter * 4, ctl->lg, table, smem, a_es, a_mi, row);
             }
         }
+        // every thread fences its own operand-tile writes, then ONE lane per warp arrives (16 arrivals per tile instead of 512)
         umma::fence_async_smem();
-        umma::mbar_arrive(&ctl->a_full[sa]);
+        __syncwarp();
+        if ((gt & 31u) == 0) umma::mbar_arrive(&ctl->a_full[sa]);
     }
 }
 
@@ -415,7 +421,7 @@ __global__ void __launch_bounds__(kThreadsR, 1) k_render_fused(inerf_field_desc 
     load_weights(smem, RSmem::W, desc.weights, K);
     init_levels(ctl->lg, desc.offsets, desc.L, desc.S, desc.H, tid);
     if (tid == 0) {
-        for (uint32_t i = 0; i < DA; i++) { umma::mbar_init(&ctl->a_full[i], kGatherT); umma::mbar_init(&ctl->a_empty[i], 1); ctl->a_flag[i] = 0; }
+        for (uint32_t i = 0; i < DA; i++) { umma::mbar_init(&ctl->a_full[i], kGatherT / 32); umma::mbar_init(&ctl->a_empty[i], 1); ctl->a_flag[i] = 0; }
         umma::mbar_init(&ctl->mma_bar, 1);
         ctl->n_done = 0;
         umma::mbar_fence_init();
