@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) k_field_forward_ws(inerf_field_
     load_weights(smem, WsSmem::W, desc.weights, K);
     init_levels(ctl->lg, desc.offsets, desc.L, desc.S, desc.H, tid);
     if (tid == 0) {
-        for (uint32_t i = 0; i < kWsStages; i++) { umma::mbar_init(&ctl->a_full[i], kWsGatherT); umma::mbar_init(&ctl->a_empty[i], 1); }
+        for (uint32_t i = 0; i < kWsStages; i++) { umma::mbar_init(&ctl->a_full[i], kWsGatherT / 32); umma::mbar_init(&ctl->a_empty[i], 1); }
         umma::mbar_init(&ctl->mma_bar, 1);
         umma::mbar_fence_init();
     }
@@ -149,7 +149,8 @@ __global__ void __launch_bounds__(kWsThreads, 1) k_field_forward_ws(inerf_field_
                 encode4(x01, oob, quarter * 4, ctl->lg, table, smem, a_es, a_mi, row);
             }
             umma::fence_async_smem();
-            umma::mbar_arrive(&ctl->a_full[sa]);
+            __syncwarp();
+            if ((gt & 31u) == 0) umma::mbar_arrive(&ctl->a_full[sa]);   // one arrival per gather warp
         }
     }
     umma::fence_before_sync();
@@ -171,7 +172,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) k_occupancy_density(inerf_field
     load_weights(smem, WsSmem::W, desc.weights, K);
     init_levels(ctl->lg, desc.offsets, desc.L, desc.S, desc.H, tid);
     if (tid == 0) {
-        for (uint32_t i = 0; i < kWsStages; i++) { umma::mbar_init(&ctl->a_full[i], kWsGatherT); umma::mbar_init(&ctl->a_empty[i], 1); }
+        for (uint32_t i = 0; i < kWsStages; i++) { umma::mbar_init(&ctl->a_full[i], kWsGatherT / 32); umma::mbar_init(&ctl->a_empty[i], 1); }
         umma::mbar_init(&ctl->mma_bar, 1);
         umma::mbar_fence_init();
     }
@@ -226,7 +227,8 @@ __global__ void __launch_bounds__(kWsThreads, 1) k_occupancy_density(inerf_field
                 encode4(x01, oob, quarter * 4, ctl->lg, table, smem, a_es, a_mi, row);
             }
             umma::fence_async_smem();
-            umma::mbar_arrive(&ctl->a_full[sa]);
+            __syncwarp();
+            if ((gt & 31u) == 0) umma::mbar_arrive(&ctl->a_full[sa]);   // one arrival per gather warp
         }
     }
     umma::fence_before_sync();

@@ -71,6 +71,8 @@ struct Rings {
 
 struct Ctrl {
     uint64_t a_full[DA], a_empty[DA], mma_bar;
+    uint64_t sel_ready[DT];       // tile descriptor st is published (4 selector warps arrive)
+    uint32_t sel_any[DT][4];      // per selector warp: some slot of its 32 had a sample for that tile
     uint32_t tmem_slot;
     int32_t n_done;               // marcher lanes that ran out of rays
     int32_t a_flag[DA];           // 1 = terminal tile
@@ -202,26 +204,45 @@ __device__ __forceinline__ void gather_role(const inerf_field_desc& desc, const 
     const float inv2b = __fdiv_rn(1.0f, __fmul_rn(2.0f, desc.bound));
     const uint2* table = reinterpret_cast<const uint2*>(desc.table_packed);
     uint32_t ghead = 0;   // entries of this row already handed to a tile (quarter-0 threads)
+    // Tile descriptors are made ONE TILE AHEAD: the four selector warps (quarter 0) describe tile t + 1 before they gather tile t
+    // and publish it through an mbarrier, so nobody waits for the selection at the top of an iteration (the group-wide barrier
+    // that used to sit there cost every gather warp its latency once per tile).  Only when a descriptor came out empty does the
+    // group fall back to the blocking selection below.
+    auto preselect = [&](uint32_t t) {
+        const uint32_t st1 = t % DT;
+        int32_t sel = -1;
+        if (ld_vol(&ctl->tail[row]) != ghead) { sel = (int32_t)(ghead % RING); ghead++; }
+        ctl->tsel[st1][row] = sel;
+        const bool any = __any_sync(0xffffffffu, sel >= 0);
+        if ((gt & 31u) == 0) ctl->sel_any[st1][gt >> 5] = any ? 1u : 0u;
+        __syncwarp();
+        if ((gt & 31u) == 0) umma::mbar_arrive(&ctl->sel_ready[st1]);
+    };
+    if (quarter == 0) preselect(0);
     for (uint32_t tile = 0;; tile++) {
         const uint32_t st = tile % DT, sa = tile % DA;
         bool stop = false;
-        while (true) {   // assemble a tile: one queued sample from every slot that has one
-            int32_t sel = -1;
-            bool not_finished = false;
-            if (quarter == 0) {
-                const int32_t nd = ld_vol(&ctl->n_done);
-                __threadfence_block();
-                if (ld_vol(&ctl->tail[row]) != ghead) sel = (int32_t)(ghead % RING);
-                not_finished = sel >= 0 || nd != (int32_t)kMarchT;
-                ctl->tsel[st][row] = sel;
+        umma::mbar_wait(&ctl->sel_ready[st], (tile / DT) & 1u);
+        if (!(ld_vol(&ctl->sel_any[st][0]) | ld_vol(&ctl->sel_any[st][1]) | ld_vol(&ctl->sel_any[st][2]) | ld_vol(&ctl->sel_any[st][3]))) {
+            while (true) {   // empty descriptor: blocking selection (start of the frame, marchers behind, end of the frame)
+                int32_t sel = -1;
+                bool not_finished = false;
+                if (quarter == 0) {
+                    const int32_t nd = ld_vol(&ctl->n_done);
+                    __threadfence_block();
+                    if (ld_vol(&ctl->tail[row]) != ghead) sel = (int32_t)(ghead % RING);
+                    not_finished = sel >= 0 || nd != (int32_t)kMarchT;
+                    ctl->tsel[st][row] = sel;
+                }
+                if (gather_any(sel >= 0)) {
+                    if (sel >= 0) ghead++;
+                    break;
+                }
+                if (!gather_any(not_finished)) { stop = true; break; }   // all marchers done and every ring drained
+                __nanosleep(128);
             }
-            if (gather_any(sel >= 0)) {   // the common case costs ONE group barrier
-                if (sel >= 0) ghead++;
-                break;
-            }
-            if (!gather_any(not_finished)) { stop = true; break; }   // all marchers done and every ring drained
-            __nanosleep(128);
         }
+        if (quarter == 0 && !stop) preselect(tile + 1);
         if (tile >= DA) umma::mbar_wait(&ctl->a_empty[sa], ((tile / DA) - 1u) & 1u);
         if (gt == 0) ctl->a_flag[sa] = stop ? 1 : 0;
         if (stop) {
@@ -423,6 +444,7 @@ __global__ void __launch_bounds__(kThreadsR, 1) k_render_fused(inerf_field_desc 
     if (tid == 0) {
         for (uint32_t i = 0; i < DA; i++) { umma::mbar_init(&ctl->a_full[i], kGatherT / 32); umma::mbar_init(&ctl->a_empty[i], 1); ctl->a_flag[i] = 0; }
         umma::mbar_init(&ctl->mma_bar, 1);
+        for (uint32_t i = 0; i < DT; i++) umma::mbar_init(&ctl->sel_ready[i], 4);
         ctl->n_done = 0;
         umma::mbar_fence_init();
     }
