@@ -31,6 +31,20 @@ def shard_frames(n_frames: int, rank: int, world: int) -> list[int]:
     return list(range(rank, n_frames, world))
 
 
+def balance_frames(costs: Sequence[float], world: int) -> list[list[int]]:
+    """Whole frames per rank with EQUAL COUNTS (+-1) and near-equal total cost: frames sorted by decreasing cost are dealt in
+    boustrophedon order (ranks 0..w-1, w-1..0, ...).  Cost is proportional to marched samples, which
+    differ by +-25 % between the poses of a multi-view job; with plain round-robin every rank's total drifts by a few percent
+    and the job waits for the slowest rank.  Deterministic (ties broken by frame index): every rank computes the same plan
+    from the same costs, no collective.  Each rank's list is returned in increasing frame order."""
+    order = sorted(range(len(costs)), key=lambda f: (-float(costs[f]), f))
+    plan: list[list[int]] = [[] for _ in range(world)]
+    for j, f in enumerate(order):
+        lap, pos = divmod(j, world)
+        plan[pos if lap % 2 == 0 else world - 1 - pos].append(f)
+    return [sorted(p) for p in plan]
+
+
 def shard_rows(H: int, W: int, rank: int, world: int, block_rows: int = 8) -> torch.Tensor:
     """Ray indices (row-major pixel ids) of one frame owned by `rank`: interleaved blocks of `block_rows` image rows."""
     rows = torch.arange(H)

@@ -22,7 +22,7 @@ from .._lib import call, lib, ptr, stream_ptr
 __all__ = [
     "near_far_from_aabb", "sph_from_ray", "morton3D", "morton3D_invert", "packbits",
     "march_rays_train", "composite_rays_train", "composite_rays_with_masks_train",
-    "march_rays", "composite_rays", "composite_rays_with_masks", "compact_alive",
+    "march_rays", "composite_rays", "composite_rays_with_masks", "compact_alive", "count_samples",
 ]
 
 
@@ -138,6 +138,25 @@ def march_rays_train(rays_o, rays_d, bound, density_bitfield, C, H, nears, fars,
     call("inerf_march_rays_train_expand", ptr(rays_o), ptr(rays_d), float(bound), float(dt_gamma), int(max_steps), N, int(C), int(H),
          M, ptr(nears), ptr(xyzs), ptr(dirs), ptr(deltas), ptr(rays), ptr(noises), ptr(t_scratch), st)
     return xyzs, dirs, deltas, rays
+
+
+def count_samples(rays_o, rays_d, bound, density_bitfield, C, H, nears, fars, step_counter, dt_gamma=0, max_steps=1024, t_scratch=None):
+    """The count pass of march_rays_train alone (extra; no host sync): adds the number of samples these rays march to
+    `step_counter[0]` (int32 [2], device) -- the cost estimate `parallel.balance_frames` plans multi-view jobs with.
+    Returns the scratch buffer so that callers can reuse it."""
+    rays_o = _f32(rays_o).view(-1, 3)
+    rays_d = _f32(rays_d).view(-1, 3)
+    nears, fars = _f32(nears).view(-1), _f32(fars).view(-1)
+    dev = rays_o.device
+    N = rays_o.shape[0]
+    need = max(1, int(lib().inerf_march_scratch_floats(N, int(max_steps))))
+    if t_scratch is None or t_scratch.numel() < need:
+        t_scratch = torch.empty(need, dtype=torch.float32, device=dev)
+    rays = torch.empty(N, 3, dtype=torch.int32, device=dev)
+    noises = torch.zeros(N, dtype=torch.float32, device=dev)
+    call("inerf_march_rays_train_count_t", ptr(rays_o), ptr(rays_d), ptr(density_bitfield.contiguous()), float(bound), float(dt_gamma),
+         int(max_steps), N, int(C), int(H), ptr(nears), ptr(fars), ptr(rays), ptr(step_counter), ptr(noises), ptr(t_scratch), stream_ptr(dev))
+    return t_scratch
 
 
 class _composite_rays_train(Function):
