@@ -308,6 +308,13 @@ int inerf_render_fused(const inerf_field_desc *desc, const float *rays_o, const 
                        float dt_gamma, uint32_t max_steps, float T_thresh, float *weights_sum, float *depth,
                        float *image, float *mask_out, int32_t *work_counter, void *stream);
 
+/* Same with the first step of every ray jittered as the reference's run_cuda does for perturb=True (mask_renderer.py:334-337 ->
+ * raymarching.cu:1004: t = near + clamp(near * dt_gamma, dt_min, dt_max) * noises[ray]); noises float [N] in [0, 1), NULL = none. */
+int inerf_render_fused_perturb(const inerf_field_desc *desc, const float *rays_o, const float *rays_d, const float *nears,
+                               const float *fars, const float *noises, const uint8_t *bitfield, uint32_t N, uint32_t C, uint32_t H,
+                               float dt_gamma, uint32_t max_steps, float T_thresh, float *weights_sum, float *depth,
+                               float *image, float *mask_out, int32_t *work_counter, void *stream);
+
 /* --------------------------------------------------------------- loss tail -- */
 
 /*

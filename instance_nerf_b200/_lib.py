@@ -112,6 +112,7 @@ _PROTOS = {
     "inerf_adam_step": [_P, _P, _P, _P, ctypes.c_uint64, _F, _F, _F, _F, _P, _P, _P, _F, _P],
     "inerf_adam_advance": [_P, _P, _P],
     "inerf_render_fused": [POINTER(FieldDesc), _P, _P, _P, _P, _P, _U, _U, _U, _F, _U, _F, _P, _P, _P, _P, _P, _P],
+    "inerf_render_fused_perturb": [POINTER(FieldDesc), _P, _P, _P, _P, _P, _P, _U, _U, _U, _F, _U, _F, _P, _P, _P, _P, _P, _P],
 }
 _SPECIAL = {
     "inerf_version": ([], c_int),

@@ -52,6 +52,7 @@ struct RenderParams {
     const float* rays_d;
     const float* nears;
     const float* fars;
+    const float* noises;     // optional per-ray jitter of the first step (perturb, raymarching.cu:1004); NULL = none
     const uint8_t* bitfield;
     uint32_t N, C, H, max_steps;
     float dt_gamma, T_thresh;
@@ -151,6 +152,7 @@ __device__ __forceinline__ void march_role(const inerf_field_desc& desc, const R
                 t = *reinterpret_cast<const volatile float*>(p.depth + idx);
                 p.depth[idx] = 0.f;
                 last_t = __ldg(p.nears + idx);
+                if (p.noises) last_t = __fmaf_rn(wk.step_size(last_t), __ldg(p.noises + idx), last_t);   // :1004, as k_first_hit started
                 nsteps = 0;
                 ray = (int32_t)idx;
                 state = EVAL;
@@ -180,10 +182,15 @@ __device__ __forceinline__ void march_role(const inerf_field_desc& desc, const R
                 if (wk.eval_cell(t, x, y, z, dt, tt)) {
                     rg->x[e][r] = x; rg->y[e][r] = y; rg->z[e][r] = z;
                     rg->dt[e][r] = dt;
-                    rg->d1[e][r] = __fsub_rn(t, last_t);
+                    const float d1 = __fsub_rn(t, last_t);
+                    rg->d1[e][r] = d1;
                     rg->ray[e][r] = ray;
                     last_t = t;
                     nsteps++;
+                    // perturb, as the reference's loop really behaves: its first iteration marches ONE jittered sample per ray
+                    // (n_step = N / n_alive = 1, mask_renderer.py:333) and composite_rays then stores rays_t = near + deltas[1]
+                    // (raymarching.cu:1216-1251 starts from the UNjittered rays_t), so the march resumes at near + d1
+                    if (p.noises != nullptr && nsteps == 1) { t = __fadd_rn(__ldg(p.nears + ray), d1); last_t = t; }
                     __threadfence_block();
                     st_vol(&ctl->tail[r], ++tail);
                     free_entries--;
@@ -420,6 +427,7 @@ __global__ void __launch_bounds__(256) k_first_hit(RenderParams p, float bound, 
     march::Walk wk;
     wk.init(p.rays_o + (size_t)idx * 3, p.rays_d + (size_t)idx * 3, p.bitfield, bound, p.dt_gamma, p.max_steps, p.C, p.H, __ldg(p.fars + idx));
     float t = __ldg(p.nears + idx), tt = 0.f;
+    if (p.noises) t = __fmaf_rn(wk.step_size(t), __ldg(p.noises + idx), t);   // raymarching.cu:1004
     while (t < wk.far) {
         const float t0 = t;
         float x, y, z, dt;
@@ -484,10 +492,10 @@ __global__ void __launch_bounds__(kThreadsR, 1) k_render_fused(inerf_field_desc 
 
 }  // namespace
 
-extern "C" int inerf_render_fused(const inerf_field_desc* desc, const float* rays_o, const float* rays_d, const float* nears,
-                                  const float* fars, const uint8_t* bitfield, uint32_t N, uint32_t C, uint32_t H, float dt_gamma,
-                                  uint32_t max_steps, float T_thresh, float* weights_sum, float* depth, float* image,
-                                  float* mask_out, int32_t* work_counter, void* stream) {
+extern "C" int inerf_render_fused_perturb(const inerf_field_desc* desc, const float* rays_o, const float* rays_d, const float* nears,
+                                          const float* fars, const float* noises, const uint8_t* bitfield, uint32_t N, uint32_t C, uint32_t H,
+                                          float dt_gamma, uint32_t max_steps, float T_thresh, float* weights_sum, float* depth, float* image,
+                                          float* mask_out, int32_t* work_counter, void* stream) {
     if (int e = field::validate(desc)) return e;
     if (C == 0 || C > 16 || H == 0 || H > 1024 || (H & (H - 1)) || max_steps == 0 || N >= 0x7fffffffu) return INERF_ERR_SIZE;
     if (N == 0) return INERF_OK;
@@ -506,7 +514,7 @@ extern "C" int inerf_render_fused(const inerf_field_desc* desc, const float* ray
     const uint64_t cells = (uint64_t)C * H * H * H;
     uint32_t coarse_bytes = 0;
     if (cells % 2048 == 0 && cells / 512 <= 48 * 1024) coarse_bytes = (uint32_t)(cells / 512);
-    RenderParams p{rays_o, rays_d, nears, fars, bitfield, N, C, H, max_steps, dt_gamma, T_thresh, weights_sum, depth, image, mask_out, work_counter, coarse_bytes};
+    RenderParams p{rays_o, rays_d, nears, fars, noises, bitfield, N, C, H, max_steps, dt_gamma, T_thresh, weights_sum, depth, image, mask_out, work_counter, coarse_bytes};
     const uint32_t smem_bytes = RSmem::bytes(desc->K, coarse_bytes);
     // the attribute is per device and cheap to set: no process-global "already done" flag (a second GPU in the same process
     // would otherwise launch without the opt-in)
@@ -522,4 +530,12 @@ extern "C" int inerf_render_fused(const inerf_field_desc* desc, const float* ray
     else k_render_fused<2><<<grid, kThreadsR, smem_bytes, st>>>(*desc, p);
     INERF_LAUNCH_CHECK();
     return INERF_OK;
+}
+
+extern "C" int inerf_render_fused(const inerf_field_desc* desc, const float* rays_o, const float* rays_d, const float* nears,
+                                  const float* fars, const uint8_t* bitfield, uint32_t N, uint32_t C, uint32_t H, float dt_gamma,
+                                  uint32_t max_steps, float T_thresh, float* weights_sum, float* depth, float* image,
+                                  float* mask_out, int32_t* work_counter, void* stream) {
+    return inerf_render_fused_perturb(desc, rays_o, rays_d, nears, fars, nullptr, bitfield, N, C, H, dt_gamma, max_steps, T_thresh, weights_sum,
+                                      depth, image, mask_out, work_counter, stream);
 }

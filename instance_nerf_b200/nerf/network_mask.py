@@ -225,7 +225,7 @@ class NeRFNetwork(NeRFMaskRenderer):
         d = d.float().contiguous().view(-1, 3)
         return _FusedInstanceField.apply(self, x, d, self.encoder_mask.embeddings, *[l.weight for l in self.mask_net])
 
-    def _render_fused(self, rays_o, rays_d, nears, fars, render_mask, dt_gamma, max_steps, T_thresh):
+    def _render_fused(self, rays_o, rays_d, nears, fars, render_mask, dt_gamma, max_steps, T_thresh, noises=None):
         N = rays_o.shape[0]
         dev = rays_o.device
         K = self.num_instances
@@ -236,8 +236,10 @@ class NeRFNetwork(NeRFMaskRenderer):
         if self._work_counter is None or self._work_counter.device != dev:
             self._work_counter = torch.zeros(4, dtype=torch.int32, device=dev)
         desc = self._field_desc(self.density_scale)
-        call("inerf_render_fused", ctypes.byref(desc), ptr(rays_o), ptr(rays_d), ptr(nears), ptr(fars), ptr(self.density_bitfield),
-             N, self.cascade, self.grid_size, float(dt_gamma), int(max_steps), float(T_thresh), ptr(weights_sum), ptr(depth),
+        if noises is not None:
+            noises = noises.to(device=dev, dtype=torch.float32).contiguous().view(-1)
+        call("inerf_render_fused_perturb", ctypes.byref(desc), ptr(rays_o), ptr(rays_d), ptr(nears), ptr(fars), ptr(noises),
+             ptr(self.density_bitfield), N, self.cascade, self.grid_size, float(dt_gamma), int(max_steps), float(T_thresh), ptr(weights_sum), ptr(depth),
              ptr(image), ptr(mask_out), ptr(self._work_counter), stream_ptr(dev))
         return weights_sum, depth, image, mask_out
 

@@ -267,12 +267,16 @@ class NeRFRenderer(nn.Module):
                     sigmas, rgbs, masks, deltas, rays, T_thresh, dense=dense)
             results["weights_sum"] = weights_sum
         else:
-            if not perturb and self.fused_render_available(render_mask):
+            # perturb (mask_renderer.py:334-337): one uniform draw per ray jitters the first step; `noises` (extra) injects it
+            noises = kwargs.get("noises")
+            if noises is None and perturb:
+                noises = torch.rand(N, dtype=torch.float32, device=rays_o.device)
+            if self.fused_render_available(render_mask):
                 weights_sum, depth, image, mask_out = self._render_fused(rays_o, rays_d, nears, fars, render_mask, dt_gamma,
-                                                                         max_steps, T_thresh)
+                                                                         max_steps, T_thresh, noises=noises)
             else:
                 weights_sum, depth, image, mask_out = self.run_cuda_loop(rays_o, rays_d, nears, fars, render_mask, dt_gamma,
-                                                                         perturb, max_steps, T_thresh)
+                                                                         perturb, max_steps, T_thresh, noises=noises)
 
         image = image + (1 - weights_sum).unsqueeze(-1) * bg_color
         depth = torch.clamp(depth - nears, min=0) / (fars - nears)
@@ -291,7 +295,7 @@ class NeRFRenderer(nn.Module):
             return out
         return out[0], out[1], None  # stage-1 network: (sigma, rgb)
 
-    def run_cuda_loop(self, rays_o, rays_d, nears, fars, render_mask, dt_gamma, perturb, max_steps, T_thresh):
+    def run_cuda_loop(self, rays_o, rays_d, nears, fars, render_mask, dt_gamma, perturb, max_steps, T_thresh, noises=None):
         """The reference's alive-ray loop (mask_renderer.py:330-374) on this library's kernels, with the
         same n_step schedule; compaction and the alive count stay on the device except for ONE 4-byte
         read per iteration (the reference pays two syncs: `.shape` of a boolean-indexed tensor, :345,:370)."""
@@ -311,7 +315,8 @@ class NeRFRenderer(nn.Module):
             n_step = max(min(N // n_alive, 8), 1)
             xyzs, dirs, deltas = raymarching.march_rays(n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, self.bound,
                                                         self.density_bitfield, self.cascade, self.grid_size, nears, fars, 128,
-                                                        perturb if step == 0 else False, dt_gamma, max_steps)
+                                                        perturb if step == 0 else False, dt_gamma, max_steps,
+                                                        noises=noises if step == 0 else None)
             sigmas, rgbs, masks = self._field(xyzs, dirs, render_mask)
             sigmas = self.density_scale * sigmas
             if not render_mask:
@@ -325,7 +330,7 @@ class NeRFRenderer(nn.Module):
             step += n_step
         return weights_sum, depth, image, mask_out
 
-    def _render_fused(self, rays_o, rays_d, nears, fars, render_mask, dt_gamma, max_steps, T_thresh):
+    def _render_fused(self, rays_o, rays_d, nears, fars, render_mask, dt_gamma, max_steps, T_thresh, noises=None):
         raise NotImplementedError()
 
     # -- occupancy grid lifecycle ------------------------------------------------------

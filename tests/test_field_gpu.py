@@ -89,6 +89,31 @@ def test_render_fused_vs_reference_loop(cuda, K, density_scale):
     assert r1["image"].shape == (1, 96 * 128, 3) and r1["instance_mask_logits"].shape == (1, 96 * 128, K)
 
 
+def test_render_fused_perturb_vs_reference_loop(cuda):
+    """perturb=True at inference (mask_renderer.py:334-337: one uniform draw per ray jitters the first step, raymarching.cu:1004):
+    the one-launch renderer with the draws injected against the alive-ray loop with the same draws; and a perturbed frame
+    differs from the unperturbed one (the jitter is really applied)."""
+    m, sc = build_model(cuda, 16, density_scale=25.0)
+    o, d = make_rays(sc, 64, 96)
+    o, d = o.to(cuda), d.to(cuda)
+    noises = torch.rand(o.shape[0], generator=torch.Generator().manual_seed(5)).to(cuda)
+    kw = dict(dt_gamma=1 / 128, max_steps=1024, T_thresh=1e-4, staged=True, render_mask=True, bg_color=1)
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
+        r1 = m.render(o[None], d[None], perturb=True, noises=noises, **kw)
+        m.use_fused = False
+        try:
+            r0 = m.render(o[None], d[None], perturb=True, noises=noises, **kw)
+        finally:
+            m.use_fused = True
+        plain = m.render(o[None], d[None], perturb=False, **kw)
+        drawn = m.render(o[None], d[None], perturb=True, **kw)        # own draw: runs, finite, differs from the plain frame
+    for key in ("image", "depth"):
+        assert (r1[key] - r0[key]).abs().max().item() < 1e-3, key
+    assert (torch.softmax(r1["instance_mask_logits"], -1) - torch.softmax(r0["instance_mask_logits"], -1)).abs().max().item() < 1e-3
+    assert (r1["depth"] - plain["depth"]).abs().max().item() > 1e-5
+    assert torch.isfinite(drawn["image"]).all() and (drawn["depth"] - plain["depth"]).abs().max().item() > 1e-5
+
+
 def test_render_fused_no_mask_and_misses(cuda):
     m, sc = build_model(cuda, 32, density_scale=25.0)
     o, d = make_rays(sc, 32, 32)
