@@ -35,28 +35,34 @@ def _host_seed() -> int:
 
 
 def sample_pdf(bins, weights, n_samples, det=False):
-    """Inverse-CDF sampling used by `run(upsample_steps>0)` (mask_renderer.py:13-47)."""
-    weights = weights + 1e-5
-    pdf = weights / torch.sum(weights, -1, keepdim=True)
-    cdf = torch.cumsum(pdf, -1)
-    cdf = torch.cat([torch.zeros_like(cdf[..., :1]), cdf], -1)
+    """Inverse-CDF sampling of `n_samples` depths per ray from the piecewise-constant density `weights` over `bins`
+    (mask_renderer.py:13-47; `run(upsample_steps > 0)`).  bins [N, B], weights [N, B - 1] -> [N, n_samples]."""
+    w = weights + 1e-5                                           # no empty bin
+    cdf = torch.cumsum(w / w.sum(-1, keepdim=True), -1)
+    cdf = torch.nn.functional.pad(cdf, (1, 0))                   # cdf[..., 0] = 0: one value per bin edge
+    N, E = cdf.shape
     if det:
-        u = torch.linspace(0.0 + 0.5 / n_samples, 1.0 - 0.5 / n_samples, steps=n_samples, device=weights.device)
-        u = u.expand(list(cdf.shape[:-1]) + [n_samples])
+        u = torch.linspace(0.5 / n_samples, 1.0 - 0.5 / n_samples, steps=n_samples, device=w.device).expand(N, n_samples)
     else:
-        u = torch.rand(list(cdf.shape[:-1]) + [n_samples], device=weights.device)
+        u = torch.rand(N, n_samples, device=w.device)
     u = u.contiguous()
-    inds = torch.searchsorted(cdf, u, right=True)
-    below = torch.clamp(inds - 1, min=0)
-    above = torch.clamp(inds, max=cdf.shape[-1] - 1)
-    inds_g = torch.stack([below, above], -1)
-    shape = [inds_g.shape[0], inds_g.shape[1], cdf.shape[-1]]
-    cdf_g = torch.gather(cdf.unsqueeze(1).expand(shape), 2, inds_g)
-    bins_g = torch.gather(bins.unsqueeze(1).expand(shape), 2, inds_g)
-    denom = cdf_g[..., 1] - cdf_g[..., 0]
-    denom = torch.where(denom < 1e-5, torch.ones_like(denom), denom)
-    t = (u - cdf_g[..., 0]) / denom
-    return bins_g[..., 0] + t * (bins_g[..., 1] - bins_g[..., 0])
+    hi = torch.searchsorted(cdf, u, right=True)                  # first edge with cdf > u
+    lo = (hi - 1).clamp(min=0)
+    hi = hi.clamp(max=E - 1)
+    c0, c1 = cdf.gather(1, lo), cdf.gather(1, hi)
+    b0, b1 = bins.gather(1, lo), bins.gather(1, hi)
+    span = c1 - c0
+    span = torch.where(span < 1e-5, torch.ones_like(span), span)
+    return b0 + (u - c0) / span * (b1 - b0)
+
+
+def alpha_weights(z_vals, last_delta, sigma, density_scale):
+    """Compositing weights of sorted depths (mask_renderer.py:131-137 = :164-170): delta_i = z_{i+1} - z_i (the last interval
+    is `last_delta`), alpha = 1 - exp(-delta * density_scale * sigma), w_i = alpha_i * prod_{j<i} (1 - alpha_j + 1e-15)."""
+    deltas = torch.cat([z_vals[..., 1:] - z_vals[..., :-1], last_delta * torch.ones_like(z_vals[..., :1])], dim=-1)
+    alphas = 1 - torch.exp(-deltas * density_scale * sigma)
+    trans = torch.cumprod(torch.cat([torch.ones_like(alphas[..., :1]), 1 - alphas + 1e-15], dim=-1), dim=-1)[..., :-1]
+    return alphas * trans, deltas
 
 
 class NeRFRenderer(nn.Module):
@@ -128,92 +134,68 @@ class NeRFRenderer(nn.Module):
 
     # -- non-cuda_ray renderer (mask_renderer.py:89-231) ------------------------------
     def run(self, rays_o, rays_d, render_mask=False, num_steps=128, upsample_steps=128, bg_color=None, perturb=False, **kwargs):
+        """Dense renderer without the occupancy grid: `num_steps` uniform depths per ray between the box entry and exit,
+        optionally `upsample_steps` more drawn from the coarse weights, density everywhere, colour / instance logits only
+        where the weight exceeds 1e-4."""
         prefix = rays_o.shape[:-1]
         rays_o = rays_o.contiguous().view(-1, 3)
         rays_d = rays_d.contiguous().view(-1, 3)
-        N = rays_o.shape[0]
-        device = rays_o.device
+        N, device = rays_o.shape[0], rays_o.device
         aabb = self.aabb_train if self.training else self.aabb_infer
+        lo, hi = aabb[:3], aabb[3:]
+
+        def points(z):      # [N, S] depths -> [N, S, 3] positions clipped to the box
+            return torch.min(torch.max(rays_o.unsqueeze(-2) + rays_d.unsqueeze(-2) * z.unsqueeze(-1), lo), hi)
+
+        def query(x, S):    # density head on [N, S, 3] -> dict of [N, S, c]
+            return {k: v.view(N, S, -1) for k, v in self.density(x.reshape(-1, 3)).items()}
 
         nears, fars = raymarching.near_far_from_aabb(rays_o, rays_d, aabb, self.min_near)
-        nears = nears.unsqueeze(-1)
-        fars = fars.unsqueeze(-1)
-
-        z_vals = torch.linspace(0.0, 1.0, num_steps, device=device).unsqueeze(0).expand((N, num_steps))
-        z_vals = nears + (fars - nears) * z_vals
-        sample_dist = (fars - nears) / num_steps
+        nears, fars = nears.unsqueeze(-1), fars.unsqueeze(-1)
+        span = fars - nears
+        sample_dist = span / num_steps
+        z_vals = nears + span * torch.linspace(0.0, 1.0, num_steps, device=device).unsqueeze(0).expand((N, num_steps))
         if perturb:
             z_vals = z_vals + (torch.rand(z_vals.shape, device=device) - 0.5) * sample_dist
-
-        xyzs = rays_o.unsqueeze(-2) + rays_d.unsqueeze(-2) * z_vals.unsqueeze(-1)
-        xyzs = torch.min(torch.max(xyzs, aabb[:3]), aabb[3:])
-
-        density_outputs = self.density(xyzs.reshape(-1, 3))
-        for k, v in density_outputs.items():
-            density_outputs[k] = v.view(N, num_steps, -1)
+        xyzs = points(z_vals)
+        fields = query(xyzs, num_steps)
 
         if upsample_steps > 0:
             with torch.no_grad():
-                deltas = z_vals[..., 1:] - z_vals[..., :-1]
-                deltas = torch.cat([deltas, sample_dist * torch.ones_like(deltas[..., :1])], dim=-1)
-                alphas = 1 - torch.exp(-deltas * self.density_scale * density_outputs["sigma"].squeeze(-1))
-                alphas_shifted = torch.cat([torch.ones_like(alphas[..., :1]), 1 - alphas + 1e-15], dim=-1)
-                weights = alphas * torch.cumprod(alphas_shifted, dim=-1)[..., :-1]
-                z_vals_mid = z_vals[..., :-1] + 0.5 * deltas[..., :-1]
-                new_z_vals = sample_pdf(z_vals_mid, weights[:, 1:-1], upsample_steps, det=not self.training).detach()
-                new_xyzs = rays_o.unsqueeze(-2) + rays_d.unsqueeze(-2) * new_z_vals.unsqueeze(-1)
-                new_xyzs = torch.min(torch.max(new_xyzs, aabb[:3]), aabb[3:])
-            new_density_outputs = self.density(new_xyzs.reshape(-1, 3))
-            for k, v in new_density_outputs.items():
-                new_density_outputs[k] = v.view(N, upsample_steps, -1)
-            z_vals = torch.cat([z_vals, new_z_vals], dim=1)
-            z_vals, z_index = torch.sort(z_vals, dim=1)
-            xyzs = torch.cat([xyzs, new_xyzs], dim=1)
-            xyzs = torch.gather(xyzs, dim=1, index=z_index.unsqueeze(-1).expand_as(xyzs))
-            for k in density_outputs:
-                tmp_output = torch.cat([density_outputs[k], new_density_outputs[k]], dim=1)
-                density_outputs[k] = torch.gather(tmp_output, dim=1, index=z_index.unsqueeze(-1).expand_as(tmp_output))
+                weights, deltas = alpha_weights(z_vals, sample_dist, fields["sigma"].squeeze(-1), self.density_scale)
+                mids = z_vals[..., :-1] + 0.5 * deltas[..., :-1]
+                new_z = sample_pdf(mids, weights[:, 1:-1], upsample_steps, det=not self.training).detach()
+                new_xyzs = points(new_z)
+            new_fields = query(new_xyzs, upsample_steps)
+            z_vals, order = torch.sort(torch.cat([z_vals, new_z], dim=1), dim=1)      # merge coarse and fine samples by depth
 
-        deltas = z_vals[..., 1:] - z_vals[..., :-1]
-        deltas = torch.cat([deltas, sample_dist * torch.ones_like(deltas[..., :1])], dim=-1)
-        alphas = 1 - torch.exp(-deltas * self.density_scale * density_outputs["sigma"].squeeze(-1))
-        alphas_shifted = torch.cat([torch.ones_like(alphas[..., :1]), 1 - alphas + 1e-15], dim=-1)
-        weights = alphas * torch.cumprod(alphas_shifted, dim=-1)[..., :-1]
+            def merged(a, b):
+                both = torch.cat([a, b], dim=1)
+                return torch.gather(both, dim=1, index=order.unsqueeze(-1).expand_as(both))
 
-        dirs = rays_d.view(-1, 1, 3).expand_as(xyzs)
-        for k, v in density_outputs.items():
-            density_outputs[k] = v.view(-1, v.shape[-1])
+            xyzs = merged(xyzs, new_xyzs)
+            fields = {k: merged(fields[k], new_fields[k]) for k in fields}
 
-        mask = weights > 1e-4
-        rgbs = self.color(xyzs.reshape(-1, 3), dirs.reshape(-1, 3), mask=mask.reshape(-1), **density_outputs)
-        rgbs = rgbs.view(N, -1, 3)
-        if render_mask:
-            instance_mask_logits = self.mask(xyzs.reshape(-1, 3), mask=mask.reshape(-1), **density_outputs)
-            instance_mask_logits = instance_mask_logits.view(N, -1, self.num_instances)
+        weights, _ = alpha_weights(z_vals, sample_dist, fields["sigma"].squeeze(-1), self.density_scale)
+        visible = (weights > 1e-4).reshape(-1)
+        flat = {k: v.reshape(-1, v.shape[-1]) for k, v in fields.items()}
+        pts = xyzs.reshape(-1, 3)
+        rgbs = self.color(pts, rays_d.view(-1, 1, 3).expand_as(xyzs).reshape(-1, 3), mask=visible, **flat).view(N, -1, 3)
 
         weights_sum = weights.sum(dim=-1)
-        ori_z_vals = ((z_vals - nears) / (fars - nears)).clamp(0, 1)
-        depth = torch.sum(weights * ori_z_vals, dim=-1)
+        depth = torch.sum(weights * ((z_vals - nears) / span).clamp(0, 1), dim=-1)
         image = torch.sum(weights.unsqueeze(-1) * rgbs, dim=-2)
-
         if self.bg_radius > 0:
-            sph = raymarching.sph_from_ray(rays_o, rays_d, self.bg_radius)
-            bg_color = self.background(sph, rays_d.reshape(-1, 3))
+            bg_color = self.background(raymarching.sph_from_ray(rays_o, rays_d, self.bg_radius), rays_d.reshape(-1, 3))
         elif bg_color is None:
             bg_color = 1
         image = image + (1 - weights_sum).unsqueeze(-1) * bg_color
 
+        logits = None
         if render_mask:
-            instance_mask_logits = torch.sum(weights.unsqueeze(-1) * instance_mask_logits, dim=-2)
-            instance_mask_logits = instance_mask_logits.view(*prefix, self.num_instances)
-        else:
-            instance_mask_logits = None
-        return {
-            "depth": depth.view(*prefix),
-            "image": image.view(*prefix, 3),
-            "instance_mask_logits": instance_mask_logits,
-            "weights_sum": weights_sum,
-        }
+            per_sample = self.mask(pts, mask=visible, **flat).view(N, -1, self.num_instances)
+            logits = torch.sum(weights.unsqueeze(-1) * per_sample, dim=-2).view(*prefix, self.num_instances)
+        return {"depth": depth.view(*prefix), "image": image.view(*prefix, 3), "instance_mask_logits": logits, "weights_sum": weights_sum}
 
     # -- cuda_ray renderer (mask_renderer.py:234-387) --------------------------------
     def run_cuda(self, rays_o, rays_d, render_mask=False, dt_gamma=0, bg_color=None, perturb=False, force_all_rays=False,
