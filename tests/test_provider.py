@@ -63,6 +63,22 @@ def test_mask_dataset_loads_like_the_reference(gold, scene_dir, fake_h5py, split
     assert [len(loader), int(loader.has_gt)] == gold[tag + "loader"].tolist() and loader._data is ds
 
 
+def test_loader_contract_rand_pose_and_error_map(scene_dir, fake_h5py):
+    """dataloader(): `size // rand_pose` extra indices select the random-pose branch (provider.py:627-631); the error map is
+    [frames, 128 * 128] of ones for training sets only (:546-549); evaluation sets keep num_rays = -1."""
+    from instance_nerf_b200.nerf.provider import NeRFMaskDataset
+    opt = ps.options(scene_dir, None)
+    opt.rand_pose, opt.error_map = 2, True
+    ds = NeRFMaskDataset(opt, "cpu", type="train")
+    loader = ds.dataloader()
+    assert len(loader) == len(ds.poses) + len(ds.poses) // 2 and loader.has_gt and loader.batch_size == 1
+    assert ds.error_map.shape == (len(ds.poses), 128 * 128) and bool((ds.error_map == 1).all())
+    dv = NeRFMaskDataset(opt, "cpu", type="val")
+    assert dv.error_map is None and dv.num_rays == -1 and len(dv.dataloader()) == 1
+    dt = NeRFMaskDataset(opt, "cpu", type="test")
+    assert dt.masks is None and not dt.dataloader().has_gt and len(dt.dataloader()) == len(dt.poses)
+
+
 def test_segmap_formats_and_errors(tmp_path, scene_dir, gold):
     from instance_nerf_b200.nerf import provider
     m = ps.unpack_scene(gold)["masks"][0]
