@@ -113,9 +113,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* mbar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t* mbar, uint32_t parity) {
     uint32_t spins = 0;
     while (!mbar_try_wait(mbar, parity)) {
-#ifndef INERF_NO_WATCHDOG   // A/B only
         if (++spins == (1u << 28)) __trap();
-#endif
     }
 }
 
