@@ -72,6 +72,9 @@ constexpr uint32_t D_d = 144;   // up to 64: logits
 // i writes them with tcgen05.st and the MMAs of layer i + 1 read them there -- they never touch shared memory
 constexpr uint32_t A_h1 = 208;  // 32: sigma hidden, then colour hidden
 constexpr uint32_t A_h2 = 240;  // 32: mask hidden
+// (render kernel) the gathered INPUT tiles as tensor-memory operands too, two stages of 56 columns: sigma-table features 16 |
+// SH 8 + geo 8 | mask-table features 16 + geo 8 (fp16 pairs)
+constexpr uint32_t T_stage0 = 272, kStageCols = 56, S_es = 0, S_ci = 16, S_mi = 32;
 
 __device__ __forceinline__ uint32_t pack_half2(__half a, __half b) {
     return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16);
@@ -190,8 +193,18 @@ __device__ __forceinline__ void encode4(const float x01[3], bool oob, uint32_t l
     *reinterpret_cast<uint4*>(smem + a_mi + umma::tile_off(row, k0, kLBO, sbo_of(48))) = make_uint4(fm[0], fm[1], fm[2], fm[3]);
 }
 
+// Same, the 4 + 4 packed feature pairs returned in registers (the render kernel stores them to tensor memory itself)
+__device__ __forceinline__ void encode4_regs(const float x01[3], bool oob, uint32_t l0, const LevelGeom* __restrict__ lg,
+                                             const uint2* __restrict__ table, uint32_t (&fs)[4], uint32_t (&fm)[4]) {
+#pragma unroll
+    for (uint32_t li = 0; li < 4; li++) {
+        encode_level(x01, lg[l0 + li], table, fs[li], fm[li]);
+        if (oob) { fs[li] = 0u; fm[li] = 0u; }
+    }
+}
+
 // SH degree 4 (same polynomials as shencode.cu) rounded to fp16 into A_ci columns 0..15
-__device__ __forceinline__ void sh16_to_smem(float x, float y, float z, uint8_t* smem, uint32_t a_ci, uint32_t row) {
+__device__ __forceinline__ void sh16_pack(float x, float y, float z, uint32_t (&p)[8]) {
     float o[16];
     const float xy = x * y, xz = x * z, yz = y * z, x2 = x * x, y2 = y * y, z2 = z * z;
     o[0] = 0.28209479177387814f;
@@ -210,9 +223,12 @@ __device__ __forceinline__ void sh16_to_smem(float x, float y, float z, uint8_t*
     o[13] = 0.45704579946446572f * x * (1.0f - 5.0f * z2);
     o[14] = 1.4453057213202769f * z * (x2 - y2);
     o[15] = 0.59004358992664352f * x * (-x2 + 3.0f * y2);
-    uint32_t p[8];
 #pragma unroll
     for (int i = 0; i < 8; i++) p[i] = pack_half2(__float2half_rn(o[2 * i]), __float2half_rn(o[2 * i + 1]));
+}
+__device__ __forceinline__ void sh16_to_smem(float x, float y, float z, uint8_t* smem, uint32_t a_ci, uint32_t row) {
+    uint32_t p[8];
+    sh16_pack(x, y, z, p);
     *reinterpret_cast<uint4*>(smem + a_ci + umma::tile_off(row, 0, kLBO, sbo_of(32))) = make_uint4(p[0], p[1], p[2], p[3]);
     *reinterpret_cast<uint4*>(smem + a_ci + umma::tile_off(row, 8, kLBO, sbo_of(32))) = make_uint4(p[4], p[5], p[6], p[7]);
 }
@@ -303,6 +319,27 @@ __device__ __forceinline__ float epilogue_sigma(uint32_t tmem_base, uint8_t* sme
     return sigma;
 }
 
+// Same with the geo columns going to the TENSOR-MEMORY input stage (`stage` = its first column): A_ci columns 8..15, A_mi 16..23
+__device__ __forceinline__ float epilogue_sigma_tmem(uint32_t tmem_base, uint32_t stage, float density_scale, uint32_t tid) {
+    const uint32_t warp = tid >> 5;
+    float sigma = 0.f;
+    if (warp < 4) {
+        uint32_t v[16];
+        umma::tmem_ld16(tmem_base + D_c + ((warp * 32u) << 16), v);
+        umma::tmem_ld_wait();
+        __half h[16];
+#pragma unroll
+        for (int i = 0; i < 16; i++) h[i] = __float2half_rn(__uint_as_float(v[i]));
+        sigma = __fmul_rn(expf(__half2float(h[0])), density_scale);
+        const __half z = __float2half_rn(0.f);
+        const uint32_t g[8] = {pack_half2(h[1], h[2]), pack_half2(h[3], h[4]), pack_half2(h[5], h[6]), pack_half2(h[7], h[8]),
+                               pack_half2(h[9], h[10]), pack_half2(h[11], h[12]), pack_half2(h[13], h[14]), pack_half2(h[15], z)};
+        umma::tmem_st8(stage + ((warp * 32u) << 16) + S_ci + 8, g);
+        umma::tmem_st8(stage + ((warp * 32u) << 16) + S_mi + 16, g);
+    }
+    return sigma;
+}
+
 // colour output: 3 of 16 columns -> fp16 round -> sigmoid (fp32) -> fp16 round.  Valid for warps 0..3.
 __device__ __forceinline__ void epilogue_rgb(uint32_t tmem_base, float rgb[3], uint32_t tid) {
     const uint32_t warp = tid >> 5;
@@ -322,17 +359,19 @@ __device__ __forceinline__ void epilogue_rgb(uint32_t tmem_base, float rgb[3], u
 // issuer commits to `release_bar` (if not null): the gathered operand tiles may then be overwritten.
 // After return: D_c holds the colour pre-activations, D_d the logits (if with_masks); returns sigma for warps 0..3.
 // `on_sigma(sigma)` runs in every thread right after the sigma-net epilogue and before the next barrier.
-template <typename Sync, typename OnSigma>
+// kInTmem: the input tiles are tensor-memory operands as well (`in_stage` = first column of the stage, render kernel).
+template <bool kInTmem = false, typename Sync, typename OnSigma>
 __device__ __forceinline__ float mlp_chain(uint8_t* smem, const ChainBufs& b, uint32_t tmem_base, uint64_t* bar, uint32_t& phase, uint32_t K,
                                            float density_scale, bool with_masks, uint32_t tid, uint64_t* release_bar, Sync&& sync,
-                                           OnSigma&& on_sigma) {
+                                           OnSigma&& on_sigma, uint32_t in_stage = 0) {
     const uint32_t sbase = umma::smem_u32(smem);
     const WeightLayout wl = weight_layout(K);
     const bool issue_warp = tid < 32;   // warp 0 of the chain group; one elected lane issues
     // sigma layer 0
     if (issue_warp && umma::elect_one()) {
         umma::fence_after_sync();
-        issue_gemm(sbase, b.a_es, b.w + wl.s0, 32, 64, tmem_base + D_a);
+        if (kInTmem) issue_gemm_ts(in_stage + S_es, sbase, b.w + wl.s0, 32, 64, tmem_base + D_a);
+        else issue_gemm(sbase, b.a_es, b.w + wl.s0, 32, 64, tmem_base + D_a);
         umma::commit(bar);
     }
     __syncwarp();
@@ -350,15 +389,21 @@ __device__ __forceinline__ float mlp_chain(uint8_t* smem, const ChainBufs& b, ui
     __syncwarp();
     umma::mbar_wait(bar, phase); phase ^= 1u;
     umma::fence_after_sync();
-    const float sigma = epilogue_sigma(tmem_base, smem, b, density_scale, tid);
+    const float sigma = kInTmem ? epilogue_sigma_tmem(tmem_base, in_stage, density_scale, tid) : epilogue_sigma(tmem_base, smem, b, density_scale, tid);
     on_sigma(sigma);
-    umma::fence_async_smem(); umma::fence_before_sync();
+    if (kInTmem) umma::tmem_st_wait(); else umma::fence_async_smem();
+    umma::fence_before_sync();
     sync();
     // colour layer 0 + mask layer 0
     if (issue_warp && umma::elect_one()) {
         umma::fence_after_sync();
-        issue_gemm(sbase, b.a_ci, b.w + wl.c0, 32, 64, tmem_base + D_a);
-        if (with_masks) issue_gemm(sbase, b.a_mi, b.w + wl.m0, 48, 64, tmem_base + D_b);
+        if (kInTmem) {
+            issue_gemm_ts(in_stage + S_ci, sbase, b.w + wl.c0, 32, 64, tmem_base + D_a);
+            if (with_masks) issue_gemm_ts(in_stage + S_mi, sbase, b.w + wl.m0, 48, 64, tmem_base + D_b);
+        } else {
+            issue_gemm(sbase, b.a_ci, b.w + wl.c0, 32, 64, tmem_base + D_a);
+            if (with_masks) issue_gemm(sbase, b.a_mi, b.w + wl.m0, 48, 64, tmem_base + D_b);
+        }
         umma::commit(bar);
         if (release_bar) umma::commit(release_bar);
     }

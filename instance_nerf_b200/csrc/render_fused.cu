@@ -13,7 +13,7 @@
 //                                          are all free pulls the next 32 consecutive rays from a global counter.
 //   gather (16 warps, thread = slot x 4    16 levels x 8 corners, one 8-byte gather per corner from the interleaved
 //           of the 16 levels)              fp16 table (both encoders at once), fp16 trilinear blend, SH degree 4 ->
-//                                          UMMA operand tiles, double buffered.
+//                                          tcgen05.st into the TENSOR-MEMORY operand stage of the tile, double buffered.
 //   chain  (8 warps, thread = TMEM lane x  sigma / colour / mask MLPs as tcgen05.mma chains (fp32 accumulators in
 //           column half)                   TMEM), ReLU / exp / sigmoid epilogues, then the per-ray alpha compositing
 //                                          of colour, depth and K instance logits in registers
@@ -37,10 +37,11 @@ constexpr uint32_t kRegsChain = 96, kRegsGather = 64, kRegsMarch = 56;
 static_assert(kChainT * kRegsChain + kGatherT * kRegsGather + kMarchT * kRegsMarch <= (kChainT + kGatherT + kMarchT) * 72,
               "register budget of the three roles");
 constexpr uint32_t kThreadsR = kChainT + kGatherT + kMarchT;
-// samples queued per ray slot: 24 x 3 KB of rings fill the 196 KB shared-memory carve-out at K <= 32 (60 KB of L1 left) now that the
-// hidden activations live in tensor memory; measured on B200 (c2): 10 / 14 / 20 / 24 deep -> tile fill 0.905 / 0.921 / 0.943 / 0.955,
-// 8.92 / 8.77 / 8.71 / 8.68 ms (14-deep fits the 164 KB carve-out with 92 KB of L1; a third operand stage instead: 8.82 ms)
-constexpr uint32_t RING = 24;
+// samples queued per ray slot.  Shared memory holds only the weights, the rings, the coarse occupancy bitmap and control words (every
+// MMA A operand is in tensor memory): 32 x 3 KB of rings keep the CTA inside the 164 KB carve-out (92 KB of L1 left).  Measured on
+// B200 (c2), with the operand stages still in shared memory: 10 / 14 / 20 / 24 deep -> tile fill 0.905 / 0.921 / 0.943 / 0.955,
+// 8.92 / 8.77 / 8.71 / 8.68 ms; with them in tensor memory: 24 / 32 / 40 deep -> 8.22 / 8.15 / 8.34 ms (40 needs the 196 KB carve-out)
+constexpr uint32_t RING = 32;
 constexpr uint32_t DT = 4;    // tile descriptors in flight (gather may run DA tiles ahead of the chain)
 constexpr uint32_t DA = 2;    // gathered operand stages
 constexpr int kMarchCells = 8;   // occupancy cells a marcher lane may evaluate per warp iteration
@@ -87,8 +88,7 @@ struct Ctrl {
 };
 
 struct RSmem {
-    static constexpr uint32_t A = 0;                                 // DA stages of (es | ci | mi)
-    static constexpr uint32_t W = A + DA * kStageBytes;
+    static constexpr uint32_t W = 0;   // weights first: the DA operand stages (es | ci | mi) and the hidden activations live in tensor memory
     static __host__ __device__ uint32_t ctrl(uint32_t K) { return (W + weight_layout(K).total + 15u) & ~15u; }
     static __host__ __device__ uint32_t rings(uint32_t K) { return (ctrl(K) + (uint32_t)sizeof(Ctrl) + 15u) & ~15u; }
     static __host__ __device__ uint32_t coarse(uint32_t K) { return rings(K) + (uint32_t)sizeof(Rings); }
@@ -206,7 +206,7 @@ __device__ __forceinline__ void march_role(const inerf_field_desc& desc, const R
 
 // ----------------------------------------------------------------------------------------------- gather --
 __device__ __forceinline__ void gather_role(const inerf_field_desc& desc, const RenderParams& p, uint8_t* smem, Ctrl* ctl, Rings* rg,
-                                            uint32_t gt) {
+                                            uint32_t gt, uint32_t tmem_base) {
     const uint32_t row = gt & (kTile - 1), quarter = gt >> 7;   // thread = (ray slot, 4 of the 16 levels)
     const float inv2b = __fdiv_rn(1.0f, __fmul_rn(2.0f, desc.bound));
     const uint2* table = reinterpret_cast<const uint2*>(desc.table_packed);
@@ -258,11 +258,11 @@ __device__ __forceinline__ void gather_role(const inerf_field_desc& desc, const 
             break;
         }
         const int32_t e = ctl->tsel[st][row];
+        uint32_t fs[4] = {0u, 0u, 0u, 0u}, fm[4] = {0u, 0u, 0u, 0u}, sh[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
         if (e >= 0) {
             __threadfence_block();
             const int32_t ray = rg->ray[e][row];
             if (rg->dt[e][row] != 0.f && ld_vol(&ctl->kill[row]) != ray) {
-                const uint32_t a_es = RSmem::A + sa * kStageBytes, a_ci = a_es + kBytesEs, a_mi = a_ci + kBytesCi;
                 float x01[3];
                 x01[0] = __fmul_rn(__fadd_rn(rg->x[e][row], desc.bound), inv2b);
                 x01[1] = __fmul_rn(__fadd_rn(rg->y[e][row], desc.bound), inv2b);
@@ -270,17 +270,27 @@ __device__ __forceinline__ void gather_role(const inerf_field_desc& desc, const 
                 const bool oob = x01[0] < 0.f || x01[0] > 1.f || x01[1] < 0.f || x01[1] > 1.f || x01[2] < 0.f || x01[2] > 1.f;
                 if (quarter == 0) {
                     const float* d = p.rays_d + (size_t)ray * 3;
-                    sh16_to_smem(__ldg(d), __ldg(d + 1), __ldg(d + 2), smem, a_ci, row);
+                    sh16_pack(__ldg(d), __ldg(d + 1), __ldg(d + 2), sh);
                 }
-                encode4(x01, oob, quarter * 4, ctl->lg, table, smem, a_es, a_mi, row);
+                encode4_regs(x01, oob, quarter * 4, ctl->lg, table, fs, fm);
             }
         }
-        // every thread fences its own operand-tile writes, then ONE lane per warp arrives (16 arrivals per tile instead of 512)
-        umma::fence_async_smem();
+        // every lane of the warp stores its row (bubble rows: zeros) into the tensor-memory stage: warp w of the CTA owns TMEM
+        // lanes 32 (w % 4) .., and gather warp gw holds rows 32 (gw % 4) ..
+        __syncwarp();
+        {
+            const uint32_t stage = tmem_base + T_stage0 + sa * kStageCols + ((((gt >> 5) & 3u) * 32u) << 16);
+            umma::tmem_st4(stage + S_es + quarter * 4, fs);
+            umma::tmem_st4(stage + S_mi + quarter * 4, fm);
+            if (quarter == 0) umma::tmem_st8(stage + S_ci, sh);
+            umma::tmem_st_wait();
+            umma::fence_before_sync();
+        }
         __syncwarp();
         if ((gt & 31u) == 0) umma::mbar_arrive(&ctl->a_full[sa]);
     }
 }
+
 
 // ------------------------------------------------------------------------------------------------ chain --
 template <int NCH>  // 16-column logit chunks owned per thread: 1 -> K <= 32, 2 -> K <= 64
@@ -312,10 +322,10 @@ __device__ __forceinline__ void chain_role(const inerf_field_desc& desc, const R
         umma::mbar_wait(&ctl->a_full[sa], (tile / DA) & 1u);
         tile_count = tile;
         if (ld_vol(&ctl->a_flag[sa])) break;
-        const uint32_t a_es = RSmem::A + sa * kStageBytes;
-        const ChainBufs bufs{a_es, a_es + kBytesEs, a_es + kBytesEs + kBytesCi, RSmem::W};
+        const ChainBufs bufs{0u, 0u, 0u, RSmem::W};   // no shared-memory operand tiles: inputs and hidden activations are in TMEM
         float weight = 0.f;
-        mlp_chain(smem, bufs, tmem_base, &ctl->mma_bar, phase, K, desc.density_scale, with_masks, ct, &ctl->a_empty[sa], chain_sync,
+        umma::fence_after_sync();
+        mlp_chain<true>(smem, bufs, tmem_base, &ctl->mma_bar, phase, K, desc.density_scale, with_masks, ct, &ctl->a_empty[sa], chain_sync,
                   [&](float sigma) {
                       if (owner) {
                           const int32_t e = ctl->tsel[st][row];
@@ -347,7 +357,7 @@ __device__ __forceinline__ void chain_role(const inerf_field_desc& desc, const R
                           ctl->w_s[row] = weight;
                           ctl->fin_s[row] = fin;
                       }
-                  });
+                  }, tmem_base + T_stage0 + sa * kStageCols);
 
         if (owner) {
             float rgb[3];
@@ -445,8 +455,7 @@ __global__ void __launch_bounds__(kThreadsR, 1) k_render_fused(inerf_field_desc 
     Rings* rg = reinterpret_cast<Rings*>(smem + RSmem::rings(K));
     const uint32_t tid = threadIdx.x;
 
-    // operand tiles start as zeros: rows of a tile without a sample (bubbles) keep whatever was there last
-    for (uint32_t i = tid; i < RSmem::W / 16; i += kThreadsR) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
+    // (rows of a tile without a sample -- bubbles -- get zero operand rows from the gather warps; their outputs are never used)
     load_weights(smem, RSmem::W, desc.weights, K);
     init_levels(ctl->lg, desc.offsets, desc.L, desc.S, desc.H, tid);
     if (tid == 0) {
@@ -479,7 +488,7 @@ __global__ void __launch_bounds__(kThreadsR, 1) k_render_fused(inerf_field_desc 
         chain_role<NCH>(desc, p, smem, ctl, rg, tmem_base, tid);
     } else if (tid < kChainT + kGatherT) {
         umma::reg_dealloc<kRegsGather>();
-        gather_role(desc, p, smem, ctl, rg, tid - kChainT);
+        gather_role(desc, p, smem, ctl, rg, tid - kChainT, tmem_base);
     } else {
         umma::reg_dealloc<kRegsMarch>();
         march_role(desc, p, ctl, rg, coarse, tid - kChainT - kGatherT);
