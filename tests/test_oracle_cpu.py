@@ -339,3 +339,31 @@ def test_checkpoint_layout_matches_reference_and_round_trips(tmp_path):
     r2 = checkpoint.load_checkpoint(str(p2), m2, model_only=True)
     assert r2["missing_keys"] == ["density_grid"] and r2["unexpected_keys"] == []
     assert torch.equal(m2.encoder_mask.embeddings, m.encoder_mask.embeddings) and m2.mean_count == 4242
+
+
+def test_dense_renderer_helpers_known_answers():
+    """nerf/renderer.py helpers of the dense (non-cuda_ray) path (mask_renderer.py:13-47, 131-137): closed forms on the CPU.
+    (The whole `run()` is compared with the reference's renderer on the GPU, tests/test_field_gpu.py.)"""
+    from instance_nerf_b200.nerf.renderer import alpha_weights, sample_pdf
+    # constant density: w_i = (1 - a) a'^i with a = exp(-delta sigma), up to the 1e-15 guard
+    z = torch.linspace(1.0, 2.0, 11).repeat(3, 1)
+    sigma = torch.full((3, 11), 2.0)
+    w, deltas = alpha_weights(z, torch.full((3, 1), 0.1), sigma, density_scale=1.5)
+    a = torch.exp(torch.tensor(-0.1 * 1.5 * 2.0))
+    want = (1 - a) * a ** torch.arange(11, dtype=torch.float32)
+    torch.testing.assert_close(w[0], want, rtol=1e-5, atol=1e-7)
+    torch.testing.assert_close(deltas[1], torch.full((11,), 0.1), rtol=1e-5, atol=1e-6)
+    assert float(w.sum(-1)[0]) < 1.0
+    # uniform pdf over equal bins + deterministic u: the samples are u mapped linearly onto [bins[0], bins[-1]]
+    bins = torch.linspace(0.0, 1.0, 9).repeat(2, 1)
+    s = sample_pdf(bins, torch.ones(2, 8), 16, det=True)
+    torch.testing.assert_close(s[0], torch.linspace(0.5 / 16, 1 - 0.5 / 16, 16), rtol=0, atol=1e-5)
+    # all the mass in one bin: every sample falls inside it
+    wts = torch.full((1, 8), 0.0)
+    wts[0, 5] = 1.0
+    s = sample_pdf(bins[:1], wts, 32, det=True)
+    inside = (s >= bins[0, 5] - 1e-4) & (s <= bins[0, 6] + 1e-4)
+    assert float(inside.float().mean()) > 0.9 and bool((s[0, 1:] >= s[0, :-1]).all())
+    torch.manual_seed(0)
+    r = sample_pdf(bins, torch.rand(2, 8) + 0.1, 64, det=False)
+    assert r.shape == (2, 64) and float(r.min()) >= 0.0 and float(r.max()) <= 1.0
